@@ -1,0 +1,56 @@
+"""ctypes binding of libmmsam_b200.so (the C ABI declared in include/mmsam_b200.h).
+
+There is no CPU or library fallback: if the shared library is missing every kernel call raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmsam_b200.so")
+
+F32, F16, BF16, F64 = 0, 1, 2, 3
+
+_c = ctypes
+_vp, _i, _ll, _f = _c.c_void_p, _c.c_int, _c.c_longlong, _c.c_float
+
+# name -> argtypes; must list every symbol include/mmsam_b200.h declares
+SIGNATURES = {
+    "mmsam_arch": [],
+    "mmsam_msda_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mmsam_layernorm_bf16": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _ll, _ll, _f, _vp],
+    "mmsam_gemm_bf16": [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp,
+                        _i, _i, _i, _i, _i, _vp],
+}
+
+_lib = None
+
+
+class MMSamError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (building nothing: use build.py / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MMSamError(
+                f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+                "Run `python __graft_entry__.py` or `python multimodal-sam-adapter_b200/build.py`.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = _c.c_int
+        _lib = lib
+    return _lib
+
+
+_ERR = {-1: "bad argument", -2: "unsupported dtype", -3: "unsupported configuration", -4: "CUDA driver entry point unavailable"}
+
+
+def check(rc, what):
+    if rc != 0:
+        if rc < 0:
+            raise MMSamError(f"{what}: {_ERR.get(rc, 'error')} ({rc})")
+        raise MMSamError(f"{what}: CUDA error {rc}")

@@ -1,0 +1,114 @@
+// Channel LayerNorm over the last dimension of a [rows, C] bf16 matrix (HBM-bound).
+//
+// Serves every nn.LayerNorm / LayerNorm2d on the path: ViT Block.norm1/norm2
+// (segmentation/mmseg_custom/models/backbones/base/image_encoder.py:398,421), Injector/Extractor
+// query_norm/feat_norm/ffn_norm (adapter_modules_multimodal_mix_mod_new_in_twin_convnext_new.py:
+// 494-501, 527-532) and ConvNeXt LN2d (mmpretrain_custom/models/utils/norm.py:52-87), which in a
+// channels-last layout is the same row-wise operation.
+//
+// One warp per row, the row lives in registers (<= 8 x 16 B per lane), two-pass mean/variance in
+// fp32 (biased variance, like F.layer_norm). An optional int32 row map scatters the output rows
+// (dst = map[src], -1 = drop): that is how norm1 writes straight into SAM's zero-padded 14x14
+// window layout (image_encoder.py:504-526) without a separate partition pass.
+#include "common.cuh"
+
+namespace mmsam {
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                 const int* __restrict__ row_map, long long rows, int C, long long ldx,
+                 long long ldy, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nvec = C >> 3;
+  for (long long row = warp; row < rows; row += nwarps) {
+    long long dst = row;
+    if (row_map) {
+      dst = row_map[row];
+      if (dst < 0) continue;
+    }
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+    float f[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        unpack8(__ldg(xr + v), f[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[i][j];
+      }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = f[i][j] - mean;
+          s2 += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(s2) / (float)C + eps);
+    uint4* yr = reinterpret_cast<uint4*>(y + dst * ldy);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v);
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v + 1);
+        float o[8];
+        o[0] = (f[i][0] - mean) * rstd * g0.x + b0.x;
+        o[1] = (f[i][1] - mean) * rstd * g0.y + b0.y;
+        o[2] = (f[i][2] - mean) * rstd * g0.z + b0.z;
+        o[3] = (f[i][3] - mean) * rstd * g0.w + b0.w;
+        o[4] = (f[i][4] - mean) * rstd * g1.x + b1.x;
+        o[5] = (f[i][5] - mean) * rstd * g1.y + b1.y;
+        o[6] = (f[i][6] - mean) * rstd * g1.z + b1.z;
+        o[7] = (f[i][7] - mean) * rstd * g1.w + b1.w;
+        yr[v] = pack8(o);
+      }
+    }
+  }
+}
+
+}  // namespace mmsam
+
+MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* y,
+                                   const int* row_map_dev, long long rows, int C, long long ldx,
+                                   long long ldy, float eps, void* stream) {
+  using namespace mmsam;
+  if (rows < 0 || C <= 0 || (C & 7) || C > 2048 || (ldx & 7) || (ldy & 7)) return MMSAM_ERR_BAD_ARG;
+  if (rows == 0) return MMSAM_OK;
+  if (!x || !gamma || !beta || !y) return MMSAM_ERR_BAD_ARG;
+  if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15)) return MMSAM_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int wpb = 8;
+  long long blocks = (rows + wpb - 1) / wpb;
+  const long long cap = (long long)kNumSMs * 16;
+  if (blocks > cap) blocks = cap;
+  const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
+  __nv_bfloat16* yo = (__nv_bfloat16*)y;
+  const int nv = (C / 8 + 31) / 32;
+#define LN_CASE(NV) \
+  layernorm_kernel<NV><<<(unsigned)blocks, wpb * 32, 0, st>>>(xi, gamma, beta, yo, row_map_dev, rows, C, ldx, ldy, eps)
+  switch (nv) {
+    case 1: LN_CASE(1); break;
+    case 2: LN_CASE(2); break;
+    case 3: LN_CASE(3); break;
+    case 4: LN_CASE(4); break;
+    case 5: case 6: LN_CASE(6); break;
+    default: LN_CASE(8); break;
+  }
+#undef LN_CASE
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}

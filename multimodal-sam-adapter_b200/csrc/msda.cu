@@ -1,0 +1,263 @@
+// Multi-scale deformable attention sampling (forward) for sm_100a.
+//
+// Replaces the reference's ms_deformable_im2col_gpu_kernel
+// (segmentation/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299, bilinear helper :33-84) and its
+// host wrapper ms_deform_attn_cuda_forward (segmentation/ops/src/cuda/ms_deform_attn_cuda.cu:20-80).
+//
+//   out[n,q,m,:] = sum_l sum_p w[n,q,m,l,p] * bilinear(value_l[n,:,m,:], loc[n,q,m,l,p])
+//
+// with the reference's conventions: h_im = loc_y*H - 0.5, w_im = loc_x*W - 0.5 (align_corners =
+// False), zero padding outside the map, loc = (x, y) order.
+//
+// Two kernels:
+//  * msda_vec_kernel  - the hot one. A thread owns VEC contiguous channels of one (query, head)
+//    pair (16-byte gathers); a CTA owns QB consecutive queries x HB heads so the gathered footprint
+//    (a band of the value map for a few heads) stays L1-resident; no pre-zeroing, one 16 B store
+//    per thread.
+//  * msda_generic_kernel - any D / dtype (incl. fp64), one thread per output element; used for the
+//    reference's own known-answer shapes (D = 2) and as the catch-all.
+#include "common.cuh"
+
+namespace mmsam {
+
+template <typename T> struct Acc { using type = float; };
+template <> struct Acc<double> { using type = double; };
+
+template <typename T> __device__ __forceinline__ typename Acc<T>::type ldv(const T* p) { return (typename Acc<T>::type)(*p); }
+template <> __device__ __forceinline__ float ldv<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float ldv<__half>(const __half* p) { return __half2float(*p); }
+
+template <typename T> __device__ __forceinline__ void stv(T* p, typename Acc<T>::type v) { *p = (T)v; }
+template <> __device__ __forceinline__ void stv<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void stv<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+// ------------------------------------------------------------------------------------------------
+// generic kernel
+// ------------------------------------------------------------------------------------------------
+template <typename VT, typename AT>
+__global__ void __launch_bounds__(256)
+msda_generic_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                    const int64_t* __restrict__ lsi, const AT* __restrict__ loc,
+                    const AT* __restrict__ attw, VT* __restrict__ out, int N, int S, int M, int D,
+                    int Lq, int L, int P) {
+  using A = typename Acc<VT>::type;
+  const long long total = (long long)N * Lq * M * D;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % D);
+    long long t = idx / D;
+    const int m = (int)(t % M);
+    t /= M;
+    const int q = (int)(t % Lq);
+    const int n = (int)(t / Lq);
+    const long long pair = ((long long)n * Lq + q) * M + m;
+    const AT* lp = loc + pair * L * P * 2;
+    const AT* wp = attw + pair * L * P;
+    const VT* vbase = value + (long long)n * S * M * D + (long long)m * D + c;
+    A acc = 0;
+    for (int l = 0; l < L; ++l) {
+      const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];
+      const VT* vl = vbase + (long long)lsi[l] * M * D;
+      for (int p = 0; p < P; ++p) {
+        const A lx = (A)ldv(lp + (l * P + p) * 2), ly = (A)ldv(lp + (l * P + p) * 2 + 1);
+        const A aw = (A)ldv(wp + l * P + p);
+        const A h_im = ly * H - (A)0.5, w_im = lx * W - (A)0.5;
+        if (h_im > -1 && w_im > -1 && h_im < H && w_im < W) {
+          const int h0 = (int)floor(h_im), w0 = (int)floor(w_im);
+          const A lh = h_im - h0, lw = w_im - w0, hh = 1 - lh, hw = 1 - lw;
+          A v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+          const long long rs = (long long)M * D;
+          if (h0 >= 0 && w0 >= 0) v1 = ldv(vl + ((long long)h0 * W + w0) * rs);
+          if (h0 >= 0 && w0 + 1 <= W - 1) v2 = ldv(vl + ((long long)h0 * W + w0 + 1) * rs);
+          if (h0 + 1 <= H - 1 && w0 >= 0) v3 = ldv(vl + ((long long)(h0 + 1) * W + w0) * rs);
+          if (h0 + 1 <= H - 1 && w0 + 1 <= W - 1) v4 = ldv(vl + ((long long)(h0 + 1) * W + w0 + 1) * rs);
+          acc += aw * (hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4);
+        }
+      }
+    }
+    stv(out + idx, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// vectorised kernel: 16-byte gathers
+// ------------------------------------------------------------------------------------------------
+template <typename VT> struct Vec16;  // 16 bytes of VT
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float* f) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    unpack8(v, f);
+  }
+  __device__ static void store(__nv_bfloat16* p, const float* f) {
+    *reinterpret_cast<uint4*>(p) = pack8(f);
+  }
+};
+template <> struct Vec16<__half> {
+  static constexpr int N = 8;
+  __device__ static void load(const __half* p, float* f) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  __device__ static void store(__half* p, const float* f) {
+    uint4 v;
+    __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+};
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float* f) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  __device__ static void store(float* p, const float* f) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+
+// One CTA: QB consecutive queries x HB heads; TPP = D / VEC threads per (query, head) pair.
+// blockDim.x = QB * HB * TPP. gridDim = (ceil(Lq / QB), M / HB, N).
+template <typename VT, typename AT, int P>
+__global__ void __launch_bounds__(256)
+msda_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                const int64_t* __restrict__ lsi, const AT* __restrict__ loc,
+                const AT* __restrict__ attw, VT* __restrict__ out, int S, int M, int D, int Lq, int L,
+                int HB, int TPP) {
+  constexpr int VEC = Vec16<VT>::N;
+  const int n = blockIdx.z;
+  const int t = threadIdx.x;
+  const int chunk = t % TPP;
+  const int pr = t / TPP;
+  const int hi = pr % HB;
+  const int qi = pr / HB;
+  const int q = blockIdx.x * (blockDim.x / (HB * TPP)) + qi;
+  const int m = blockIdx.y * HB + hi;
+  if (q >= Lq) return;
+  const long long pair = ((long long)n * Lq + q) * M + m;
+  const AT* lp = loc + pair * L * P * 2;
+  const AT* wp = attw + pair * L * P;
+  const long long rs = (long long)M * D;  // elements between neighbouring spatial positions
+  const VT* vbase = value + (long long)n * S * rs + (long long)m * D + chunk * VEC;
+
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+
+  for (int l = 0; l < L; ++l) {
+    const int H = (int)__ldg(shapes + 2 * l), W = (int)__ldg(shapes + 2 * l + 1);
+    const VT* vl = vbase + (long long)__ldg(lsi + l) * rs;
+    float lx[P], ly[P], aw[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      lx[p] = (float)ldv(lp + (l * P + p) * 2);
+      ly[p] = (float)ldv(lp + (l * P + p) * 2 + 1);
+      aw[p] = (float)ldv(wp + l * P + p);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const float h_im = ly[p] * H - 0.5f, w_im = lx[p] * W - 0.5f;
+      if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        const int h0 = (int)hf, w0 = (int)wf;
+        const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+        const float c1 = aw[p] * hh * hw, c2 = aw[p] * hh * lw, c3 = aw[p] * lh * hw,
+                    c4 = aw[p] * lh * lw;
+        const bool t0 = h0 >= 0, b0 = h0 + 1 <= H - 1, l0 = w0 >= 0, r0 = w0 + 1 <= W - 1;
+        const VT* p00 = vl + ((long long)h0 * W + w0) * rs;
+        float v[VEC];
+        if (t0 && l0) {
+          Vec16<VT>::load(p00, v);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c1, v[i], acc[i]);
+        }
+        if (t0 && r0) {
+          Vec16<VT>::load(p00 + rs, v);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c2, v[i], acc[i]);
+        }
+        if (b0 && l0) {
+          Vec16<VT>::load(p00 + (long long)W * rs, v);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c3, v[i], acc[i]);
+        }
+        if (b0 && r0) {
+          Vec16<VT>::load(p00 + (long long)W * rs + rs, v);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c4, v[i], acc[i]);
+        }
+      }
+    }
+  }
+  Vec16<VT>::store(out + pair * D + chunk * VEC, acc);
+}
+
+template <typename VT, typename AT>
+static int launch_msda(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
+                       const void* attw, void* out, int N, int S, int M, int D, int Lq, int L, int P,
+                       cudaStream_t st) {
+  const VT* v = (const VT*)value;
+  const AT* lc = (const AT*)loc;
+  const AT* aw = (const AT*)attw;
+  VT* o = (VT*)out;
+  if (N == 0 || Lq == 0 || M == 0 || D == 0) return MMSAM_OK;
+  if constexpr (!std::is_same<VT, double>::value) {
+    constexpr int VEC = Vec16<VT>::N;
+    const bool aligned = (((uintptr_t)value | (uintptr_t)out) & 15) == 0;
+    if (aligned && D % VEC == 0 && D / VEC <= 32 && (P == 4 || P == 8 || P == 2 || P == 1) && N <= 65535 && M <= 65535) {
+      const int TPP = D / VEC;
+      int HB = 1;
+      for (int h = 2; h >= 1; --h)
+        if (M % h == 0) { HB = h; break; }
+      int QB = 256 / (HB * TPP);
+      if (QB > 32) QB = 32;
+      if (QB < 1) QB = 1;
+      dim3 grid((Lq + QB - 1) / QB, M / HB, N), block(QB * HB * TPP);
+      switch (P) {
+        case 1: msda_vec_kernel<VT, AT, 1><<<grid, block, 0, st>>>(v, shapes, lsi, lc, aw, o, S, M, D, Lq, L, HB, TPP); break;
+        case 2: msda_vec_kernel<VT, AT, 2><<<grid, block, 0, st>>>(v, shapes, lsi, lc, aw, o, S, M, D, Lq, L, HB, TPP); break;
+        case 4: msda_vec_kernel<VT, AT, 4><<<grid, block, 0, st>>>(v, shapes, lsi, lc, aw, o, S, M, D, Lq, L, HB, TPP); break;
+        default: msda_vec_kernel<VT, AT, 8><<<grid, block, 0, st>>>(v, shapes, lsi, lc, aw, o, S, M, D, Lq, L, HB, TPP); break;
+      }
+      MMSAM_LAUNCH_CHECK();
+      return MMSAM_OK;
+    }
+  }
+  const long long total = (long long)N * Lq * M * D;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)kNumSMs * 32) blocks = (long long)kNumSMs * 32;
+  msda_generic_kernel<VT, AT><<<(unsigned)blocks, 256, 0, st>>>(v, shapes, lsi, lc, aw, o, N, S, M, D, Lq, L, P);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+}  // namespace mmsam
+
+// See include/mmsam_b200.h for the contract.
+MMSAM_API int mmsam_msda_forward(const void* value, const int64_t* spatial_shapes_dev,
+                                 const int64_t* level_start_index_dev, const void* sampling_loc,
+                                 const void* attn_weight, void* out, int N, int S, int M, int D,
+                                 int Lq, int L, int P, int value_dtype, int aux_dtype,
+                                 void* stream) {
+  using namespace mmsam;
+  if (N < 0 || S < 0 || M < 0 || D < 0 || Lq < 0 || L < 0 || P < 0) return MMSAM_ERR_BAD_ARG;
+  if (N > 0 && Lq > 0 && M > 0 && D > 0 &&
+      (!value || !spatial_shapes_dev || !level_start_index_dev || !sampling_loc || !attn_weight || !out))
+    return MMSAM_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+#define MSDA_CASE(VD, AD, VT, AT) \
+  if (value_dtype == VD && aux_dtype == AD) \
+    return launch_msda<VT, AT>(value, spatial_shapes_dev, level_start_index_dev, sampling_loc, attn_weight, out, N, S, M, D, Lq, L, P, st);
+  MSDA_CASE(MMSAM_BF16, MMSAM_F32, __nv_bfloat16, float)
+  MSDA_CASE(MMSAM_BF16, MMSAM_BF16, __nv_bfloat16, __nv_bfloat16)
+  MSDA_CASE(MMSAM_F16, MMSAM_F32, __half, float)
+  MSDA_CASE(MMSAM_F16, MMSAM_F16, __half, __half)
+  MSDA_CASE(MMSAM_F32, MMSAM_F32, float, float)
+  MSDA_CASE(MMSAM_F64, MMSAM_F64, double, double)
+#undef MSDA_CASE
+  return MMSAM_ERR_BAD_DTYPE;
+}

@@ -1,0 +1,104 @@
+"""Thin torch-tensor front ends over the C ABI (include/mmsam_b200.h).
+
+torch is used for device memory and the current CUDA stream only; every op below launches one of
+this repo's sm_100a kernels and raises if the tensors are not on a CUDA device.
+"""
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.float64: _lib.F64}
+
+LAUNCHES = 0  # number of kernel launches issued through this module (bench.py reports it)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.MMSamError("mmsam_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def msda_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out=None):
+    """value [N,S,M,D]; spatial_shapes [L,2] i64 (device); level_start_index [L] i64 (device);
+    sampling_loc [N,Lq,M,L,P,2]; attn_weight [N,Lq,M,L,P]  ->  [N,Lq,M*D] in value's dtype."""
+    _need_cuda(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    for t in (value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+        if not t.is_contiguous():
+            raise _lib.MMSamError("msda_forward: all tensors must be contiguous")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise _lib.MMSamError("msda_forward: spatial_shapes / level_start_index must be int64")
+    if sampling_loc.dtype != attn_weight.dtype:
+        raise _lib.MMSamError("msda_forward: sampling_loc and attn_weight must share a dtype")
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_loc.shape
+    if out is None:
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+    rc = _lib.load().mmsam_msda_forward(
+        _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc), _ptr(attn_weight),
+        _ptr(out), N, S, M, D, Lq, L, P, _DT[value.dtype], _DT[sampling_loc.dtype], _stream())
+    _lib.check(rc, "mmsam_msda_forward")
+    _count()
+    return out
+
+
+def layernorm(x, gamma, beta, eps, out=None, row_map=None, out_rows=None):
+    """x bf16 [..., C] (rows contiguous) -> LN over C. row_map (int32 [rows]) scatters rows into an
+    `out` of out_rows rows (rows never written keep their previous contents)."""
+    _need_cuda(x, gamma, beta)
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    rows = x2.shape[0]
+    if out is None:
+        if row_map is None:
+            out = torch.empty_like(x2)
+        else:
+            out = torch.zeros((out_rows, C), dtype=x.dtype, device=x.device)
+    rc = _lib.load().mmsam_layernorm_bf16(
+        _ptr(x2), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(row_map), rows, C, x2.stride(0), out.stride(0),
+        float(eps), _stream())
+    _lib.check(rc, "mmsam_layernorm_bf16")
+    _count()
+    return out if row_map is not None else out.view(x.shape)
+
+
+ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "relu6": 3}
+
+
+def gemm(a, w, bias=None, act=None, scale=None, residual=None, out=None, out_dtype=torch.bfloat16,
+         row_map=None, out_rows=None, pixel_shuffle=None, block_n=0, max_ctas=0):
+    """out = epilogue(a[M,K] @ w[N,K]^T); a, w bf16 with contiguous K. See include/mmsam_b200.h."""
+    _need_cuda(a, w, bias, scale, residual, out, row_map)
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    row_mode, ps_h, ps_w, ps_c = 0, 0, 0, 0
+    n_out, m_out = N, M
+    if row_map is not None:
+        row_mode, m_out = 1, (out_rows if out_rows is not None else M)
+    if pixel_shuffle is not None:
+        ps_h, ps_w = pixel_shuffle
+        ps_c = N // 4
+        row_mode, m_out, n_out = 2, M * 4, ps_c
+    if out is None:
+        out = torch.empty((m_out, n_out), dtype=out_dtype, device=a.device)
+    rc = _lib.load().mmsam_gemm_bf16(
+        _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(scale), _ptr(residual),
+        residual.stride(0) if residual is not None else 0, _ptr(out), out.stride(0), M, N, K, ACT[act],
+        1 if out.dtype == torch.float32 else 0, row_mode, _ptr(row_map), ps_h, ps_w, ps_c, block_n, max_ctas,
+        _stream())
+    _lib.check(rc, "mmsam_gemm_bf16")
+    _count()
+    return out

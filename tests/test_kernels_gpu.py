@@ -1,0 +1,213 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C ABI."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _k():
+    import mmsam_b200  # noqa: F401
+    from mmsam_b200 import kernels
+    return kernels
+
+
+def _msda_inputs(N, M, D, Lq, shapes, P, seed, spread=1.2, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    shapes_t = torch.as_tensor(shapes, dtype=torch.long)
+    S = int(shapes_t.prod(1).sum())
+    L = len(shapes)
+    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+    value = (torch.rand(N, S, M, D, generator=g) * scale).to(dtype)
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g) * spread - (spread - 1) / 2
+    aw = torch.rand(N, Lq, M, L, P, generator=g) + 1e-5
+    aw = aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    return value, shapes_t, lsi, loc, aw
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_msda_reference_known_answer_shapes(dtype):
+    """The reference's own check (segmentation/ops/test.py:16-75): N1 M2 D2 Lq2 L2 P2, seed 3."""
+    from oracle.msda import ms_deform_attn_core
+    k = _k()
+    N, M, D, Lq, L, P = 1, 2, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    torch.manual_seed(3)
+    value = torch.rand(N, S, M, D) * 0.01
+    loc = torch.rand(N, Lq, M, L, P, 2)
+    aw = torch.rand(N, Lq, M, L, P) + 1e-5
+    aw /= aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    ref = ms_deform_attn_core(value.to(dtype), shapes, loc.to(dtype), aw.to(dtype))
+    out = k.msda_forward(value.to(dtype).cuda(), shapes.cuda(), lsi.cuda(), loc.to(dtype).cuda(), aw.to(dtype).cuda()).cpu()
+    if dtype == torch.float64:
+        assert torch.allclose(out, ref)  # reference criterion for double (ops/test.py:44)
+    else:
+        assert torch.allclose(out, ref, rtol=1e-2, atol=1e-3)  # ops/test.py:68
+        assert (out - ref).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("vdt,adt", [(torch.bfloat16, torch.float32), (torch.float32, torch.float32),
+                                     (torch.float16, torch.float16), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("cfg", [
+    dict(N=2, M=16, D=32, Lq=256, shapes=[(32, 32), (16, 16), (8, 8)], P=4),    # injector-like (3 levels)
+    dict(N=2, M=16, D=32, Lq=1344, shapes=[(16, 16)], P=4),                      # extractor-like (1 level)
+    dict(N=1, M=12, D=32, Lq=77, shapes=[(19, 25), (10, 13)], P=4),              # non-square, ragged Lq
+    dict(N=1, M=3, D=24, Lq=5, shapes=[(7, 5)], P=2),                            # odd head count
+    dict(N=1, M=2, D=7, Lq=9, shapes=[(4, 4), (2, 2)], P=3),                     # generic path
+])
+def test_msda_vs_oracle(cfg, vdt, adt):
+    from oracle.msda import ms_deform_attn_core
+    k = _k()
+    value, shapes, lsi, loc, aw = _msda_inputs(seed=1, **cfg)
+    v = value.to(vdt)
+    lc, w = loc.to(adt), aw.to(adt)
+    ref = ms_deform_attn_core(v.double(), shapes, lc.double(), w.double())
+    out = k.msda_forward(v.cuda(), shapes.cuda(), lsi.cuda(), lc.cuda(), w.cuda()).cpu().double()
+    err = (out - ref).abs().max().item()
+    # north_star: within 1e-3 of ms_deform_attn_core_pytorch (same rounded inputs, fp32 accumulate);
+    # bf16/fp16 outputs add one rounding of an O(1) value
+    tol = 1e-3 if vdt == torch.float32 else (8e-3 if vdt == torch.bfloat16 else 2e-3)
+    assert err < tol, err
+
+
+def test_msda_unit_scale_and_small_scale():
+    """ops/test.py scales value by 0.01; also check at unit scale with rtol 1e-2 / atol 1e-3."""
+    from oracle.msda import ms_deform_attn_core
+    k = _k()
+    for scale in (0.01, 1.0):
+        value, shapes, lsi, loc, aw = _msda_inputs(N=1, M=16, D=32, Lq=512, shapes=[(24, 24), (12, 12), (6, 6)], P=4,
+                                                   seed=5, scale=scale)
+        v = value.to(torch.bfloat16)
+        ref = ms_deform_attn_core(v.float(), shapes, loc, aw)
+        out = k.msda_forward(v.cuda(), shapes.cuda(), lsi.cuda(), loc.cuda(), aw.cuda()).cpu().float()
+        assert torch.allclose(out, ref, rtol=1e-2, atol=1e-3), (out - ref).abs().max()
+        if scale == 0.01:
+            assert (out - ref).abs().max() < 1e-3
+
+
+def test_msda_empty():
+    k = _k()
+    shapes = torch.as_tensor([(4, 4)], dtype=torch.long).cuda()
+    lsi = torch.zeros(1, dtype=torch.long).cuda()
+    v = torch.zeros(1, 16, 2, 8, device="cuda", dtype=torch.bfloat16)
+    out = k.msda_forward(v, shapes, lsi, torch.zeros(1, 0, 2, 1, 4, 2, device="cuda"), torch.zeros(1, 0, 2, 1, 4, device="cuda"))
+    assert out.shape == (1, 0, 16)
+
+
+@pytest.mark.parametrize("C", [96, 192, 384, 768, 1024, 1536, 64])
+def test_layernorm(C):
+    k = _k()
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(1000, C, generator=g) * 2 + 0.5).to(torch.bfloat16)
+    w = 1 + 0.1 * torch.randn(C, generator=g)
+    b = 0.1 * torch.randn(C, generator=g)
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), w, b, 1e-6)
+    out = k.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-6).cpu().float()
+    assert (out - ref).abs().max() < 0.04  # one bf16 rounding of |y| <~ 5
+    assert ((out - ref).abs() <= 0.004 * ref.abs() + 1e-3).all()
+
+
+def test_layernorm_row_map():
+    k = _k()
+    C = 128
+    x = torch.randn(10, C).to(torch.bfloat16)
+    rm = torch.tensor([3, -1, 0, 5, 11, -1, 7, 8, 1, 2], dtype=torch.int32)
+    w, b = torch.ones(C), torch.zeros(C)
+    out = k.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-6, row_map=rm.cuda(), out_rows=12).cpu().float()
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), w, b, 1e-6)
+    exp = torch.zeros(12, C)
+    for i, d in enumerate(rm.tolist()):
+        if d >= 0:
+            exp[d] = ref[i]
+    assert (out - exp).abs().max() < 0.04
+
+
+def _gemm_ref(a, w, bias=None, act=None, scale=None, residual=None):
+    y = a.double() @ w.double().t()
+    if bias is not None:
+        y = y + bias.double()
+    if act == "gelu":
+        y = torch.nn.functional.gelu(y)
+    elif act == "relu":
+        y = torch.relu(y)
+    elif act == "relu6":
+        y = torch.clamp(y, 0, 6)
+    if scale is not None:
+        y = y * scale.double()
+    if residual is not None:
+        y = y + residual.double()
+    return y
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 256, 64, 256), (128, 256, 256, 256), (256, 512, 1024, 256), (300, 200, 96, 0), (128, 128, 128, 128),
+    (1000, 64, 768, 64), (4096, 3072, 1024, 0), (4900, 1024, 1024, 0), (77, 25, 512, 0), (513, 384, 48, 0),
+    (20000, 4096, 1024, 256), (640, 1024, 4096, 128),
+])
+def test_gemm_plain(M, N, K, bn):
+    k = _k()
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    out = k.gemm(a.cuda(), w.cuda(), bias=bias.cuda(), block_n=bn, out_dtype=torch.float32).cpu().double()
+    ref = _gemm_ref(a, w, bias)
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3, err
+    outb = k.gemm(a.cuda(), w.cuda(), bias=bias.cuda(), block_n=bn).cpu().double()
+    assert ((outb - ref).abs() <= 0.008 * ref.abs() + 2e-3).all()
+
+
+@pytest.mark.parametrize("act", ["gelu", "relu", "relu6", None])
+def test_gemm_epilogues(act):
+    k = _k()
+    M, N, K = 777, 512, 256
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K) * 3).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    scale = torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g).to(torch.bfloat16)
+    out = k.gemm(a.cuda(), w.cuda(), bias=bias.cuda(), act=act, scale=scale.cuda(), residual=res.cuda(),
+                 out_dtype=torch.float32).cpu().double()
+    ref = _gemm_ref(a, w, bias, act, scale, res)
+    assert (out - ref).abs().max() < 3e-3
+
+
+def test_gemm_strided_operands_and_row_map():
+    k = _k()
+    M, N, K = 392, 256, 128
+    g = torch.Generator().manual_seed(5)
+    big = torch.randn(M, 3 * K, generator=g).to(torch.bfloat16).cuda()
+    a = big[:, K:2 * K]                      # lda = 3K
+    w = (torch.randn(N, K, generator=g) / 8).to(torch.bfloat16).cuda()
+    rm = torch.randperm(M + 50, generator=g)[:M].to(torch.int32)
+    rm[::7] = -1
+    res = torch.randn(M + 50, N, generator=g).to(torch.bfloat16)
+    out = torch.full((M + 50, N), 7.0, dtype=torch.bfloat16, device="cuda")
+    k.gemm(a, w, residual=res.cuda(), out=out, row_map=rm.cuda())
+    ref = _gemm_ref(a.cpu(), w.cpu())
+    exp = torch.full((M + 50, N), 7.0, dtype=torch.float64)
+    for i, d in enumerate(rm.tolist()):
+        if d >= 0:
+            exp[d] = ref[i] + res[d].double()
+    assert (out.cpu().double() - exp).abs().max() < 0.05
+
+
+def test_gemm_pixel_shuffle():
+    """ConvTranspose2d(C, C, 2, 2) as one GEMM + pixel-shuffle store (backbone `up`, ..._new.py:324)."""
+    k = _k()
+    B, H, W, Cin, Cout = 2, 6, 5, 64, 32
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(Cin, Cout, 2, 2, generator=g) / 8).to(torch.bfloat16)
+    bias = torch.randn(Cout, generator=g)
+    ref = torch.nn.functional.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, stride=2)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, Cout)
+    wg = wt.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).contiguous()
+    out = k.gemm(x.reshape(-1, Cin).cuda(), wg.cuda(), bias=bias.repeat(4).cuda(), pixel_shuffle=(H, W),
+                 out_dtype=torch.float32).cpu()
+    assert (out - ref).abs().max() < 2e-3
