@@ -37,6 +37,7 @@ struct GemmEpi {
   int act;        // 0 none, 1 gelu(erf), 2 relu, 3 relu6
   int out_f32;    // 0: bf16 output, 1: fp32 output
   int row_mode;   // 0 identity, 1 row_map, 2 pixel-shuffle 2x2 (ConvTranspose2d k=2 s=2)
+  int vec_ok;     // rows of out/residual are 16-byte aligned -> vector epilogue allowed
   int ps_h, ps_w, ps_c;
 };
 
@@ -176,7 +177,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (drow < 0) continue;
         float v[32];
-        const bool full32 = col + 32 <= ep.N;
+        const bool full32 = ep.vec_ok && col + 32 <= ep.N;
         if (full32) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -308,8 +309,9 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
     return MMSAM_ERR_BAD_ARG;
   // the vector epilogue needs 16-byte aligned rows; ragged N tails fall back to scalar stores
   const int oelt = out_f32 ? 4 : 2;
-  if ((((uintptr_t)out) & 15) || ((ldo * oelt) & 15)) return MMSAM_ERR_BAD_ARG;
-  if (residual && ((((uintptr_t)residual) & 15) || (ldr & 7))) return MMSAM_ERR_BAD_ARG;
+  int vec_ok = 1;
+  if ((((uintptr_t)out) & 15) || ((ldo * oelt) & 15)) vec_ok = 0;
+  if (residual && ((((uintptr_t)residual) & 15) || (ldr & 7))) vec_ok = 0;
   if (bias && (((uintptr_t)bias) & 15)) return MMSAM_ERR_BAD_ARG;
   if (scale && (((uintptr_t)scale) & 15)) return MMSAM_ERR_BAD_ARG;
   if (max_ctas <= 0 || max_ctas > kNumSMs) max_ctas = kNumSMs;
@@ -332,7 +334,7 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
   GemmEpi ep;
   ep.bias = bias; ep.scale = scale; ep.residual = (const __nv_bfloat16*)residual; ep.out = out;
   ep.row_map = row_map_dev; ep.ldo = ldo; ep.ldr = ldr; ep.M = M; ep.N = N; ep.K = K; ep.act = act;
-  ep.out_f32 = out_f32; ep.row_mode = row_mode; ep.ps_h = ps_h; ep.ps_w = ps_w; ep.ps_c = ps_c;
+  ep.out_f32 = out_f32; ep.row_mode = row_mode; ep.vec_ok = vec_ok; ep.ps_h = ps_h; ep.ps_w = ps_w; ep.ps_c = ps_c;
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 256) return launch_gemm<256>(tmA, tmB, ep, max_ctas, st);
   if (bn == 128) return launch_gemm<128>(tmA, tmB, ep, max_ctas, st);
