@@ -64,6 +64,15 @@ int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, 
                     const int* row_map_dev, int ps_h, int ps_w, int ps_c, int block_n, int max_ctas,
                     void* stream);
 
+/* Fused multi-head attention (head_dim 64) with SAM's decomposed relative-position bias.
+ * Replaces Attention.forward + add_decomposed_rel_pos (base/image_encoder.py:483-501, 587-623).
+ *   qkv [Bp, T, 3, nh, 64] bf16 (the qkv Linear output), out [Bp, T, nh*64] bf16,
+ *   tab_h / tab_w: bf16 [pad16(2*Kh-1), 64] / [pad16(2*Kw-1), 64] relative-position tables
+ *   (row r = q - k + K - 1, zero padded; both NULL = no bias), T == Kh*Kw, scale = 64^-0.5.
+ *   All T keys take part in the softmax (SAM does not mask its zero-padded window tokens). */
+int mmsam_attention_bf16(const void* qkv, void* out, const void* tab_h, const void* tab_w, int Bp, int T,
+                         int nh, int Kh, int Kw, float scale, int max_ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@ SIGNATURES = {
     "mmsam_layernorm_bf16": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _ll, _ll, _f, _vp],
     "mmsam_gemm_bf16": [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp,
                         _i, _i, _i, _i, _i, _vp],
+    "mmsam_attention_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp],
 }
 
 _lib = None

@@ -1,0 +1,436 @@
+// Fused multi-head attention with SAM's decomposed relative-position bias, head_dim 64,
+// on tcgen05 tensor cores (TMEM accumulators, TMA-fed), flash-style: the score matrix never
+// leaves the SM.
+//
+// Replaces Attention.forward + add_decomposed_rel_pos
+// (segmentation/mmseg_custom/models/backbones/base/image_encoder.py:483-501, 587-623):
+//     attn = softmax((q*scale) k^T + rel_h[q, kh] + rel_w[q, kw]);  out = attn v
+// with rel_h[q,kh] = q . Rh[qh-kh+Kh-1], rel_w[q,kw] = q . Rw[qw-kw+Kw-1] computed from the
+// UNSCALED q (image_encoder.py:492-495). Window blocks call it with Bp = B*windows, T = 196,
+// (Kh,Kw) = (14,14) — the zero-padded window tokens are ordinary keys (no masking, image_encoder.py
+// :504-526); global blocks with Bp = B, T = H*W.
+//
+// One CTA per SM, persistent over (batch', head, 128-query tile); 6 warps:
+//   warp 4  TMA producer: Q tile, K/V 128-key blocks (SWIZZLE_128B boxes straight out of the
+//           [Bp,T,3,nh,64] qkv GEMM output through a 4-D tensor map), rel-pos tables once per CTA.
+//   warp 5  MMA issuer: G = Q.table^T (bias pre-products), S_j = Q.K_j^T into a double-buffered
+//           TMEM tile, O_j = P_j.V_j (V as an MN-major operand) into a third TMEM tile.
+//   warps 0-3  softmax: thread = query row (tcgen05.ld 32x32b). Scatter G into per-row bias rows in
+//           shared memory (Toeplitz gather), then per key block: t = S*scale + bias, online max /
+//           sum in base 2, P -> bf16 into the swizzled K-major smem tile for the PV MMA, and the
+//           running output is rescaled/accumulated in registers (no TMEM read-modify-write).
+#include "common.cuh"
+
+namespace mmsam {
+
+struct AttnParams {
+  __nv_bfloat16* out;   // [Bp, T, nh*64]
+  int Bp, T, nh, Kh, Kw;
+  int nh_rows, nw_rows;        // table rows (2K-1), 0 = no relative position bias
+  int nh_pad, nw_pad;          // padded to a multiple of 16
+  int kv_stages;               // 2 or 3
+  int bh_stride, bw_stride;    // floats per bias row in shared memory
+  float scale_log2;            // scale * log2(e)
+  int num_tiles, nqb;
+};
+
+static constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 64;
+static constexpr int TILE_BYTES = 128 * 64 * 2;  // one 128 x 64 bf16 SW128 tile
+static constexpr float kLog2e = 1.4426950408889634f;
+
+// TMEM column plan
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+static constexpr int TM_S = 0;      // 2 x 128
+static constexpr int TM_PV = 256;   // 64
+static constexpr int TM_G = 320;    // 128
+
+__global__ void __launch_bounds__(192, 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTabH,
+                 const __grid_constant__ CUtensorMap tmTabW, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // layout: Q | KV stages | P (2 panels) | tables | bias rows | barriers
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + TILE_BYTES;
+  uint8_t* sP = sKV + p.kv_stages * 2 * TILE_BYTES;
+  uint8_t* sTab = sP + 2 * TILE_BYTES;
+  const int tab_bytes = (p.nh_pad + p.nw_pad) * 128;
+  float* sBias = reinterpret_cast<float*>(sTab + ((tab_bytes + 1023) & ~1023));
+  const int bh_stride = p.bh_stride, bw_stride = p.bw_stride;  // row-private rows, stride chosen odd
+  float* sBh = sBias;
+  float* sBw = sBias + ATT_BM * bh_stride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(
+      (reinterpret_cast<uintptr_t>(sBw + ATT_BM * bw_stride) + 15) & ~(uintptr_t)15);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* g_full = bars + 2;
+  uint64_t* g_empty = bars + 3;
+  uint64_t* p_full = bars + 4;
+  uint64_t* pv_done = bars + 5;
+  uint64_t* tab_full = bars + 6;
+  uint64_t* s_full = bars + 7;    // [2]
+  uint64_t* s_empty = bars + 9;   // [2]
+  uint64_t* kv_full = bars + 11;  // [3]
+  uint64_t* kv_empty = bars + 14; // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool has_bias = p.nh_rows > 0;
+  const int nkb = (p.T + ATT_BN - 1) / ATT_BN;
+  // G chunks of <= 128 table rows each: first the h table, then the w table
+  const int nch_h = has_bias ? (p.nh_pad + 127) / 128 : 0;
+  const int nch_w = has_bias ? (p.nw_pad + 127) / 128 : 0;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    mbar_init(g_empty, 4);
+    mbar_init(p_full, 4);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      if (has_bias) {
+        mbar_arrive_expect_tx(tab_full, tab_bytes);
+        tma_load_2d(sTab, &tmTabH, tab_full, 0, 0);
+        tma_load_2d(sTab + p.nh_pad * 128, &tmTabW, tab_full, 0, 0);
+      }
+      int st = 0; uint32_t kph = 0; uint32_t qph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int qb = tile % p.nqb;
+        const int bh = tile / p.nqb;
+        const int head = bh % p.nh, bp = bh / p.nh;
+        mbar_wait(q_empty, qph ^ 1);
+        mbar_arrive_expect_tx(q_full, TILE_BYTES);
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(smem_u32(sQ)), "l"(reinterpret_cast<uint64_t>(&tmQKV)), "r"(smem_u32(q_full)), "r"(0),
+            "r"(head), "r"(qb * ATT_BM), "r"(bp)
+            : "memory");
+        qph ^= 1;
+        for (int j = 0; j < nkb; ++j) {
+          mbar_wait(&kv_empty[st], kph ^ 1);
+          mbar_arrive_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+          uint8_t* sk = sKV + st * 2 * TILE_BYTES;
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+              ::"r"(smem_u32(sk)), "l"(reinterpret_cast<uint64_t>(&tmQKV)), "r"(smem_u32(&kv_full[st])), "r"(0),
+              "r"(p.nh + head), "r"(j * ATT_BN), "r"(bp)
+              : "memory");
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+              ::"r"(smem_u32(sk + TILE_BYTES)), "l"(reinterpret_cast<uint64_t>(&tmQKV)), "r"(smem_u32(&kv_full[st])),
+              "r"(0), "r"(2 * p.nh + head), "r"(j * ATT_BN), "r"(bp)
+              : "memory");
+          if (++st == p.kv_stages) { st = 0; kph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, ATT_BN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, ATT_D, 0, 1);  // V is MN-major
+      if (has_bias) { mbar_wait(tab_full, 0); }
+      int st = 0; uint32_t kph = 0;       // kv ring (QK side)
+      int st_pv = 0;                      // kv ring (PV side)
+      uint32_t qph = 0, gph = 0, pph = 0;
+      uint32_t g = 0;                     // global key-block counter (S buffer parity)
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      auto issue_pv = [&](int stage) {
+        mbar_wait(p_full, pph);
+        pph ^= 1;
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sKV + stage * 2 * TILE_BYTES + TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+          const uint32_t a = p_addr + (kk >> 2) * TILE_BYTES + (kk & 3) * 32;
+          const uint32_t b = v_addr + kk * 16 * 128;
+          umma_f16_ss(tmem + TM_PV, umma_desc_sw128(a), umma_desc_sw128(b), idesc_pv, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(pv_done);
+        umma_commit(&kv_empty[stage]);
+      };
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(q_full, qph);
+        qph ^= 1;
+        tc_fence_after();
+        // ---- bias pre-products G = Q . table^T, chunk by chunk through TM_G ----
+        for (int ci = 0; ci < nch_h + nch_w; ++ci) {
+          const bool is_w = ci >= nch_h;
+          const int c0 = (is_w ? ci - nch_h : ci) * 128;
+          const int npad = is_w ? p.nw_pad : p.nh_pad;
+          const int n = npad - c0 < 128 ? npad - c0 : 128;
+          mbar_wait(g_empty, gph ^ 1);
+          tc_fence_after();
+          const uint32_t t_addr = smem_u32(sTab) + ((is_w ? p.nh_pad : 0) + c0) * 128;
+          const uint32_t idesc_g = umma_idesc_bf16(128, n, 0, 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem + TM_G, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(t_addr + k * 32), idesc_g,
+                        k != 0 ? 1u : 0u);
+          umma_commit(g_full);
+          gph ^= 1;
+        }
+        // ---- main loop: QK_j issued ahead of PV_{j-1} ----
+        for (int j = 0; j < nkb; ++j, ++g) {
+          mbar_wait(&kv_full[st], kph);
+          mbar_wait(&s_empty[g & 1], ((g >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(sKV + st * 2 * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem + TM_S + (g & 1) * ATT_BN, umma_desc_sw128(q_addr + k * 32),
+                        umma_desc_sw128(k_addr + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[g & 1]);
+          if (j == nkb - 1) umma_commit(q_empty);
+          if (++st == p.kv_stages) { st = 0; kph ^= 1; }
+          if (j >= 1) {
+            issue_pv(st_pv);
+            if (++st_pv == p.kv_stages) st_pv = 0;
+          }
+        }
+        issue_pv(st_pv);
+        if (++st_pv == p.kv_stages) st_pv = 0;
+      }
+    }
+  } else {
+    // =========================== softmax / output (warps 0..3) ===========================
+    const int row = warp * 32 + lane;  // TMEM lane == query row within the tile
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    float* bh = sBh + row * bh_stride;
+    float* bw = sBw + row * bw_stride;
+    uint32_t gph = 0, pvph = 0;
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int qb = tile % p.nqb;
+      const int bhid = tile / p.nqb;
+      const int head = bhid % p.nh, bp = bhid / p.nh;
+      const int q = qb * ATT_BM + row;
+      const int qh = q / p.Kw, qw = q - qh * p.Kw;
+      // ---- scatter the bias pre-products into this row's bias rows (pre-scaled by log2 e) ----
+      for (int ci = 0; ci < nch_h + nch_w; ++ci) {
+        const bool is_w = ci >= nch_h;
+        const int c0 = (is_w ? ci - nch_h : ci) * 128;
+        const int npad = is_w ? p.nw_pad : p.nh_pad;
+        const int n = npad - c0 < 128 ? npad - c0 : 128;
+        const int K1 = is_w ? p.Kw : p.Kh;
+        const int qpos = is_w ? qw : qh;
+        float* dst = is_w ? bw : bh;
+        mbar_wait(g_full, gph);
+        gph ^= 1;
+        tc_fence_after();
+        for (int c = 0; c < n; c += 16) {
+          uint32_t r[16];
+          __syncwarp();
+          tmem_ld_32x32b_x16(lane_addr + TM_G + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int kpos = qpos + K1 - 1 - (c0 + c + i);  // table row r = qpos - kpos + K1 - 1
+            if (kpos >= 0 && kpos < K1) dst[kpos] = __uint_as_float(r[i]) * kLog2e;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g_empty);
+      }
+      float acc[ATT_D];
+#pragma unroll
+      for (int i = 0; i < ATT_D; ++i) acc[i] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+      for (int j = 0; j < nkb; ++j, ++g) {
+        // ---- 1. scores of key block j ----
+        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
+        float t[ATT_BN];
+#pragma unroll
+        for (int c = 0; c < ATT_BN; c += 32) {
+          __syncwarp();
+          tmem_ld_32x32b_x32(lane_addr + TM_S + (g & 1) * ATT_BN + c, reinterpret_cast<uint32_t*>(t + c));
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[g & 1]);
+        const int k0 = j * ATT_BN;
+        const int nvalid = p.T - k0 < ATT_BN ? p.T - k0 : ATT_BN;
+        float m_new = m_run;
+        if (has_bias) {
+          int kh = k0 / p.Kw, kw = k0 - kh * p.Kw;
+          float bhv = bh[kh < p.Kh ? kh : p.Kh - 1];
+#pragma unroll
+          for (int c = 0; c < ATT_BN; ++c) {
+            float v = fmaf(t[c], p.scale_log2, bhv + bw[kw]);
+            v = c < nvalid ? v : -INFINITY;
+            t[c] = v;
+            m_new = fmaxf(m_new, v);
+            if (++kw == p.Kw) {
+              kw = 0;
+              ++kh;
+              bhv = bh[kh < p.Kh ? kh : p.Kh - 1];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < ATT_BN; ++c) {
+            float v = t[c] * p.scale_log2;
+            v = c < nvalid ? v : -INFINITY;
+            t[c] = v;
+            m_new = fmaxf(m_new, v);
+          }
+        }
+        const float alpha = ex2(m_run - m_new);
+        float lsum = 0.f;
+        uint32_t pk[ATT_BN / 2];
+#pragma unroll
+        for (int c = 0; c < ATT_BN; c += 2) {
+          const float p0 = ex2(t[c] - m_new), p1 = ex2(t[c + 1] - m_new);
+          lsum += p0 + p1;
+          pk[c >> 1] = pack_bf16(p0, p1);
+        }
+        l_run = l_run * alpha + lsum;
+        m_run = m_new;
+        // ---- 2. fold in P_{j-1} V_{j-1} (the tensor core finished it while we did step 1) ----
+        if (j > 0) {
+          mbar_wait(pv_done, pvph);
+          pvph ^= 1;
+          tc_fence_after();
+          uint32_t o[ATT_D];
+          __syncwarp();
+          tmem_ld_32x32b_x32(lane_addr + TM_PV, o);
+          tmem_ld_32x32b_x32(lane_addr + TM_PV + 32, o + 32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < ATT_D; ++i) acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(o[i]));
+          tc_fence_before();
+        }
+        alpha_prev = alpha;
+        // ---- 3. P_j -> swizzled K-major bf16 smem tile, hand it to the MMA warp ----
+#pragma unroll
+        for (int c8 = 0; c8 < ATT_BN / 8; ++c8) {
+          const uint4 v = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+          const int panel = c8 >> 3, chunk = c8 & 7;
+          *reinterpret_cast<uint4*>(sP + panel * TILE_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      // ---- tile epilogue: last PV, normalise, store ----
+      {
+        mbar_wait(pv_done, pvph);
+        pvph ^= 1;
+        tc_fence_after();
+        uint32_t o[ATT_D];
+        __syncwarp();
+        tmem_ld_32x32b_x32(lane_addr + TM_PV, o);
+        tmem_ld_32x32b_x32(lane_addr + TM_PV + 32, o + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        const float inv = 1.f / l_run;
+#pragma unroll
+        for (int i = 0; i < ATT_D; ++i) acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(o[i])) * inv;
+        if (q < p.T) {
+          uint4* op = reinterpret_cast<uint4*>(p.out + ((long long)bp * p.T + q) * (p.nh * ATT_D) + head * ATT_D);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) op[i] = pack8(acc + 8 * i);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace mmsam
+
+// See include/mmsam_b200.h for the contract.
+MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const void* tab_h, const void* tab_w, int Bp,
+                                   int T, int nh, int Kh, int Kw, float scale, int max_ctas, void* stream) {
+  using namespace mmsam;
+  if (Bp < 0 || T <= 0 || nh <= 0) return MMSAM_ERR_BAD_ARG;
+  if (Bp == 0) return MMSAM_OK;
+  if (!qkv || !out) return MMSAM_ERR_BAD_ARG;
+  if ((((uintptr_t)qkv | (uintptr_t)out) & 15)) return MMSAM_ERR_BAD_ARG;
+  const bool has_bias = tab_h != nullptr && tab_w != nullptr;
+  if ((tab_h != nullptr) != (tab_w != nullptr)) return MMSAM_ERR_BAD_ARG;
+  if (has_bias && (Kh <= 0 || Kw <= 0 || Kh * Kw != T)) return MMSAM_ERR_BAD_ARG;
+  if (!has_bias) { Kh = 1; Kw = T; }
+  AttnParams p;
+  p.out = (__nv_bfloat16*)out;
+  p.Bp = Bp; p.T = T; p.nh = nh; p.Kh = Kh; p.Kw = Kw;
+  p.nh_rows = has_bias ? 2 * Kh - 1 : 0;
+  p.nw_rows = has_bias ? 2 * Kw - 1 : 0;
+  p.nh_pad = (p.nh_rows + 15) & ~15;
+  p.nw_pad = (p.nw_rows + 15) & ~15;
+  if (p.nh_pad > 256 || p.nw_pad > 256) return MMSAM_ERR_UNSUPPORTED;
+  p.scale_log2 = scale * kLog2e;
+  p.nqb = (T + ATT_BM - 1) / ATT_BM;
+  p.num_tiles = Bp * nh * p.nqb;
+  const int tab_bytes = ((p.nh_pad + p.nw_pad) * 128 + 1023) & ~1023;
+  const int bias_bytes = has_bias ? ATT_BM * ((Kh | 1) + (Kw | 1)) * 4 : ATT_BM * 2 * 4;
+  const int fixed = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*P*/ + tab_bytes + bias_bytes + 256 /*barriers*/ + 1024 /*align*/ + 64;
+  const int budget = 227 * 1024;
+  p.kv_stages = 3;
+  if (fixed + 3 * 2 * TILE_BYTES > budget) p.kv_stages = 2;
+  const int smem_bytes = fixed + p.kv_stages * 2 * TILE_BYTES;
+  if (smem_bytes > budget) return MMSAM_ERR_UNSUPPORTED;
+  p.bh_stride = has_bias ? (Kh | 1) + ((Kh & 1) ? 0 : 0) : 1;
+  p.bw_stride = has_bias ? (Kw | 1) : 1;
+  if (!has_bias) { p.Kh = 1; p.Kw = 1 << 30; }
+
+  mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
+  if (!enc) return MMSAM_ERR_DRIVER;
+  CUtensorMap tmQKV, tmH, tmW;
+  {
+    const uint64_t C3 = (uint64_t)3 * nh * ATT_D;
+    cuuint64_t dims[4] = {(cuuint64_t)ATT_D, (cuuint64_t)(3 * nh), (cuuint64_t)T, (cuuint64_t)Bp};
+    cuuint64_t strides[3] = {(cuuint64_t)ATT_D * 2, C3 * 2, (cuuint64_t)T * C3 * 2};
+    cuuint32_t box[4] = {ATT_D, 1, ATT_BM, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&tmQKV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(qkv), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MMSAM_ERR_DRIVER;
+  }
+  if (has_bias) {
+    if ((((uintptr_t)tab_h | (uintptr_t)tab_w) & 15)) return MMSAM_ERR_BAD_ARG;
+    int rc = mmsam_host::make_tmap_2d_bf16(&tmH, tab_h, p.nh_pad, ATT_D, ATT_D, p.nh_pad, ATT_D);
+    if (rc) return rc;
+    rc = mmsam_host::make_tmap_2d_bf16(&tmW, tab_w, p.nw_pad, ATT_D, ATT_D, p.nw_pad, ATT_D);
+    if (rc) return rc;
+  } else {
+    tmH = tmQKV; tmW = tmQKV;
+  }
+  static int configured_smem = 0;
+  if (smem_bytes > configured_smem) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, budget);
+    if (e != cudaSuccess) return (int)e;
+    configured_smem = budget;
+  }
+  if (max_ctas <= 0 || max_ctas > kNumSMs) max_ctas = kNumSMs;
+  const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
+  attention_kernel<<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(tmQKV, tmH, tmW, p);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}

@@ -1,0 +1,181 @@
+// Depthwise KxK convolution (stride 1, "same" zero padding) over channels-last bf16 maps.
+//
+// Serves ConvNeXtBlock.depthwise_conv 7x7 (segmentation/mmseg_custom/models/backbones/base/
+// twin_convnext.py:98-101), ConvFFN's DWConv 3x3 applied with SHARED weights to the three token
+// grids 128^2 | 64^2 | 32^2 of the concatenated sequence, fused with the GELU that follows it
+// (adapter_modules_multimodal_mix_mod_new_in_twin_convnext_new.py:446-471), and MobileNetV2's
+// 3x3 depthwise conv + ReLU6 (:281-295).
+//
+// HBM-bound. A CTA owns a TH x TW pixel tile x 64 channels: the (TH+K-1) x (TW+K-1) x 64 input halo
+// is staged in shared memory with 16-byte loads (coalesced along C), weights for the 64 channels sit in
+// shared memory as fp32 [K*K][64]. A thread owns one channel pair and 4 adjacent output columns for
+// all TH rows: per filter row it keeps the K weights in registers and slides over 4+K-1 staged inputs,
+// so the inner loop is pure fp32 FMA (K*K per output, the CUDA-core floor) with conflict-free 4-byte
+// shared-memory reads.
+#include "common.cuh"
+
+namespace mmsam {
+
+struct DwGrid {
+  long long in_off, out_off;  // element offsets of this grid inside a batch item
+  int H, W;
+};
+struct DwParams {
+  const __nv_bfloat16* x;
+  __nv_bfloat16* y;
+  const float* w;     // [K*K][C] fp32 (tap-major)
+  const float* bias;  // [C] or null
+  long long in_bstride, out_bstride;  // elements between batch items
+  int C, B, ngrids, act;              // act: 0 none, 1 gelu, 3 relu6
+  DwGrid g[3];
+  int tiles_x[3], tiles_y[3], tile_start[4];
+};
+
+template <int K, int TH, int TW>
+__global__ void __launch_bounds__(256, 2)
+dwconv_kernel(const DwParams p) {
+  constexpr int R = K / 2;
+  constexpr int IH = TH + K - 1, IW = TW + K - 1;
+  constexpr int CB = 64;  // channels per CTA
+  constexpr int XO = 4;   // adjacent output columns per thread
+  static_assert(TW == 32, "thread map assumes 8 column groups of 4");
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(dw_smem);                 // [IH*IW][CB]
+  float* s_w = reinterpret_cast<float*>(dw_smem + IH * IW * CB * 2);               // [K*K][CB]
+
+  // which grid / tile
+  int t = blockIdx.x, gi = 0;
+  while (gi + 1 < p.ngrids && t >= p.tile_start[gi + 1]) ++gi;
+  t -= p.tile_start[gi];
+  const int tx = t % p.tiles_x[gi], ty = t / p.tiles_x[gi];
+  const int H = p.g[gi].H, W = p.g[gi].W;
+  const int c0 = blockIdx.y * CB;
+  const int b = blockIdx.z;
+  const __nv_bfloat16* xin = p.x + (long long)b * p.in_bstride + p.g[gi].in_off;
+  __nv_bfloat16* yout = p.y + (long long)b * p.out_bstride + p.g[gi].out_off;
+  const int y0 = ty * TH, x0 = tx * TW;
+  const int cvalid = p.C - c0 < CB ? p.C - c0 : CB;  // multiple of 8
+
+  for (int i = threadIdx.x; i < K * K * CB; i += blockDim.x) {
+    const int c = i % CB;
+    s_w[i] = c < cvalid ? p.w[(i / CB) * p.C + c0 + c] : 0.f;
+  }
+  // stage the halo: 8 threads x 16 B cover the 64 channels of one pixel
+  for (int i = threadIdx.x; i < IH * IW * (CB / 8); i += blockDim.x) {
+    const int cv = i % (CB / 8);
+    const int pix = i / (CB / 8);
+    const int iy = y0 + pix / IW - R, ix = x0 + pix % IW - R;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W && cv * 8 < cvalid)
+      v = __ldg(reinterpret_cast<const uint4*>(xin + ((long long)iy * W + ix) * p.C + c0 + cv * 8));
+    *reinterpret_cast<uint4*>(&s_in[(pix * CB) + cv * 8]) = v;
+  }
+  __syncthreads();
+
+  // thread -> (channel pair cp, group of 4 output columns xg); all TH rows of the tile
+  const int cp = threadIdx.x & 31;
+  const int xg = threadIdx.x >> 5;
+  const int c = c0 + cp * 2;
+  float acc[TH][XO][2];
+  {
+    float b0 = 0.f, b1 = 0.f;
+    if (p.bias && cp * 2 < cvalid) { b0 = p.bias[c]; b1 = p.bias[c + 1]; }
+#pragma unroll
+    for (int r = 0; r < TH; ++r)
+#pragma unroll
+      for (int xo = 0; xo < XO; ++xo) { acc[r][xo][0] = b0; acc[r][xo][1] = b1; }
+  }
+  const uint32_t* s_in32 = reinterpret_cast<const uint32_t*>(s_in);
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    float2 w[K];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) w[kx] = *reinterpret_cast<const float2*>(&s_w[(ky * K + kx) * CB + cp * 2]);
+#pragma unroll
+    for (int r = 0; r < TH; ++r) {
+      float in0[XO + K - 1], in1[XO + K - 1];
+#pragma unroll
+      for (int i = 0; i < XO + K - 1; ++i) {
+        const uint32_t v = s_in32[((r + ky) * IW + xg * XO + i) * (CB / 2) + cp];
+        in0[i] = bf16lo(v);
+        in1[i] = bf16hi(v);
+      }
+#pragma unroll
+      for (int xo = 0; xo < XO; ++xo)
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          acc[r][xo][0] = fmaf(in0[xo + kx], w[kx].x, acc[r][xo][0]);
+          acc[r][xo][1] = fmaf(in1[xo + kx], w[kx].y, acc[r][xo][1]);
+        }
+    }
+  }
+  if (cp * 2 >= cvalid) return;
+#pragma unroll
+  for (int r = 0; r < TH; ++r) {
+    const int oy = y0 + r;
+    if (oy >= H) break;
+#pragma unroll
+    for (int xo = 0; xo < XO; ++xo) {
+      const int ox = x0 + xg * XO + xo;
+      if (ox >= W) continue;
+      float a0 = acc[r][xo][0], a1 = acc[r][xo][1];
+      if (p.act == 1) { a0 = gelu_erf(a0); a1 = gelu_erf(a1); }
+      else if (p.act == 3) { a0 = fminf(fmaxf(a0, 0.f), 6.f); a1 = fminf(fmaxf(a1, 0.f), 6.f); }
+      *reinterpret_cast<uint32_t*>(yout + ((long long)oy * W + ox) * p.C + c) = pack_bf16(a0, a1);
+    }
+  }
+}
+
+template <int K, int TH, int TW>
+static int launch_dw(const DwParams& p, dim3 grid, cudaStream_t st) {
+  constexpr int smem = (TH + K - 1) * (TW + K - 1) * 64 * 2 + K * K * 64 * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_kernel<K, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  dwconv_kernel<K, TH, TW><<<grid, 256, smem, st>>>(p);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+}  // namespace mmsam
+
+// See include/mmsam_b200.h for the contract.
+MMSAM_API int mmsam_dwconv_bf16(const void* x, void* y, const float* w_tap_major, const float* bias, int B,
+                                int C, int ksize, int ngrids, const int* grid_hw_host,
+                                const long long* grid_in_off_host, const long long* grid_out_off_host,
+                                long long in_bstride, long long out_bstride, int act, void* stream) {
+  using namespace mmsam;
+  if (B < 0 || C <= 0 || (C & 7) || ngrids < 1 || ngrids > 3) return MMSAM_ERR_BAD_ARG;
+  if (ksize != 3 && ksize != 7) return MMSAM_ERR_UNSUPPORTED;
+  if (act != 0 && act != 1 && act != 3) return MMSAM_ERR_BAD_ARG;
+  if (B == 0) return MMSAM_OK;
+  if (!x || !y || !w_tap_major || !grid_hw_host) return MMSAM_ERR_BAD_ARG;
+  if ((((uintptr_t)x | (uintptr_t)y) & 15) || (in_bstride & 7) || (out_bstride & 7)) return MMSAM_ERR_BAD_ARG;
+  DwParams p;
+  p.x = (const __nv_bfloat16*)x; p.y = (__nv_bfloat16*)y; p.w = w_tap_major; p.bias = bias;
+  p.in_bstride = in_bstride; p.out_bstride = out_bstride; p.C = C; p.B = B; p.ngrids = ngrids; p.act = act;
+  const int TH = ksize == 7 ? 4 : 8, TW = 32;
+  int total = 0;
+  for (int i = 0; i < 3; ++i) {
+    if (i < ngrids) {
+      p.g[i].H = grid_hw_host[2 * i]; p.g[i].W = grid_hw_host[2 * i + 1];
+      p.g[i].in_off = grid_in_off_host ? grid_in_off_host[i] : 0;
+      p.g[i].out_off = grid_out_off_host ? grid_out_off_host[i] : 0;
+      if (p.g[i].H <= 0 || p.g[i].W <= 0 || (p.g[i].in_off & 7) || (p.g[i].out_off & 7)) return MMSAM_ERR_BAD_ARG;
+      p.tiles_x[i] = (p.g[i].W + TW - 1) / TW;
+      p.tiles_y[i] = (p.g[i].H + TH - 1) / TH;
+    } else {
+      p.g[i].H = p.g[i].W = 0; p.g[i].in_off = p.g[i].out_off = 0; p.tiles_x[i] = p.tiles_y[i] = 0;
+    }
+    p.tile_start[i] = total;
+    total += p.tiles_x[i] * p.tiles_y[i];
+  }
+  p.tile_start[3] = total;
+  dim3 grid(total, (C + 63) / 64, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ksize == 7) return launch_dw<7, 4, 32>(p, grid, st);
+  return launch_dw<3, 8, 32>(p, grid, st);
+}

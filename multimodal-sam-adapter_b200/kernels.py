@@ -102,3 +102,33 @@ def gemm(a, w, bias=None, act=None, scale=None, residual=None, out=None, out_dty
     _lib.check(rc, "mmsam_gemm_bf16")
     _count()
     return out
+
+
+def relpos_table(rel_pos, size):
+    """SAM get_rel_pos for q_size == k_size == size (base/image_encoder.py:554-584): linear
+    interpolation of the [L, 64] table to 2*size-1 rows when L differs; row r = q - k + size - 1.
+    Returns a zero-padded bf16 [pad16(2*size-1), 64] table for attention()."""
+    n = 2 * size - 1
+    t = rel_pos.detach().float()
+    if t.shape[0] != n:
+        t = torch.nn.functional.interpolate(t.t()[None], size=n, mode="linear")[0].t()
+    pad = (n + 15) // 16 * 16
+    out = torch.zeros((pad, t.shape[1]), dtype=torch.bfloat16, device=rel_pos.device)
+    out[:n] = t.to(torch.bfloat16)
+    return out.contiguous()
+
+
+def attention(qkv, num_heads, hw, tab_h=None, tab_w=None, out=None, max_ctas=0):
+    """qkv bf16 [Bp, T, 3*nh*64] (qkv Linear output) -> [Bp, T, nh*64]; hw = (Kh, Kw), T = Kh*Kw."""
+    _need_cuda(qkv, tab_h, tab_w)
+    Bp, T, C3 = qkv.shape
+    hd = C3 // (3 * num_heads)
+    if hd != 64 or not qkv.is_contiguous():
+        raise _lib.MMSamError("attention: head_dim must be 64 and qkv contiguous")
+    if out is None:
+        out = torch.empty((Bp, T, num_heads * hd), dtype=torch.bfloat16, device=qkv.device)
+    rc = _lib.load().mmsam_attention_bf16(_ptr(qkv), _ptr(out), _ptr(tab_h), _ptr(tab_w), Bp, T, num_heads,
+                                          hw[0], hw[1], float(hd) ** -0.5, max_ctas, _stream())
+    _lib.check(rc, "mmsam_attention_bf16")
+    _count()
+    return out

@@ -81,22 +81,29 @@ def get_rel_pos(q_size, k_size, rel_pos):
     return r[rc.long()]
 
 
+def attention_core(q, k, v, h, w, rel_pos_h=None, rel_pos_w=None):
+    """V:492-498, 587-623. q,k,v [Bn, h*w, hd] -> [Bn, h*w, hd]; rel-pos bias uses the UNSCALED q."""
+    Bn, T, hd = q.shape
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    if rel_pos_h is not None:
+        Rh = get_rel_pos(h, h, rel_pos_h)
+        Rw = get_rel_pos(w, w, rel_pos_w)
+        rq = q.reshape(Bn, h, w, hd)
+        rel_h = torch.einsum("bhwc,hkc->bhwk", rq, Rh)
+        rel_w = torch.einsum("bhwc,wkc->bhwk", rq, Rw)
+        attn = (attn.view(-1, h, w, h, w) + rel_h[:, :, :, :, None] + rel_w[:, :, :, None, :]).view(-1, h * w, h * w)
+    return attn.softmax(dim=-1) @ v
+
+
 def attention(x, s, num_heads):
-    """V:483-501, 587-623. x [B',h,w,C]; rel-pos bias uses the UNSCALED q."""
+    """V:483-501. x [B',h,w,C]."""
     Bp, h, w, C = x.shape
     hd = C // num_heads
     qkv = linear(x, s.sub("qkv")).reshape(Bp, h * w, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv.reshape(3, Bp * num_heads, h * w, hd).unbind(0)
-    attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
-    if s.has("rel_pos_h"):
-        Rh = get_rel_pos(h, h, s("rel_pos_h"))
-        Rw = get_rel_pos(w, w, s("rel_pos_w"))
-        rq = q.reshape(Bp * num_heads, h, w, hd)
-        rel_h = torch.einsum("bhwc,hkc->bhwk", rq, Rh)
-        rel_w = torch.einsum("bhwc,wkc->bhwk", rq, Rw)
-        attn = (attn.view(-1, h, w, h, w) + rel_h[:, :, :, :, None] + rel_w[:, :, :, None, :]).view(-1, h * w, h * w)
-    attn = attn.softmax(dim=-1)
-    o = (attn @ v).view(Bp, num_heads, h, w, hd).permute(0, 2, 3, 1, 4).reshape(Bp, h, w, C)
+    o = attention_core(q, k, v, h, w, s("rel_pos_h") if s.has("rel_pos_h") else None,
+                       s("rel_pos_w") if s.has("rel_pos_w") else None)
+    o = o.view(Bp, num_heads, h, w, hd).permute(0, 2, 3, 1, 4).reshape(Bp, h, w, C)
     return linear(o, s.sub("proj"))
 
 

@@ -212,3 +212,52 @@ def test_gemm_pixel_shuffle():
     out = k.gemm(x.reshape(-1, Cin).cuda(), wg.cuda(), bias=bias.repeat(4).cuda(), pixel_shuffle=(H, W),
                  out_dtype=torch.float32).cpu()
     assert (out - ref).abs().max() < 2e-3
+
+
+@pytest.mark.parametrize("Bp,nh,Kh,Kw,bias", [
+    (2, 2, 14, 14, True),     # SAM window (196 keys, ragged 2nd key block)
+    (1, 2, 16, 16, True),     # 256 tokens, two full key blocks
+    (1, 1, 8, 16, False),     # single block, no bias
+    (1, 2, 32, 32, True),     # ViT-B/512 global (1024 tokens)
+    (2, 3, 19, 25, True),     # non-square grid (475 tokens, ragged)
+    (50, 16, 14, 14, True),   # many windows: exercises the persistent tile loop (2 images x 25 windows)
+    (1, 16, 64, 64, True),    # ViT-L/1024 global: 4096 tokens, 127-row tables, two G chunks
+])
+def test_attention_vs_oracle(Bp, nh, Kh, Kw, bias):
+    from oracle.model import attention_core
+    k = _k()
+    T = Kh * Kw
+    g = torch.Generator().manual_seed(Bp * 1000 + T)
+    qkv = (torch.randn(Bp, T, 3, nh, 64, generator=g) * 1.5).to(torch.bfloat16)
+    rph = (torch.randn(2 * Kh - 1, 64, generator=g) * 0.2).to(torch.bfloat16)
+    rpw = (torch.randn(2 * Kw - 1, 64, generator=g) * 0.2).to(torch.bfloat16)
+    th = tw = None
+    if bias:
+        th, tw = k.relpos_table(rph.cuda(), Kh), k.relpos_table(rpw.cuda(), Kw)
+    out = k.attention(qkv.view(Bp, T, -1).cuda(), nh, (Kh, Kw), th, tw).cpu().float()
+    q, kk, v = qkv.float().permute(2, 0, 3, 1, 4).reshape(3, Bp * nh, T, 64).unbind(0)
+    nchk = min(Bp * nh, 48)
+    ref = attention_core(q[:nchk].double(), kk[:nchk].double(), v[:nchk].double(), Kh, Kw,
+                         rph.double() if bias else None, rpw.double() if bias else None).float()
+    got = out.view(Bp, T, nh, 64).permute(0, 2, 1, 3).reshape(Bp * nh, T, 64)[:nchk]
+    err = (got - ref).abs().max().item()
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel < 1e-2 and err < 0.05, (rel, err)
+
+
+def test_attention_relpos_interpolated_table():
+    """FMB-shaped case: a 127-row table interpolated to 2*50-1 = 99 rows (get_rel_pos :566-575)."""
+    from oracle.model import attention_core
+    k = _k()
+    Kh = Kw = 20
+    T = Kh * Kw
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(1, T, 3, 2, 64, generator=g).to(torch.bfloat16)
+    rph = (torch.randn(127, 64, generator=g) * 0.2)
+    rpw = (torch.randn(127, 64, generator=g) * 0.2)
+    th, tw = k.relpos_table(rph.cuda(), Kh), k.relpos_table(rpw.cuda(), Kw)
+    out = k.attention(qkv.view(1, T, -1).cuda(), 2, (Kh, Kw), th, tw).cpu().float()
+    q, kk, v = qkv.float().permute(2, 0, 3, 1, 4).reshape(3, 2, T, 64).unbind(0)
+    ref = attention_core(q, kk, v, Kh, Kw, rph, rpw)
+    got = out.view(1, T, 2, 64).permute(0, 2, 1, 3).reshape(2, T, 64)
+    assert ((got - ref).norm() / ref.norm()).item() < 1.5e-2
