@@ -45,10 +45,13 @@ int mmsam_msda_forward(const void* value, const int64_t* spatial_shapes_dev,
 /* Row LayerNorm over the last dim of a bf16 [rows, C] matrix, fp32 affine, biased variance.
  * Replaces nn.LayerNorm / LayerNorm2d calls on the path (base/image_encoder.py:398,421;
  * adapter_modules_...new.py:494-501,527-532; mmpretrain_custom/models/utils/norm.py:52-87).
- * row_map_dev (optional int32[rows]): destination row of each source row, -1 = drop. */
+ * row_map_dev (optional int32[rows]): destination row of each source row, -1 = drop.
+ * ps_h, ps_w > 0 (and no row map): rows are (b, y<ps_h, x<ps_w); row goes to row (b, y/2, x/2), column
+ * block (y&1)*2+(x&1) of a [rows/4, 4C] matrix = the 2x2 patchify of ConvNeXt's LN2d -> Conv2d(k2,s2)
+ * downsample (base/twin_convnext.py:313-336). */
 int mmsam_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* y,
                          const int* row_map_dev, long long rows, int C, long long ldx, long long ldy,
-                         float eps, void* stream);
+                         float eps, int ps_h, int ps_w, void* stream);
 
 /* out = epilogue(A[M,K] . W[N,K]^T): bf16 operands, fp32 accumulation on tcgen05 tensor cores.
  * Replaces every nn.Linear / 1x1 conv / patchified conv on the path (see csrc/gemm.cu header).
@@ -72,6 +75,51 @@ int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, 
  *   All T keys take part in the softmax (SAM does not mask its zero-padded window tokens). */
 int mmsam_attention_bf16(const void* qkv, void* out, const void* tab_h, const void* tab_w, int Bp, int T,
                          int nh, int Kh, int Kw, float scale, int max_ctas, void* stream);
+
+/* MSDeformAttn core fused with its front end (bf16 value/out): reads the raw fp32 output of the
+ * query projection (columns [M*L*P*2 sampling offsets | M*L*P attention logits], row stride ldq;
+ * ops/modules/ms_deform_attn.py:108-113) and the per-query reference point ref_xy [Lq,2] (broadcast
+ * over batch and levels, adapter_modules_...new.py:397-431), doing softmax over L*P and
+ * loc = ref + off / (W_l, H_l) (ms_deform_attn.py:115-119) in registers. P must be 4. */
+int mmsam_msda_fused_bf16(const void* value, const int64_t* spatial_shapes_dev,
+                          const int64_t* level_start_index_dev, const float* qproj, long long ldq,
+                          const float* ref_xy, void* out, int N, int S, int M, int D, int Lq, int L, int P,
+                          void* stream);
+
+/* Depthwise k x k conv (k = 3 or 7, stride 1, zero "same" padding) on channels-last bf16 maps, fp32
+ * weights given tap-major [k*k][C], optional bias[C], act 0 none / 1 exact GELU / 3 ReLU6.
+ * Up to 3 grids per batch item share the weights (ConvFFN DWConv over the 128^2|64^2|32^2 token
+ * grids, adapter_modules_...new.py:456-471); grid i starts grid_*_off_host[i] elements into a batch
+ * item of in_bstride / out_bstride elements. Also ConvNeXt's 7x7 (base/twin_convnext.py:98-101).
+ * The *_host arrays are HOST pointers read before the call returns. */
+int mmsam_dwconv_bf16(const void* x, void* y, const float* w_tap_major, const float* bias, int B, int C,
+                      int ksize, int ngrids, const int* grid_hw_host, const long long* grid_in_off_host,
+                      const long long* grid_out_off_host, long long in_bstride, long long out_bstride, int act,
+                      void* stream);
+
+/* NCHW fp32 image channels [c_off, c_off+C) -> bf16 rows [(b,py,px), (c,ky,kx)] for p x p / stride p
+ * convs as GEMMs (patch embed base/image_encoder.py:662-671; ConvNeXt stem twin_convnext.py:295-312). */
+int mmsam_patchify_f32(const float* img, void* out, int B, int Ctot, int c_off, int C, int H, int W, int p,
+                       void* stream);
+
+/* out[b,y,x,:] = (base[b,y,x,:] + bilinear(src[b])[y,x,:]) * scale + shift on channels-last bf16
+ * (align_corners=False; base and scale/shift optional; ld* = elements between pixels, *_bstride =
+ * elements between batch items). Backbone tail (..._new.py:326-337) and head resize-into-concat
+ * (decode_heads/segformer_head.py:55-61). */
+int mmsam_resize_add_affine_bf16(const void* src, const void* base, const float* scale, const float* shift,
+                                 void* out, int B, int Hs, int Ws, int Ho, int Wo, int C, long long src_bstride,
+                                 long long lds, long long base_bstride, long long ldb, long long out_bstride,
+                                 long long ldo, void* stream);
+
+/* labels_u8[b, y<Hc, x<Wc] = argmax_c bilinear(logits[b] (hs x ws x ldl fp32, ncls valid) -> Ho x Wo):
+ * resize + softmax + argmax (+ crop) of segmentors/encoder_decoder.py:96-117, 329-414, 449, 477. */
+int mmsam_upsample_argmax_f32(const float* logits, void* labels_u8, int B, int hs, int ws, int ldl, int ncls,
+                              int Ho, int Wo, int Hc, int Wc, void* stream);
+
+/* conf_u64[gt*ncls + pred] += 1 for every pixel with gt != ignore_index: device-side
+ * intersect_and_union (mmseg_custom/apis/evaluation/metrics_micro.py:26-86). */
+int mmsam_confusion_u8(const void* pred_u8, const void* gt_u8, void* conf_u64, long long n, int ncls,
+                       int ignore_index, void* stream);
 
 #ifdef __cplusplus
 }

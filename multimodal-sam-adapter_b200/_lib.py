@@ -17,9 +17,15 @@ _vp, _i, _ll, _f = _c.c_void_p, _c.c_int, _c.c_longlong, _c.c_float
 SIGNATURES = {
     "mmsam_arch": [],
     "mmsam_msda_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "mmsam_layernorm_bf16": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _ll, _ll, _f, _vp],
+    "mmsam_layernorm_bf16": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _ll, _ll, _f, _i, _i, _vp],
     "mmsam_gemm_bf16": [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp,
                         _i, _i, _i, _i, _i, _vp],
+    "mmsam_msda_fused_bf16": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mmsam_dwconv_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _ll, _i, _vp],
+    "mmsam_patchify_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mmsam_resize_add_affine_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _vp],
+    "mmsam_upsample_argmax_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mmsam_confusion_u8": [_vp, _vp, _vp, _ll, _i, _i, _vp],
     "mmsam_attention_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp],
 }
 

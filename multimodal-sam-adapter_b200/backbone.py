@@ -1,0 +1,257 @@
+"""Registry entries of the drop-in boundary: same class names, constructor kwargs,
+forward contract and state-dict schema as the reference backbones / head / segmentor."""
+import math
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import nn_modules as M
+from .engine import EncoderEngine
+from .ops.modules import MSDeformAttn
+from .registry import BACKBONES, HEADS, SEGMENTORS, build_backbone, build_head
+
+
+def _trunc_normal(t, std=0.02):
+    nn.init.trunc_normal_(t, std=std)
+
+
+def _init_weights(m):
+    """..._new.py:119-134."""
+    if isinstance(m, nn.Linear):
+        _trunc_normal(m.weight)
+        if m.bias is not None:
+            nn.init.constant_(m.bias, 0)
+    elif isinstance(m, (nn.LayerNorm, nn.BatchNorm2d)):
+        nn.init.constant_(m.bias, 0)
+        nn.init.constant_(m.weight, 1.0)
+    elif isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+        fan_out = m.kernel_size[0] * m.kernel_size[1] * m.out_channels // m.groups
+        m.weight.data.normal_(0, math.sqrt(2.0 / fan_out))
+        if m.bias is not None:
+            m.bias.data.zero_()
+
+
+@BACKBONES.register_module(force=True)
+class ImageEncoderViT(nn.Module):
+    """SAM ViT encoder weights (base/image_encoder.py:187-328)."""
+
+    def __init__(self, img_size=1024, patch_size=16, in_chans=3, embed_dim=1024, depth=24, num_heads=16, mlp_ratio=4.0,
+                 qkv_bias=True, norm_layer=None, act_layer=None, use_abs_pos=True, use_rel_pos=True,
+                 rel_pos_zero_init=True, window_size=14, global_attn_indexes=(5, 11, 17, 23), pretrained=None,
+                 with_cp=False, pretrained_size=1024, fix=False):
+        super().__init__()
+        if embed_dim % num_heads or embed_dim // num_heads != 64:
+            raise ValueError("the B200 attention kernel is built for head_dim 64 (SAM ViT-B/L/H); got "
+                             f"embed_dim={embed_dim}, num_heads={num_heads}")
+        self.img_size, self.embed_dim, self.num_heads, self.patch_size = img_size, embed_dim, num_heads, patch_size
+        self.patch_embed = M.PatchEmbed((patch_size, patch_size), (patch_size, patch_size), in_chans, embed_dim)
+        self.pos_embed = None
+        if use_abs_pos:
+            self.pos_embed = nn.Parameter(torch.zeros(1, pretrained_size // patch_size, pretrained_size // patch_size, embed_dim))
+        self.blocks = nn.ModuleList()
+        gidx = list(global_attn_indexes)
+        for i in range(depth):
+            self.blocks.append(M.Block(embed_dim, num_heads, mlp_ratio, qkv_bias, use_rel_pos,
+                                       window_size if i not in gidx else 0,
+                                       (pretrained_size // patch_size, pretrained_size // patch_size)))
+        if isinstance(pretrained, str):
+            self.init_weights(pretrained)
+
+    def init_weights(self, pretrained=None):
+        if isinstance(pretrained, str):
+            sd = torch.load(pretrained, map_location="cpu")
+            sd = sd.get("state_dict", sd.get("model", sd))
+            self.load_state_dict(sd, strict=False)
+
+
+@BACKBONES.register_module(force=True)
+class TwinConvNeXt(M.TwinConvNeXt):
+    pass
+
+
+class _AdapterBase(ImageEncoderViT):
+    def __init__(self, pretrain_size=1024, num_heads=12, conv_inplane=64, n_points=4,
+                 modalities_name=("rgb", "depth", "lidar", "event"), modalities_ch=(3, 3, 3, 1), deform_num_heads=6,
+                 init_values=0., gamma_init_values=0., interaction_indexes=None, with_cffn=True, cffn_ratio=0.25,
+                 deform_ratio=1.0, add_vit_feature=True, pretrained=None, use_extra_extractor=True, with_cp=True,
+                 drop_path_rate=0.4, drop_rate=0., drop_multimodal_path=0.2, arch="base", checkpoint="check",
+                 conv_drop_path_rate=None, *args, **kwargs):
+        super().__init__(num_heads=num_heads, pretrained=pretrained, with_cp=with_cp, *args, **kwargs)
+        modalities_name, modalities_ch = list(modalities_name), list(modalities_ch)
+        if "rgb" not in modalities_name or len(modalities_name) != 2:
+            raise NotImplementedError("the B200 path implements the bimodal (rgb + one auxiliary modality) adapter "
+                                      "(SpatialPriorModuleBimodal); got modalities " + str(modalities_name))
+        self.in_ch_im = modalities_ch[modalities_name.index("rgb")]
+        img_size = kwargs.get("img_size")
+        self.cfg = dict(img_size=img_size, modalities_name=modalities_name, modalities_ch=modalities_ch,
+                        interaction_indexes=[list(i) for i in interaction_indexes], add_vit_feature=add_vit_feature,
+                        use_extra_extractor=use_extra_extractor, num_heads=num_heads, deform_num_heads=deform_num_heads,
+                        n_points=n_points, arch=arch)
+        self.interaction_indexes = interaction_indexes
+        self.add_vit_feature = add_vit_feature
+        E = self.embed_dim
+        self.spm = M.SpatialPriorModuleBimodal(conv_inplane, E, img_size, arch)
+        self.up = nn.ConvTranspose2d(E, E, 2, 2)
+        self.up.apply(_init_weights)
+        self.level_embed = nn.Parameter(torch.zeros(3, E))
+        n_int = len(interaction_indexes)
+        self.interactions = nn.Sequential(*[
+            M.InteractionBlock(E, deform_num_heads, n_points, with_cffn, cffn_ratio, init_values, deform_ratio,
+                               (i == n_int - 1) and use_extra_extractor, MSDeformAttn) for i in range(n_int)])
+        self.norm1 = nn.BatchNorm2d(E)
+        self.norm2 = nn.BatchNorm2d(E)
+        self.norm3 = nn.BatchNorm2d(E)
+        self.norm4 = nn.BatchNorm2d(E)
+        self.interactions.apply(_init_weights)
+        for m in self.modules():
+            if isinstance(m, MSDeformAttn):
+                m._reset_parameters()
+        nn.init.normal_(self.level_embed)
+        self._engine = None
+
+    # ------------------------------------------------------------------
+    def engine(self, head=None):
+        dev = next(self.parameters()).device
+        if self._engine is None or self._engine[0] != (str(dev), id(head)):
+            self._engine = ((str(dev), id(head)), EncoderEngine(self, head, dev))
+        return self._engine[1]
+
+    def invalidate(self):
+        """Call after changing weights in place (load_state_dict does it automatically)."""
+        self._engine = None
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self._engine = None
+        return r
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    @torch.no_grad()
+    def forward(self, x):
+        """x [B, sum(modalities_ch), H, W] -> ([f1..f4] NCHW, None)   (..._new.py:161-349)."""
+        if self.training:
+            raise RuntimeError("the B200 path is inference-only: call .eval() first")
+        feats = self.engine().backbone_nhwc(x)
+        return [f.permute(0, 3, 1, 2).contiguous().to(x.dtype) for f in feats], None
+
+
+@BACKBONES.register_module(force=True)
+class SAMAdapterbimodalMixModNewInTwinConvNEW(_AdapterBase):
+    pass
+
+
+@BACKBONES.register_module(force=True)
+class SAMAdapterbimodalMixModNewInTwinConvNEWwithcp(_AdapterBase):
+    pass
+
+
+@HEADS.register_module(force=True)
+class SegformerHead(M.SegformerHeadParams):
+    """decode_heads/segformer_head.py:11-66; kwargs of mmseg BaseDecodeHead accepted."""
+
+    def __init__(self, interpolate_mode="bilinear", in_channels=None, in_index=None, channels=None, num_classes=None,
+                 dropout_ratio=0.1, norm_cfg=None, act_cfg=None, align_corners=False, loss_decode=None,
+                 input_transform="multiple_select", **_ignored):
+        if interpolate_mode != "bilinear" or align_corners:
+            raise NotImplementedError("SegformerHead (B200): bilinear, align_corners=False only")
+        in_index = list(range(len(in_channels))) if in_index is None else list(in_index)
+        assert len(in_channels) == len(in_index)
+        super().__init__(list(in_channels), channels, num_classes)
+        self.in_channels, self.in_index, self.channels, self.num_classes = list(in_channels), in_index, channels, num_classes
+        self.align_corners = align_corners
+
+
+@SEGMENTORS.register_module(force=True)
+class EncoderDecoder(nn.Module):
+    """Inference side of segmentors/encoder_decoder.py: extract_feat, encode_decode, whole_dim /
+    whole_dim_cut / whole / slide inference, simple_test."""
+
+    def __init__(self, backbone, decode_head, neck=None, auxiliary_head=None, train_cfg=None, test_cfg=None,
+                 pretrained=None, init_cfg=None):
+        super().__init__()
+        backbone = dict(backbone)
+        if pretrained is not None:
+            assert backbone.get("pretrained") is None, "both backbone and segmentor set pretrained weight"
+            backbone["pretrained"] = pretrained
+        if neck is not None or auxiliary_head is not None:
+            raise NotImplementedError("neck / auxiliary_head are not part of the shipped configs")
+        self.backbone = build_backbone(backbone)
+        self.decode_head = build_head(decode_head)
+        self.align_corners = self.decode_head.align_corners
+        self.num_classes = self.decode_head.num_classes
+        self.train_cfg, self.test_cfg = train_cfg, dict(test_cfg or {})
+
+    def extract_feat(self, img):
+        x, *_ = self.backbone(img)
+        return x
+
+    def _engine(self):
+        return self.backbone.engine(self.decode_head)
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.backbone.invalidate()
+        return r
+
+    @torch.no_grad()
+    def encode_decode_labels(self, img, out_hw=None, crop_hw=None):
+        return self._engine().segment(img, out_hw, crop_hw)
+
+    @torch.no_grad()
+    def encode_decode(self, img, img_metas=None):
+        """Logits at image size (bilinear, align_corners=False): [B, num_classes, H, W] fp32."""
+        eng = self._engine()
+        feats = eng.backbone_nhwc(img)
+        logits, (h0, w0) = eng.head_logits(feats)
+        B = img.shape[0]
+        lg = logits.view(B, h0, w0, -1)[..., : self.num_classes].permute(0, 3, 1, 2)
+        return torch.nn.functional.interpolate(lg, size=img.shape[2:], mode="bilinear", align_corners=False)
+
+    @torch.no_grad()
+    def slide_labels(self, img):
+        """slide_inference (encoder_decoder.py:191-234): overlapping crops, logits averaged by count."""
+        h_stride, w_stride = self.test_cfg["stride"]
+        h_crop, w_crop = self.test_cfg["crop_size"]
+        B, _, h_img, w_img = img.shape
+        h_grids = max(h_img - h_crop + h_stride - 1, 0) // h_stride + 1
+        w_grids = max(w_img - w_crop + w_stride - 1, 0) // w_stride + 1
+        preds = img.new_zeros((B, self.num_classes, h_img, w_img))
+        count = img.new_zeros((B, 1, h_img, w_img))
+        for hi in range(h_grids):
+            for wi in range(w_grids):
+                y1, x1 = hi * h_stride, wi * w_stride
+                y2, x2 = min(y1 + h_crop, h_img), min(x1 + w_crop, w_img)
+                y1, x1 = max(y2 - h_crop, 0), max(x2 - w_crop, 0)
+                preds[:, :, y1:y2, x1:x2] += self.encode_decode(img[:, :, y1:y2, x1:x2].contiguous())
+                count[:, :, y1:y2, x1:x2] += 1
+        return (preds / count).argmax(1).to(torch.uint8)
+
+    @torch.no_grad()
+    def simple_test(self, img, img_meta=None, rescale=True):
+        """-> list of np.int64 [H, W] label maps, one per image (encoder_decoder.py:471-508)."""
+        mode = self.test_cfg.get("mode", "whole")
+        if mode == "slide":
+            lab = self.slide_labels(img)
+        else:
+            out_hw = crop = None
+            if mode in ("whole_dim", "whole_dim_cut") and rescale:
+                out_hw = tuple(self.test_cfg["dim"])
+                if tuple(out_hw) != tuple(img.shape[2:]):
+                    raise NotImplementedError("test_cfg.dim different from the network input size")
+            if mode == "whole_dim_cut":
+                cw, ch = self.test_cfg["cut_dim"]
+                crop = (ch, cw)
+            lab = self.encode_decode_labels(img, out_hw, crop)
+        return list(lab.cpu().numpy().astype(np.int64))
+
+    def forward(self, img, img_metas=None, return_loss=False, rescale=True, **kw):
+        if return_loss:
+            raise RuntimeError("inference-only build")
+        if isinstance(img, (list, tuple)):
+            img = img[0]
+        return self.simple_test(img, img_metas, rescale)

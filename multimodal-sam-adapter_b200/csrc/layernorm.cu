@@ -9,7 +9,9 @@
 // One warp per row, the row lives in registers (<= 8 x 16 B per lane), two-pass mean/variance in
 // fp32 (biased variance, like F.layer_norm). An optional int32 row map scatters the output rows
 // (dst = map[src], -1 = drop): that is how norm1 writes straight into SAM's zero-padded 14x14
-// window layout (image_encoder.py:504-526) without a separate partition pass.
+// window layout (image_encoder.py:504-526) without a separate partition pass. A second scatter mode
+// writes each row into its slot of the 2x2-patchified matrix consumed by ConvNeXt's stride-2
+// downsample conv (LN2d -> Conv2d(k=2,s=2), twin_convnext.py:313-336), which is then a plain GEMM.
 #include "common.cuh"
 
 namespace mmsam {
@@ -19,16 +21,26 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                  const int* __restrict__ row_map, long long rows, int C, long long ldx,
-                 long long ldy, float eps) {
+                 long long ldy, float eps, int ps_h, int ps_w) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = C >> 3;
   for (long long row = warp; row < rows; row += nwarps) {
     long long dst = row;
+    long long dcol = 0;
     if (row_map) {
       dst = row_map[row];
       if (dst < 0) continue;
+    } else if (ps_h > 0) {
+      // 2x2 patchify scatter for the stride-2 downsample conv: row (b,y,x) -> row (b,y/2,x/2),
+      // column block (y&1)*2 + (x&1)
+      const long long hw = (long long)ps_h * ps_w;
+      const long long b = row / hw;
+      const int r = (int)(row - b * hw);
+      const int yy = r / ps_w, xx = r - yy * ps_w;
+      dst = (b * (ps_h / 2) + yy / 2) * (ps_w / 2) + xx / 2;
+      dcol = ((yy & 1) * 2 + (xx & 1)) * C;
     }
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
     float f[NV][8];
@@ -56,7 +68,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
       }
     }
     const float rstd = rsqrtf(warp_sum(s2) / (float)C + eps);
-    uint4* yr = reinterpret_cast<uint4*>(y + dst * ldy);
+    uint4* yr = reinterpret_cast<uint4*>(y + dst * ldy + dcol);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + 32 * i;
@@ -84,9 +96,10 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
 
 MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* y,
                                    const int* row_map_dev, long long rows, int C, long long ldx,
-                                   long long ldy, float eps, void* stream) {
+                                   long long ldy, float eps, int ps_h, int ps_w, void* stream) {
   using namespace mmsam;
   if (rows < 0 || C <= 0 || (C & 7) || C > 2048 || (ldx & 7) || (ldy & 7)) return MMSAM_ERR_BAD_ARG;
+  if (ps_h < 0 || ps_w < 0 || (ps_h > 0 && ((ps_h | ps_w) & 1))) return MMSAM_ERR_BAD_ARG;
   if (rows == 0) return MMSAM_OK;
   if (!x || !gamma || !beta || !y) return MMSAM_ERR_BAD_ARG;
   if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15)) return MMSAM_ERR_BAD_ARG;
@@ -99,7 +112,7 @@ MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const floa
   __nv_bfloat16* yo = (__nv_bfloat16*)y;
   const int nv = (C / 8 + 31) / 32;
 #define LN_CASE(NV) \
-  layernorm_kernel<NV><<<(unsigned)blocks, wpb * 32, 0, st>>>(xi, gamma, beta, yo, row_map_dev, rows, C, ldx, ldy, eps)
+  layernorm_kernel<NV><<<(unsigned)blocks, wpb * 32, 0, st>>>(xi, gamma, beta, yo, row_map_dev, rows, C, ldx, ldy, eps, ps_h, ps_w)
   switch (nv) {
     case 1: LN_CASE(1); break;
     case 2: LN_CASE(2); break;

@@ -1,2 +1,217 @@
+// Small HBM-bound layout / resampling kernels around the GEMMs.
 #include "common.cuh"
+
 MMSAM_API int mmsam_arch(void) { return 100; }
+
+namespace mmsam {
+
+// NCHW fp32 image -> patch-major bf16 rows [(b, py, px), (c, ky, kx)]: turns the non-overlapping
+// strided convs (ViT patch embed 16x16/s16, image_encoder.py:662-671; ConvNeXt stem 4x4/s4,
+// twin_convnext.py:295-312) into GEMMs against the flattened conv weight [Cout, C*p*p].
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int Ctot, int c_off,
+                int C, int H, int W, int p) {
+  const int PW = W / p, PH = H / p;
+  const long long total = (long long)B * PH * PW * C * p * p;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    // consecutive threads walk kx fastest within a row of the patch: coalesced p-float reads
+    const int kx = (int)(idx % p);
+    long long t = idx / p;
+    const int px = (int)(t % PW); t /= PW;
+    const int ky = (int)(t % p); t /= p;
+    const int c = (int)(t % C); t /= C;
+    const int py = (int)(t % PH);
+    const int b = (int)(t / PH);
+    const float v = __ldg(img + (((long long)b * Ctot + c_off + c) * H + py * p + ky) * W + px * p + kx);
+    out[(((long long)b * PH + py) * PW + px) * (C * p * p) + (c * p + ky) * p + kx] = __float2bfloat16_rn(v);
+  }
+}
+
+// out[b,y,x,c] = (base[b,y,x,c] + bilinear(src[b])[y,x,c]) * scale[c] + shift[c]   (NHWC bf16)
+// PyTorch bilinear, align_corners=False. Serves the ViT-feature fusion + eval BatchNorm at the end of
+// the backbone (..._new.py:326-337) and the head's resize-into-concat (segformer_head.py:55-61).
+__global__ void __launch_bounds__(256)
+resize_add_affine_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ base,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         __nv_bfloat16* __restrict__ out, int B, int Hs, int Ws, int Ho, int Wo, int C,
+                         long long src_bstride, long long base_bstride, long long out_bstride, long long ldo,
+                         long long lds, long long ldb, float rh, float rw) {
+  const int CV = C >> 3;
+  const long long total = (long long)B * Ho * Wo * CV;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % CV);
+    long long t = idx / CV;
+    const int x = (int)(t % Wo); t /= Wo;
+    const int y = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float f[8];
+    if (Hs == Ho && Ws == Wo) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(src + b * src_bstride + ((long long)y * Ws + x) * lds + cv * 8)), f);
+    } else {
+      float sy = (y + 0.5f) * rh - 0.5f, sx = (x + 0.5f) * rw - 0.5f;
+      sy = sy < 0.f ? 0.f : sy;
+      sx = sx < 0.f ? 0.f : sx;
+      int y0 = (int)sy, x0 = (int)sx;
+      y0 = y0 > Hs - 1 ? Hs - 1 : y0;
+      x0 = x0 > Ws - 1 ? Ws - 1 : x0;
+      const int y1 = y0 < Hs - 1 ? y0 + 1 : y0, x1 = x0 < Ws - 1 ? x0 + 1 : x0;
+      const float ly = sy - y0, lx = sx - x0;
+      const __nv_bfloat16* sb = src + b * src_bstride + cv * 8;
+      float a[8], c[8], d[8], e[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(sb + ((long long)y0 * Ws + x0) * lds)), a);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(sb + ((long long)y0 * Ws + x1) * lds)), c);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(sb + ((long long)y1 * Ws + x0) * lds)), d);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(sb + ((long long)y1 * Ws + x1) * lds)), e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        f[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * c[j]) + ly * ((1.f - lx) * d[j] + lx * e[j]);
+    }
+    if (base) {
+      float g[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + b * base_bstride + ((long long)y * Wo + x) * ldb + cv * 8)), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += g[j];
+    }
+    if (scale) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = f[j] * __ldg(scale + cv * 8 + j) + __ldg(shift + cv * 8 + j);
+    }
+    *reinterpret_cast<uint4*>(out + b * out_bstride + ((long long)y * Wo + x) * ldo + cv * 8) = pack8(f);
+  }
+}
+
+// labels[b,y,x] = argmax_c bilinear(logits[b])[y,x,c]  (first maximum wins, like torch.argmax).
+// Replaces resize(logits -> image size) + softmax + argmax of EncoderDecoder.encode_decode_test /
+// whole_inference_dim(_cut) / simple_test (encoder_decoder.py:96-117, 329-414, 449, 477); softmax is
+// monotone so it is skipped; the crop of whole_inference_dim_cut is the (Hc, Wc) output window.
+__global__ void __launch_bounds__(256)
+upsample_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ labels, int B, int hs, int ws,
+                       int ldl, int ncls, int Ho, int Wo, int Hc, int Wc, float rh, float rw) {
+  const long long total = (long long)B * Hc * Wc;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % Wc);
+    long long t = idx / Wc;
+    const int y = (int)(t % Hc);
+    const int b = (int)(t / Hc);
+    float sy = (y + 0.5f) * rh - 0.5f, sx = (x + 0.5f) * rw - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    sx = sx < 0.f ? 0.f : sx;
+    int y0 = (int)sy, x0 = (int)sx;
+    y0 = y0 > hs - 1 ? hs - 1 : y0;
+    x0 = x0 > ws - 1 ? ws - 1 : x0;
+    const int y1 = y0 < hs - 1 ? y0 + 1 : y0, x1 = x0 < ws - 1 ? x0 + 1 : x0;
+    const float ly = sy - y0, lx = sx - x0;
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const float* lb = logits + (long long)b * hs * ws * ldl;
+    const float* p00 = lb + ((long long)y0 * ws + x0) * ldl;
+    const float* p01 = lb + ((long long)y0 * ws + x1) * ldl;
+    const float* p10 = lb + ((long long)y1 * ws + x0) * ldl;
+    const float* p11 = lb + ((long long)y1 * ws + x1) * ldl;
+    float best = -INFINITY;
+    int arg = 0;
+    for (int c = 0; c < ncls; c += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p00 + c));
+      const float4 bq = __ldg(reinterpret_cast<const float4*>(p01 + c));
+      const float4 cq = __ldg(reinterpret_cast<const float4*>(p10 + c));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(p11 + c));
+      const float v0 = w00 * a.x + w01 * bq.x + w10 * cq.x + w11 * d.x;
+      const float v1 = w00 * a.y + w01 * bq.y + w10 * cq.y + w11 * d.y;
+      const float v2 = w00 * a.z + w01 * bq.z + w10 * cq.z + w11 * d.z;
+      const float v3 = w00 * a.w + w01 * bq.w + w10 * cq.w + w11 * d.w;
+      if (v0 > best) { best = v0; arg = c; }
+      if (c + 1 < ncls && v1 > best) { best = v1; arg = c + 1; }
+      if (c + 2 < ncls && v2 > best) { best = v2; arg = c + 2; }
+      if (c + 3 < ncls && v3 > best) { best = v3; arg = c + 3; }
+    }
+    labels[((long long)b * Hc + y) * Wc + x] = (uint8_t)arg;
+  }
+}
+
+// confusion[gt, pred] += 1 over all pixels with gt != ignore (the device-side form of
+// intersect_and_union, mmseg_custom/apis/evaluation/metrics_micro.py:26-86).
+__global__ void __launch_bounds__(256)
+confusion_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt, unsigned long long* conf,
+                 long long n, int ncls, int ignore) {
+  extern __shared__ unsigned int s_conf[];
+  for (int i = threadIdx.x; i < ncls * ncls; i += blockDim.x) s_conf[i] = 0;
+  __syncthreads();
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = gt[idx], p = pred[idx];
+    if (g != ignore && g < ncls && p < ncls) atomicAdd(&s_conf[g * ncls + p], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncls * ncls; i += blockDim.x)
+    if (s_conf[i]) atomicAdd(&conf[i], (unsigned long long)s_conf[i]);
+}
+
+static inline unsigned grid_for(long long total, int per_block = 256, int waves = 8) {
+  long long b = (total + per_block - 1) / per_block;
+  const long long cap = (long long)kNumSMs * waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace mmsam
+
+MMSAM_API int mmsam_patchify_f32(const float* img, void* out, int B, int Ctot, int c_off, int C, int H, int W,
+                                 int p, void* stream) {
+  using namespace mmsam;
+  if (B < 0 || C <= 0 || p <= 0 || H % p || W % p || c_off < 0 || c_off + C > Ctot) return MMSAM_ERR_BAD_ARG;
+  if (B == 0) return MMSAM_OK;
+  if (!img || !out) return MMSAM_ERR_BAD_ARG;
+  const long long total = (long long)B * C * H * W;
+  patchify_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)out, B, Ctot, c_off, C, H, W, p);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+MMSAM_API int mmsam_resize_add_affine_bf16(const void* src, const void* base, const float* scale,
+                                           const float* shift, void* out, int B, int Hs, int Ws, int Ho, int Wo,
+                                           int C, long long src_bstride, long long lds, long long base_bstride,
+                                           long long ldb, long long out_bstride, long long ldo, void* stream) {
+  using namespace mmsam;
+  if (B < 0 || C <= 0 || (C & 7) || Hs <= 0 || Ws <= 0 || Ho <= 0 || Wo <= 0) return MMSAM_ERR_BAD_ARG;
+  if ((lds | ldb | ldo | src_bstride | base_bstride | out_bstride) & 7) return MMSAM_ERR_BAD_ARG;
+  if ((scale == nullptr) != (shift == nullptr)) return MMSAM_ERR_BAD_ARG;
+  if (B == 0) return MMSAM_OK;
+  if (!src || !out) return MMSAM_ERR_BAD_ARG;
+  if ((((uintptr_t)src | (uintptr_t)out | (uintptr_t)base) & 15)) return MMSAM_ERR_BAD_ARG;
+  const long long total = (long long)B * Ho * Wo * (C / 8);
+  resize_add_affine_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)src, (const __nv_bfloat16*)base, scale, shift, (__nv_bfloat16*)out, B, Hs, Ws, Ho, Wo, C,
+      src_bstride, base_bstride, out_bstride, ldo, lds, ldb, (float)Hs / (float)Ho, (float)Ws / (float)Wo);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+MMSAM_API int mmsam_upsample_argmax_f32(const float* logits, void* labels_u8, int B, int hs, int ws, int ldl,
+                                        int ncls, int Ho, int Wo, int Hc, int Wc, void* stream) {
+  using namespace mmsam;
+  if (B < 0 || hs <= 0 || ws <= 0 || ncls <= 0 || ncls > 256 || (ldl & 3) || ldl < ((ncls + 3) & ~3) || Ho <= 0 ||
+      Wo <= 0 || Hc <= 0 || Wc <= 0 || Hc > Ho || Wc > Wo)
+    return MMSAM_ERR_BAD_ARG;
+  if (B == 0) return MMSAM_OK;
+  if (!logits || !labels_u8 || (((uintptr_t)logits) & 15)) return MMSAM_ERR_BAD_ARG;
+  const long long total = (long long)B * Hc * Wc;
+  upsample_argmax_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+      logits, (uint8_t*)labels_u8, B, hs, ws, ldl, ncls, Ho, Wo, Hc, Wc, (float)hs / (float)Ho, (float)ws / (float)Wo);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+MMSAM_API int mmsam_confusion_u8(const void* pred_u8, const void* gt_u8, void* conf_u64, long long n, int ncls,
+                                 int ignore_index, void* stream) {
+  using namespace mmsam;
+  if (n < 0 || ncls <= 0 || ncls > 64) return MMSAM_ERR_BAD_ARG;
+  if (n == 0) return MMSAM_OK;
+  if (!pred_u8 || !gt_u8 || !conf_u64) return MMSAM_ERR_BAD_ARG;
+  confusion_kernel<<<grid_for(n, 256 * 16, 4), 256, ncls * ncls * 4, (cudaStream_t)stream>>>(
+      (const uint8_t*)pred_u8, (const uint8_t*)gt_u8, (unsigned long long*)conf_u64, n, ncls, ignore_index);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}

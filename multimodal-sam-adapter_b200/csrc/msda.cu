@@ -196,6 +196,91 @@ msda_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes
   Vec16<VT>::store(out + pair * D + chunk * VEC, acc);
 }
 
+// Fused front end used by the backbone's Injector / Extractor path: instead of materialised
+// sampling_locations / attention_weights it reads the raw output of ONE query projection GEMM
+// (ops/modules/ms_deform_attn.py:108-119: sampling_offsets | attention_weights Linear outputs, fp32,
+// row = query, columns = [M*L*P*2 offsets | M*L*P logits]) plus the reference point of each query,
+// and does the softmax over L*P and  loc = ref + off / (W_l, H_l)  in registers.
+template <typename VT, int P>
+__global__ void __launch_bounds__(256)
+msda_fused_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                  const int64_t* __restrict__ lsi, const float* __restrict__ qproj, long long ldq,
+                  const float* __restrict__ ref, VT* __restrict__ out, int S, int M, int D, int Lq, int L,
+                  int HB, int TPP) {
+  constexpr int VEC = Vec16<VT>::N;
+  const int n = blockIdx.z;
+  const int t = threadIdx.x;
+  const int chunk = t % TPP;
+  const int pr = t / TPP;
+  const int hi = pr % HB;
+  const int qi = pr / HB;
+  const int q = blockIdx.x * (blockDim.x / (HB * TPP)) + qi;
+  const int m = blockIdx.y * HB + hi;
+  if (q >= Lq) return;
+  const long long row = (long long)n * Lq + q;
+  const float* offp = qproj + row * ldq + (long long)m * L * P * 2;
+  const float* lgp = qproj + row * ldq + (long long)M * L * P * 2 + (long long)m * L * P;
+  const float rx = __ldg(ref + 2 * q), ry = __ldg(ref + 2 * q + 1);
+  const long long rs = (long long)M * D;
+  const VT* vbase = value + (long long)n * S * rs + (long long)m * D + chunk * VEC;
+
+  // softmax statistics over the L*P logits of this (query, head)
+  float mx = -INFINITY;
+  for (int i = 0; i < L * P; ++i) mx = fmaxf(mx, __ldg(lgp + i));
+  float den = 0.f;
+  for (int i = 0; i < L * P; ++i) den += __expf(__ldg(lgp + i) - mx);
+  const float inv = 1.f / den;
+
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const int H = (int)__ldg(shapes + 2 * l), W = (int)__ldg(shapes + 2 * l + 1);
+    const VT* vl = vbase + (long long)__ldg(lsi + l) * rs;
+    float ox[P], oy[P], aw[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const float2 o = __ldg(reinterpret_cast<const float2*>(offp + (l * P + p) * 2));
+      ox[p] = o.x; oy[p] = o.y;
+      aw[p] = __expf(__ldg(lgp + l * P + p) - mx) * inv;
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const float h_im = (ry + oy[p] / H) * H - 0.5f, w_im = (rx + ox[p] / W) * W - 0.5f;
+      if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        const int h0 = (int)hf, w0 = (int)wf;
+        const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+        const float c1 = aw[p] * hh * hw, c2 = aw[p] * hh * lw, c3 = aw[p] * lh * hw, c4 = aw[p] * lh * lw;
+        const bool t0 = h0 >= 0, b0 = h0 + 1 <= H - 1, l0 = w0 >= 0, r0 = w0 + 1 <= W - 1;
+        const VT* p00 = vl + ((long long)h0 * W + w0) * rs;
+        float v[VEC];
+        if (t0 && l0) {
+          Vec16<VT>::load(p00, v);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c1, v[i], acc[i]);
+        }
+        if (t0 && r0) {
+          Vec16<VT>::load(p00 + rs, v);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c2, v[i], acc[i]);
+        }
+        if (b0 && l0) {
+          Vec16<VT>::load(p00 + (long long)W * rs, v);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c3, v[i], acc[i]);
+        }
+        if (b0 && r0) {
+          Vec16<VT>::load(p00 + (long long)W * rs + rs, v);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c4, v[i], acc[i]);
+        }
+      }
+    }
+  }
+  Vec16<VT>::store(out + (row * M + m) * D + chunk * VEC, acc);
+}
+
 template <typename VT, typename AT>
 static int launch_msda(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
                        const void* attw, void* out, int N, int S, int M, int D, int Lq, int L, int P,
@@ -260,4 +345,28 @@ MMSAM_API int mmsam_msda_forward(const void* value, const int64_t* spatial_shape
   MSDA_CASE(MMSAM_F64, MMSAM_F64, double, double)
 #undef MSDA_CASE
   return MMSAM_ERR_BAD_DTYPE;
+}
+
+// Fused variant (bf16 value/out): see msda_fused_kernel. qproj fp32 [N*Lq, ldq], ref fp32 [Lq,2] (x,y).
+MMSAM_API int mmsam_msda_fused_bf16(const void* value, const int64_t* spatial_shapes_dev,
+                                    const int64_t* level_start_index_dev, const float* qproj, long long ldq,
+                                    const float* ref_xy, void* out, int N, int S, int M, int D, int Lq, int L,
+                                    int P, void* stream) {
+  using namespace mmsam;
+  if (N < 0 || S < 0 || M <= 0 || D <= 0 || Lq < 0 || L <= 0) return MMSAM_ERR_BAD_ARG;
+  if (N == 0 || Lq == 0) return MMSAM_OK;
+  if (!value || !spatial_shapes_dev || !level_start_index_dev || !qproj || !ref_xy || !out) return MMSAM_ERR_BAD_ARG;
+  if ((D & 7) || D / 8 > 32 || P != 4 || (((uintptr_t)value | (uintptr_t)out) & 15) || (((uintptr_t)qproj) & 7) || (ldq & 1))
+    return MMSAM_ERR_UNSUPPORTED;
+  const int TPP = D / 8;
+  int HB = (M % 2 == 0) ? 2 : 1;
+  int QB = 256 / (HB * TPP);
+  if (QB > 32) QB = 32;
+  if (QB < 1) QB = 1;
+  dim3 grid((Lq + QB - 1) / QB, M / HB, N), block(QB * HB * TPP);
+  msda_fused_kernel<__nv_bfloat16, 4><<<grid, block, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)value, spatial_shapes_dev, level_start_index_dev, qproj, ldq, ref_xy,
+      (__nv_bfloat16*)out, S, M, D, Lq, L, HB, TPP);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
 }

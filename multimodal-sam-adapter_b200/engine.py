@@ -1,0 +1,476 @@
+"""Inference engine: packs the weights of the parameter containers (nn_modules.py) into kernel-ready
+device buffers and runs the MM SAM-Adapter forward as a sequence of this repo's sm_100a kernels.
+
+Data layout in HBM: every activation is channels-last bf16 ([B, H, W, C] == token-major [B*H*W, C]),
+so LayerNorm / LN2d are row ops, 1x1 convs and Linears are the same GEMM, and the token sequence
+c = [c2 | c3 | c4] is one [B, 21*HW/... , C] buffer. fp32 is kept for: LN statistics, GEMM / attention
+accumulation, MSDeformAttn sampling offsets + attention logits, the class logits.
+
+Follows the reference forward (segmentation/mmseg_custom/models/backbones/
+image_encoder_adapter_bimodal_mix_mod_new_in_twin_convnext_new.py:161-349) step by step; the cited
+line ranges are given at each stage below.
+"""
+import math
+
+import torch
+
+from . import kernels as K
+from . import neck_torch
+
+
+def _bf(t, dev):
+    return t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+class _Lin:
+    """weight bf16 [N, K] (K contiguous), bias fp32 [N] or None, optional per-channel scale."""
+
+    def __init__(self, w, b, dev, scale=None):
+        self.w = _bf(w.reshape(w.shape[0], -1), dev)
+        self.b = None if b is None else _f32(b, dev)
+        self.scale = None if scale is None else _f32(scale, dev)
+        self.n, self.k = self.w.shape
+
+
+class _LN:
+    def __init__(self, m, dev, eps=None):
+        self.w, self.b = _f32(m.weight, dev), _f32(m.bias, dev)
+        self.eps = m.eps if eps is None else eps
+
+
+def _bn_fold(bn, dev):
+    s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    t = bn.bias.detach().float() - bn.running_mean.detach().float() * s
+    return _f32(s, dev), _f32(t, dev)
+
+
+def _pad_rows(w, n):
+    if w.shape[0] == n:
+        return w
+    out = w.new_zeros((n,) + tuple(w.shape[1:]))
+    out[: w.shape[0]] = w
+    return out
+
+
+class _MSDA:
+    """Packed MSDeformAttn weights: one fused query projection (offsets | logits) with fp32 output."""
+
+    def __init__(self, m, dev):
+        self.n_heads, self.n_levels, self.n_points = m.n_heads, m.n_levels, m.n_points
+        self.value = _Lin(m.value_proj.weight, m.value_proj.bias, dev)
+        wq = torch.cat((m.sampling_offsets.weight.detach(), m.attention_weights.weight.detach()), 0)
+        bq = torch.cat((m.sampling_offsets.bias.detach(), m.attention_weights.bias.detach()), 0)
+        self.qproj = _Lin(wq, bq, dev)
+        self.out = _Lin(m.output_proj.weight, m.output_proj.bias, dev)
+
+
+def pack_block(blk, dev):
+    return dict(norm1=_LN(blk.norm1, dev), norm2=_LN(blk.norm2, dev), window=blk.window_size,
+                qkv=_Lin(blk.attn.qkv.weight, blk.attn.qkv.bias, dev),
+                proj=_Lin(blk.attn.proj.weight, blk.attn.proj.bias, dev),
+                lin1=_Lin(blk.mlp.lin1.weight, blk.mlp.lin1.bias, dev),
+                lin2=_Lin(blk.mlp.lin2.weight, blk.mlp.lin2.bias, dev),
+                rel_h=blk.attn.rel_pos_h.detach().float().to(dev) if blk.attn.use_rel_pos else None,
+                rel_w=blk.attn.rel_pos_w.detach().float().to(dev) if blk.attn.use_rel_pos else None)
+
+
+def pack_interaction(it, dev):
+    d = dict(inj=dict(qn=_LN(it.injector.query_norm, dev), fn=_LN(it.injector.feat_norm, dev),
+                      attn=_MSDA(it.injector.attn, dev), gamma=_f32(it.injector.gamma, dev)))
+    exts = [it.extractor] + (list(it.extra_extractors) if it.extra_extractors is not None else [])
+    d["ext"] = []
+    for ex in exts:
+        e = dict(qn=_LN(ex.query_norm, dev), fn=_LN(ex.feat_norm, dev), attn=_MSDA(ex.attn, dev), ffn=None)
+        if ex.with_cffn:
+            hc = ex.ffn.fc1.weight.shape[0]
+            e["ffn"] = dict(norm=_LN(ex.ffn_norm, dev), fc1=_Lin(ex.ffn.fc1.weight, ex.ffn.fc1.bias, dev),
+                            dw_w=_f32(ex.ffn.dwconv.dwconv.weight.detach().reshape(hc, 9).t(), dev),
+                            dw_b=_f32(ex.ffn.dwconv.dwconv.bias, dev),
+                            fc2=_Lin(ex.ffn.fc2.weight, ex.ffn.fc2.bias, dev))
+        d["ext"].append(e)
+    return d
+
+
+def window_maps(B, H, W, ws, C, dev):
+    """Row maps of SAM's window_partition / window_unpartition (base/image_encoder.py:504-551)."""
+    nwh, nww = (H + ws - 1) // ws, (W + ws - 1) // ws
+    b_i = torch.arange(B).view(B, 1, 1)
+    y_i = torch.arange(H).view(1, H, 1)
+    x_i = torch.arange(W).view(1, 1, W)
+    dst = (((b_i * nwh + y_i // ws) * nww + x_i // ws) * (ws * ws) + (y_i % ws) * ws + (x_i % ws)).reshape(-1)
+    nrows = B * nwh * nww * ws * ws
+    inv = torch.full((nrows,), -1, dtype=torch.int64)
+    inv[dst] = torch.arange(B * H * W)
+    return dict(win_fwd=dst.to(torch.int32).to(dev), win_inv=inv.to(torch.int32).to(dev), win_rows=nrows,
+                win_bp=B * nwh * nww, ws=ws,
+                win_buf=torch.zeros((nrows, C), dtype=torch.bfloat16, device=dev))  # pad rows stay 0
+
+
+def deform_geometry(B, Hi, Wi, dev):
+    """deform_inputs (adapter_modules_...new.py:397-431): reference points, level shapes, row maps."""
+    s3 = [(Hi // 8, Wi // 8), (Hi // 16, Wi // 16), (Hi // 32, Wi // 32)]
+    s1 = [(Hi // 16, Wi // 16)]
+
+    def ref(shapes):
+        pts = []
+        for (h, w) in shapes:
+            ys = torch.linspace(0.5, h - 0.5, h, dtype=torch.float32) / h
+            xs = torch.linspace(0.5, w - 0.5, w, dtype=torch.float32) / w
+            yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+            pts.append(torch.stack((xx.reshape(-1), yy.reshape(-1)), -1))
+        return torch.cat(pts, 0).contiguous().to(dev)
+
+    def lv(shapes):
+        t = torch.as_tensor(shapes, dtype=torch.long)
+        lsi = torch.cat((t.new_zeros((1,)), t.prod(1).cumsum(0)[:-1]))
+        return t.to(dev), lsi.to(dev)
+
+    sc = dict(ref1=ref(s1), ref2=ref(s3), lv3=lv(s3), lv1=lv(s1), s3=s3, S3=sum(h * w for h, w in s3))
+    offs, o = [], 0
+    for (h, w) in s3:
+        n = h * w
+        rm = (torch.arange(B).view(B, 1) * sc["S3"] + o + torch.arange(n).view(1, n)).reshape(-1)
+        offs.append(rm.to(torch.int32).to(dev))
+        o += n
+    sc["c_rowmaps"] = offs
+    return sc
+
+
+class _Ops:
+    """Kernel-level building blocks shared by the full engine and the component runners."""
+
+    def _gemm(self, a, lin, **kw):
+        return K.gemm(a, lin.w, bias=lin.b, scale=lin.scale, **kw)
+
+    def _ln(self, x, ln, **kw):
+        return K.layernorm(x, ln.w, ln.b, ln.eps, **kw)
+
+    def _msda(self, pk, query_n, feat_n, ref, lv, B):
+        """MSDeformAttn.forward up to (not including) output_proj (ops/modules/ms_deform_attn.py:83-127)."""
+        value = self._gemm(feat_n, pk.value)                                   # [B*S, M*D]
+        qp = self._gemm(query_n, pk.qproj, out_dtype=torch.float32)            # [B*Lq, M*L*P*3]
+        S = feat_n.shape[0] // B
+        return K.msda_fused(value.view(B, S, -1), lv[0], lv[1], qp, ref, pk.n_heads, pk.n_levels, pk.n_points)
+
+    def _block(self, x, blk, sc, tabs, B, out=None):
+        """Block.forward (base/image_encoder.py:382-423). x [B*T, C] is updated in place unless out is given."""
+        H, W, T = sc["H"], sc["W"], sc["T"]
+        if blk["window"] > 0:
+            ws = sc["ws"]
+            y = self._ln(x, blk["norm1"], out=sc["win_buf"], row_map=sc["win_fwd"])
+            qkv = self._gemm(y, blk["qkv"])
+            a = K.attention(qkv.view(sc["win_bp"], ws * ws, -1), self.nh, (ws, ws), tabs[0], tabs[1])
+            self._gemm(a.view(-1, self.C), blk["proj"], residual=x, out=x, row_map=sc["win_inv"])
+        else:
+            y = self._ln(x, blk["norm1"])
+            qkv = self._gemm(y, blk["qkv"])
+            a = K.attention(qkv.view(B, T, -1), self.nh, (H, W), tabs[0], tabs[1])
+            self._gemm(a.view(-1, self.C), blk["proj"], residual=x, out=x)
+        y = self._ln(x, blk["norm2"])
+        h = self._gemm(y, blk["lin1"], act="gelu")
+        dst = x if out is None else out
+        self._gemm(h, blk["lin2"], residual=x, out=dst)
+        return dst
+
+    def _injector(self, x, c, inj, sc, B):
+        """Injector.forward (adapter_modules_...new.py:525-542); x [B*T, C] updated in place."""
+        qn = self._ln(x, inj["qn"])
+        fn = self._ln(c, inj["fn"])
+        o = self._msda(inj["attn"], qn, fn, sc["ref1"], sc["lv3"], B)
+        K.gemm(o.view(-1, o.shape[-1]), inj["attn"].out.w, bias=inj["attn"].out.b, scale=inj["gamma"], residual=x, out=x)
+
+    def _extractor(self, c, x, e, sc, B):
+        """Extractor.forward (adapter_modules_...new.py:490-511); c [B*S3, C] updated in place."""
+        qn = self._ln(c, e["qn"])
+        fn = self._ln(x, e["fn"])
+        o = self._msda(e["attn"], qn, fn, sc["ref2"], sc["lv1"], B)
+        self._gemm(o.view(-1, o.shape[-1]), e["attn"].out, residual=c, out=c)
+        f = e["ffn"]
+        if f is not None:
+            y = self._ln(c, f["norm"])
+            h = self._gemm(y, f["fc1"])
+            hc = h.shape[1]
+            h2 = K.dwconv(h, f["dw_w"], f["dw_b"], 3, sc["s3"], B, hc, sc["S3"] * hc, sc["S3"] * hc, act="gelu")
+            self._gemm(h2, f["fc2"], residual=c, out=c)
+
+
+class ComponentRunner(_Ops):
+    """Runs a single reference-shaped component (Block / InteractionBlock container) on the kernels;
+    used by the component-level parity tests (non-square token grids)."""
+
+    def __init__(self, dim, num_heads, device="cuda"):
+        self.C, self.nh, self.dev = dim, num_heads, torch.device(device)
+
+    @torch.no_grad()
+    def block(self, blk_module, x, H, W):
+        """x [B, H*W, C] (any float dtype, CUDA) -> same shape, bf16."""
+        B = x.shape[0]
+        pk = pack_block(blk_module, self.dev)
+        sc = dict(H=H, W=W, T=H * W)
+        if pk["window"] > 0:
+            sc.update(window_maps(B, H, W, pk["window"], self.C, self.dev))
+        kh, kw = (pk["window"], pk["window"]) if pk["window"] > 0 else (H, W)
+        tabs = (None, None)
+        if pk["rel_h"] is not None:
+            tabs = (K.relpos_table(pk["rel_h"], kh), K.relpos_table(pk["rel_w"], kw))
+        xb = x.reshape(B * H * W, self.C).to(torch.bfloat16).contiguous().clone()
+        return self._block(xb, pk, sc, tabs, B).view(B, H * W, self.C)
+
+    @torch.no_grad()
+    def interaction(self, it_module, x, c, Hi, Wi, blocks=()):
+        """InteractionBlock.forward (adapter_modules_...new.py:567-581) for an Hi x Wi image geometry."""
+        B = x.shape[0]
+        pk = pack_interaction(it_module, self.dev)
+        H, W = Hi // 16, Wi // 16
+        sc = dict(H=H, W=W, T=H * W)
+        sc.update(deform_geometry(B, Hi, Wi, self.dev))
+        xb = x.reshape(-1, self.C).to(torch.bfloat16).contiguous().clone()
+        cb = c.reshape(-1, self.C).to(torch.bfloat16).contiguous().clone()
+        self._injector(xb, cb, pk["inj"], sc, B)
+        for blk in blocks:
+            xb = self.block(blk, xb.view(B, H * W, self.C), H, W).reshape(-1, self.C)
+        for e in pk["ext"]:
+            self._extractor(cb, xb, e, sc, B)
+        return xb.view(B, H * W, self.C), cb.view(B, -1, self.C)
+
+
+class EncoderEngine(_Ops):
+    def __init__(self, backbone, head=None, device="cuda"):
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise K._lib.MMSamError("EncoderEngine needs a CUDA device: the path has no CPU fallback")
+        K._lib.load()
+        self.bb = backbone
+        self.cfg = backbone.cfg
+        self._shape_cache = {}
+        self._pack_backbone(backbone)
+        self.head = None
+        if head is not None:
+            self._pack_head(head)
+
+    # ------------------------------------------------------------------ packing
+    def _pack_backbone(self, m):
+        dev = self.dev
+        self.C = m.embed_dim
+        self.nh = m.num_heads
+        self.patch = m.patch_size
+        self.cin = m.in_ch_im
+        pe = m.patch_embed.proj
+        self.patch_embed = _Lin(pe.weight, pe.bias, dev)
+        self.pos_embed = m.pos_embed.detach().float().to(dev)  # [1, ps, ps, C]
+        self.blocks = []
+        for blk in m.blocks:
+            self.blocks.append(pack_block(blk, dev))
+        # --- TwinConvNeXt (base/twin_convnext.py) ---
+        tw = m.spm.twin_conv
+        self.cnx = {}
+        for br in ("x", "y"):
+            ds = getattr(tw, f"downsample_layers_{br}")
+            st = getattr(tw, f"stages_{br}")
+            stages = []
+            for i in range(len(tw.depths)):
+                e = {}
+                if i == 0:
+                    e["ds"] = _Lin(ds[0][0].weight, ds[0][0].bias, dev)          # [C0, 3*p*p] (c,ky,kx)
+                    e["ds_ln"] = _LN(ds[0][1], dev)
+                else:
+                    w = ds[i][1].weight.detach()                                    # [Co, Ci, 2, 2]
+                    e["ds"] = _Lin(w.permute(0, 2, 3, 1).contiguous(), ds[i][1].bias, dev)  # (ky,kx,ci)
+                    e["ds_ln"] = _LN(ds[i][0], dev)
+                blocks = []
+                for b in st[i]:
+                    c = b.depthwise_conv.weight.shape[0]
+                    blocks.append(dict(
+                        dw_w=_f32(b.depthwise_conv.weight.detach().reshape(c, 49).t(), dev),
+                        dw_b=_f32(b.depthwise_conv.bias, dev), ln=_LN(b.norm, dev),
+                        pw1=_Lin(b.pointwise_conv1.weight, b.pointwise_conv1.bias, dev),
+                        pw2=_Lin(b.pointwise_conv2.weight, b.pointwise_conv2.bias, dev,
+                                 scale=b.gamma if b.gamma is not None else None)))
+                e["blocks"] = blocks
+                e["out_ln"] = _LN(getattr(tw, f"norm_{br}{i}"), dev)
+                stages.append(e)
+            self.cnx[br] = stages
+        self.cnx_channels = list(tw.channels)
+        self.neck = neck_torch.NeckTorch(m.spm.smart_fusion, dev)
+        le = m.level_embed.detach().float()
+        self.fc = []
+        for i in range(4):
+            fc = getattr(m.spm, f"fc{i + 1}")
+            b = fc.bias.detach().float()
+            if i >= 1:
+                b = b + le[i - 1]          # _add_level_embed (..._new.py:149-159) folded into the bias
+            self.fc.append(_Lin(fc.weight, b, dev))
+        # up: ConvTranspose2d(C, C, 2, 2): weight [Cin, Cout, 2, 2] -> rows (dy, dx, co)
+        uw = m.up.weight.detach().permute(2, 3, 1, 0).reshape(4 * self.C, self.C)
+        self.up = _Lin(uw, m.up.bias.detach().repeat(4), dev)
+        self.inter = []
+        for it in m.interactions:
+            self.inter.append(pack_interaction(it, dev))
+        self.final_bn = [_bn_fold(getattr(m, f"norm{i + 1}"), dev) for i in range(4)]
+
+    def _pack_head(self, h):
+        dev = self.dev
+        hd = {"convs": []}
+        for cm in h.convs:
+            s, t = _bn_fold(cm.bn, dev)
+            w = cm.conv.weight.detach().float().reshape(cm.conv.weight.shape[0], -1) * s.cpu()[:, None]
+            hd["convs"].append(_Lin(w, t, dev))
+        s, t = _bn_fold(h.fusion_conv.bn, dev)
+        w = h.fusion_conv.conv.weight.detach().float().reshape(h.fusion_conv.conv.weight.shape[0], -1) * s.cpu()[:, None]
+        hd["fusion"] = _Lin(w, t, dev)
+        ncls = h.conv_seg.weight.shape[0]
+        npad = (ncls + 31) // 32 * 32
+        hd["cls"] = _Lin(_pad_rows(h.conv_seg.weight.detach().float().reshape(ncls, -1), npad),
+                         _pad_rows(h.conv_seg.bias.detach().float(), npad), dev)
+        hd["ncls"], hd["npad"], hd["channels"] = ncls, npad, h.conv_seg.weight.shape[1]
+        self.head = hd
+
+    # ------------------------------------------------------------------ shape-dependent constants
+    def _shape(self, B, Hi, Wi):
+        key = (B, Hi, Wi)
+        sc = self._shape_cache.get(key)
+        if sc is not None:
+            return sc
+        dev = self.dev
+        p = self.patch
+        H, W = Hi // p, Wi // p
+        sc = dict(H=H, W=W, T=H * W)
+        # pos_embed: always bicubic-resized (..._new.py:136-143)
+        pe = torch.nn.functional.interpolate(self.pos_embed.permute(0, 3, 1, 2), size=(H, W), mode="bicubic",
+                                             align_corners=False)
+        pe = pe.reshape(1, -1, H * W).permute(0, 2, 1).to(torch.bfloat16)
+        sc["pos"] = pe.expand(B, -1, -1).reshape(B * H * W, -1).contiguous()
+        ws = max((b["window"] for b in self.blocks), default=0)
+        if ws > 0:
+            sc.update(window_maps(B, H, W, ws, self.C, dev))
+        # relative position tables per block (get_rel_pos, image_encoder.py:554-584)
+        tabs = []
+        for blk in self.blocks:
+            if blk["rel_h"] is None:
+                tabs.append((None, None))
+            elif blk["window"] > 0:
+                tabs.append((K.relpos_table(blk["rel_h"], blk["window"]), K.relpos_table(blk["rel_w"], blk["window"])))
+            else:
+                tabs.append((K.relpos_table(blk["rel_h"], H), K.relpos_table(blk["rel_w"], W)))
+        sc["tabs"] = tabs
+        sc.update(deform_geometry(B, Hi, Wi, dev))
+        self._shape_cache[key] = sc
+        return sc
+
+    # ------------------------------------------------------------------ building blocks
+    def _convnext_branch(self, img, c_off, stages, B, Hi, Wi):
+        """twin_convnext.py:445-476 for one modality; returns the 4 normalised stage outputs [B*h*w, C]."""
+        feats = []
+        t = None
+        h, w = Hi, Wi
+        for i, st in enumerate(stages):
+            if i == 0:
+                pch = K.patchify(img, c_off, 3, 4)
+                h, w = Hi // 4, Wi // 4
+                t = self._gemm(pch, st["ds"])
+                t = self._ln(t, st["ds_ln"])
+            else:
+                pt = self._ln(t, st["ds_ln"], patchify_hw=(h, w))
+                h, w = h // 2, w // 2
+                t = self._gemm(pt, st["ds"])
+            C = t.shape[1]
+            for b in st["blocks"]:      # ConvNeXtBlock (twin_convnext.py:98-132)
+                y = K.dwconv(t, b["dw_w"], b["dw_b"], 7, [(h, w)], B, C, h * w * C, h * w * C)
+                y = self._ln(y, b["ln"])
+                y = self._gemm(y, b["pw1"], act="gelu")
+                self._gemm(y, b["pw2"], residual=t, out=t)
+            feats.append((self._ln(t, st["out_ln"]), h, w))
+        return feats
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def backbone_nhwc(self, img):
+        """img fp32 [B, 3+3, Hi, Wi] on the device -> [f1, f2, f3, f4] channels-last bf16 [B, h, w, C]."""
+        if not img.is_cuda:
+            raise K._lib.MMSamError("input must be a CUDA tensor")
+        img = img.contiguous().float()
+        B, _, Hi, Wi = img.shape
+        if Hi % 32 or Wi % 32:
+            raise ValueError("input height/width must be multiples of 32")
+        sc = self._shape(B, Hi, Wi)
+        H, W, T, C, S3 = sc["H"], sc["W"], sc["T"], self.C, sc["S3"]
+        # --- SPM (adapter_modules_...new.py:929-964): twin ConvNeXt -> fusion neck -> fc1..4 ---
+        fx = self._convnext_branch(img, 0, self.cnx["x"], B, Hi, Wi)
+        fy = self._convnext_branch(img, self.cin, self.cnx["y"], B, Hi, Wi)
+        fused = self.neck(fx, fy, B)                                    # 4 x [B*h*w, 2*Ci] bf16
+        c1 = self._gemm(fused[0], self.fc[0])                            # [B*16T, C]
+        c = torch.empty((B * S3, C), dtype=torch.bfloat16, device=self.dev)
+        for i in range(3):
+            self._gemm(fused[i + 1], self.fc[i + 1], out=c, row_map=sc["c_rowmaps"][i], out_rows=B * S3)
+        # --- patch embed + pos embed (image_encoder.py:662-671, ..._new.py:268-278) ---
+        pch = K.patchify(img, 0, self.cin, self.patch)
+        x = self._gemm(pch, self.patch_embed, residual=sc["pos"])
+        # --- interactions (..._new.py:283-292; adapter_modules_...new.py:567-581) ---
+        outs = []
+        idxs = self.cfg["interaction_indexes"]
+        for i, (lo, hi) in enumerate(idxs):
+            it = self.inter[i]
+            self._injector(x, c, it["inj"], sc, B)
+            for bi in range(lo, hi + 1):
+                if bi == hi:
+                    x = self._block(x, self.blocks[bi], sc, sc["tabs"][bi], B, out=torch.empty_like(x))
+                else:
+                    self._block(x, self.blocks[bi], sc, sc["tabs"][bi], B)
+            for e in it["ext"]:
+                self._extractor(c, x, e, sc, B)
+            outs.append(x)
+        # --- tail (..._new.py:316-337): up(c2) + c1, add resized ViT features, eval BatchNorm ---
+        c3d = c.view(B, S3, C)
+        n2, n3 = 4 * T, T
+        g1 = torch.empty((B, 16 * T, C), dtype=torch.bfloat16, device=self.dev)
+        c1v = c1.view(B, 16 * T, C)
+        for b in range(B):
+            K.gemm(c3d[b, :n2], self.up.w, bias=self.up.b, residual=c1v[b], out=g1[b], pixel_shuffle=(2 * H, 2 * W))
+        fs = []
+        bases = [(g1, 16 * T * C, 0), (c3d, S3 * C, 0), (c3d, S3 * C, n2), (c3d, S3 * C, n2 + n3)]
+        sizes = [(4 * H, 4 * W), (2 * H, 2 * W), (H, W), (H // 2, W // 2)]
+        add_vit = self.cfg.get("add_vit_feature", True)
+        for i in range(4):
+            base, bstride, roff = bases[i]
+            basev = base[:, roff:] if roff else base
+            s, t = self.final_bn[i]
+            if add_vit:
+                f = K.resize_add_affine(outs[i], (H, W), sizes[i], B, C, base=basev, scale=s, shift=t,
+                                        base_bstride=bstride)
+            else:
+                f = K.resize_add_affine(basev, sizes[i], sizes[i], B, C, scale=s, shift=t, src_bstride=bstride)
+            fs.append(f)
+        return fs
+
+    @torch.no_grad()
+    def head_logits(self, feats):
+        """SegformerHead.forward (decode_heads/segformer_head.py:48-66) -> fp32 logits [B*h*w, npad]."""
+        hd = self.head
+        B, h0, w0, _ = feats[0].shape
+        ch = hd["channels"]
+        n = len(feats)
+        cat = torch.empty((B * h0 * w0, n * ch), dtype=torch.bfloat16, device=self.dev)
+        for i, f in enumerate(feats):
+            _, h, w, Cf = f.shape
+            if i == 0:
+                self._gemm(f.view(-1, Cf), hd["convs"][i], act="relu", out=cat[:, :ch])
+            else:
+                t = self._gemm(f.view(-1, Cf), hd["convs"][i], act="relu")
+                K.resize_add_affine(t, (h, w), (h0, w0), B, ch, out=cat[:, i * ch:], ldo=n * ch,
+                                    out_bstride=h0 * w0 * n * ch)
+        o = self._gemm(cat, hd["fusion"], act="relu")
+        return self._gemm(o, hd["cls"], out_dtype=torch.float32), (h0, w0)
+
+    @torch.no_grad()
+    def segment(self, img, out_hw=None, crop_hw=None):
+        """encode_decode_test + whole_inference_dim(_cut) + softmax/argmax -> uint8 labels [B, H, W]
+        (segmentors/encoder_decoder.py:96-117, 329-414, 417-508)."""
+        B, _, Hi, Wi = img.shape
+        feats = self.backbone_nhwc(img)
+        logits, (h0, w0) = self.head_logits(feats)
+        out_hw = (Hi, Wi) if out_hw is None else tuple(out_hw)
+        return K.upsample_argmax(logits, B, (h0, w0), self.head["ncls"], out_hw, crop_hw)

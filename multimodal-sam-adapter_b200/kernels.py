@@ -54,24 +54,32 @@ def msda_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_we
     return out
 
 
-def layernorm(x, gamma, beta, eps, out=None, row_map=None, out_rows=None):
+def layernorm(x, gamma, beta, eps, out=None, row_map=None, out_rows=None, patchify_hw=None):
     """x bf16 [..., C] (rows contiguous) -> LN over C. row_map (int32 [rows]) scatters rows into an
-    `out` of out_rows rows (rows never written keep their previous contents)."""
+    `out` of out_rows rows (rows never written keep their previous contents). patchify_hw=(H, W):
+    rows are (b,y,x) and the result is the 2x2-patchified [rows/4, 4C] matrix."""
     _need_cuda(x, gamma, beta)
     C = x.shape[-1]
     x2 = x.reshape(-1, C)
     rows = x2.shape[0]
+    ps_h = ps_w = 0
+    if patchify_hw is not None:
+        ps_h, ps_w = patchify_hw
     if out is None:
-        if row_map is None:
+        if patchify_hw is not None:
+            out = torch.empty((rows // 4, 4 * C), dtype=x.dtype, device=x.device)
+        elif row_map is None:
             out = torch.empty_like(x2)
         else:
             out = torch.zeros((out_rows, C), dtype=x.dtype, device=x.device)
     rc = _lib.load().mmsam_layernorm_bf16(
         _ptr(x2), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(row_map), rows, C, x2.stride(0), out.stride(0),
-        float(eps), _stream())
+        float(eps), ps_h, ps_w, _stream())
     _lib.check(rc, "mmsam_layernorm_bf16")
     _count()
-    return out if row_map is not None else out.view(x.shape)
+    if row_map is not None or patchify_hw is not None:
+        return out
+    return out.view(x.shape)
 
 
 ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "relu6": 3}
@@ -130,5 +138,111 @@ def attention(qkv, num_heads, hw, tab_h=None, tab_w=None, out=None, max_ctas=0):
     rc = _lib.load().mmsam_attention_bf16(_ptr(qkv), _ptr(out), _ptr(tab_h), _ptr(tab_w), Bp, T, num_heads,
                                           hw[0], hw[1], float(hd) ** -0.5, max_ctas, _stream())
     _lib.check(rc, "mmsam_attention_bf16")
+    _count()
+    return out
+
+
+def msda_fused(value, spatial_shapes, level_start_index, qproj, ref_xy, n_heads, n_levels, n_points=4, out=None):
+    """value bf16 [N,S,M*D]; qproj fp32 [N*Lq, >= M*L*P*3] (offsets | logits); ref_xy fp32 [Lq,2]."""
+    _need_cuda(value, spatial_shapes, level_start_index, qproj, ref_xy)
+    N, S, MD = value.shape
+    D = MD // n_heads
+    Lq = ref_xy.shape[0]
+    assert qproj.shape[0] == N * Lq and qproj.dtype == torch.float32 and qproj.stride(1) == 1
+    if out is None:
+        out = torch.empty((N, Lq, MD), dtype=value.dtype, device=value.device)
+    rc = _lib.load().mmsam_msda_fused_bf16(
+        _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(qproj), qproj.stride(0), _ptr(ref_xy),
+        _ptr(out), N, S, n_heads, D, Lq, n_levels, n_points, _stream())
+    _lib.check(rc, "mmsam_msda_fused_bf16")
+    _count()
+    return out
+
+
+def dwconv(x, w_tap_major, bias, ksize, grids, B, C, in_bstride, out_bstride, act=None, out=None,
+           in_offs=None, out_offs=None):
+    """Depthwise conv over channels-last bf16 maps. grids: [(H, W), ...] (<= 3) inside each batch item."""
+    import ctypes
+    _need_cuda(x, w_tap_major, bias)
+    if out is None:
+        out = torch.empty_like(x)
+    n = len(grids)
+    hw = (ctypes.c_int * (2 * n))(*[v for g in grids for v in g])
+    if in_offs is None:
+        in_offs, o = [], 0
+        for (h, w) in grids:
+            in_offs.append(o)
+            o += h * w * C
+    if out_offs is None:
+        out_offs = in_offs
+    io = (ctypes.c_longlong * n)(*in_offs)
+    oo = (ctypes.c_longlong * n)(*out_offs)
+    rc = _lib.load().mmsam_dwconv_bf16(_ptr(x), _ptr(out), _ptr(w_tap_major), _ptr(bias), B, C, ksize, n,
+                                       ctypes.cast(hw, ctypes.c_void_p), ctypes.cast(io, ctypes.c_void_p),
+                                       ctypes.cast(oo, ctypes.c_void_p), in_bstride, out_bstride, ACT[act], _stream())
+    _lib.check(rc, "mmsam_dwconv_bf16")
+    _count()
+    return out
+
+
+def patchify(img, c_off, C, p, out=None):
+    """img fp32 NCHW [B, Ctot, H, W] -> bf16 [B*(H/p)*(W/p), C*p*p]."""
+    _need_cuda(img)
+    assert img.dtype == torch.float32 and img.is_contiguous()
+    B, Ctot, H, W = img.shape
+    if out is None:
+        out = torch.empty((B * (H // p) * (W // p), C * p * p), dtype=torch.bfloat16, device=img.device)
+    rc = _lib.load().mmsam_patchify_f32(_ptr(img), _ptr(out), B, Ctot, c_off, C, H, W, p, _stream())
+    _lib.check(rc, "mmsam_patchify_f32")
+    _count()
+    return out
+
+
+def resize_add_affine(src, src_hw, out_hw, B, C, base=None, scale=None, shift=None, out=None,
+                      src_bstride=None, lds=None, base_bstride=None, ldb=None, out_bstride=None, ldo=None):
+    """Channels-last bf16: out = (base + bilinear(src)) * scale + shift. Strides in elements."""
+    _need_cuda(src, base, scale, shift, out)
+    Hs, Ws = src_hw
+    Ho, Wo = out_hw
+    lds = C if lds is None else lds
+    ldb = C if ldb is None else ldb
+    ldo = C if ldo is None else ldo
+    src_bstride = Hs * Ws * lds if src_bstride is None else src_bstride
+    base_bstride = Ho * Wo * ldb if base_bstride is None else base_bstride
+    out_bstride = Ho * Wo * ldo if out_bstride is None else out_bstride
+    if out is None:
+        out = torch.empty((B, Ho, Wo, C), dtype=torch.bfloat16, device=src.device)
+    rc = _lib.load().mmsam_resize_add_affine_bf16(
+        _ptr(src), _ptr(base), _ptr(scale), _ptr(shift), _ptr(out), B, Hs, Ws, Ho, Wo, C, src_bstride, lds,
+        base_bstride, ldb, out_bstride, ldo, _stream())
+    _lib.check(rc, "mmsam_resize_add_affine_bf16")
+    _count()
+    return out
+
+
+def upsample_argmax(logits, B, hw, ncls, out_hw, crop_hw=None, out=None):
+    """logits fp32 [B*h*w, ldl] -> uint8 labels [B, Hc, Wc] (bilinear to out_hw, argmax, crop)."""
+    _need_cuda(logits)
+    hs, ws = hw
+    Ho, Wo = out_hw
+    Hc, Wc = crop_hw if crop_hw is not None else out_hw
+    if out is None:
+        out = torch.empty((B, Hc, Wc), dtype=torch.uint8, device=logits.device)
+    rc = _lib.load().mmsam_upsample_argmax_f32(_ptr(logits), _ptr(out), B, hs, ws, logits.stride(0), ncls, Ho, Wo,
+                                               Hc, Wc, _stream())
+    _lib.check(rc, "mmsam_upsample_argmax_f32")
+    _count()
+    return out
+
+
+def confusion(pred, gt, ncls, ignore_index=255, out=None):
+    """uint8 pred / gt -> int64 [ncls, ncls] confusion counts (rows = gt), accumulated into `out`."""
+    _need_cuda(pred, gt)
+    assert pred.dtype == torch.uint8 and gt.dtype == torch.uint8 and pred.numel() == gt.numel()
+    if out is None:
+        out = torch.zeros((ncls, ncls), dtype=torch.int64, device=pred.device)
+    rc = _lib.load().mmsam_confusion_u8(_ptr(pred.contiguous()), _ptr(gt.contiguous()), _ptr(out), pred.numel(), ncls,
+                                        ignore_index, _stream())
+    _lib.check(rc, "mmsam_confusion_u8")
     _count()
     return out

@@ -1,0 +1,51 @@
+"""Shared test configuration: model configs, deterministic weight construction."""
+import hashlib
+
+import torch
+
+TINY = dict(img_size=128, modalities_name=["rgb", "lidar"], modalities_ch=[3, 3], init_values=1e-6,
+            gamma_init_values=1e-6, patch_size=16, embed_dim=128, depth=4, num_heads=2, mlp_ratio=4,
+            drop_path_rate=0.3, drop_multimodal_path=0, conv_inplane=16, n_points=4, deform_num_heads=2,
+            cffn_ratio=0.25, deform_ratio=0.5, with_cp=True, interaction_indexes=[[0, 0], [1, 1], [2, 2], [3, 3]],
+            global_attn_indexes=[1, 3], window_size=14, arch=dict(depths=[1, 1, 2, 1], channels=[32, 64, 128, 256]),
+            checkpoint="none", pretrained_size=256)
+
+# BASELINE.json config 1 as defined in SURVEY.md §8(d): ViT-B MM-adapter, 512x512
+VITB = dict(img_size=512, modalities_name=["rgb", "lidar"], modalities_ch=[3, 3], init_values=1e-6,
+            gamma_init_values=1e-6, patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4,
+            drop_path_rate=0.3, drop_multimodal_path=0, conv_inplane=48, n_points=4, deform_num_heads=12,
+            cffn_ratio=0.25, deform_ratio=0.5, with_cp=True, interaction_indexes=[[0, 2], [3, 5], [6, 8], [9, 11]],
+            global_attn_indexes=[2, 5, 8, 11], window_size=14, arch="small", checkpoint="none")
+
+TINY_HEAD = dict(in_channels=[128] * 4, in_index=[0, 1, 2, 3], channels=64, dropout_ratio=0.1, num_classes=25,
+                 norm_cfg=dict(type="SyncBN", requires_grad=True), align_corners=False)
+VITB_HEAD = dict(in_channels=[768] * 4, in_index=[0, 1, 2, 3], channels=512, dropout_ratio=0.1, num_classes=25,
+                 norm_cfg=dict(type="SyncBN", requires_grad=True), align_corners=False)
+
+
+def build_segmentor(bcfg, hcfg, seed=0, perturb_seed=1, test_cfg=None):
+    """Deterministic CPU construction of our modules + the Appendix-D perturbation. Returns
+    (segmentor module on CPU, state_dict of fp32 CPU tensors)."""
+    import mmsam_b200  # noqa: F401
+    from mmsam_b200 import backbone as _b  # noqa: F401  (registers the classes)
+    from mmsam_b200.registry import SEGMENTORS
+    from oracle.perturb import perturb_state_dict
+    torch.manual_seed(seed)
+    seg = SEGMENTORS.build(dict(type="EncoderDecoder", backbone=dict(type="SAMAdapterbimodalMixModNewInTwinConvNEW", **bcfg),
+                                decode_head=dict(type="SegformerHead", **hcfg),
+                                test_cfg=test_cfg or dict(mode="whole")))
+    sd = perturb_state_dict(seg.state_dict(), seed=perturb_seed)
+    seg.load_state_dict(sd)
+    return seg.eval(), sd
+
+
+def sd_digest(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()

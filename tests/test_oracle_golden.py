@@ -1,0 +1,195 @@
+"""CPU tests: the oracle against the golden vectors produced by the UNMODIFIED reference
+(tools/make_golden.py), the C-ABI surface, and host-side logic. No GPU needed."""
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+from common import TINY, TINY_HEAD, VITB, VITB_HEAD, build_segmentor, rel_l2, sd_digest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_msda_oracle_known_answer_vectors():
+    """segmentation/ops/test.py:16-75 — the reference's only known-answer test."""
+    from oracle.msda import ms_deform_attn_core
+    rec = torch.load(os.path.join(GOLD, "msda_known_answer.pt"))
+    d = rec["double"]
+    out = ms_deform_attn_core(d["value"].double(), rec["shapes"], d["loc"].double(), d["aw"].double())
+    assert torch.allclose(out, d["out"])                         # ops/test.py:44 criterion
+    f = rec["float"]
+    out = ms_deform_attn_core(f["value"], rec["shapes"], f["loc"], f["aw"])
+    assert torch.allclose(out, f["out"], rtol=1e-2, atol=1e-3)  # ops/test.py:68 criterion
+    assert (out - f["out"]).abs().max() < 1e-8
+
+
+def test_msda_oracle_shapes():
+    from oracle.msda import ms_deform_attn_core
+    for c in torch.load(os.path.join(GOLD, "msda_shapes.pt")):
+        out = ms_deform_attn_core(c["value"].double(), c["shapes"], c["loc"].double(), c["aw"].double())
+        assert (out.float() - c["out"]).abs().max() < 1e-5
+
+
+def test_oracle_tiny_backbone_matches_reference():
+    from oracle import model as om
+    from oracle.perturb import synthetic_batch
+    rec = torch.load(os.path.join(GOLD, "tiny_backbone.pt"))
+    _, sd = build_segmentor(TINY, TINY_HEAD)
+    assert sd_digest(sd) == rec["digest"], "deterministic weight construction drifted from the golden run"
+    with torch.no_grad():
+        outs = om.backbone_forward(sd, TINY, synthetic_batch(1, TINY["img_size"]), prefix="backbone.")
+    for o, r in zip(outs, rec["outs"]):
+        assert rel_l2(o, r) < 1e-5
+
+
+def test_oracle_block_nonsquare_matches_reference():
+    """Window (padded 19x25 -> 28x28) and global (127-row table interpolated to 37 / 49 rows) blocks."""
+    from oracle import model as om
+    from oracle.perturb import perturb_state_dict
+    import mmsam_b200  # noqa
+    from mmsam_b200 import nn_modules as M
+    rec = torch.load(os.path.join(GOLD, "block_nonsquare.pt"))
+    for name, ws in (("window", 14), ("global", 0)):
+        torch.manual_seed(21)
+        sd = perturb_state_dict(M.Block(128, 2, 4.0, True, True, ws, (64, 64)).state_dict(), seed=3)
+        assert sd_digest(sd) == rec[name + "_digest"]
+        with torch.no_grad():
+            out = om.vit_block(rec["x"], om.SD(sd), rec["H"], rec["W"], ws, 2)
+        assert rel_l2(out, rec[name]) < 1e-5
+
+
+def test_oracle_interaction_nonsquare_matches_reference():
+    from oracle import model as om
+    from oracle.perturb import perturb_state_dict
+    import mmsam_b200  # noqa
+    from mmsam_b200 import nn_modules as M
+    from mmsam_b200.ops.modules import MSDeformAttn
+    rec = torch.load(os.path.join(GOLD, "interaction_nonsquare.pt"))
+    torch.manual_seed(22)
+    sd = perturb_state_dict(M.InteractionBlock(128, 2, 4, True, 0.25, 0.5, 0.5, True, MSDeformAttn).state_dict(), seed=4)
+    assert sd_digest(sd) == rec["digest"]
+    s = om.SD(sd)
+    Hi, Wi = rec["Hi"], rec["Wi"]
+    (ref1, sh1), (ref2, sh2) = om.deform_inputs(Hi, Wi, torch.float32)
+    with torch.no_grad():
+        x = om.injector(rec["x"], rec["c"], ref1, sh1, s.sub("injector"), 2, 4)
+        c = om.extractor(rec["c"], x, ref2, sh2, s.sub("extractor"), 2, 4, Hi // 16, Wi // 16)
+        for j in range(2):
+            c = om.extractor(c, x, ref2, sh2, s.sub(f"extra_extractors.{j}"), 2, 4, Hi // 16, Wi // 16)
+    assert rel_l2(x, rec["xo"]) < 1e-5 and rel_l2(c, rec["co"]) < 1e-5
+
+
+@pytest.mark.timeout(600)
+def test_oracle_vitb512_matches_reference_samples():
+    """BASELINE config 1 (ViT-B MM-adapter, 512x512, fp32 CPU): sampled outputs of the reference run."""
+    from oracle import model as om
+    from oracle.perturb import synthetic_batch
+    rec = torch.load(os.path.join(GOLD, "vitb512_samples.pt"))
+    _, sd = build_segmentor(VITB, VITB_HEAD)
+    assert sd_digest(sd) == rec["digest"]
+    with torch.no_grad():
+        outs = om.backbone_forward(sd, VITB, synthetic_batch(1, 512), prefix="backbone.")
+    for o, idx, vals, nrm in zip(outs, rec["idx"], rec["vals"], rec["norms"]):
+        assert rel_l2(o.reshape(-1)[idx], vals) < 1e-4
+        assert abs(o.norm().item() - nrm) / nrm < 1e-4
+
+
+def test_state_dict_schema_matches_reference():
+    """Key names + shapes of the ViT-L DELIVER backbone, dumped from the reference module."""
+    import json
+    import mmsam_b200  # noqa
+    from mmsam_b200 import backbone  # noqa
+    from mmsam_b200.registry import BACKBONES
+    want = json.load(open(os.path.join(GOLD, "state_dict_schema_vitl_deliver.json")))
+    cfg = dict(type="SAMAdapterbimodalMixModNewInTwinConvNEW", img_size=1024, modalities_name=["rgb", "lidar"],
+               modalities_ch=[3, 3], init_values=1e-6, gamma_init_values=1e-6, patch_size=16, embed_dim=1024, depth=24,
+               num_heads=16, mlp_ratio=4, drop_path_rate=0.3, drop_multimodal_path=0, conv_inplane=48, n_points=4,
+               deform_num_heads=16, cffn_ratio=0.25, deform_ratio=0.5, with_cp=True,
+               interaction_indexes=[[0, 5], [6, 11], [12, 17], [18, 23]], global_attn_indexes=[5, 11, 17, 23],
+               window_size=14, arch="small", checkpoint="x")
+    with torch.device("meta"):
+        net = BACKBONES.build(cfg)
+    got = {k: list(v.shape) for k, v in net.state_dict().items()}
+    assert got == want
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/segmentation/configs"), reason="reference tree not present")
+def test_reference_configs_build_unchanged():
+    """All 10 shipped configs load through the Config shim and name registered classes."""
+    import glob
+    import mmsam_b200  # noqa
+    from mmsam_b200 import backbone  # noqa
+    from mmsam_b200.registry import BACKBONES, HEADS, SEGMENTORS, load_config
+    files = sorted(glob.glob("/root/reference/segmentation/configs/*/Segformer_MMSAM*.py"))
+    assert len(files) == 10
+    for f in files:
+        cfg = load_config(f)
+        assert SEGMENTORS.get(cfg.model.type) is not None
+        assert BACKBONES.get(cfg.model.backbone.type) is not None
+        assert HEADS.get(cfg.model.decode_head.type) is not None
+        with torch.device("meta"):
+            seg = SEGMENTORS.build({k: v for k, v in cfg.model.items() if k != "train_cfg"} | {"pretrained": None})
+        assert seg.num_classes == cfg.model.decode_head.num_classes
+
+
+def test_c_abi_exports_every_declared_symbol():
+    import ctypes
+    import mmsam_b200  # noqa
+    from mmsam_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mmsam_b200.h")).read()
+    declared = set(re.findall(r"^int\s+(mmsam_\w+)\s*\(", hdr, flags=re.M))
+    assert declared and declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().mmsam_arch() == 100
+
+
+def test_no_cpu_fallback():
+    import mmsam_b200  # noqa
+    from mmsam_b200 import kernels
+    from mmsam_b200._lib import MMSamError
+    with pytest.raises(MMSamError):
+        kernels.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+    with pytest.raises(MMSamError):
+        kernels.layernorm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.ones(8), torch.zeros(8), 1e-6)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "multimodal-sam-adapter_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_window_maps_roundtrip():
+    import mmsam_b200  # noqa
+    from mmsam_b200.engine import window_maps
+    B, H, W, ws = 2, 19, 25, 14
+    m = window_maps(B, H, W, ws, 8, "cpu")
+    x = torch.arange(B * H * W, dtype=torch.float32)
+    y = torch.zeros(m["win_rows"])
+    y[m["win_fwd"].long()] = x
+    ref = torch.nn.functional.pad(x.view(B, H, W), (0, 28 - W, 0, 28 - H))
+    ref = ref.view(B, 2, ws, 2, ws).permute(0, 1, 3, 2, 4).reshape(-1)
+    assert torch.equal(y, ref)
+    inv = m["win_inv"].long()
+    back = torch.zeros(B * H * W)
+    back[inv[inv >= 0]] = y[inv >= 0]
+    assert torch.equal(back, x)
+
+
+def test_msdeformattn_module_contract():
+    import mmsam_b200  # noqa
+    from mmsam_b200.ops.modules import MSDeformAttn
+    m = MSDeformAttn(d_model=64, n_levels=3, n_heads=4, n_points=4, ratio=0.5)
+    assert m.im2col_step == 64 and set(dict(m.named_children())) == {"sampling_offsets", "attention_weights", "value_proj", "output_proj"}
+    assert m.sampling_offsets.weight.abs().sum() == 0 and m.attention_weights.bias.abs().sum() == 0
+    assert m.value_proj.weight.shape == (32, 64) and m.output_proj.weight.shape == (64, 32)
+    with pytest.raises(ValueError):
+        MSDeformAttn(d_model=65, n_heads=4)
