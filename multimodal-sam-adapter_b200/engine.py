@@ -177,11 +177,13 @@ class _Ops:
         return dst
 
     def _injector(self, x, c, inj, sc, B):
-        """Injector.forward (adapter_modules_...new.py:525-542); x [B*T, C] updated in place."""
+        """Injector.forward (adapter_modules_...new.py:525-542); returns a NEW [B*T, C] buffer (the input
+        is one of the saved ViT outputs `outs` and must stay intact)."""
         qn = self._ln(x, inj["qn"])
         fn = self._ln(c, inj["fn"])
         o = self._msda(inj["attn"], qn, fn, sc["ref1"], sc["lv3"], B)
-        K.gemm(o.view(-1, o.shape[-1]), inj["attn"].out.w, bias=inj["attn"].out.b, scale=inj["gamma"], residual=x, out=x)
+        return K.gemm(o.view(-1, o.shape[-1]), inj["attn"].out.w, bias=inj["attn"].out.b, scale=inj["gamma"],
+                      residual=x, out=torch.empty_like(x))
 
     def _extractor(self, c, x, e, sc, B):
         """Extractor.forward (adapter_modules_...new.py:490-511); c [B*S3, C] updated in place."""
@@ -230,7 +232,7 @@ class ComponentRunner(_Ops):
         sc.update(deform_geometry(B, Hi, Wi, self.dev))
         xb = x.reshape(-1, self.C).to(torch.bfloat16).contiguous().clone()
         cb = c.reshape(-1, self.C).to(torch.bfloat16).contiguous().clone()
-        self._injector(xb, cb, pk["inj"], sc, B)
+        xb = self._injector(xb, cb, pk["inj"], sc, B)
         for blk in blocks:
             xb = self.block(blk, xb.view(B, H * W, self.C), H, W).reshape(-1, self.C)
         for e in pk["ext"]:
@@ -317,10 +319,10 @@ class EncoderEngine(_Ops):
         hd = {"convs": []}
         for cm in h.convs:
             s, t = _bn_fold(cm.bn, dev)
-            w = cm.conv.weight.detach().float().reshape(cm.conv.weight.shape[0], -1) * s.cpu()[:, None]
+            w = cm.conv.weight.detach().float().reshape(cm.conv.weight.shape[0], -1).to(dev) * s[:, None]
             hd["convs"].append(_Lin(w, t, dev))
         s, t = _bn_fold(h.fusion_conv.bn, dev)
-        w = h.fusion_conv.conv.weight.detach().float().reshape(h.fusion_conv.conv.weight.shape[0], -1) * s.cpu()[:, None]
+        w = h.fusion_conv.conv.weight.detach().float().reshape(h.fusion_conv.conv.weight.shape[0], -1).to(dev) * s[:, None]
         hd["fusion"] = _Lin(w, t, dev)
         ncls = h.conv_seg.weight.shape[0]
         npad = (ncls + 31) // 32 * 32
@@ -388,7 +390,7 @@ class EncoderEngine(_Ops):
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def backbone_nhwc(self, img):
+    def backbone_nhwc(self, img, debug=None):
         """img fp32 [B, 3+3, Hi, Wi] on the device -> [f1, f2, f3, f4] channels-last bf16 [B, h, w, C]."""
         if not img.is_cuda:
             raise K._lib.MMSamError("input must be a CUDA tensor")
@@ -402,6 +404,8 @@ class EncoderEngine(_Ops):
         fx = self._convnext_branch(img, 0, self.cnx["x"], B, Hi, Wi)
         fy = self._convnext_branch(img, self.cin, self.cnx["y"], B, Hi, Wi)
         fused = self.neck(fx, fy, B)                                    # 4 x [B*h*w, 2*Ci] bf16
+        if debug is not None:
+            debug.update(fx=[(t.clone(), h, w) for t, h, w in fx], fy=[(t.clone(), h, w) for t, h, w in fy], fused=[t.clone() for t in fused])
         c1 = self._gemm(fused[0], self.fc[0])                            # [B*16T, C]
         c = torch.empty((B * S3, C), dtype=torch.bfloat16, device=self.dev)
         for i in range(3):
@@ -409,20 +413,22 @@ class EncoderEngine(_Ops):
         # --- patch embed + pos embed (image_encoder.py:662-671, ..._new.py:268-278) ---
         pch = K.patchify(img, 0, self.cin, self.patch)
         x = self._gemm(pch, self.patch_embed, residual=sc["pos"])
+        if debug is not None:
+            debug.update(c1=c1.clone(), c_0=c.clone(), x_0=x.clone())
         # --- interactions (..._new.py:283-292; adapter_modules_...new.py:567-581) ---
         outs = []
         idxs = self.cfg["interaction_indexes"]
         for i, (lo, hi) in enumerate(idxs):
             it = self.inter[i]
-            self._injector(x, c, it["inj"], sc, B)
+            x = self._injector(x, c, it["inj"], sc, B)
             for bi in range(lo, hi + 1):
-                if bi == hi:
-                    x = self._block(x, self.blocks[bi], sc, sc["tabs"][bi], B, out=torch.empty_like(x))
-                else:
-                    self._block(x, self.blocks[bi], sc, sc["tabs"][bi], B)
+                self._block(x, self.blocks[bi], sc, sc["tabs"][bi], B)
             for e in it["ext"]:
                 self._extractor(c, x, e, sc, B)
             outs.append(x)
+            if debug is not None:
+                debug[f"x{i}"] = x.clone()
+                debug[f"c_{i}"] = c.clone()
         # --- tail (..._new.py:316-337): up(c2) + c1, add resized ViT features, eval BatchNorm ---
         c3d = c.view(B, S3, C)
         n2, n3 = 4 * T, T

@@ -321,9 +321,14 @@ def roadformer_neck(feats, s):
     return out
 
 
-def spm_bimodal(x, y, s, depths):
+def spm_bimodal(x, y, s, depths, stages=None):
     """A:929-964."""
-    feats = roadformer_neck(twin_convnext(x, y, s.sub("twin_conv"), depths), s.sub("smart_fusion"))
+    tw = twin_convnext(x, y, s.sub("twin_conv"), depths)
+    if stages is not None:
+        stages["twin"] = [t.clone() for t in tw]
+    feats = roadformer_neck(tw, s.sub("smart_fusion"))
+    if stages is not None:
+        stages["fused"] = [t.clone() for t in feats]
     cs = []
     for i, f in enumerate(feats):
         t = F.conv2d(f, s(f"fc{i + 1}.weight"), s(f"fc{i + 1}.bias"))
@@ -343,7 +348,7 @@ def backbone_forward(sd, cfg, img, prefix="", stages=None):
     cin = cfg["modalities_ch"][cfg["modalities_name"].index("rgb")]
     x, xo = img[:, :cin], img[:, cin:]
     B, _, Hi, Wi = x.shape
-    c1, c2, c3, c4 = spm_bimodal(x, xo, s.sub("spm"), depths)
+    c1, c2, c3, c4 = spm_bimodal(x, xo, s.sub("spm"), depths, stages)
     if stages is not None:
         stages.update(c1=c1, c2=c2, c3=c3, c4=c4)
     le = s("level_embed")
@@ -355,6 +360,9 @@ def backbone_forward(sd, cfg, img, prefix="", stages=None):
     t = t.permute(0, 2, 3, 1).flatten(1, 2)
     pe = F.interpolate(s("pos_embed").permute(0, 3, 1, 2), size=(H, W), mode="bicubic", align_corners=False)
     t = t + pe.reshape(1, -1, H * W).permute(0, 2, 1)
+    if stages is not None:
+        stages["x_0"] = t.clone()
+        stages["c_0"] = c.clone()
     C = t.shape[-1]
     outs = []
     idxs = cfg["interaction_indexes"]

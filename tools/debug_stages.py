@@ -1,0 +1,43 @@
+"""Stage-by-stage comparison of the CUDA path with the CPU oracle (GPU box)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from common import TINY, TINY_HEAD, VITB, VITB_HEAD, build_segmentor, rel_l2  # noqa
+from oracle import model as om  # noqa
+from oracle.perturb import synthetic_batch  # noqa
+
+which = sys.argv[1] if len(sys.argv) > 1 else "tiny"
+cfg, hcfg = (TINY, TINY_HEAD) if which == "tiny" else (VITB, VITB_HEAD)
+seg, sd = build_segmentor(cfg, hcfg)
+x = synthetic_batch(1, cfg["img_size"])
+st = {}
+with torch.no_grad():
+    want = om.backbone_forward(sd, cfg, x, prefix="backbone.", stages=st)
+seg = seg.cuda()
+dbg = {}
+eng = seg.backbone.engine(seg.decode_head)
+got = eng.backbone_nhwc(x.cuda(), debug=dbg)
+
+
+def tok(t):  # NCHW -> [HW, C]
+    return t[0].flatten(1).t()
+
+
+for i in range(4):
+    tw = st["twin"][i]
+    ci = tw.shape[1] // 2
+    print(f"twin level {i}: rgb {rel_l2(dbg['fx'][i][0].float().cpu(), tok(tw[:, :ci])):.3e} aux {rel_l2(dbg['fy'][i][0].float().cpu(), tok(tw[:, ci:])):.3e}")
+for i in range(4):
+    print(f"fused level {i}: {rel_l2(dbg['fused'][i].float().cpu(), tok(st['fused'][i])):.3e}")
+print("c1", rel_l2(dbg["c1"].float().cpu(), st["c1"][0]))
+print("c_0", rel_l2(dbg["c_0"].float().cpu(), st["c_0"][0]))
+print("x_0", rel_l2(dbg["x_0"].float().cpu(), st["x_0"][0]))
+for i in range(4):
+    print(f"x{i}", rel_l2(dbg[f"x{i}"].float().cpu(), st[f"x{i}"][0]), f"c_{i}", rel_l2(dbg[f"c_{i}"].float().cpu(), st[f"c_{i}"][0]))
+for i, (g, w) in enumerate(zip(got, want)):
+    print(f"f{i + 1}", rel_l2(g.permute(0, 3, 1, 2).float().cpu(), w))
