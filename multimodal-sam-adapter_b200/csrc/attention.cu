@@ -49,11 +49,13 @@ static constexpr int TM_S = 0;      // 2 x 128
 static constexpr int TM_PV = 256;   // 64
 static constexpr int TM_G = 320;    // 128
 
+template <int KW>
 __global__ void __launch_bounds__(192, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTabH,
                  const __grid_constant__ CUtensorMap tmTabW, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // keep the pointer derived from the __shared__ array (so loads compile to LDS, not generic LD)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // layout: Q | KV stages | P (2 panels) | tables | bias rows | barriers
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + TILE_BYTES;
@@ -64,8 +66,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   const int bh_stride = p.bh_stride, bw_stride = p.bw_stride;  // row-private rows, stride chosen odd
   float* sBh = sBias;
   float* sBw = sBias + ATT_BM * bh_stride;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(
-      (reinterpret_cast<uintptr_t>(sBw + ATT_BM * bw_stride) + 15) & ~(uintptr_t)15);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBw + ((ATT_BM * bw_stride + 3) & ~3));
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
   uint64_t* g_full = bars + 2;
@@ -270,41 +271,76 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         if (lane == 0) mbar_arrive(&s_empty[g & 1]);
         const int k0 = j * ATT_BN;
         const int nvalid = p.T - k0 < ATT_BN ? p.T - k0 : ATT_BN;
-        float m_new = m_run;
-        if (has_bias) {
-          int kh = k0 / p.Kw, kw = k0 - kh * p.Kw;
-          float bhv = bh[kh < p.Kh ? kh : p.Kh - 1];
+        // 4 independent max / sum chains: with one softmax warp per scheduler the dependent-issue
+        // latency is otherwise fully exposed.
+        float mx[4] = {m_run, -INFINITY, -INFINITY, -INFINITY};
+        if (!has_bias) {
 #pragma unroll
           for (int c = 0; c < ATT_BN; ++c) {
-            float v = fmaf(t[c], p.scale_log2, bhv + bw[kw]);
-            v = c < nvalid ? v : -INFINITY;
-            t[c] = v;
-            m_new = fmaxf(m_new, v);
-            if (++kw == p.Kw) {
-              kw = 0;
-              ++kh;
-              bhv = bh[kh < p.Kh ? kh : p.Kh - 1];
+            t[c] *= p.scale_log2;
+            mx[c & 3] = fmaxf(mx[c & 3], t[c]);
+          }
+        } else if (KW == 64 || KW == 32) {
+          // key grid width divides the key block: (kh, kw) of column c are compile-time constants
+          const int kh0 = k0 / KW;
+#pragma unroll
+          for (int seg = 0; seg < ATT_BN / (KW > 0 ? KW : ATT_BN); ++seg) {
+            const float bhv = bh[kh0 + seg];
+#pragma unroll
+            for (int i = 0; i < (KW > 0 ? KW : 1); ++i) {
+              const int c = seg * KW + i;
+              t[c] = fmaf(t[c], p.scale_log2, bhv + bw[i]);
+              mx[c & 3] = fmaxf(mx[c & 3], t[c]);
+            }
+          }
+        } else if (KW == 14) {
+          // SAM window: 196 keys = key block 0 (keys 0..127) + block 1 (keys 128..195)
+          if (j == 0) {
+#pragma unroll
+            for (int c = 0; c < ATT_BN; ++c) {
+              t[c] = fmaf(t[c], p.scale_log2, bh[c / 14] + bw[c % 14]);
+              mx[c & 3] = fmaxf(mx[c & 3], t[c]);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 196 - ATT_BN; ++c) {
+              t[c] = fmaf(t[c], p.scale_log2, bh[(c + ATT_BN) / 14] + bw[(c + ATT_BN) % 14]);
+              mx[c & 3] = fmaxf(mx[c & 3], t[c]);
             }
           }
         } else {
+          // generic grid: branch-free running (kh, kw)
+          int kh = k0 / p.Kw, kw = k0 - kh * p.Kw;
 #pragma unroll
           for (int c = 0; c < ATT_BN; ++c) {
-            float v = t[c] * p.scale_log2;
-            v = c < nvalid ? v : -INFINITY;
-            t[c] = v;
-            m_new = fmaxf(m_new, v);
+            const int khc = kh < p.Kh ? kh : p.Kh - 1;
+            t[c] = fmaf(t[c], p.scale_log2, bh[khc] + bw[kw]);
+            mx[c & 3] = fmaxf(mx[c & 3], t[c]);
+            ++kw;
+            const bool wrap = kw == p.Kw;
+            kw = wrap ? 0 : kw;
+            kh += wrap ? 1 : 0;
           }
         }
+        if (nvalid < ATT_BN) {  // ragged last key block: keys >= T do not exist
+          mx[0] = m_run; mx[1] = mx[2] = mx[3] = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < ATT_BN; ++c) {
+            t[c] = c < nvalid ? t[c] : -INFINITY;
+            mx[c & 3] = fmaxf(mx[c & 3], t[c]);
+          }
+        }
+        const float m_new = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
         const float alpha = ex2(m_run - m_new);
-        float lsum = 0.f;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[ATT_BN / 2];
 #pragma unroll
         for (int c = 0; c < ATT_BN; c += 2) {
           const float p0 = ex2(t[c] - m_new), p1 = ex2(t[c + 1] - m_new);
-          lsum += p0 + p1;
+          ls[(c >> 1) & 3] += p0 + p1;
           pk[c >> 1] = pack_bf16(p0, p1);
         }
-        l_run = l_run * alpha + lsum;
+        l_run = l_run * alpha + ((ls[0] + ls[1]) + (ls[2] + ls[3]));
         m_run = m_new;
         // ---- 2. fold in P_{j-1} V_{j-1} (the tensor core finished it while we did step 1) ----
         if (j > 0) {
@@ -422,15 +458,27 @@ MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const void* tab_h
   } else {
     tmH = tmQKV; tmW = tmQKV;
   }
-  static int configured_smem = 0;
-  if (smem_bytes > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, budget);
-    if (e != cudaSuccess) return (int)e;
-    configured_smem = budget;
-  }
   if (max_ctas <= 0 || max_ctas > kNumSMs) max_ctas = kNumSMs;
   const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
-  attention_kernel<<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(tmQKV, tmH, tmW, p);
+  int kw_mode = 0;
+  if (has_bias && Kw == 64 && T % ATT_BN == 0) kw_mode = 64;
+  else if (has_bias && Kw == 32 && T % ATT_BN == 0) kw_mode = 32;
+  else if (has_bias && Kw == 14 && Kh == 14) kw_mode = 14;
+#define ATT_LAUNCH(KWM)                                                                                         \
+  do {                                                                                                          \
+    static bool configured = false;                                                                             \
+    if (!configured) {                                                                                          \
+      cudaError_t e = cudaFuncSetAttribute(attention_kernel<KWM>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget); \
+      if (e != cudaSuccess) return (int)e;                                                                      \
+      configured = true;                                                                                        \
+    }                                                                                                           \
+    attention_kernel<KWM><<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(tmQKV, tmH, tmW, p);                 \
+  } while (0)
+  if (kw_mode == 64) ATT_LAUNCH(64);
+  else if (kw_mode == 32) ATT_LAUNCH(32);
+  else if (kw_mode == 14) ATT_LAUNCH(14);
+  else ATT_LAUNCH(0);
+#undef ATT_LAUNCH
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }

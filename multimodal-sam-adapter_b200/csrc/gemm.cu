@@ -65,7 +65,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // keep the pointer derived from the __shared__ array (so loads compile to LDS, not generic LD)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
@@ -159,13 +160,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ps_y = r / ep.ps_w;
         ps_x = r - ps_y * ep.ps_w;
       }
-#pragma unroll 1
-      for (int c = 0; c < BN / 2; c += 32) {
-        const int col_l = half * (BN / 2) + c;
-        uint32_t r[32];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the guarded stores below
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + col_l, r);
-        tmem_ld_wait();
+      // All TMEM loads of this warp's column half are issued up front (BN/2 <= 128 fp32 columns =
+      // BN/2 registers) and the accumulator is handed back to the MMA warp right after they land, so the
+      // global-memory part of the epilogue (bias / residual loads, stores) overlaps the next tile's MMAs
+      // instead of sitting between them.
+      constexpr int NCH = BN / 64;  // 32-column chunks per warp
+      uint32_t r[NCH][32];
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci)
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + half * (BN / 2) + ci * 32, r[ci]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int col_l = half * (BN / 2) + ci * 32;
         const int col = n_blk * BN + col_l;
         if (!row_ok || col >= ep.N) continue;
         long long drow = dst_row;
@@ -179,14 +189,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float v[32];
         const bool full32 = ep.vec_ok && col + 32 <= ep.N;
         if (full32) {
+          uint4 rres[4];
+          if (ep.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + drow * ep.ldr + dcol);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rres[j] = __ldg(rp + j);
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ep.bias) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
-            v[j] = __uint_as_float(r[j]) + b.x;
-            v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
-            v[j + 2] = __uint_as_float(r[j + 2]) + b.z;
-            v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+            v[j] = __uint_as_float(r[ci][j]) + b.x;
+            v[j + 1] = __uint_as_float(r[ci][j + 1]) + b.y;
+            v[j + 2] = __uint_as_float(r[ci][j + 2]) + b.z;
+            v[j + 3] = __uint_as_float(r[ci][j + 3]) + b.w;
           }
           if (ep.act) {
 #pragma unroll
@@ -200,11 +216,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (ep.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + drow * ep.ldr + dcol);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float f[8];
-              unpack8(__ldg(rp + j), f);
+              unpack8(rres[j], f);
 #pragma unroll
               for (int k = 0; k < 8; ++k) v[8 * j + k] += f[k];
             }
@@ -219,21 +234,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 4; ++j) op[j] = pack8(v + 8 * j);
           }
         } else {
-          // ragged last column chunk: scalar, fully guarded
-          for (int j = 0; j < 32 && col + j < ep.N; ++j) {
-            float x = __uint_as_float(r[j]);
-            if (ep.bias) x += ep.bias[col + j];
-            x = apply_act(x, ep.act);
-            if (ep.scale) x *= ep.scale[col + j];
-            if (ep.residual) x += __bfloat162float(ep.residual[drow * ep.ldr + dcol + j]);
-            if (ep.out_f32) reinterpret_cast<float*>(ep.out)[drow * ep.ldo + dcol + j] = x;
-            else reinterpret_cast<__nv_bfloat16*>(ep.out)[drow * ep.ldo + dcol + j] = __float2bfloat16_rn(x);
+          // ragged last column chunk / unaligned rows: scalar, fully guarded
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col + j < ep.N) {
+              float x = __uint_as_float(r[ci][j]);
+              if (ep.bias) x += ep.bias[col + j];
+              x = apply_act(x, ep.act);
+              if (ep.scale) x *= ep.scale[col + j];
+              if (ep.residual) x += __bfloat162float(ep.residual[drow * ep.ldr + dcol + j]);
+              if (ep.out_f32) reinterpret_cast<float*>(ep.out)[drow * ep.ldo + dcol + j] = x;
+              else reinterpret_cast<__nv_bfloat16*>(ep.out)[drow * ep.ldo + dcol + j] = __float2bfloat16_rn(x);
+            }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
     }
   }
   tc_fence_before();

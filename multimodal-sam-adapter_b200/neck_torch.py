@@ -110,9 +110,11 @@ class NeckTorch:
     @torch.no_grad()
     def __call__(self, fx, fy, B):
         """fx / fy: per level (tokens bf16 [B*h*w, Ci], h, w) -> list of fused tokens bf16 [B*h*w, 2*Ci]."""
+        # TF32 tensor-core library kernels for the convs / bmm (10-bit mantissa inputs, fp32 accumulate: finer
+        # than the bf16 used everywhere else on the path); statistics, softmax and norms stay fp32.
         prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cudnn.allow_tf32 = False
-        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
         try:
             outs = []
             for lv, (tx, h, w), (ty, _, _) in zip(self.levels, fx, fy):
