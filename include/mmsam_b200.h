@@ -48,8 +48,9 @@ int mmsam_msda_forward(const void* value, const int64_t* spatial_shapes_dev,
  * row_map_dev (optional int32[rows]): destination row of each source row, -1 = drop.
  * ps_h, ps_w > 0 (and no row map): rows are (b, y<ps_h, x<ps_w); row goes to row (b, y/2, x/2), column
  * block (y&1)*2+(x&1) of a [rows/4, 4C] matrix = the 2x2 patchify of ConvNeXt's LN2d -> Conv2d(k2,s2)
- * downsample (base/twin_convnext.py:313-336). */
-int mmsam_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* y,
+ * downsample (base/twin_convnext.py:313-336).
+ * y2 (optional): second output x + LN(x) with the same row mapping (GFE residual, adapter_modules_...new.py:143). */
+int mmsam_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* y, void* y2,
                          const int* row_map_dev, long long rows, int C, long long ldx, long long ldy,
                          float eps, int ps_h, int ps_w, void* stream);
 
@@ -120,6 +121,41 @@ int mmsam_upsample_argmax_f32(const float* logits, void* labels_u8, int B, int h
  * intersect_and_union (mmseg_custom/apis/evaluation/metrics_micro.py:26-86). */
 int mmsam_confusion_u8(const void* pred_u8, const void* gt_u8, void* conf_u64, long long n, int ncls,
                        int ignore_index, void* stream);
+
+/* Grouped 3x3 conv (stride 1, pad 1, no bias) on channels-last bf16 as a tcgen05 implicit GEMM.
+ * Replaces AttentionBase.qkv2 and Mlp.dwconv of the fusion neck (adapter_modules_...new.py:84, 118-119).
+ * w_packed: bf16 [(ceil(Cout/64) * 9 * KC) * 64, 64], KC = mmsam_conv3x3_kblocks(Cin, Cout, groups); block
+ * (n-tile, tap, k-block) = W[co, ci, tap] for co in the tile, ci in the 64-channel window starting at
+ * ((n-tile*64) / (Cout/groups)) * (Cin/groups) + k-block*64, zero outside co's group. */
+int mmsam_conv3x3_kblocks(int Cin, int Cout, int groups);
+int mmsam_conv3x3_bf16(const void* x, const void* w_packed, void* out, int B, int H, int W, int Cin, int Cout,
+                       int groups, int max_ctas, void* stream);
+
+/* S[b,i,j] += sum_pix X[b,pix,qoff+i] * X[b,pix,koff+j] (fp32, caller zeroes S), optional squared row norms
+ * nq/nk [B,n]; blk > 0 restricts to the block diagonal (per-head). AttentionBase q@k^T / F.normalize
+ * (adapter_modules_...new.py:98-103) and GFFM energies (:250-254). X is [B, HW, ld] bf16. */
+int mmsam_gram_bf16(const void* X, long long ld, int qoff, int koff, int n, int B, int HW, int blk, float* S,
+                    float* nq, float* nk, void* stream);
+
+/* Per-512-pixel-chunk column statistics {sum o, sum o^2, sum o*w[pix]} of o [B,HW,C] bf16 for GFFM's
+ * LayerNorm over the spatial axis (:262-264): part fp32 [mmsam_colstats_chunks(HW), B, C, 3]. */
+int mmsam_colstats_chunks(int HW);
+int mmsam_colstats_bf16(const void* o, const float* wpix, float* part, int B, int HW, int C, void* stream);
+
+/* u[r, c] = gelu(a[r, c]) * a[r, C + c], a bf16 [rows, 2C] -> u bf16 [rows, C]  (Mlp gate, :129-130). */
+int mmsam_gate_bf16(const void* a, void* u, long long rows, int C, void* stream);
+
+/* f = s1 * ((o - mu) * rstd * w[pix] + b[pix]) * gate + s2 * lo  (GFFM LayerNorm over HW, FFRM gate, Scale2;
+ * :262-264, 158-162, 279-280) plus the coordinate-attention pools: ph [B,H,C] row sums and per-strip column sums
+ * pw_part [ceil(H/RS), B, W, C], RS = mmsam_combine_pool_rows(H). mu/rstd/gate fp32 [B,C]; wpix/bpix fp32 [H*W]. */
+int mmsam_combine_pool_rows(int H);
+int mmsam_combine_pool_bf16(const void* o, const void* lo, const float* mu, const float* rstd, const float* gate,
+                            const float* wpix, const float* bpix, float s1, float s2, void* f, float* ph,
+                            float* pw_part, int B, int H, int W, int C, void* stream);
+
+/* out = f * (1 + aw[b,x,c] * ah[b,y,c])  (CoordinateAttention + CA residual, :187-221); ah [B,H,C], aw [B,W,C]. */
+int mmsam_ca_apply_bf16(const void* f, const float* ah, const float* aw, void* out, int B, int H, int W, int C,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ _vp, _i, _ll, _f = _c.c_void_p, _c.c_int, _c.c_longlong, _c.c_float
 SIGNATURES = {
     "mmsam_arch": [],
     "mmsam_msda_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "mmsam_layernorm_bf16": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _ll, _ll, _f, _i, _i, _vp],
+    "mmsam_layernorm_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _ll, _ll, _f, _i, _i, _vp],
     "mmsam_gemm_bf16": [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp,
                         _i, _i, _i, _i, _i, _vp],
     "mmsam_msda_fused_bf16": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
@@ -26,6 +26,15 @@ SIGNATURES = {
     "mmsam_resize_add_affine_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _vp],
     "mmsam_upsample_argmax_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_confusion_u8": [_vp, _vp, _vp, _ll, _i, _i, _vp],
+    "mmsam_conv3x3_kblocks": [_i, _i, _i],
+    "mmsam_conv3x3_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mmsam_gram_bf16": [_vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "mmsam_colstats_chunks": [_i],
+    "mmsam_colstats_bf16": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "mmsam_gate_bf16": [_vp, _vp, _ll, _i, _vp],
+    "mmsam_combine_pool_rows": [_i],
+    "mmsam_combine_pool_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "mmsam_ca_apply_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "mmsam_attention_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp],
 }
 

@@ -1,0 +1,219 @@
+// Grouped 3x3 convolution (stride 1, zero pad 1, no bias) on channels-last bf16 maps as an implicit GEMM
+// on tcgen05 tensor cores — no im2col buffer.
+//
+// Serves the fusion neck's grouped convs (segmentation/mmseg_custom/models/backbones/
+// adapter_modules_multimodal_mix_mod_new_in_twin_convnext_new.py): AttentionBase.qkv2
+// (Conv2d(3c, 3c, 3, padding=1, groups=32), :84) and Mlp.dwconv (Conv2d(2c, 2c, 3, padding=1,
+// groups=c), :118-119). Any groups count works, including 1 (dense 3x3).
+//
+// Tile = 128 output pixels (an 8 x 16 spatial patch of one image) x 64 output channels. For every filter
+// tap (dy, dx) the A operand is the same patch shifted by (dy-1, dx-1): ONE 4-D TMA box
+// {64 ch, 16 w, 8 h, 1 b} out of the NHWC input, with the hardware's out-of-bounds zero fill doing the
+// spatial zero padding and the channel tail. Because the conv is grouped, the 64 output channels of a
+// tile only read a short window of input channels (the groups they belong to): the K loop is
+// 9 taps x KC 64-channel blocks of that window, against weight blocks pre-packed per
+// (n-tile, tap, k-block) with zeros outside each group. Same warp specialisation as gemm.cu
+// (TMA producer warp, one MMA-issuer lane, 8 epilogue warps, 2 TMEM accumulators).
+#include "common.cuh"
+
+namespace mmsam {
+
+struct ConvParams {
+  __nv_bfloat16* out;
+  int B, H, W, Cin, Cout;
+  int cg_in, cg_out;   // channels per group
+  int KC;              // 64-channel k-blocks per tap
+  int tiles_x, tiles_y, num_n, num_tiles;
+};
+
+static constexpr int CV_BN = 64, CV_STAGES = 8;
+static constexpr int CV_A_BYTES = 128 * 64 * 2, CV_B_BYTES = CV_BN * 64 * 2;
+static constexpr int CV_STAGE_BYTES = CV_A_BYTES + CV_B_BYTES;
+static constexpr int CV_SMEM = CV_STAGES * CV_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(320, 1)
+conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CV_STAGES * CV_STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + CV_STAGES;
+  uint64_t* tfull = bars + 2 * CV_STAGES;
+  uint64_t* tempty = bars + 2 * CV_STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CV_STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = 9 * p.KC;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < CV_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 2 * CV_BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (n tile fastest, then x, y, b)
+  auto decode = [&](int tile, int& nt, int& x0, int& y0, int& b) {
+    nt = tile % p.num_n;
+    int t = tile / p.num_n;
+    x0 = (t % p.tiles_x) * 16;
+    t /= p.tiles_x;
+    y0 = (t % p.tiles_y) * 8;
+    b = t / p.tiles_y;
+  };
+
+  if (warp == 8) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int nt, x0, y0, b;
+        decode(tile, nt, x0, y0, b);
+        const int kwin = ((nt * CV_BN) / p.cg_out) * p.cg_in;  // first input channel of the first group touched
+        for (int kb = 0; kb < num_k; ++kb) {
+          const int tap = kb / p.KC, kc = kb - tap * p.KC;
+          const int dy = tap / 3, dx = tap - dy * 3;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], CV_STAGE_BYTES);
+          uint8_t* sa = smem + s * CV_STAGE_BYTES;
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+              ::"r"(smem_u32(sa)), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(&full[s])),
+              "r"(kwin + kc * 64), "r"(x0 + dx - 1), "r"(y0 + dy - 1), "r"(b)
+              : "memory");
+          tma_load_2d(sa + CV_A_BYTES, &tmW, &full[s], 0, ((nt * 9 + tap) * p.KC + kc) * 64);
+          if (++s == CV_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, CV_BN, 0, 0);
+      int s = 0; uint32_t ph = 0; int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * CV_BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * CV_STAGE_BYTES);
+          const uint32_t b_addr = a_addr + CV_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);
+          if (++s == CV_STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    const int quad = warp & 3, half = warp >> 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      int nt, x0, y0, b;
+      decode(tile, nt, x0, y0, b);
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], aph);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * CV_BN + half * 32, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      const int rr = quad * 32 + lane;
+      const int y = y0 + (rr >> 4), x = x0 + (rr & 15);
+      const int col = nt * CV_BN + half * 32;
+      if (y < p.H && x < p.W && col < p.Cout) {
+        __nv_bfloat16* op = p.out + (((long long)b * p.H + y) * p.W + x) * p.Cout + col;
+        if (col + 32 <= p.Cout) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(op)[j] = pack8(v + 8 * j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col + j < p.Cout) op[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * CV_BN);
+  }
+}
+
+}  // namespace mmsam
+
+// Number of 64-channel k-blocks per tap for a given grouping (host helper, also used by the weight packer).
+MMSAM_API int mmsam_conv3x3_kblocks(int Cin, int Cout, int groups) {
+  if (groups <= 0 || Cin % groups || Cout % groups) return -1;
+  const int cgi = Cin / groups, cgo = Cout / groups;
+  int kc = 1;
+  for (int n0 = 0; n0 < Cout; n0 += 64) {
+    const int n1 = (n0 + 64 < Cout ? n0 + 64 : Cout) - 1;
+    const int g0 = n0 / cgo, g1 = n1 / cgo;
+    const int len = (g1 - g0 + 1) * cgi;
+    const int need = (len + 63) / 64;
+    if (need > kc) kc = need;
+  }
+  return kc;
+}
+
+// x [B,H,W,Cin] bf16, w_packed bf16 [(ceil(Cout/64) * 9 * KC) * 64, 64]: block (nt, tap, kc) holds
+// W[co = nt*64 + r, ci = kwin(nt) + kc*64 + c, tap] (0 outside co's group), out [B,H,W,Cout] bf16.
+MMSAM_API int mmsam_conv3x3_bf16(const void* x, const void* w_packed, void* out, int B, int H, int W, int Cin,
+                                 int Cout, int groups, int max_ctas, void* stream) {
+  using namespace mmsam;
+  if (B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (Cin & 7) || (Cout & 7)) return MMSAM_ERR_BAD_ARG;
+  const int KC = mmsam_conv3x3_kblocks(Cin, Cout, groups);
+  if (KC < 0) return MMSAM_ERR_BAD_ARG;
+  if (B == 0) return MMSAM_OK;
+  if (!x || !w_packed || !out || (((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)out) & 15)) return MMSAM_ERR_BAD_ARG;
+  ConvParams p;
+  p.out = (__nv_bfloat16*)out;
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.cg_in = Cin / groups; p.cg_out = Cout / groups; p.KC = KC;
+  p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 7) / 8; p.num_n = (Cout + 63) / 64;
+  p.num_tiles = p.num_n * p.tiles_x * p.tiles_y * B;
+  mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
+  if (!enc) return MMSAM_ERR_DRIVER;
+  CUtensorMap tmX, tmW;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[4] = {64, 16, 8, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MMSAM_ERR_DRIVER;
+  }
+  int rc = mmsam_host::make_tmap_2d_bf16(&tmW, w_packed, (uint64_t)p.num_n * 9 * KC * 64, 64, 64, 64, 64);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  if (max_ctas <= 0 || max_ctas > kNumSMs) max_ctas = kNumSMs;
+  const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
+  conv3x3_kernel<<<grid, 320, CV_SMEM, (cudaStream_t)stream>>>(tmX, tmW, p);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}

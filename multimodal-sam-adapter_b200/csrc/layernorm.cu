@@ -19,7 +19,7 @@ namespace mmsam {
 template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y2,
                  const int* __restrict__ row_map, long long rows, int C, long long ldx,
                  long long ldy, float eps, int ps_h, int ps_w) {
   const int lane = threadIdx.x & 31;
@@ -69,6 +69,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
     }
     const float rstd = rsqrtf(warp_sum(s2) / (float)C + eps);
     uint4* yr = reinterpret_cast<uint4*>(y + dst * ldy + dcol);
+    uint4* yr2 = y2 ? reinterpret_cast<uint4*>(y2 + dst * ldy + dcol) : nullptr;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + 32 * i;
@@ -87,6 +88,11 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
         o[6] = (f[i][6] - mean) * rstd * g1.z + b1.z;
         o[7] = (f[i][7] - mean) * rstd * g1.w + b1.w;
         yr[v] = pack8(o);
+        if (yr2) {  // second output: x + LN(x)  (GFE: x + attn(norm1(x)) keeps norm1(x) as a residual)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += f[i][j];
+          yr2[v] = pack8(o);
+        }
       }
     }
   }
@@ -94,7 +100,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
 
 }  // namespace mmsam
 
-MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* y,
+MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* y, void* y2,
                                    const int* row_map_dev, long long rows, int C, long long ldx,
                                    long long ldy, float eps, int ps_h, int ps_w, void* stream) {
   using namespace mmsam;
@@ -110,9 +116,10 @@ MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const floa
   if (blocks > cap) blocks = cap;
   const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
   __nv_bfloat16* yo = (__nv_bfloat16*)y;
+  __nv_bfloat16* yo2 = (__nv_bfloat16*)y2;
   const int nv = (C / 8 + 31) / 32;
 #define LN_CASE(NV) \
-  layernorm_kernel<NV><<<(unsigned)blocks, wpb * 32, 0, st>>>(xi, gamma, beta, yo, row_map_dev, rows, C, ldx, ldy, eps, ps_h, ps_w)
+  layernorm_kernel<NV><<<(unsigned)blocks, wpb * 32, 0, st>>>(xi, gamma, beta, yo, yo2, row_map_dev, rows, C, ldx, ldy, eps, ps_h, ps_w)
   switch (nv) {
     case 1: LN_CASE(1); break;
     case 2: LN_CASE(2); break;

@@ -15,6 +15,7 @@ import math
 import torch
 
 from . import kernels as K
+from . import neck as neck_b200
 from . import neck_torch
 
 
@@ -297,7 +298,11 @@ class EncoderEngine(_Ops):
                 stages.append(e)
             self.cnx[br] = stages
         self.cnx_channels = list(tw.channels)
-        self.neck = neck_torch.NeckTorch(m.spm.smart_fusion, dev)
+        import os
+        if os.environ.get("MMSAM_NECK", "b200") == "torch":   # library cross-check path (tests only)
+            self.neck = neck_torch.NeckTorch(m.spm.smart_fusion, dev)
+        else:
+            self.neck = neck_b200.NeckB200(m.spm.smart_fusion, dev)
         le = m.level_embed.detach().float()
         self.fc = []
         for i in range(4):

@@ -54,7 +54,7 @@ def msda_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_we
     return out
 
 
-def layernorm(x, gamma, beta, eps, out=None, row_map=None, out_rows=None, patchify_hw=None):
+def layernorm(x, gamma, beta, eps, out=None, row_map=None, out_rows=None, patchify_hw=None, out2=None):
     """x bf16 [..., C] (rows contiguous) -> LN over C. row_map (int32 [rows]) scatters rows into an
     `out` of out_rows rows (rows never written keep their previous contents). patchify_hw=(H, W):
     rows are (b,y,x) and the result is the 2x2-patchified [rows/4, 4C] matrix."""
@@ -73,7 +73,7 @@ def layernorm(x, gamma, beta, eps, out=None, row_map=None, out_rows=None, patchi
         else:
             out = torch.zeros((out_rows, C), dtype=x.dtype, device=x.device)
     rc = _lib.load().mmsam_layernorm_bf16(
-        _ptr(x2), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(row_map), rows, C, x2.stride(0), out.stride(0),
+        _ptr(x2), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(out2), _ptr(row_map), rows, C, x2.stride(0), out.stride(0),
         float(eps), ps_h, ps_w, _stream())
     _lib.check(rc, "mmsam_layernorm_bf16")
     _count()
@@ -244,5 +244,98 @@ def confusion(pred, gt, ncls, ignore_index=255, out=None):
     rc = _lib.load().mmsam_confusion_u8(_ptr(pred.contiguous()), _ptr(gt.contiguous()), _ptr(out), pred.numel(), ncls,
                                         ignore_index, _stream())
     _lib.check(rc, "mmsam_confusion_u8")
+    _count()
+    return out
+
+
+def pack_conv3x3_weight(w, groups):
+    """Conv2d weight [Cout, Cin/groups, 3, 3] -> the block layout mmsam_conv3x3_bf16 expects (bf16, on w's device)."""
+    Cout, cgi = w.shape[0], w.shape[1]
+    Cin = cgi * groups
+    cgo = Cout // groups
+    KC = _lib.load().mmsam_conv3x3_kblocks(Cin, Cout, groups)
+    nn = (Cout + 63) // 64
+    wf = w.detach().float().cpu().reshape(Cout, cgi, 9)
+    out = torch.zeros((nn, 9, KC, 64, 64), dtype=torch.float32)
+    co = torch.arange(Cout)
+    nt, r = co // 64, co % 64
+    kwin = ((nt * 64) // cgo) * cgi                 # first input channel of the tile's channel window
+    base = (co // cgo) * cgi - kwin                 # window column of each output channel's group start
+    for ci in range(cgi):
+        col = base + ci
+        out[nt, :, col // 64, r, col % 64] = wf[:, ci, :]
+    return out.reshape(nn * 9 * KC * 64, 64).to(torch.bfloat16).to(w.device).contiguous()
+
+
+def conv3x3(x, w_packed, B, H, W, Cin, Cout, groups, out=None, max_ctas=0):
+    """x bf16 [B*H*W, Cin] channels-last -> [B*H*W, Cout]; grouped 3x3, pad 1, no bias."""
+    _need_cuda(x, w_packed)
+    if out is None:
+        out = torch.empty((B * H * W, Cout), dtype=torch.bfloat16, device=x.device)
+    rc = _lib.load().mmsam_conv3x3_bf16(_ptr(x), _ptr(w_packed), _ptr(out), B, H, W, Cin, Cout, groups, max_ctas, _stream())
+    _lib.check(rc, "mmsam_conv3x3_bf16")
+    _count()
+    return out
+
+
+def gram(x, ld, qoff, koff, n, B, HW, blk=0, norms=False):
+    """-> S fp32 [B,n,n] (and nq, nk fp32 [B,n] when norms)."""
+    _need_cuda(x)
+    S = torch.zeros((B, n, n), dtype=torch.float32, device=x.device)
+    nq = nk = None
+    if norms:
+        nq = torch.zeros((B, n), dtype=torch.float32, device=x.device)
+        nk = torch.zeros((B, n), dtype=torch.float32, device=x.device)
+    rc = _lib.load().mmsam_gram_bf16(_ptr(x), ld, qoff, koff, n, B, HW, blk, _ptr(S), _ptr(nq), _ptr(nk), _stream())
+    _lib.check(rc, "mmsam_gram_bf16")
+    _count()
+    return (S, nq, nk) if norms else S
+
+
+def colstats(o, wpix, B, HW, C):
+    """-> fp64 [B, C, 3] = {sum o, sum o^2, sum o*w[pix]} over the HW pixels of each image."""
+    _need_cuda(o, wpix)
+    lib = _lib.load()
+    nch = lib.mmsam_colstats_chunks(HW)
+    part = torch.empty((nch, B, C, 3), dtype=torch.float32, device=o.device)
+    rc = lib.mmsam_colstats_bf16(_ptr(o), _ptr(wpix), _ptr(part), B, HW, C, _stream())
+    _lib.check(rc, "mmsam_colstats_bf16")
+    _count()
+    return part.double().sum(0)
+
+
+def gate(a, C, out=None):
+    _need_cuda(a)
+    rows = a.shape[0]
+    if out is None:
+        out = torch.empty((rows, C), dtype=torch.bfloat16, device=a.device)
+    rc = _lib.load().mmsam_gate_bf16(_ptr(a), _ptr(out), rows, C, _stream())
+    _lib.check(rc, "mmsam_gate_bf16")
+    _count()
+    return out
+
+
+def combine_pool(o, lo, mu, rstd, gate_v, wpix, bpix, s1, s2, B, H, W, C):
+    """-> f bf16 [B*H*W, C], ph fp32 [B,H,C] (row sums), pw fp32 [B,W,C] (column sums)."""
+    _need_cuda(o, lo, mu, rstd, gate_v, wpix, bpix)
+    lib = _lib.load()
+    RS = lib.mmsam_combine_pool_rows(H)
+    ns = (H + RS - 1) // RS
+    f = torch.empty((B * H * W, C), dtype=torch.bfloat16, device=o.device)
+    ph = torch.empty((B, H, C), dtype=torch.float32, device=o.device)
+    pwp = torch.empty((ns, B, W, C), dtype=torch.float32, device=o.device)
+    rc = lib.mmsam_combine_pool_bf16(_ptr(o), _ptr(lo), _ptr(mu), _ptr(rstd), _ptr(gate_v), _ptr(wpix), _ptr(bpix),
+                                     float(s1), float(s2), _ptr(f), _ptr(ph), _ptr(pwp), B, H, W, C, _stream())
+    _lib.check(rc, "mmsam_combine_pool_bf16")
+    _count()
+    return f, ph, pwp.sum(0)
+
+
+def ca_apply(f, ah, aw, B, H, W, C, out=None):
+    _need_cuda(f, ah, aw)
+    if out is None:
+        out = torch.empty_like(f)
+    rc = _lib.load().mmsam_ca_apply_bf16(_ptr(f), _ptr(ah), _ptr(aw), _ptr(out), B, H, W, C, _stream())
+    _lib.check(rc, "mmsam_ca_apply_bf16")
     _count()
     return out

@@ -1,0 +1,169 @@
+"""RoadFormer2Neck fusion (adapter_modules_multimodal_mix_mod_new_in_twin_convnext_new.py:75-394) on the
+sm_100a kernels. Per pyramid level (C = both modalities, ci = C/2, HW pixels, channels-last bf16 tokens):
+
+  GFE (per modality)   LN(eps 1e-5) [layernorm, dual output n and x+n] -> qkv1 grouped 1x1 as a block-diagonal
+                       GEMM -> qkv2 grouped 3x3 [conv3x3, tcgen05 implicit GEMM] -> q k^T over HW + row norms
+                       [gram] -> softmax(cos * temperature) and proj folded into one [ci, ci] matrix per image
+                       -> v . Weff^T + (x + n) [gemm, per image]
+  MobileNetV2          1x1 + ReLU6 [gemm] -> depthwise 3x3 + ReLU6 [dwconv] -> 1x1 * scale + x [gemm]
+  GFFM                 cross-modal energy fx^T fy over HW [gram] -> row softmaxes -> attn . f + f [gemm, per
+                       image] -> LayerNorm over the SPATIAL axis: column statistics [colstats]
+  Mlp                  1x1 [gemm] -> grouped 3x3 (2 ch / group) [conv3x3] -> gelu(a) * b [gate] -> 1x1 [gemm]
+  FFRM / Scale2 / CA   GAP from the statistics, C x C + GroupNorm gate, weighted sum, coordinate-attention
+                       pools [combine_pool] -> two tiny 1x1s -> out = f * (1 + a_w a_h) [ca_apply]
+
+Everything that touches a pixel is one of this repo's kernels. The O(B*C^2)-sized glue between them
+(softmax of the [ch, ch] / [ci, ci] matrices, folding proj into Weff, the FFRM / CA vectors: a few kFLOP
+per image) is done with torch tensor ops on the device, in fp32/fp64.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import kernels as K
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _bf(t, dev):
+    return t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+
+
+def _blockdiag_1x1(w, groups):
+    """Conv2d(k=1, groups) weight [Cout, Cin/groups, 1, 1] -> dense [Cout, Cin] with zeros off the groups."""
+    Cout, cgi = w.shape[0], w.shape[1]
+    Cin, cgo = cgi * groups, Cout // groups
+    out = torch.zeros((Cout, Cin), dtype=torch.float32)
+    wf = w.detach().float().cpu().reshape(Cout, cgi)
+    for g in range(groups):
+        out[g * cgo:(g + 1) * cgo, g * cgi:(g + 1) * cgi] = wf[g * cgo:(g + 1) * cgo]
+    return out
+
+
+class NeckB200:
+    def __init__(self, m, dev):
+        self.dev = dev
+        self.levels = []
+        for i, C in enumerate(m.in_channels):
+            ci = C // 2
+            lv = dict(C=C, ci=ci)
+            for name, key in (("rgb", "global_feature_encoder_rgb"), ("sne", "global_feature_encoder_sne")):
+                g = getattr(m, key)[i]
+                a = g.attn
+                heads, groups = a.num_heads, a.qkv1.groups
+                lv["gfe_" + name] = dict(
+                    lnw=_f32(g.norm1.body.weight, dev), lnb=_f32(g.norm1.body.bias, dev),
+                    w1=_bf(_blockdiag_1x1(a.qkv1.weight, groups), dev),
+                    w2=K.pack_conv3x3_weight(a.qkv2.weight.to(dev), groups), groups=groups, heads=heads,
+                    temp=_f32(a.scale.reshape(-1), dev), scale2=_f32(a.scale2, dev),
+                    wp=_f32(a.proj.weight.reshape(ci, heads, ci // heads), dev))
+            for name, key in (("rgb", "local_feature_encoder_rgb"), ("sne", "local_feature_encoder_sne")):
+                l = getattr(m, key)[i]
+                bb = l.bottleneckBlock
+                lv["mb_" + name] = dict(
+                    w0=_bf(bb[0].weight.reshape(2 * ci, ci), dev),
+                    dw=_f32(bb[2].weight.detach().reshape(2 * ci, 9).t(), dev),
+                    w4=_bf(bb[4].weight.reshape(ci, 2 * ci), dev),
+                    scale=_f32(l.scale.detach().reshape(1).expand(ci), dev))
+            f = m.fuse_blocks[i]
+            wpix, bpix = _f32(f.norm.weight, dev), _f32(f.norm.bias, dev)
+            lv["gffm"] = dict(gx=_f32(f.gammax.scale.detach().reshape(1).expand(ci), dev),
+                              gy=_f32(f.gammay.scale.detach().reshape(1).expand(ci), dev), wpix=wpix, bpix=bpix,
+                              sum_w=wpix.double().sum(), mean_b=bpix.double().mean(), eps=f.norm.eps)
+            d = m.detail_feature_extractions[i]
+            lv["mlp"] = dict(win=_bf(d.project_in.weight.reshape(2 * C, C), dev),
+                             wdw=K.pack_conv3x3_weight(d.dwconv.weight.to(dev), d.dwconv.groups), groups=d.dwconv.groups,
+                             wout=_bf(d.project_out.weight.reshape(C, C), dev))
+            e = m.enhance_blocks[i].conv_atten
+            lv["ffrm"] = dict(w=_f32(e.conv.weight.reshape(C, C), dev), gw=_f32(e.gn.weight, dev), gb=_f32(e.gn.bias, dev),
+                              groups=e.gn.num_groups, eps=e.gn.eps)
+            s = m.scale_layers[i]
+            lv["s1"], lv["s2"] = float(s.scale1.detach()), float(s.scale2.detach())
+            ca = m.ca_blocks[i].coord_atten
+            bn = ca.bn1
+            bs = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            bt = bn.bias.detach().float() - bn.running_mean.detach().float() * bs
+            mip = ca.conv1.weight.shape[0]
+            lv["ca"] = dict(w1=_f32(ca.conv1.weight.reshape(mip, C), dev), b1=_f32(ca.conv1.bias, dev), bs=_f32(bs, dev),
+                            bt=_f32(bt, dev), wh=_f32(ca.conv_h.weight.reshape(C, mip), dev), bh=_f32(ca.conv_h.bias, dev),
+                            ww=_f32(ca.conv_w.weight.reshape(C, mip), dev), bw=_f32(ca.conv_w.bias, dev))
+            self.levels.append(lv)
+
+    # ------------------------------------------------------------------ pieces
+    def _gfe(self, x, p, g_out, col0, B, h, w, ci):
+        """GFE.forward (:133-145) + AttentionBase.forward (:90-109); writes g_out[:, col0:col0+ci]."""
+        HW = h * w
+        r = torch.empty_like(x)
+        n = K.layernorm(x, p["lnw"], p["lnb"], 1e-5, out2=r)
+        qa = K.gemm(n, p["w1"])
+        qkv = K.conv3x3(qa, p["w2"], B, h, w, 3 * ci, 3 * ci, p["groups"])
+        heads = p["heads"]
+        ch = ci // heads
+        S, nq, nk = K.gram(qkv, 3 * ci, 0, ci, ci, B, HW, blk=ch, norms=True)
+        # [B, heads, ch, ch] diagonal blocks, cosine similarity, temperature, softmax; proj folded in
+        Sb = S.view(B, heads, ch, heads, ch).diagonal(dim1=1, dim2=3).permute(0, 3, 1, 2)
+        qn = nq.sqrt().clamp_min(1e-12).view(B, heads, ch, 1)
+        kn = nk.sqrt().clamp_min(1e-12).view(B, heads, 1, ch)
+        att = torch.softmax(Sb / (qn * kn) * p["temp"].view(1, heads, 1, 1), dim=-1)
+        weff = (torch.einsum("iha,bhaj->bihj", p["wp"], att) * p["scale2"]).reshape(B, ci, ci).to(torch.bfloat16).contiguous()
+        qkv3 = qkv.view(B, HW, 3 * ci)
+        r3, g3 = r.view(B, HW, ci), g_out.view(B, HW, -1)
+        for b in range(B):
+            K.gemm(qkv3[b, :, 2 * ci:], weff[b], residual=r3[b], out=g3[b, :, col0:col0 + ci])
+
+    def _mobilenet(self, x, p, l_out, col0, B, h, w, ci):
+        """MobileNetV2.forward (:293-295); writes l_out[:, col0:col0+ci]."""
+        h1 = K.gemm(x, p["w0"], act="relu6")
+        h2 = K.dwconv(h1, p["dw"], None, 3, [(h, w)], B, 2 * ci, h * w * 2 * ci, h * w * 2 * ci, act="relu6")
+        K.gemm(h2, p["w4"], scale=p["scale"], residual=x, out=l_out[:, col0:col0 + ci])
+
+    def _level(self, lv, tx, ty, B, h, w):
+        dev = self.dev
+        C, ci, HW = lv["C"], lv["ci"], h * w
+        g = torch.empty((B * HW, C), dtype=torch.bfloat16, device=dev)
+        l = torch.empty((B * HW, C), dtype=torch.bfloat16, device=dev)
+        self._gfe(tx, lv["gfe_rgb"], g, 0, B, h, w, ci)
+        self._gfe(ty, lv["gfe_sne"], g, ci, B, h, w, ci)
+        self._mobilenet(tx, lv["mb_rgb"], l, 0, B, h, w, ci)
+        self._mobilenet(ty, lv["mb_sne"], l, ci, B, h, w, ci)
+        # ---- GFFM (:242-267) ----
+        gf = lv["gffm"]
+        E = K.gram(g, C, 0, ci, ci, B, HW, blk=0)
+        ax = torch.softmax(E, dim=-1).to(torch.bfloat16).contiguous()
+        ay = torch.softmax(E.transpose(1, 2), dim=-1).to(torch.bfloat16).contiguous()
+        o = torch.empty_like(g)
+        g3, o3 = g.view(B, HW, C), o.view(B, HW, C)
+        for b in range(B):
+            K.gemm(g3[b, :, ci:], ax[b], scale=gf["gx"], residual=g3[b, :, :ci], out=o3[b, :, :ci])
+            K.gemm(g3[b, :, :ci], ay[b], scale=gf["gy"], residual=g3[b, :, ci:], out=o3[b, :, ci:])
+        st = K.colstats(o, gf["wpix"], B, HW, C)                           # fp64 [B, C, 3]
+        mu = st[..., 0] / HW
+        var = (st[..., 1] / HW - mu * mu).clamp_min(0)
+        rstd = 1.0 / torch.sqrt(var + gf["eps"])
+        gap = (rstd * (st[..., 2] - mu * gf["sum_w"]) / HW + gf["mean_b"]).float()      # GAP of LN_HW(o), [B, C]
+        # ---- FFRM gate (:148-162): 1x1 conv (no bias) -> GN(32) -> ReLU -> sigmoid ----
+        ff = lv["ffrm"]
+        a = F.group_norm((gap @ ff["w"].t()).unsqueeze(-1), ff["groups"], ff["gw"], ff["gb"], ff["eps"]).squeeze(-1)
+        gate_v = (1.0 + torch.sigmoid(torch.relu(a))).contiguous()
+        # ---- gated Mlp on the local branch (:110-132) ----
+        mp = lv["mlp"]
+        a1 = K.gemm(l, mp["win"])
+        a2 = K.conv3x3(a1, mp["wdw"], B, h, w, 2 * C, 2 * C, mp["groups"])
+        u = K.gate(a2, C)
+        lo = K.gemm(u, mp["wout"])
+        # ---- LN_HW * gate * s1 + local * s2, coordinate-attention pools ----
+        f, ph, pw = K.combine_pool(o, lo, mu.float().contiguous(), rstd.float().contiguous(), gate_v, gf["wpix"],
+                                   gf["bpix"], lv["s1"], lv["s2"], B, h, w, C)
+        ca = lv["ca"]
+        y = torch.cat((ph / w, pw / h), 1)                                  # [B, h + w, C] pooled means
+        y = (y @ ca["w1"].t() + ca["b1"]) * ca["bs"] + ca["bt"]
+        y = y * F.relu6(y + 3) / 6
+        ah = torch.sigmoid(y[:, :h] @ ca["wh"].t() + ca["bh"]).contiguous()
+        aw = torch.sigmoid(y[:, h:] @ ca["ww"].t() + ca["bw"]).contiguous()
+        return K.ca_apply(f, ah, aw, B, h, w, C)
+
+    @torch.no_grad()
+    def __call__(self, fx, fy, B):
+        """fx / fy: per level (tokens bf16 [B*h*w, ci], h, w) -> list of fused tokens bf16 [B*h*w, C]."""
+        return [self._level(lv, tx, ty, B, h, w) for lv, (tx, h, w), (ty, _, _) in zip(self.levels, fx, fy)]

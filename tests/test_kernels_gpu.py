@@ -261,3 +261,79 @@ def test_attention_relpos_interpolated_table():
     ref = attention_core(q, kk, v, Kh, Kw, rph, rpw)
     got = out.view(1, T, 2, 64).permute(0, 2, 1, 3).reshape(2, T, 64)
     assert ((got - ref).norm() / ref.norm()).item() < 1.5e-2
+
+
+@pytest.mark.parametrize("B,H,W,Cin,groups", [
+    (2, 16, 16, 288, 32),   # GFE qkv2 at level 0 (cg = 9, two k-blocks)
+    (1, 8, 24, 64, 32),     # cg = 2 (Mlp dwconv style), one k-block
+    (1, 4, 4, 192, 96),     # map smaller than the 8x16 tile, 2 ch / group
+    (1, 13, 9, 2304, 32),   # cg = 72, three k-blocks, ragged map
+    (2, 32, 32, 128, 1),    # dense 3x3
+])
+def test_conv3x3_grouped(B, H, W, Cin, groups):
+    k = _k()
+    g = torch.Generator().manual_seed(Cin + groups)
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cin, Cin // groups, 3, 3, generator=g) / math.sqrt(9 * Cin // groups)).to(torch.bfloat16)
+    wp = k.pack_conv3x3_weight(w.float().cuda(), groups)
+    out = k.conv3x3(x.reshape(-1, Cin).cuda(), wp, B, H, W, Cin, Cin, groups).float().cpu().view(B, H, W, Cin)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=1, groups=groups).permute(0, 2, 3, 1)
+    assert ((out - ref).abs() <= 0.01 * ref.abs() + 5e-3).all(), (out - ref).abs().max()
+
+
+@pytest.mark.parametrize("n,blk,HW", [(96, 12, 4096), (64, 0, 1000), (192, 0, 300), (768, 96, 256)])
+def test_gram(n, blk, HW):
+    k = _k()
+    B, ld = 2, 3 * n
+    g = torch.Generator().manual_seed(n + HW)
+    x = torch.randn(B, HW, ld, generator=g).to(torch.bfloat16)
+    S, nq, nk = k.gram(x.reshape(-1, ld).cuda(), ld, 0, n, n, B, HW, blk=blk, norms=True)
+    q, kk = x[..., :n].double(), x[..., n:2 * n].double()
+    ref = q.transpose(1, 2) @ kk
+    if blk:
+        m = (torch.arange(n)[:, None] // blk) == (torch.arange(n)[None, :] // blk)
+        ref = ref * m
+    assert (S.cpu().double() - ref).abs().max() < 2e-3 * math.sqrt(HW)
+    assert torch.allclose(nq.cpu().double(), (q * q).sum(1), rtol=1e-4) and torch.allclose(nk.cpu().double(), (kk * kk).sum(1), rtol=1e-4)
+
+
+def test_colstats_gate_ln_dual():
+    k = _k()
+    B, HW, C = 2, 1500, 192
+    g = torch.Generator().manual_seed(8)
+    o = (torch.randn(B, HW, C, generator=g) + 0.3).to(torch.bfloat16)
+    wp = torch.randn(HW, generator=g)
+    st = k.colstats(o.reshape(-1, C).cuda(), wp.cuda(), B, HW, C).cpu()
+    od = o.double()
+    ref = torch.stack((od.sum(1), (od * od).sum(1), (od * wp.double()[None, :, None]).sum(1)), -1)
+    assert torch.allclose(st, ref, rtol=1e-5, atol=1e-3)
+    a = torch.randn(1000, 2 * C, generator=g).to(torch.bfloat16)
+    u = k.gate(a.cuda(), C).float().cpu()
+    refu = torch.nn.functional.gelu(a[:, :C].float()) * a[:, C:].float()
+    assert (u - refu).abs().max() < 0.03
+    x = torch.randn(500, C, generator=g).to(torch.bfloat16)
+    w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    r = torch.empty_like(x).cuda()
+    n = k.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-5, out2=r).float().cpu()
+    refn = torch.nn.functional.layer_norm(x.float(), (C,), w, b, 1e-5)
+    assert (n - refn).abs().max() < 0.05 and (r.float().cpu() - (refn + x.float())).abs().max() < 0.06
+
+
+def test_combine_pool_and_ca_apply():
+    k = _k()
+    B, H, W, C = 2, 20, 37, 192
+    g = torch.Generator().manual_seed(12)
+    o = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
+    lo = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
+    mu, rstd, gt = torch.randn(B, C, generator=g), torch.rand(B, C, generator=g) + 0.5, torch.rand(B, C, generator=g) + 1
+    wp, bp = torch.randn(H * W, generator=g), torch.randn(H * W, generator=g)
+    f, ph, pw = k.combine_pool(o.reshape(-1, C).cuda(), lo.reshape(-1, C).cuda(), mu.cuda(), rstd.cuda(), gt.cuda(),
+                               wp.cuda(), bp.cuda(), 0.7, 1.3, B, H, W, C)
+    ref = 0.7 * (((o.float() - mu[:, None, None]) * rstd[:, None, None]) * wp.view(1, H, W, 1) + bp.view(1, H, W, 1)) \
+        * gt[:, None, None] + 1.3 * lo.float()
+    assert (f.float().cpu().view(B, H, W, C) - ref).abs().max() < 0.08
+    assert (ph.cpu() - ref.sum(2)).abs().max() < 0.3 and (pw.cpu() - ref.sum(1)).abs().max() < 0.3
+    ah, aw = torch.rand(B, H, C, generator=g), torch.rand(B, W, C, generator=g)
+    out = k.ca_apply(f, ah.cuda(), aw.cuda(), B, H, W, C).float().cpu().view(B, H, W, C)
+    ref2 = f.float().cpu().view(B, H, W, C) * (1 + aw[:, None] * ah[:, :, None])
+    assert (out - ref2).abs().max() < 0.06
