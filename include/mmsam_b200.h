@@ -126,7 +126,7 @@ int mmsam_confusion_u8(const void* pred_u8, const void* gt_u8, void* conf_u64, l
  * Replaces AttentionBase.qkv2 and Mlp.dwconv of the fusion neck (adapter_modules_...new.py:84, 118-119).
  * w_packed: bf16 [(ceil(Cout/64) * 9 * KC) * 64, 64], KC = mmsam_conv3x3_kblocks(Cin, Cout, groups); block
  * (n-tile, tap, k-block) = W[co, ci, tap] for co in the tile, ci in the 64-channel window starting at
- * ((n-tile*64) / (Cout/groups)) * (Cin/groups) + k-block*64, zero outside co's group. */
+ * (((n-tile*64) / (Cout/groups)) * (Cin/groups) & ~7) + k-block*64, zero outside co's group. */
 int mmsam_conv3x3_kblocks(int Cin, int Cout, int groups);
 int mmsam_conv3x3_bf16(const void* x, const void* w_packed, void* out, int B, int H, int W, int Cin, int Cout,
                        int groups, int max_ctas, void* stream);

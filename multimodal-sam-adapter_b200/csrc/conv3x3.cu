@@ -73,7 +73,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int nt, x0, y0, b;
         decode(tile, nt, x0, y0, b);
-        const int kwin = ((nt * CV_BN) / p.cg_out) * p.cg_in;  // first input channel of the first group touched
+        // first input channel of the first group touched, aligned down to 8 channels: a TMA box must start on
+        // a 16-byte boundary of the innermost dimension
+        const int kwin = (((nt * CV_BN) / p.cg_out) * p.cg_in) & ~7;
         for (int kb = 0; kb < num_k; ++kb) {
           const int tap = kb / p.KC, kc = kb - tap * p.KC;
           const int dy = tap / 3, dx = tap - dy * 3;
@@ -168,7 +170,7 @@ MMSAM_API int mmsam_conv3x3_kblocks(int Cin, int Cout, int groups) {
   for (int n0 = 0; n0 < Cout; n0 += 64) {
     const int n1 = (n0 + 64 < Cout ? n0 + 64 : Cout) - 1;
     const int g0 = n0 / cgo, g1 = n1 / cgo;
-    const int len = (g1 - g0 + 1) * cgi;
+    const int len = (g1 + 1) * cgi - ((g0 * cgi) & ~7);
     const int need = (len + 63) / 64;
     if (need > kc) kc = need;
   }
@@ -176,7 +178,8 @@ MMSAM_API int mmsam_conv3x3_kblocks(int Cin, int Cout, int groups) {
 }
 
 // x [B,H,W,Cin] bf16, w_packed bf16 [(ceil(Cout/64) * 9 * KC) * 64, 64]: block (nt, tap, kc) holds
-// W[co = nt*64 + r, ci = kwin(nt) + kc*64 + c, tap] (0 outside co's group), out [B,H,W,Cout] bf16.
+// W[co = nt*64 + r, ci = kwin(nt) + kc*64 + c, tap] (0 outside co's group), kwin(nt) = first input channel of the
+// first group the tile touches rounded down to 8; out [B,H,W,Cout] bf16.
 MMSAM_API int mmsam_conv3x3_bf16(const void* x, const void* w_packed, void* out, int B, int H, int W, int Cin,
                                  int Cout, int groups, int max_ctas, void* stream) {
   using namespace mmsam;

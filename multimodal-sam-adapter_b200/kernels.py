@@ -259,7 +259,7 @@ def pack_conv3x3_weight(w, groups):
     out = torch.zeros((nn, 9, KC, 64, 64), dtype=torch.float32)
     co = torch.arange(Cout)
     nt, r = co // 64, co % 64
-    kwin = ((nt * 64) // cgo) * cgi                 # first input channel of the tile's channel window
+    kwin = (((nt * 64) // cgo) * cgi) // 8 * 8      # first input channel of the tile's window (16-byte aligned)
     base = (co // cgo) * cgi - kwin                 # window column of each output channel's group start
     for ci in range(cgi):
         col = base + ci

@@ -331,9 +331,10 @@ def test_combine_pool_and_ca_apply():
                                wp.cuda(), bp.cuda(), 0.7, 1.3, B, H, W, C)
     ref = 0.7 * (((o.float() - mu[:, None, None]) * rstd[:, None, None]) * wp.view(1, H, W, 1) + bp.view(1, H, W, 1)) \
         * gt[:, None, None] + 1.3 * lo.float()
-    assert (f.float().cpu().view(B, H, W, C) - ref).abs().max() < 0.08
+    fo = f.float().cpu().view(B, H, W, C)
+    assert ((fo - ref).abs() <= 0.01 * ref.abs() + 0.02).all()
     assert (ph.cpu() - ref.sum(2)).abs().max() < 0.3 and (pw.cpu() - ref.sum(1)).abs().max() < 0.3
     ah, aw = torch.rand(B, H, C, generator=g), torch.rand(B, W, C, generator=g)
     out = k.ca_apply(f, ah.cuda(), aw.cuda(), B, H, W, C).float().cpu().view(B, H, W, C)
     ref2 = f.float().cpu().view(B, H, W, C) * (1 + aw[:, None] * ah[:, :, None])
-    assert (out - ref2).abs().max() < 0.06
+    assert ((out - ref2).abs() <= 0.01 * ref2.abs() + 0.02).all()
