@@ -198,8 +198,14 @@ class EncoderDecoder(nn.Module):
         self.backbone.invalidate()
         return r
 
+    use_cuda_graph = True
+
     @torch.no_grad()
     def encode_decode_labels(self, img, out_hw=None, crop_hw=None):
+        """uint8 labels [B, H, W] on the device. With use_cuda_graph the forward is replayed from a per-shape CUDA
+        graph and the result lives in the graph's static buffer (copy it before the next call)."""
+        if self.use_cuda_graph:
+            return self._engine().segment_graphed(img, out_hw, crop_hw)
         return self._engine().segment(img, out_hw, crop_hw)
 
     @torch.no_grad()

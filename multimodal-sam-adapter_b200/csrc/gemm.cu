@@ -48,7 +48,7 @@ template <int BN> struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -140,7 +140,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ---------------- epilogue (warps 0..7) ----------------
     const int quad = warp & 3;   // TMEM lane quadrant this warp may touch
     const int half = warp >> 2;  // which half of the BN columns
-    float* stg = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256) + warp * 1024;  // 32x32 fp32
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -148,9 +147,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
+      const int row = m_blk * Cfg::BM + quad * 32 + lane;
+      const bool row_ok = row < ep.M;
+      long long dst_row = row;
+      int ps_y = 0, ps_x = 0, ps_b = 0;
+      if (ep.row_mode == 1) {
+        dst_row = row_ok ? (long long)ep.row_map[row] : -1;
+      } else if (ep.row_mode == 2) {
+        const int hw = ep.ps_h * ep.ps_w;
+        ps_b = row / hw;
+        const int r = row - ps_b * hw;
+        ps_y = r / ep.ps_w;
+        ps_x = r - ps_y * ep.ps_w;
+      }
       // All TMEM loads of this warp's column half are issued up front (BN/2 <= 128 fp32 columns =
       // BN/2 registers) and the accumulator is handed back to the MMA warp right after they land, so the
-      // global-memory part of the epilogue overlaps the next tile's MMAs.
+      // global-memory part of the epilogue (bias / residual loads, stores) overlaps the next tile's MMAs
+      // instead of sitting between them.
       constexpr int NCH = BN / 64;  // 32-column chunks per warp
       uint32_t r[NCH][32];
 #pragma unroll
@@ -160,105 +173,78 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-
-      // tcgen05.ld hands every thread one accumulator ROW; storing that way would touch 32 different
-      // 128-byte lines per instruction. Each 32x32 chunk is therefore transposed through a per-warp
-      // XOR-swizzled fp32 staging tile so that 4 lanes cover one row (8 columns = 16 B of bf16 each):
-      // full-sector, 4x fewer L2 transactions for stores and residual loads.
-      const int sub_r = lane >> 2, cgp = lane & 3;
-      long long drow[4];
-      int psb[4], psy[4], psx[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int row = m_blk * Cfg::BM + quad * 32 + k * 8 + sub_r;
-        drow[k] = row < ep.M ? (long long)row : -1;
-        psb[k] = psy[k] = psx[k] = 0;
-        if (row < ep.M) {
-          if (ep.row_mode == 1) {
-            drow[k] = (long long)ep.row_map[row];
-          } else if (ep.row_mode == 2) {
-            const int hw = ep.ps_h * ep.ps_w;
-            psb[k] = row / hw;
-            const int rr = row - psb[k] * hw;
-            psy[k] = rr / ep.ps_w;
-            psx[k] = rr - psy[k] * ep.ps_w;
-          }
-        }
-      }
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) {
-        const int col0 = n_blk * BN + half * (BN / 2) + ci * 32;
-        if (col0 >= ep.N) continue;  // warp-uniform
-        __syncwarp();
+        const int col_l = half * (BN / 2) + ci * 32;
+        const int col = n_blk * BN + col_l;
+        if (!row_ok || col >= ep.N) continue;
+        long long drow = dst_row;
+        int dcol = col;
+        if (ep.row_mode == 2) {
+          const int sub = col / ep.ps_c;
+          dcol = col - sub * ep.ps_c;
+          drow = ((long long)ps_b * 2 * ep.ps_h + 2 * ps_y + (sub >> 1)) * (2 * ep.ps_w) + 2 * ps_x + (sub & 1);
+        }
+        if (drow < 0) continue;
+        float v[32];
+        const bool full32 = ep.vec_ok && col + 32 <= ep.N;
+        if (full32) {
+          uint4 rres[4];
+          if (ep.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + drow * ep.ldr + dcol);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-              make_float4(__uint_as_float(r[ci][4 * j]), __uint_as_float(r[ci][4 * j + 1]),
-                          __uint_as_float(r[ci][4 * j + 2]), __uint_as_float(r[ci][4 * j + 3]));
-        __syncwarp();
-        const int col = col0 + cgp * 8;
-        const bool vec = ep.vec_ok && col + 8 <= ep.N;
-        float bs[8], sc[8];
+            for (int j = 0; j < 4; ++j) rres[j] = __ldg(rp + j);
+          }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { bs[e] = 0.f; sc[e] = 1.f; }
-        if (vec) {
-          if (ep.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 4));
-            bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w; bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+          for (int j = 0; j < 32; j += 4) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.bias) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
+            v[j] = __uint_as_float(r[ci][j]) + b.x;
+            v[j + 1] = __uint_as_float(r[ci][j + 1]) + b.y;
+            v[j + 2] = __uint_as_float(r[ci][j + 2]) + b.z;
+            v[j + 3] = __uint_as_float(r[ci][j + 3]) + b.w;
+          }
+          if (ep.act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
           }
           if (ep.scale) {
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(ep.scale + col));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(ep.scale + col + 4));
-            sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(ep.scale + col + j));
+              v[j] *= sc.x; v[j + 1] *= sc.y; v[j + 2] *= sc.z; v[j + 3] *= sc.w;
+            }
+          }
+          if (ep.residual) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float f[8];
+              unpack8(rres[j], f);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[8 * j + k] += f[k];
+            }
+          }
+          if (ep.out_f32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + drow * ep.ldo + dcol);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + drow * ep.ldo + dcol);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) op[j] = pack8(v + 8 * j);
           }
         } else {
+          // ragged last column chunk / unaligned rows: scalar, fully guarded
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (col + e < ep.N) {
-              if (ep.bias) bs[e] = ep.bias[col + e];
-              if (ep.scale) sc[e] = ep.scale[col + e];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int rr = k * 8 + sub_r;
-          const float4 a0 = *reinterpret_cast<const float4*>(stg + rr * 32 + (((2 * cgp) ^ (rr & 7)) << 2));
-          const float4 a1 = *reinterpret_cast<const float4*>(stg + rr * 32 + (((2 * cgp + 1) ^ (rr & 7)) << 2));
-          long long dr = drow[k];
-          int dcol = col;
-          if (ep.row_mode == 2 && dr >= 0) {
-            const int sub = col / ep.ps_c;
-            dcol = col - sub * ep.ps_c;
-            dr = ((long long)psb[k] * 2 * ep.ps_h + 2 * psy[k] + (sub >> 1)) * (2 * ep.ps_w) + 2 * psx[k] + (sub & 1);
-          }
-          if (dr < 0 || col >= ep.N) continue;
-          float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = apply_act(v[e] + bs[e], ep.act) * sc[e];
-          if (vec) {
-            if (ep.residual) {
-              float f[8];
-              unpack8(__ldg(reinterpret_cast<const uint4*>(ep.residual + dr * ep.ldr + dcol)), f);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] += f[e];
-            }
-            if (ep.out_f32) {
-              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + dr * ep.ldo + dcol);
-              op[0] = make_float4(v[0], v[1], v[2], v[3]);
-              op[1] = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + dr * ep.ldo + dcol) = pack8(v);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              if (col + e < ep.N) {
-                float x = v[e];
-                if (ep.residual) x += __bfloat162float(ep.residual[dr * ep.ldr + dcol + e]);
-                if (ep.out_f32) reinterpret_cast<float*>(ep.out)[dr * ep.ldo + dcol + e] = x;
-                else reinterpret_cast<__nv_bfloat16*>(ep.out)[dr * ep.ldo + dcol + e] = __float2bfloat16_rn(x);
-              }
+          for (int j = 0; j < 32; ++j) {
+            if (col + j < ep.N) {
+              float x = __uint_as_float(r[ci][j]);
+              if (ep.bias) x += ep.bias[col + j];
+              x = apply_act(x, ep.act);
+              if (ep.scale) x *= ep.scale[col + j];
+              if (ep.residual) x += __bfloat162float(ep.residual[drow * ep.ldr + dcol + j]);
+              if (ep.out_f32) reinterpret_cast<float*>(ep.out)[drow * ep.ldo + dcol + j] = x;
+              else reinterpret_cast<__nv_bfloat16*>(ep.out)[drow * ep.ldo + dcol + j] = __float2bfloat16_rn(x);
             }
           }
         }
