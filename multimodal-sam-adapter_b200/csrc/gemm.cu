@@ -23,6 +23,7 @@
 // L2-resident: A is read from HBM once.
 #include "common.cuh"
 #include <type_traits>
+#include <cstdlib>
 
 namespace mmsam {
 
@@ -38,6 +39,7 @@ struct GemmEpi {
   int out_f32;    // 0: bf16 output, 1: fp32 output
   int row_mode;   // 0 identity, 1 row_map, 2 pixel-shuffle 2x2 (ConvTranspose2d k=2 s=2)
   int vec_ok;     // rows of out/residual are 16-byte aligned -> vector epilogue allowed
+  int dbg;        // perf-debug switches (env MMSAM_GEMM_DBG): 1 skip stores, 2 skip bias/scale loads, 4 skip the whole epilogue math
   int ps_h, ps_w, ps_c;
 };
 
@@ -48,7 +50,7 @@ template <int BN> struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 256 * 80 /*store staging*/;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -140,6 +142,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ---------------- epilogue (warps 0..7) ----------------
     const int quad = warp & 3;   // TMEM lane quadrant this warp may touch
     const int half = warp >> 2;  // which half of the BN columns
+    // 80-byte-stride private staging rows (64 B payload): conflict-free 16-byte shared stores
+    uint8_t* stg_row = smem + STAGES * Cfg::STAGE_BYTES + 256 + (warp * 32 + lane) * 80;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -177,7 +181,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int ci = 0; ci < NCH; ++ci) {
         const int col_l = half * (BN / 2) + ci * 32;
         const int col = n_blk * BN + col_l;
-        if (!row_ok || col >= ep.N) continue;
+        if (!row_ok || col >= ep.N || (ep.dbg & 4)) continue;
         long long drow = dst_row;
         int dcol = col;
         if (ep.row_mode == 2) {
@@ -198,7 +202,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ep.bias) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
+            if (ep.bias && !(ep.dbg & 2)) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
             v[j] = __uint_as_float(r[ci][j]) + b.x;
             v[j + 1] = __uint_as_float(r[ci][j + 1]) + b.y;
             v[j + 2] = __uint_as_float(r[ci][j + 2]) + b.z;
@@ -224,14 +228,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int k = 0; k < 8; ++k) v[8 * j + k] += f[k];
             }
           }
-          if (ep.out_f32) {
+          if (ep.dbg & 1) {
+            if (v[0] == 12345.678f) reinterpret_cast<float*>(ep.out)[0] = v[1];
+          } else if (ep.out_f32) {
             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + drow * ep.ldo + dcol);
 #pragma unroll
             for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + drow * ep.ldo + dcol);
+            // bf16 row segment (32 cols = 64 B) -> this thread's private staging row -> one asynchronous bulk
+            // copy to global: full 32-byte sectors instead of 4 half-filled ones per row, and the LSU is
+            // not held by the store. Only this thread touches the row, so no cross-thread sync is needed.
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous copy has drained the row
 #pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = pack8(v + 8 * j);
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg_row + 16 * j) = pack8(v + 8 * j);
+            fence_proxy_async();
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 64;" ::"l"(
+                             reinterpret_cast<__nv_bfloat16*>(ep.out) + drow * ep.ldo + dcol),
+                         "r"(smem_u32(stg_row))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         } else {
           // ragged last column chunk / unaligned rows: scalar, fully guarded
@@ -250,6 +265,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk stores of this thread are complete
   }
   tc_fence_before();
   __syncthreads();
@@ -349,7 +365,7 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
   GemmEpi ep;
   ep.bias = bias; ep.scale = scale; ep.residual = (const __nv_bfloat16*)residual; ep.out = out;
   ep.row_map = row_map_dev; ep.ldo = ldo; ep.ldr = ldr; ep.M = M; ep.N = N; ep.K = K; ep.act = act;
-  ep.out_f32 = out_f32; ep.row_mode = row_mode; ep.vec_ok = vec_ok; ep.ps_h = ps_h; ep.ps_w = ps_w; ep.ps_c = ps_c;
+  ep.out_f32 = out_f32; ep.row_mode = row_mode; ep.vec_ok = vec_ok; { const char* d = getenv("MMSAM_GEMM_DBG"); ep.dbg = d ? atoi(d) : 0; } ep.ps_h = ps_h; ep.ps_w = ps_w; ep.ps_c = ps_c;
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 256) return launch_gemm<256>(tmA, tmB, ep, max_ctas, st);
   if (bn == 128) return launch_gemm<128>(tmA, tmB, ep, max_ctas, st);
