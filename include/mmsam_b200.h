@@ -73,9 +73,12 @@ int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, 
  *   qkv [Bp, T, 3, nh, 64] bf16 (the qkv Linear output), out [Bp, T, nh*64] bf16,
  *   tab_h / tab_w: bf16 [pad16(2*Kh-1), 64] / [pad16(2*Kw-1), 64] relative-position tables
  *   (row r = q - k + K - 1, zero padded; both NULL = no bias), T == Kh*Kw, scale = 64^-0.5.
- *   All T keys take part in the softmax (SAM does not mask its zero-padded window tokens). */
-int mmsam_attention_bf16(const void* qkv, void* out, const void* tab_h, const void* tab_w, int Bp, int T,
-                         int nh, int Kh, int Kw, float scale, int max_ctas, void* stream);
+ *   All T keys take part in the softmax (SAM does not mask its zero-padded window tokens).
+ *   out_row_map_dev (optional int32[Bp*T]): destination row of each (b', t) output row, -1 = drop: fuses
+ *   window_unpartition (base/image_encoder.py:529-551) into the store. */
+int mmsam_attention_bf16(const void* qkv, void* out, const int* out_row_map_dev, const void* tab_h,
+                         const void* tab_w, int Bp, int T, int nh, int Kh, int Kw, float scale, int max_ctas,
+                         void* stream);
 
 /* MSDeformAttn core fused with its front end (bf16 value/out): reads the raw fp32 output of the
  * query projection (columns [M*L*P*2 sampling offsets | M*L*P attention logits], row stride ldq;

@@ -24,7 +24,8 @@
 namespace mmsam {
 
 struct AttnParams {
-  __nv_bfloat16* out;   // [Bp, T, nh*64]
+  __nv_bfloat16* out;   // [Bp, T, nh*64], or [rows, nh*64] indexed through out_map
+  const int* out_map;   // optional: destination row of each (bp, t) row, -1 = drop (window un-partition)
   int Bp, T, nh, Kh, Kw;
   int nh_rows, nw_rows;        // table rows (2K-1), 0 = no relative position bias
   int nh_pad, nw_pad;          // padded to a multiple of 16
@@ -382,8 +383,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         const float inv = 1.f / l_run;
 #pragma unroll
         for (int i = 0; i < ATT_D; ++i) acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(o[i])) * inv;
-        if (q < p.T) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + ((long long)bp * p.T + q) * (p.nh * ATT_D) + head * ATT_D);
+        long long orow = (long long)bp * p.T + q;
+        if (q < p.T && p.out_map) orow = p.out_map[orow];
+        if (q < p.T && orow >= 0) {
+          uint4* op = reinterpret_cast<uint4*>(p.out + orow * (p.nh * ATT_D) + head * ATT_D);
 #pragma unroll
           for (int i = 0; i < 8; ++i) op[i] = pack8(acc + 8 * i);
         }
@@ -401,8 +404,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 }  // namespace mmsam
 
 // See include/mmsam_b200.h for the contract.
-MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const void* tab_h, const void* tab_w, int Bp,
-                                   int T, int nh, int Kh, int Kw, float scale, int max_ctas, void* stream) {
+MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const int* out_row_map_dev, const void* tab_h,
+                                   const void* tab_w, int Bp, int T, int nh, int Kh, int Kw, float scale,
+                                   int max_ctas, void* stream) {
   using namespace mmsam;
   if (Bp < 0 || T <= 0 || nh <= 0) return MMSAM_ERR_BAD_ARG;
   if (Bp == 0) return MMSAM_OK;
@@ -414,6 +418,7 @@ MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const void* tab_h
   if (!has_bias) { Kh = 1; Kw = T; }
   AttnParams p;
   p.out = (__nv_bfloat16*)out;
+  p.out_map = out_row_map_dev;
   p.Bp = Bp; p.T = T; p.nh = nh; p.Kh = Kh; p.Kw = Kw;
   p.nh_rows = has_bias ? 2 * Kh - 1 : 0;
   p.nw_rows = has_bias ? 2 * Kw - 1 : 0;

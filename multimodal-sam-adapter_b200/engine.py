@@ -164,8 +164,10 @@ class _Ops:
             ws = sc["ws"]
             y = self._ln(x, blk["norm1"], out=sc["win_buf"], row_map=sc["win_fwd"])
             qkv = self._gemm(y, blk["qkv"])
-            a = K.attention(qkv.view(sc["win_bp"], ws * ws, -1), self.nh, (ws, ws), tabs[0], tabs[1])
-            self._gemm(a.view(-1, self.C), blk["proj"], residual=x, out=x, row_map=sc["win_inv"])
+            # window_unpartition is fused into the attention store: pad rows are dropped, proj runs on B*T rows
+            a = K.attention(qkv.view(sc["win_bp"], ws * ws, -1), self.nh, (ws, ws), tabs[0], tabs[1],
+                            out_map=sc["win_inv"], out_rows=B * T)
+            self._gemm(a, blk["proj"], residual=x, out=x)
         else:
             y = self._ln(x, blk["norm1"])
             qkv = self._gemm(y, blk["qkv"])

@@ -126,17 +126,21 @@ def relpos_table(rel_pos, size):
     return out.contiguous()
 
 
-def attention(qkv, num_heads, hw, tab_h=None, tab_w=None, out=None, max_ctas=0):
-    """qkv bf16 [Bp, T, 3*nh*64] (qkv Linear output) -> [Bp, T, nh*64]; hw = (Kh, Kw), T = Kh*Kw."""
-    _need_cuda(qkv, tab_h, tab_w)
+def attention(qkv, num_heads, hw, tab_h=None, tab_w=None, out=None, max_ctas=0, out_map=None, out_rows=None):
+    """qkv bf16 [Bp, T, 3*nh*64] (qkv Linear output) -> [Bp, T, nh*64]; hw = (Kh, Kw), T = Kh*Kw.
+    out_map (int32 [Bp*T]) scatters the output rows into a [out_rows, nh*64] matrix (-1 = drop)."""
+    _need_cuda(qkv, tab_h, tab_w, out_map)
     Bp, T, C3 = qkv.shape
     hd = C3 // (3 * num_heads)
     if hd != 64 or not qkv.is_contiguous():
         raise _lib.MMSamError("attention: head_dim must be 64 and qkv contiguous")
     if out is None:
-        out = torch.empty((Bp, T, num_heads * hd), dtype=torch.bfloat16, device=qkv.device)
-    rc = _lib.load().mmsam_attention_bf16(_ptr(qkv), _ptr(out), _ptr(tab_h), _ptr(tab_w), Bp, T, num_heads,
-                                          hw[0], hw[1], float(hd) ** -0.5, max_ctas, _stream())
+        if out_map is not None:
+            out = torch.empty((out_rows, num_heads * hd), dtype=torch.bfloat16, device=qkv.device)
+        else:
+            out = torch.empty((Bp, T, num_heads * hd), dtype=torch.bfloat16, device=qkv.device)
+    rc = _lib.load().mmsam_attention_bf16(_ptr(qkv), _ptr(out), _ptr(out_map), _ptr(tab_h), _ptr(tab_w), Bp, T,
+                                          num_heads, hw[0], hw[1], float(hd) ** -0.5, max_ctas, _stream())
     _lib.check(rc, "mmsam_attention_bf16")
     _count()
     return out
