@@ -62,7 +62,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 template <int BN>
-__global__ void __maxnreg__(200)
+__global__ void __maxnreg__(192)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmEpi ep) {
   using Cfg = GemmCfg<BN>;
