@@ -9,17 +9,28 @@
 // embed (image_encoder.py:662-671) and the Segformer head 1x1 convs (decode_heads/
 // segformer_head.py:34-46). Both operands are K-major, exactly nn.Linear's (x, weight) layout.
 //
-// Design (one persistent CTA per SM, 320 threads, warp-specialised):
-//   warp 8      TMA producer: 128x64 A tile + BNx64 W tile per stage, SWIZZLE_128B boxes,
-//               mbarrier complete_tx; OOB rows/cols are zero-filled so ragged M/N/K need no masks.
-//   warp 9      MMA issuer: one elected lane issues 4 x tcgen05.mma (M128 x N=BN x K16) per stage
-//               into a TMEM accumulator; tcgen05.commit releases the smem stage / publishes the
-//               accumulator. Two TMEM accumulators (2 x BN columns) so the epilogue of tile i
-//               overlaps the main loop of tile i+1.
-//   warps 0-7   epilogue: tcgen05.ld (32 lanes x 32 columns), fused bias / activation (exact-erf
-//               GELU, ReLU, ReLU6) / per-channel scale / residual add, bf16 or fp32 stores, with an
-//               optional output-row remap (window un-partition, 2x2 pixel shuffle).
-// Tiles are walked n-fastest so CTAs of one wave share the A tile through L2 and weights stay
+// Design: persistent CTA PAIRS (cluster 2x1x1, one pair per TPC, 74 pairs), 320 threads per CTA.
+//   A pair owns a 256 x BN output tile and drives it with tcgen05.mma.cta_group::2 (M=256): each CTA
+//   stages its own 128 rows of A and only HALF of the BN weight rows, the tensor core reads the
+//   other half out of the peer's shared memory. Per SM that is 32 KB of operands per 64-deep k-step
+//   instead of 48 KB, which is what takes the kernel off the L2 -> SM bandwidth limit the 1-CTA
+//   128x256 version sat on (profiles/r01_gemm_notes.md).
+//   warp 8      TMA producer (one lane): 128x64 A box + (BN/2)x64 W box per stage, SWIZZLE_128B,
+//               complete_tx on the LEADER CTA's full barrier; OOB rows/cols are zero-filled so ragged
+//               M/N/K need no masks.
+//   warp 9      MMA issuer (leader CTA, one lane): 4 x tcgen05.mma (M256 x N=BN x K16) per stage;
+//               tcgen05.commit (multicast to both CTAs) frees the smem stage / publishes the
+//               accumulator. Two TMEM accumulators (2 x BN columns): the epilogue of tile i overlaps
+//               the main loop of tile i+1.
+//   warps 0-7   epilogue, two warps per TMEM lane quadrant (one per half of the BN columns). Per
+//               128-byte-wide panel: tcgen05.ld -> bias / activation (exact-erf GELU, ReLU, ReLU6) /
+//               per-channel scale / residual -> bf16 or fp32 -> the warp's private swizzled 32-row
+//               slab in shared memory -> ONE TMA tensor store per slab (plain outputs), or coalesced
+//               128-byte row segments through a row map (window un-partition, c2|c3|c4 packing) or a
+//               2x2 pixel shuffle (ConvTranspose2d k2 s2). A thread never stores its accumulator row
+//               straight to global: that costs one L1 wavefront per 16 bytes and was the limiter.
+//               Residual rows are fetched the same way (coalesced, through the slab).
+// Tiles are walked n-fastest so the pairs of one wave share A tiles through L2 and the weights stay
 // L2-resident: A is read from HBM once.
 #include "common.cuh"
 #include <type_traits>
@@ -38,20 +49,26 @@ struct GemmEpi {
   int act;        // 0 none, 1 gelu(erf), 2 relu, 3 relu6
   int out_f32;    // 0: bf16 output, 1: fp32 output
   int row_mode;   // 0 identity, 1 row_map, 2 pixel-shuffle 2x2 (ConvTranspose2d k=2 s=2)
-  int vec_ok;     // rows of out/residual are 16-byte aligned -> vector epilogue allowed
-  int tma_store;  // output goes through the panel-staged TMA tensor store (row_mode 0, aligned rows)
-  int dbg;        // perf-debug switches (env MMSAM_GEMM_DBG): 1 skip stores, 2 skip bias/scale loads, 4 skip the whole epilogue math
+  int store_mode; // 0 TMA tensor store, 1 coalesced row segments from the slab, 2 scalar (unaligned / ragged)
+  int dbg;        // perf-debug switches (env MMSAM_GEMM_DBG): 1 skip stores, 4 skip the epilogue math too
   int ps_h, ps_w, ps_c;
 };
 
 template <int BN> struct GemmCfg {
-  static constexpr int BM = 128, BK = 64;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int BM = 128;            // rows per CTA (the pair computes 256)
+  static constexpr int BK = 64;
+  static constexpr int BNH = BN / 2;        // weight rows staged per CTA
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = BNH * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * 16384 /*store panels*/ + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGES = BN == 256 ? 5 : (BN == 128 ? 6 : 8);
+  static constexpr int NUM_EPI_WARPS = 8;
+  static constexpr int SLAB_BYTES = 32 * 128;   // 32 rows x 128 B
+  static constexpr int SLABS_PER_WARP = 2;
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * SLABS_PER_WARP * SLAB_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -61,8 +78,274 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// ---- cluster / 2-CTA helpers -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on an mbarrier that may live in the peer CTA (address from mapa). Default (.release.cta) semantics on
+// purpose: a cluster-scope release costs a full memory barrier per arrive (measured: ~0.8 us per k-step, it
+// serialised the peer's producer); the data these arrivals order is written by the async proxy (TMA / tcgen05).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are counted on `bar_cluster_addr` (the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once all previously issued MMAs are complete) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t swz128(int row, int chunk) {   // byte offset inside a [rows x 128 B] SWIZZLE_128B slab
+  return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// One accumulator tile of one epilogue warp: rows [row0, row0+32) of the output, the warp's share of
+// the BN columns, PC columns (one 128-byte panel) at a time.
+template <int BN, bool F32>
+__device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const CUtensorMap* tmC, uint32_t tmem_acc, uint32_t slab0,
+                                              int& slab_sel, int row0, int n0, int half, int lane,
+                                              uint32_t tempty_addr) {
+  constexpr int PC = F32 ? 32 : 64;                      // columns per 128-byte panel row
+  constexpr int COLS_PER_HALF = (BN / 2 >= PC) ? BN / 2 : PC;
+  constexpr int NPAN = COLS_PER_HALF / PC;
+  const int row = row0 + lane;                           // the accumulator row this thread reads from TMEM
+  const bool row_ok = row < ep.M;
+  // destination row of this thread's source row (mode 2: row of the (dy,dx)=(0,0) sub-pixel)
+  int my_dst = row_ok ? row : -1;
+  if (ep.row_mode == 1) {
+    my_dst = row_ok ? ep.row_map[row] : -1;
+  } else if (ep.row_mode == 2 && row_ok) {
+    const int hw = ep.ps_h * ep.ps_w;
+    const int b = row / hw, r = row - b * hw;
+    const int y = r / ep.ps_w, x = r - y * ep.ps_w;
+    my_dst = (b * 2 * ep.ps_h + 2 * y) * (2 * ep.ps_w) + 2 * x;
+  }
+  bool released = false;
+  auto release = [&]() {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(tempty_addr);
+    released = true;
+  };
+  if (half * COLS_PER_HALF >= BN) {   // BN == 64 with bf16 output: the second column-half has no panel
+    release();
+    return;
+  }
+#pragma unroll
+  for (int pi = 0; pi < NPAN; ++pi) {
+    const int col_l = half * COLS_PER_HALF + pi * PC;
+    const int col0 = n0 + col_l;
+    if (col0 >= ep.N) break;                              // warp-uniform
+    uint32_t r[PC / 32][32];
+#pragma unroll
+    for (int cc = 0; cc < PC / 32; ++cc) tmem_ld_32x32b_x32(tmem_acc + col_l + cc * 32, r[cc]);
+    tmem_ld_wait();
+    if (pi == NPAN - 1 || col0 + PC >= ep.N) release();
+    if (ep.dbg & 4) continue;
+
+    const uint32_t slab = slab0 + (uint32_t)slab_sel * GemmCfg<BN>::SLAB_BYTES;
+    slab_sel ^= 1;
+    // the TMA store that last read this slab (two panels ago) must have drained it
+    if (ep.store_mode == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+
+    const bool use_slab_res = ep.residual && !F32 && ep.store_mode != 2;
+    if (use_slab_res) {
+      // coalesced fetch of the 32 x 128 B residual block into the slab: 8 lanes per row, 4 rows per instruction
+      const int c = lane & 7;
+      const int colc = col0 + c * 8;
+      int dcolc = colc, sub = 0;
+      if (ep.row_mode == 2) { sub = colc / ep.ps_c; dcolc = colc - sub * ep.ps_c; }
+      uint4 rv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rl = i * 4 + (lane >> 3);
+        int d = __shfl_sync(0xffffffffu, my_dst, rl);
+        if (ep.row_mode == 2 && d >= 0) d += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
+        rv[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (d >= 0 && colc + 8 <= ep.N) rv[i] = __ldg(reinterpret_cast<const uint4*>(ep.residual + (long long)d * ep.ldr + dcolc));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sts128(slab + swz128(i * 4 + (lane >> 3), c), rv[i]);
+      __syncwarp();
+    }
+
+    uint4 pk[8];
+#pragma unroll
+    for (int cc = 0; cc < PC / 32; ++cc) {
+      const int col = col0 + cc * 32;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[cc][j]);
+      if (col < ep.N) {
+        const bool colfull = col + 32 <= ep.N;
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b;
+            if (colfull) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
+            else {
+              b.x = col + j < ep.N ? ep.bias[col + j] : 0.f; b.y = col + j + 1 < ep.N ? ep.bias[col + j + 1] : 0.f;
+              b.z = col + j + 2 < ep.N ? ep.bias[col + j + 2] : 0.f; b.w = col + j + 3 < ep.N ? ep.bias[col + j + 3] : 0.f;
+            }
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (ep.act) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+        }
+        if (ep.scale) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 s;
+            if (colfull) s = __ldg(reinterpret_cast<const float4*>(ep.scale + col + j));
+            else {
+              s.x = col + j < ep.N ? ep.scale[col + j] : 0.f; s.y = col + j + 1 < ep.N ? ep.scale[col + j + 1] : 0.f;
+              s.z = col + j + 2 < ep.N ? ep.scale[col + j + 2] : 0.f; s.w = col + j + 3 < ep.N ? ep.scale[col + j + 3] : 0.f;
+            }
+            v[j] *= s.x; v[j + 1] *= s.y; v[j + 2] *= s.z; v[j + 3] *= s.w;
+          }
+        }
+        if (use_slab_res) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f[8];
+            unpack8(lds128(slab + swz128(lane, cc * 4 + j)), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[8 * j + k] += f[k];
+          }
+        }
+      }
+      if (ep.store_mode == 2) {
+        // scalar, fully guarded: unaligned rows / ragged N (rare, small outputs)
+        int d = my_dst;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int cj = col + j;
+          if (d < 0 || cj >= ep.N || (ep.dbg & 1)) continue;
+          long long drow = d;
+          int dcol = cj;
+          if (ep.row_mode == 2) {
+            const int sub = cj / ep.ps_c;
+            dcol = cj - sub * ep.ps_c;
+            drow += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
+          }
+          float x = v[j];
+          if (ep.residual) x += __bfloat162float(ep.residual[drow * ep.ldr + dcol]);
+          if (ep.out_f32) reinterpret_cast<float*>(ep.out)[drow * ep.ldo + dcol] = x;
+          else reinterpret_cast<__nv_bfloat16*>(ep.out)[drow * ep.ldo + dcol] = __float2bfloat16_rn(x);
+        }
+        continue;
+      }
+      if constexpr (F32) {
+        if (ep.residual && my_dst >= 0) {   // fp32 output with a residual: not on the hot path, per-thread loads
+          long long drow = my_dst;
+          int dcol = col;
+          if (ep.row_mode == 2) {
+            const int sub = col / ep.ps_c;
+            dcol = col - sub * ep.ps_c;
+            drow += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col + j < ep.N) v[j] += __bfloat162float(ep.residual[drow * ep.ldr + dcol + j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          pk[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                             __float_as_uint(v[4 * j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pk[cc * 4 + j] = pack8(v + 8 * j);
+      }
+    }
+    if (ep.store_mode == 2) continue;
+
+    // own accumulator row -> swizzled slab (conflict-free 16-byte stores)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts128(slab + swz128(lane, j), pk[j]);
+    if (ep.store_mode == 0) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && !(ep.dbg & 1)) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(tmC)),
+                     "r"(slab), "r"(col0), "r"(row0)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      __syncwarp();
+      // coalesced row segments: 8 lanes write one 128-byte row piece, 4 rows per instruction
+      constexpr int EPC = F32 ? 4 : 8;                     // elements per 16-byte chunk
+      const int c = lane & 7;
+      const int colc = col0 + c * EPC;
+      int dcolc = colc, sub = 0;
+      if (ep.row_mode == 2) { sub = colc / ep.ps_c; dcolc = colc - sub * ep.ps_c; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rl = i * 4 + (lane >> 3);
+        int d = __shfl_sync(0xffffffffu, my_dst, rl);
+        if (ep.row_mode == 2 && d >= 0) d += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
+        const uint4 val = lds128(slab + swz128(rl, c));
+        if (d >= 0 && colc + EPC <= ep.N && !(ep.dbg & 1)) {
+          if (F32) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(ep.out) + (long long)d * ep.ldo + dcolc) = val;
+          else *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)d * ep.ldo + dcolc) = val;
+        }
+      }
+    }
+  }
+  if (!released) release();
+}
+
 template <int BN>
-__global__ void __maxnreg__(192)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmEpi ep) {
   using Cfg = GemmCfg<BN>;
@@ -70,293 +353,123 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from the __shared__ array (so loads compile to LDS, not generic LD)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* stage_out = smem + STAGES * Cfg::STAGE_BYTES;                 // 2 x [128 rows x 128 B] store panels
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + 2 * 16384);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tfull = bars + 2 * STAGES;
-  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;                    // 8 warps x 2 slabs x 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
+  uint64_t* full = bars;                     // used in the leader CTA only (both CTAs' TMA bytes land here)
+  uint64_t* empty = bars + STAGES;           // per CTA, armed by the multicast commit
+  uint64_t* tfull = bars + 2 * STAGES;       // per CTA, armed by the multicast commit
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // used in the leader CTA only (16 epilogue warps arrive)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m = (ep.M + Cfg::BM - 1) / Cfg::BM;
+  const uint32_t rank = cluster_ctarank();
+  const int num_mp = (ep.M + 2 * Cfg::BM - 1) / (2 * Cfg::BM);
   const int num_n = (ep.N + BN - 1) / BN;
   const int num_k = (ep.K + Cfg::BK - 1) / Cfg::BK;
-  const int num_tiles = num_m * num_n;
+  const int num_tiles = num_mp * num_n;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    tma_prefetch_desc(&tmC);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * Cfg::NUM_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  cluster_sync_all();                         // both CTAs are resident before the paired TMEM allocation
+  if (warp == 9) tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();                         // barrier inits + TMEM address visible cluster-wide
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The two single-lane roles take the HIGHEST warp ids: the SMSP arbiter prefers high warp ids, so the TMA and
+  // MMA issue slots are never starved by epilogue math running on the same scheduler.
   if (warp == 8) {
-    // ---------------- TMA producer ----------------
+    // ---------------- TMA producer (both CTAs) ----------------
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int mp = tile / num_n, n_blk = tile % num_n;
+        const int m0 = mp * (2 * Cfg::BM) + (int)rank * Cfg::BM;
+        const int nb0 = n_blk * BN + (int)rank * Cfg::BNH;
         for (int kb = 0; kb < num_k; ++kb) {
+          if (ep.dbg & 16) continue;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
-          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-          tma_load_2d(sa, &tmA, &full[s], kb * Cfg::BK, m_blk * Cfg::BM);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], kb * Cfg::BK, n_blk * BN);
+          const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
+          else mbar_arrive_cluster(lead_full);
+          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          tma_load_2d_cg2(sa, &tmA, lead_full, kb * Cfg::BK, m0);
+          tma_load_2d_cg2(sa + Cfg::A_BYTES, &tmB, lead_full, kb * Cfg::BK, nb0);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 9) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(Cfg::BM, BN, 0, 0);
+    // ---------------- MMA issuer (leader CTA only) ----------------
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * Cfg::BM, BN, 0, 0);
       int s = 0; uint32_t ph = 0; int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
         const int acc = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty[acc], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&full[s], ph);
+          if (!(ep.dbg & 16)) mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < Cfg::BK / 16; ++k) {
-            umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32),
-                        idesc, (kb | k) != 0 ? 1u : 0u);
+            if (ep.dbg & 8) break;
+            umma_f16_ss_cg2(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                            (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[s]);
+          umma_commit_cg2(&empty[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        umma_commit_cg2(&tfull[acc]);
+      }
+      // the peer's last remote arrivals must have landed before this CTA's barriers can go away
+      if (it > 0) {
+        const int last = it - 1;
+        mbar_wait(&tempty[last & 1], (last >> 1) & 1);
       }
     }
+    __syncwarp();
   } else {
-    // ---------------- epilogue (warps 0..7) ----------------
+    // ---------------- epilogue (warps 0..7, both CTAs) ----------------
+    const int ew = warp;
     const int quad = warp & 3;   // TMEM lane quadrant this warp may touch
-    const int half = warp >> 2;  // which half of the BN columns
+    const int half = ew >> 2;    // which half of the BN columns
+    const uint32_t slab0 = smem_u32(staging) + (uint32_t)ew * Cfg::SLABS_PER_WARP * Cfg::SLAB_BYTES;
+    int slab_sel = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int mp = tile / num_n, n_blk = tile % num_n;
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
-      const int row = m_blk * Cfg::BM + quad * 32 + lane;
-      const bool row_ok = row < ep.M;
-      long long dst_row = row;
-      int ps_y = 0, ps_x = 0, ps_b = 0;
-      if (ep.row_mode == 1) {
-        dst_row = row_ok ? (long long)ep.row_map[row] : -1;
-      } else if (ep.row_mode == 2) {
-        const int hw = ep.ps_h * ep.ps_w;
-        ps_b = row / hw;
-        const int r = row - ps_b * hw;
-        ps_y = r / ep.ps_w;
-        ps_x = r - ps_y * ep.ps_w;
-      }
-      // All TMEM loads of this warp's column half are issued up front (BN/2 <= 128 fp32 columns =
-      // BN/2 registers) and the accumulator is handed back to the MMA warp right after they land, so the
-      // global-memory part of the epilogue (bias / residual loads, stores) overlaps the next tile's MMAs
-      // instead of sitting between them.
-      constexpr int NCH = BN / 64;  // 32-column chunks per warp
-      uint32_t r[NCH][32];
-#pragma unroll
-      for (int ci = 0; ci < NCH; ++ci)
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + half * (BN / 2) + ci * 32, r[ci]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (ep.tma_store) {
-        // ---- panel-staged TMA tensor store ----
-        // A thread owns one accumulator ROW; storing rows straight to global costs one L2 request per 16 B
-        // (measured: 0.95 TB/s, 35 % of the qkv GEMM). Instead the 4 warps of a column half assemble a
-        // [128 rows x 128 B] panel in shared memory (SWIZZLE_128B layout: conflict-free 16 B stores) and one
-        // thread issues a single TMA tensor store for it; the hardware also clips rows >= M / cols >= N.
-        uint8_t* panel = stage_out + half * 16384;
-        const int rloc = quad * 32 + lane;
-        const bool leader = (warp & 3) == 0 && lane == 0;
-        auto run_panels = [&](auto pc_tag) {
-          constexpr int PC = decltype(pc_tag)::value;   // columns per 128-byte panel row (64 bf16 / 32 fp32)
-          constexpr bool F32 = PC == 32;
-#pragma unroll
-          for (int pi = 0; pi < (BN / 2) / PC; ++pi) {
-            const int col0 = n_blk * BN + half * (BN / 2) + pi * PC;
-            if (col0 >= ep.N || (ep.dbg & 4)) break;      // uniform over the 4 warps of this half
-            uint4 pk[8];
-#pragma unroll
-            for (int cc = 0; cc < PC / 32; ++cc) {
-              constexpr int dummy = 0; (void)dummy;
-              const int ci = pi * (PC / 32) + cc;          // compile-time after unrolling
-              const int col = col0 + cc * 32;
-              float v[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[ci][j]);
-              if (col < ep.N) {
-                const bool colfull = col + 32 <= ep.N;
-                if (ep.bias && !(ep.dbg & 2)) {
-#pragma unroll
-                  for (int j = 0; j < 32; j += 4) {
-                    float4 b;
-                    if (colfull) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
-                    else {
-                      b.x = col + j < ep.N ? ep.bias[col + j] : 0.f; b.y = col + j + 1 < ep.N ? ep.bias[col + j + 1] : 0.f;
-                      b.z = col + j + 2 < ep.N ? ep.bias[col + j + 2] : 0.f; b.w = col + j + 3 < ep.N ? ep.bias[col + j + 3] : 0.f;
-                    }
-                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                  }
-                }
-                if (ep.act) {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-                }
-                if (ep.scale) {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) v[j] *= (colfull || col + j < ep.N) ? __ldg(ep.scale + col + j) : 0.f;
-                }
-                if (ep.residual && row_ok) {
-                  if (colfull) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + (long long)row * ep.ldr + col);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      float f[8];
-                      unpack8(__ldg(rp + j), f);
-#pragma unroll
-                      for (int k = 0; k < 8; ++k) v[8 * j + k] += f[k];
-                    }
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                      if (col + j < ep.N) v[j] += __bfloat162float(ep.residual[(long long)row * ep.ldr + col + j]);
-                  }
-                }
-              }
-              if constexpr (F32) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  pk[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
-                                     __float_as_uint(v[4 * j + 3]));
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pk[cc * 4 + j] = pack8(v + 8 * j);
-              }
-            }
-            if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous panel drained
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(panel + rloc * 128 + ((j ^ (rloc & 7)) << 4)) = pk[j];
-            fence_proxy_async();
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-            if (leader && !(ep.dbg & 1)) {
-              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                               reinterpret_cast<uint64_t>(&tmC)),
-                           "r"(smem_u32(panel)), "r"(col0), "r"(m_blk * Cfg::BM)
-                           : "memory");
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-          }
-        };
-        if (ep.out_f32) run_panels(std::integral_constant<int, 32>{});
-        else run_panels(std::integral_constant<int, 64>{});
-        continue;   // next tile
-      }
-#pragma unroll
-      for (int ci = 0; ci < NCH; ++ci) {
-        const int col_l = half * (BN / 2) + ci * 32;
-        const int col = n_blk * BN + col_l;
-        if (!row_ok || col >= ep.N || (ep.dbg & 4)) continue;
-        long long drow = dst_row;
-        int dcol = col;
-        if (ep.row_mode == 2) {
-          const int sub = col / ep.ps_c;
-          dcol = col - sub * ep.ps_c;
-          drow = ((long long)ps_b * 2 * ep.ps_h + 2 * ps_y + (sub >> 1)) * (2 * ep.ps_w) + 2 * ps_x + (sub & 1);
-        }
-        if (drow < 0) continue;
-        float v[32];
-        const bool full32 = ep.vec_ok && col + 32 <= ep.N;
-        if (full32) {
-          uint4 rres[4];
-          if (ep.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + drow * ep.ldr + dcol);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rres[j] = __ldg(rp + j);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ep.bias && !(ep.dbg & 2)) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
-            v[j] = __uint_as_float(r[ci][j]) + b.x;
-            v[j + 1] = __uint_as_float(r[ci][j + 1]) + b.y;
-            v[j + 2] = __uint_as_float(r[ci][j + 2]) + b.z;
-            v[j + 3] = __uint_as_float(r[ci][j + 3]) + b.w;
-          }
-          if (ep.act) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-          }
-          if (ep.scale) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(ep.scale + col + j));
-              v[j] *= sc.x; v[j + 1] *= sc.y; v[j + 2] *= sc.z; v[j + 3] *= sc.w;
-            }
-          }
-          if (ep.residual) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float f[8];
-              unpack8(rres[j], f);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) v[8 * j + k] += f[k];
-            }
-          }
-          if (ep.dbg & 1) {
-            // perf-debug: keep all the math (the stores below stay reachable), skip only the stores
-          } else if (ep.out_f32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + drow * ep.ldo + dcol);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + drow * ep.ldo + dcol);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = pack8(v + 8 * j);
-          }
-        } else {
-          // ragged last column chunk / unaligned rows: scalar, fully guarded
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col + j < ep.N) {
-              float x = __uint_as_float(r[ci][j]);
-              if (ep.bias) x += ep.bias[col + j];
-              x = apply_act(x, ep.act);
-              if (ep.scale) x *= ep.scale[col + j];
-              if (ep.residual) x += __bfloat162float(ep.residual[drow * ep.ldr + dcol + j]);
-              if (ep.out_f32) reinterpret_cast<float*>(ep.out)[drow * ep.ldo + dcol + j] = x;
-              else reinterpret_cast<__nv_bfloat16*>(ep.out)[drow * ep.ldo + dcol + j] = __float2bfloat16_rn(x);
-            }
-          }
-        }
-      }
+      const int row0 = mp * (2 * Cfg::BM) + (int)rank * Cfg::BM + quad * 32;
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      const uint32_t tempty_addr = mapa_shared(smem_u32(&tempty[acc]), 0);
+      if (ep.out_f32) epilogue_tile<BN, true>(ep, &tmC, tmem_acc, slab0, slab_sel, row0, n_blk * BN, half, lane, tempty_addr);
+      else epilogue_tile<BN, false>(ep, &tmC, tmem_acc, slab0, slab_sel, row0, n_blk * BN, half, lane, tempty_addr);
     }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this thread's TMA stores (if any) are complete
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's TMA stores are complete
+    __syncwarp();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -370,9 +483,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const int num_tiles = ((ep.M + 127) / 128) * ((ep.N + BN - 1) / BN);
-  int grid = num_tiles < max_ctas ? num_tiles : max_ctas;
-  gemm_bf16_kernel<BN><<<grid, 320, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, ep);
+  const int num_tiles = ((ep.M + 255) / 256) * ((ep.N + BN - 1) / BN);
+  int pairs = max_ctas / 2;
+  if (num_tiles < pairs) pairs = num_tiles;
+  gemm_bf16_kernel<BN><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, ep);
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }
@@ -423,52 +537,52 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
   if (row_mode == 1 && !row_map_dev) return MMSAM_ERR_BAD_ARG;
   if (row_mode == 2 && (ps_h <= 0 || ps_w <= 0 || ps_c <= 0 || (ps_c & 31) || N != 4 * ps_c || M % (ps_h * ps_w)))
     return MMSAM_ERR_BAD_ARG;
-  // the vector epilogue needs 16-byte aligned rows; ragged N tails fall back to scalar stores
+  // the vector epilogues need 16-byte aligned rows and whole 16-byte chunks; anything else goes scalar
   const int oelt = out_f32 ? 4 : 2;
   int vec_ok = 1;
   if ((((uintptr_t)out) & 15) || ((ldo * oelt) & 15)) vec_ok = 0;
   if (residual && ((((uintptr_t)residual) & 15) || (ldr & 7))) vec_ok = 0;
   if (bias && (((uintptr_t)bias) & 15)) return MMSAM_ERR_BAD_ARG;
   if (scale && (((uintptr_t)scale) & 15)) return MMSAM_ERR_BAD_ARG;
-  if (max_ctas <= 0 || max_ctas > kNumSMs) max_ctas = kNumSMs;
+  if (max_ctas <= 1 || max_ctas > kNumSMs) max_ctas = kNumSMs;
 
   int bn = block_n;
   if (bn != 64 && bn != 128 && bn != 256) {
-    // auto: widest tile that still gives every SM a tile, then prefer the least padded N
-    const long long num_m = (M + 127) / 128;
+    // auto: widest tile that still gives every SM pair a tile, then prefer the least padded N
+    const long long num_mp = (M + 255) / 256;
+    const int pairs = kNumSMs / 2;
     bn = 256;
     if (N <= 64) bn = 64;
     else if (N <= 128) bn = 128;
-    else if (num_m * ((N + 255) / 256) < kNumSMs && num_m * ((N + 127) / 128) >= num_m * ((N + 255) / 256) * 2 - 1) bn = 128;
+    else if (num_mp * ((N + 255) / 256) < pairs && num_mp * ((N + 127) / 128) >= num_mp * ((N + 255) / 256) * 2 - 1) bn = 128;
     if (bn == 256 && (N % 256) != 0 && (N % 256) <= 128 && N < 1024) bn = 128;
   }
   CUtensorMap tmA, tmB;
   int rc = mmsam_host::make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64);
   if (rc) return rc;
-  rc = mmsam_host::make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn, 64);
+  rc = mmsam_host::make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(bn / 2), 64);
   if (rc) return rc;
   GemmEpi ep;
   ep.bias = bias; ep.scale = scale; ep.residual = (const __nv_bfloat16*)residual; ep.out = out;
   ep.row_map = row_map_dev; ep.ldo = ldo; ep.ldr = ldr; ep.M = M; ep.N = N; ep.K = K; ep.act = act;
-  ep.out_f32 = out_f32; ep.row_mode = row_mode; ep.vec_ok = vec_ok; { const char* d = getenv("MMSAM_GEMM_DBG"); ep.dbg = d ? atoi(d) : 0; } ep.ps_h = ps_h; ep.ps_w = ps_w; ep.ps_c = ps_c;
+  ep.out_f32 = out_f32; ep.row_mode = row_mode; ep.ps_h = ps_h; ep.ps_w = ps_w; ep.ps_c = ps_c;
+  { const char* d = getenv("MMSAM_GEMM_DBG"); ep.dbg = d ? atoi(d) : 0; }
   cudaStream_t st = (cudaStream_t)stream;
-  // output tensor map for the TMA-store epilogue (plain row mapping, 16-byte aligned rows)
+  // store mode: 0 = TMA tensor store (identity rows), 1 = coalesced row segments (row map / pixel shuffle),
+  // 2 = scalar (unaligned rows or an N that is not a whole number of 16-byte chunks)
   CUtensorMap tmC = tmA;
-  ep.tma_store = 0;
-  {
-    const char* e = getenv("MMSAM_GEMM_TMA_STORE");
-    const bool want = !(e && e[0] == '0');
-    if (want && row_mode == 0 && vec_ok) {
-      mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
-      cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
-      cuuint64_t strides[1] = {(cuuint64_t)ldo * oelt};
-      cuuint32_t box[2] = {(cuuint32_t)(out_f32 ? 32 : 64), 128};
-      cuuint32_t estr[2] = {1, 1};
-      if (enc && enc(&tmC, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, dims, strides,
-                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
-        ep.tma_store = 1;
-    }
+  const int epc = out_f32 ? 4 : 8;
+  ep.store_mode = (!vec_ok || (N % epc) != 0) ? 2 : (row_mode == 0 ? 0 : 1);
+  if (ep.store_mode == 0) {
+    mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)ldo * oelt};
+    cuuint32_t box[2] = {(cuuint32_t)(out_f32 ? 32 : 64), 32};
+    cuuint32_t estr[2] = {1, 1};
+    if (!enc || enc(&tmC, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      ep.store_mode = 1;   // fall back to the coalesced row-segment store (same results)
   }
   if (bn == 256) return launch_gemm<256>(tmA, tmB, tmC, ep, max_ctas, st);
   if (bn == 128) return launch_gemm<128>(tmA, tmB, tmC, ep, max_ctas, st);
