@@ -49,7 +49,6 @@ struct GemmEpi {
   int act;        // 0 none, 1 gelu(erf), 2 relu, 3 relu6
   int out_f32;    // 0: bf16 output, 1: fp32 output
   int row_mode;   // 0 identity, 1 row_map, 2 pixel-shuffle 2x2 (ConvTranspose2d k=2 s=2)
-  int store_mode; // 0 TMA tensor store, 1 coalesced row segments from the slab, 2 scalar (unaligned / ragged)
   int dbg;        // perf-debug switches (env MMSAM_GEMM_DBG): 1 skip stores, 4 skip the epilogue math too
   int ps_h, ps_w, ps_c;
 };
@@ -144,207 +143,263 @@ __device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// One accumulator tile of one epilogue warp: rows [row0, row0+32) of the output, the warp's share of
-// the BN columns, PC columns (one 128-byte panel) at a time.
-template <int BN, bool F32>
-__device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const CUtensorMap* tmC, uint32_t tmem_acc, uint32_t slab0,
-                                              int& slab_sel, int row0, int n0, int half, int lane,
-                                              uint32_t tempty_addr) {
-  constexpr int PC = F32 ? 32 : 64;                      // columns per 128-byte panel row
-  constexpr int COLS_PER_HALF = (BN / 2 >= PC) ? BN / 2 : PC;
-  constexpr int NPAN = COLS_PER_HALF / PC;
-  const int row = row0 + lane;                           // the accumulator row this thread reads from TMEM
-  const bool row_ok = row < ep.M;
-  // destination row of this thread's source row (mode 2: row of the (dy,dx)=(0,0) sub-pixel)
-  int my_dst = row_ok ? row : -1;
-  if (ep.row_mode == 1) {
-    my_dst = row_ok ? ep.row_map[row] : -1;
-  } else if (ep.row_mode == 2 && row_ok) {
-    const int hw = ep.ps_h * ep.ps_w;
-    const int b = row / hw, r = row - b * hw;
-    const int y = r / ep.ps_w, x = r - y * ep.ps_w;
-    my_dst = (b * 2 * ep.ps_h + 2 * y) * (2 * ep.ps_w) + 2 * x;
-  }
-  bool released = false;
-  auto release = [&]() {
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive_cluster(tempty_addr);
-    released = true;
-  };
-  if (half * COLS_PER_HALF >= BN) {   // BN == 64 with bf16 output: the second column-half has no panel
-    release();
-    return;
-  }
-#pragma unroll
-  for (int pi = 0; pi < NPAN; ++pi) {
-    const int col_l = half * COLS_PER_HALF + pi * PC;
-    const int col0 = n0 + col_l;
-    if (col0 >= ep.N) break;                              // warp-uniform
-    uint32_t r[PC / 32][32];
-#pragma unroll
-    for (int cc = 0; cc < PC / 32; ++cc) tmem_ld_32x32b_x32(tmem_acc + col_l + cc * 32, r[cc]);
-    tmem_ld_wait();
-    if (pi == NPAN - 1 || col0 + PC >= ep.N) release();
-    if (ep.dbg & 4) continue;
+enum { V_BF16 = 0, V_BF16_GELU = 1, V_BF16_MAP = 2, V_F32 = 3, V_GENERIC = 4 };
 
-    const uint32_t slab = slab0 + (uint32_t)slab_sel * GemmCfg<BN>::SLAB_BYTES;
-    slab_sel ^= 1;
-    // the TMA store that last read this slab (two panels ago) must have drained it
-    if (ep.store_mode == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-    __syncwarp();
+__device__ __forceinline__ float4 ldg4_guard(const float* p, int col, int N) {   // N % 4 == 0 on the fast paths
+  return col < N ? __ldg(reinterpret_cast<const float4*>(p + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
 
-    const bool use_slab_res = ep.residual && !F32 && ep.store_mode != 2;
-    if (use_slab_res) {
-      // coalesced fetch of the 32 x 128 B residual block into the slab: 8 lanes per row, 4 rows per instruction
-      const int c = lane & 7;
-      const int colc = col0 + c * 8;
-      int dcolc = colc, sub = 0;
-      if (ep.row_mode == 2) { sub = colc / ep.ps_c; dcolc = colc - sub * ep.ps_c; }
-      uint4 rv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rl = i * 4 + (lane >> 3);
-        int d = __shfl_sync(0xffffffffu, my_dst, rl);
-        if (ep.row_mode == 2 && d >= 0) d += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
-        rv[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (d >= 0 && colc + 8 <= ep.N) rv[i] = __ldg(reinterpret_cast<const uint4*>(ep.residual + (long long)d * ep.ldr + dcolc));
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sts128(slab + swz128(i * 4 + (lane >> 3), c), rv[i]);
-      __syncwarp();
+// Slow, fully general epilogue (unaligned rows, N not a whole number of 16-byte chunks, fp32 + residual,
+// fp32 + row map ...): thread = accumulator row, guarded scalar stores. Small outputs only.
+template <int BN>
+__device__ __forceinline__ void epilogue_generic(const GemmEpi& ep, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
+                                                 int warp, int lane, uint32_t rank, int pair, int num_pairs, int num_tiles,
+                                                 int num_n) {
+  const int quad = warp & 3, half = warp >> 2;
+  int it = 0;
+  for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+    const int mp = tile / num_n, n_blk = tile % num_n;
+    const int acc = it & 1;
+    mbar_wait(&tfull[acc], (it >> 1) & 1);
+    tc_fence_after();
+    const int row = mp * 256 + (int)rank * 128 + quad * 32 + lane;
+    const bool row_ok = row < ep.M;
+    long long drow0 = row_ok ? row : -1;
+    if (ep.row_mode == 1) drow0 = row_ok ? ep.row_map[row] : -1;
+    else if (ep.row_mode == 2 && row_ok) {
+      const int hw = ep.ps_h * ep.ps_w;
+      const int b = row / hw, r = row - b * hw;
+      const int y = r / ep.ps_w, x = r - y * ep.ps_w;
+      drow0 = ((long long)b * 2 * ep.ps_h + 2 * y) * (2 * ep.ps_w) + 2 * x;
     }
-
-    uint4 pk[8];
-#pragma unroll
-    for (int cc = 0; cc < PC / 32; ++cc) {
-      const int col = col0 + cc * 32;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[cc][j]);
-      if (col < ep.N) {
-        const bool colfull = col + 32 <= ep.N;
-        if (ep.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 b;
-            if (colfull) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
-            else {
-              b.x = col + j < ep.N ? ep.bias[col + j] : 0.f; b.y = col + j + 1 < ep.N ? ep.bias[col + j + 1] : 0.f;
-              b.z = col + j + 2 < ep.N ? ep.bias[col + j + 2] : 0.f; b.w = col + j + 3 < ep.N ? ep.bias[col + j + 3] : 0.f;
-            }
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (ep.act) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-        }
-        if (ep.scale) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 s;
-            if (colfull) s = __ldg(reinterpret_cast<const float4*>(ep.scale + col + j));
-            else {
-              s.x = col + j < ep.N ? ep.scale[col + j] : 0.f; s.y = col + j + 1 < ep.N ? ep.scale[col + j + 1] : 0.f;
-              s.z = col + j + 2 < ep.N ? ep.scale[col + j + 2] : 0.f; s.w = col + j + 3 < ep.N ? ep.scale[col + j + 3] : 0.f;
-            }
-            v[j] *= s.x; v[j + 1] *= s.y; v[j + 2] *= s.z; v[j + 3] *= s.w;
-          }
-        }
-        if (use_slab_res) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float f[8];
-            unpack8(lds128(slab + swz128(lane, cc * 4 + j)), f);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[8 * j + k] += f[k];
-          }
-        }
+    const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+    for (int ci = 0; ci < BN / 64; ++ci) {
+      const int col_l = half * (BN / 2) + ci * 32;
+      const int col = n_blk * BN + col_l;
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_acc + col_l, r);
+      tmem_ld_wait();
+      if (ci == BN / 64 - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));
       }
-      if (ep.store_mode == 2) {
-        // scalar, fully guarded: unaligned rows / ragged N (rare, small outputs)
-        int d = my_dst;
+      if (drow0 < 0 || col >= ep.N || (ep.dbg & 5)) continue;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int cj = col + j;
-          if (d < 0 || cj >= ep.N || (ep.dbg & 1)) continue;
-          long long drow = d;
+      for (int j = 0; j < 32; ++j) {
+        const int cj = col + j;
+        if (cj < ep.N) {
+          long long drow = drow0;
           int dcol = cj;
           if (ep.row_mode == 2) {
             const int sub = cj / ep.ps_c;
             dcol = cj - sub * ep.ps_c;
             drow += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
           }
-          float x = v[j];
+          float x = __uint_as_float(r[j]);
+          if (ep.bias) x += ep.bias[cj];
+          x = apply_act(x, ep.act);
+          if (ep.scale) x *= ep.scale[cj];
           if (ep.residual) x += __bfloat162float(ep.residual[drow * ep.ldr + dcol]);
           if (ep.out_f32) reinterpret_cast<float*>(ep.out)[drow * ep.ldo + dcol] = x;
           else reinterpret_cast<__nv_bfloat16*>(ep.out)[drow * ep.ldo + dcol] = __float2bfloat16_rn(x);
         }
-        continue;
-      }
-      if constexpr (F32) {
-        if (ep.residual && my_dst >= 0) {   // fp32 output with a residual: not on the hot path, per-thread loads
-          long long drow = my_dst;
-          int dcol = col;
-          if (ep.row_mode == 2) {
-            const int sub = col / ep.ps_c;
-            dcol = col - sub * ep.ps_c;
-            drow += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col + j < ep.N) v[j] += __bfloat162float(ep.residual[drow * ep.ldr + dcol + j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          pk[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
-                             __float_as_uint(v[4 * j + 3]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pk[cc * 4 + j] = pack8(v + 8 * j);
-      }
-    }
-    if (ep.store_mode == 2) continue;
-
-    // own accumulator row -> swizzled slab (conflict-free 16-byte stores)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sts128(slab + swz128(lane, j), pk[j]);
-    if (ep.store_mode == 0) {
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0 && !(ep.dbg & 1)) {
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                         reinterpret_cast<uint64_t>(tmC)),
-                     "r"(slab), "r"(col0), "r"(row0)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-    } else {
-      __syncwarp();
-      // coalesced row segments: 8 lanes write one 128-byte row piece, 4 rows per instruction
-      constexpr int EPC = F32 ? 4 : 8;                     // elements per 16-byte chunk
-      const int c = lane & 7;
-      const int colc = col0 + c * EPC;
-      int dcolc = colc, sub = 0;
-      if (ep.row_mode == 2) { sub = colc / ep.ps_c; dcolc = colc - sub * ep.ps_c; }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rl = i * 4 + (lane >> 3);
-        int d = __shfl_sync(0xffffffffu, my_dst, rl);
-        if (ep.row_mode == 2 && d >= 0) d += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
-        const uint4 val = lds128(slab + swz128(rl, c));
-        if (d >= 0 && colc + EPC <= ep.N && !(ep.dbg & 1)) {
-          if (F32) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(ep.out) + (long long)d * ep.ldo + dcolc) = val;
-          else *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)d * ep.ldo + dcolc) = val;
-        }
       }
     }
   }
-  if (!released) release();
 }
 
-template <int BN>
+// Fast epilogues. One warp = one TMEM lane quadrant (32 accumulator rows) x one half of the BN columns, walked
+// in 128-byte-wide panels (64 bf16 / 32 fp32 columns). The residual block of the NEXT panel (possibly of the
+// next tile: the tile sequence is static) is fetched into registers while the current panel is computed.
+template <int BN, int VAR>
+__device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorMap* tmC, uint32_t tmem_base, uint32_t slab0,
+                                              uint64_t* tfull, uint64_t* tempty, int warp, int lane, uint32_t rank, int pair,
+                                              int num_pairs, int num_tiles, int num_n) {
+  constexpr bool F32 = VAR == V_F32;
+  constexpr bool MAPPED = VAR == V_BF16_MAP;
+  constexpr int PC = F32 ? 32 : 64;                      // columns per 128-byte panel row
+  constexpr int CPH = (BN / 2 >= PC) ? BN / 2 : PC;      // columns per warp-half
+  constexpr int NPAN = CPH / PC;
+  constexpr int EPC = F32 ? 4 : 8;                       // elements per 16-byte chunk
+  const int quad = warp & 3, half = warp >> 2;
+  const bool active = half * CPH < BN;                   // BN == 64 with bf16 output: the second half has no panel
+  const bool has_res = !F32 && ep.residual != nullptr;
+  const int c = lane & 7, rsub = lane >> 3;
+
+  // destination row of this thread's accumulator row in tile t (mode 2: row of the (dy,dx)=(0,0) sub-pixel)
+  auto dst_of = [&](int t) -> int {
+    const int row = (t / num_n) * 256 + (int)rank * 128 + quad * 32 + lane;
+    if (row >= ep.M) return -1;
+    if (!MAPPED) return row;
+    if (ep.row_mode == 1) return __ldg(ep.row_map + row);
+    if (ep.row_mode == 2) {
+      const int hw = ep.ps_h * ep.ps_w;
+      const int b = row / hw, r = row - b * hw;
+      const int y = r / ep.ps_w, x = r - y * ep.ps_w;
+      return (b * 2 * ep.ps_h + 2 * y) * (2 * ep.ps_w) + 2 * x;
+    }
+    return row;
+  };
+  uint4 rv[8];
+  // coalesced fetch of a 32 x 128 B residual block: 8 lanes per row, 4 rows per instruction
+  auto issue_res = [&](int dst, int col0) {
+    const int colc = col0 + c * 8;
+    int dcolc = colc, sub = 0;
+    if (MAPPED && ep.row_mode == 2) { sub = colc / ep.ps_c; dcolc = colc - sub * ep.ps_c; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int d = __shfl_sync(0xffffffffu, dst, i * 4 + rsub);
+      if (MAPPED && ep.row_mode == 2 && d >= 0) d += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
+      rv[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (d >= 0 && colc < ep.N) rv[i] = __ldg(reinterpret_cast<const uint4*>(ep.residual + (long long)d * ep.ldr + dcolc));
+    }
+  };
+
+  int slab_sel = 0, it = 0;
+  int tile = pair;
+  int my_dst = (active && tile < num_tiles) ? dst_of(tile) : -1;
+  if (has_res && active && tile < num_tiles) {
+    const int col0 = (tile % num_n) * BN + half * CPH;
+    if (col0 < ep.N) issue_res(my_dst, col0);
+  }
+  for (; tile < num_tiles; tile += num_pairs, ++it) {
+    const int mp = tile / num_n, n_blk = tile % num_n;
+    const int acc = it & 1;
+    const int next_tile = tile + num_pairs;
+    // issued now, first used when the last panel of this tile prefetches the next tile's residual / stores
+    const int my_dst_next = (active && next_tile < num_tiles) ? dst_of(next_tile) : -1;
+    mbar_wait(&tfull[acc], (it >> 1) & 1);
+    tc_fence_after();
+    const uint32_t tempty_addr = mapa_shared(smem_u32(&tempty[acc]), 0);
+    bool released = false;
+    auto release = [&]() {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_addr);
+      released = true;
+    };
+    if (active) {
+      const int row0 = mp * 256 + (int)rank * 128 + quad * 32;
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll
+      for (int pi = 0; pi < NPAN; ++pi) {
+        const int col_l = half * CPH + pi * PC;
+        const int col0 = n_blk * BN + col_l;
+        if (col0 >= ep.N) break;                            // warp-uniform
+        const uint32_t slab = slab0 + (uint32_t)slab_sel * GemmCfg<BN>::SLAB_BYTES;
+        slab_sel ^= 1;
+        // the TMA store that last read this slab (two panels ago) must have drained it
+        if (!MAPPED && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        if (has_res) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sts128(slab + swz128(i * 4 + rsub, c), rv[i]);
+          // prefetch the next panel's residual block (same tile, or the first panel of the next tile)
+          if (pi + 1 < NPAN && col0 + PC < ep.N) issue_res(my_dst, col0 + PC);
+          else if (next_tile < num_tiles) {
+            const int ncol0 = (next_tile % num_n) * BN + half * CPH;
+            if (ncol0 < ep.N) issue_res(my_dst_next, ncol0);
+          }
+        }
+        uint32_t r[PC / 32][32];
+#pragma unroll
+        for (int cc = 0; cc < PC / 32; ++cc) tmem_ld_32x32b_x32(tmem_acc + col_l + cc * 32, r[cc]);
+        tmem_ld_wait();
+        if (pi == NPAN - 1 || col0 + PC >= ep.N) release();
+        if (has_res) __syncwarp();                          // residual block visible to the row owners
+        if (ep.dbg & 4) continue;
+
+        uint4 pk[8];
+#pragma unroll
+        for (int cc = 0; cc < PC / 32; ++cc) {
+          const int col = col0 + cc * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[cc][j]);
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = ldg4_guard(ep.bias, col + j, ep.N);
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (VAR == V_BF16_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (ep.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (ep.act == 3) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
+          }
+          if (ep.scale) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 s = ldg4_guard(ep.scale, col + j, ep.N);
+              v[j] *= s.x; v[j + 1] *= s.y; v[j + 2] *= s.z; v[j + 3] *= s.w;
+            }
+          }
+          if (has_res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float f[8];
+              unpack8(lds128(slab + swz128(lane, cc * 4 + j)), f);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[8 * j + k] += f[k];
+            }
+          }
+          if constexpr (F32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              pk[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                 __float_as_uint(v[4 * j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pk[cc * 4 + j] = pack8(v + 8 * j);
+          }
+        }
+        // own accumulator row -> swizzled slab (conflict-free 16-byte stores)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts128(slab + swz128(lane, j), pk[j]);
+        if constexpr (!MAPPED) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(ep.dbg & 1)) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(tmC)),
+                         "r"(slab), "r"(col0), "r"(row0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else {
+          __syncwarp();
+          // coalesced row segments: 8 lanes write one 128-byte row piece, 4 rows per instruction
+          const int colc = col0 + c * EPC;
+          int dcolc = colc, sub = 0;
+          if (ep.row_mode == 2) { sub = colc / ep.ps_c; dcolc = colc - sub * ep.ps_c; }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = i * 4 + rsub;
+            int d = __shfl_sync(0xffffffffu, my_dst, rl);
+            if (ep.row_mode == 2 && d >= 0) d += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
+            const uint4 val = lds128(slab + swz128(rl, c));
+            if (d >= 0 && colc < ep.N && !(ep.dbg & 1))
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)d * ep.ldo + dcolc) = val;
+          }
+        }
+      }
+    }
+    if (!released) release();
+    my_dst = my_dst_next;
+  }
+  if (!MAPPED && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's TMA stores are complete
+  __syncwarp();
+}
+
+template <int BN, int VAR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmEpi ep) {
@@ -444,26 +499,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else {
     // ---------------- epilogue (warps 0..7, both CTAs) ----------------
-    const int ew = warp;
-    const int quad = warp & 3;   // TMEM lane quadrant this warp may touch
-    const int half = ew >> 2;    // which half of the BN columns
-    const uint32_t slab0 = smem_u32(staging) + (uint32_t)ew * Cfg::SLABS_PER_WARP * Cfg::SLAB_BYTES;
-    int slab_sel = 0;
-    int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-      const int mp = tile / num_n, n_blk = tile % num_n;
-      const int acc = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
-      mbar_wait(&tfull[acc], aph);
-      tc_fence_after();
-      const int row0 = mp * (2 * Cfg::BM) + (int)rank * Cfg::BM + quad * 32;
-      const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-      const uint32_t tempty_addr = mapa_shared(smem_u32(&tempty[acc]), 0);
-      if (ep.out_f32) epilogue_tile<BN, true>(ep, &tmC, tmem_acc, slab0, slab_sel, row0, n_blk * BN, half, lane, tempty_addr);
-      else epilogue_tile<BN, false>(ep, &tmC, tmem_acc, slab0, slab_sel, row0, n_blk * BN, half, lane, tempty_addr);
+    if constexpr (VAR == V_GENERIC) {
+      epilogue_generic<BN>(ep, tmem_base, tfull, tempty, warp, lane, rank, pair, num_pairs, num_tiles, num_n);
+    } else {
+      const uint32_t slab0 = smem_u32(staging) + (uint32_t)warp * Cfg::SLABS_PER_WARP * Cfg::SLAB_BYTES;
+      epilogue_fast<BN, VAR>(ep, &tmC, tmem_base, slab0, tfull, tempty, warp, lane, rank, pair, num_pairs, num_tiles, num_n);
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's TMA stores are complete
-    __syncwarp();
   }
   tc_fence_before();
   cluster_sync_all();
@@ -473,22 +514,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN>
+template <int BN, int VAR>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmEpi& ep,
                        int max_ctas, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   const int num_tiles = ((ep.M + 255) / 256) * ((ep.N + BN - 1) / BN);
   int pairs = max_ctas / 2;
   if (num_tiles < pairs) pairs = num_tiles;
-  gemm_bf16_kernel<BN><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, ep);
+  gemm_bf16_kernel<BN, VAR><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, ep);
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
+}
+
+template <int VAR>
+static int launch_gemm_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmEpi& ep,
+                          int max_ctas, cudaStream_t st) {
+  if (bn == 256) return launch_gemm<256, VAR>(tmA, tmB, tmC, ep, max_ctas, st);
+  if (bn == 128) return launch_gemm<128, VAR>(tmA, tmB, tmC, ep, max_ctas, st);
+  return launch_gemm<64, VAR>(tmA, tmB, tmC, ep, max_ctas, st);
 }
 
 }  // namespace mmsam
@@ -538,9 +587,8 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
   if (row_mode == 2 && (ps_h <= 0 || ps_w <= 0 || ps_c <= 0 || (ps_c & 31) || N != 4 * ps_c || M % (ps_h * ps_w)))
     return MMSAM_ERR_BAD_ARG;
   // the vector epilogues need 16-byte aligned rows and whole 16-byte chunks; anything else goes scalar
-  const int oelt = out_f32 ? 4 : 2;
   int vec_ok = 1;
-  if ((((uintptr_t)out) & 15) || ((ldo * oelt) & 15)) vec_ok = 0;
+  if ((((uintptr_t)out) & 15) || ((ldo * (out_f32 ? 4 : 2)) & 15)) vec_ok = 0;
   if (residual && ((((uintptr_t)residual) & 15) || (ldr & 7))) vec_ok = 0;
   if (bias && (((uintptr_t)bias) & 15)) return MMSAM_ERR_BAD_ARG;
   if (scale && (((uintptr_t)scale) & 15)) return MMSAM_ERR_BAD_ARG;
@@ -557,6 +605,16 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
     else if (num_mp * ((N + 255) / 256) < pairs && num_mp * ((N + 127) / 128) >= num_mp * ((N + 255) / 256) * 2 - 1) bn = 128;
     if (bn == 256 && (N % 256) != 0 && (N % 256) <= 128 && N < 1024) bn = 128;
   }
+  // epilogue variant: fast paths need 16-byte aligned rows and whole 16-byte chunks
+  const int oelt = out_f32 ? 4 : 2;
+  const int epc = out_f32 ? 4 : 8;
+  int var;
+  if (!vec_ok || (N % epc) != 0 || (out_f32 && (residual || row_mode != 0 || act == 1)) || (row_mode != 0 && act == 1))
+    var = V_GENERIC;
+  else if (out_f32) var = V_F32;
+  else if (row_mode != 0) var = V_BF16_MAP;
+  else var = act == 1 ? V_BF16_GELU : V_BF16;
+  if (var == V_GENERIC) bn = 128;   // the general epilogue is instantiated for one tile width only
   CUtensorMap tmA, tmB;
   int rc = mmsam_host::make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64);
   if (rc) return rc;
@@ -568,12 +626,9 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
   ep.out_f32 = out_f32; ep.row_mode = row_mode; ep.ps_h = ps_h; ep.ps_w = ps_w; ep.ps_c = ps_c;
   { const char* d = getenv("MMSAM_GEMM_DBG"); ep.dbg = d ? atoi(d) : 0; }
   cudaStream_t st = (cudaStream_t)stream;
-  // store mode: 0 = TMA tensor store (identity rows), 1 = coalesced row segments (row map / pixel shuffle),
-  // 2 = scalar (unaligned rows or an N that is not a whole number of 16-byte chunks)
   CUtensorMap tmC = tmA;
-  const int epc = out_f32 ? 4 : 8;
-  ep.store_mode = (!vec_ok || (N % epc) != 0) ? 2 : (row_mode == 0 ? 0 : 1);
-  if (ep.store_mode == 0) {
+  if (var == V_BF16 || var == V_BF16_GELU || var == V_F32) {
+    // output tensor map for the per-warp TMA tensor stores: box = one 32-row x 128-byte slab
     mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
     cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
     cuuint64_t strides[1] = {(cuuint64_t)ldo * oelt};
@@ -582,9 +637,13 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
     if (!enc || enc(&tmC, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, dims, strides,
                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      ep.store_mode = 1;   // fall back to the coalesced row-segment store (same results)
+      return MMSAM_ERR_DRIVER;
   }
-  if (bn == 256) return launch_gemm<256>(tmA, tmB, tmC, ep, max_ctas, st);
-  if (bn == 128) return launch_gemm<128>(tmA, tmB, tmC, ep, max_ctas, st);
-  return launch_gemm<64>(tmA, tmB, tmC, ep, max_ctas, st);
+  switch (var) {
+    case V_BF16: return launch_gemm_bn<V_BF16>(bn, tmA, tmB, tmC, ep, max_ctas, st);
+    case V_BF16_GELU: return launch_gemm_bn<V_BF16_GELU>(bn, tmA, tmB, tmC, ep, max_ctas, st);
+    case V_BF16_MAP: return launch_gemm_bn<V_BF16_MAP>(bn, tmA, tmB, tmC, ep, max_ctas, st);
+    case V_F32: return launch_gemm_bn<V_F32>(bn, tmA, tmB, tmC, ep, max_ctas, st);
+    default: return launch_gemm<128, V_GENERIC>(tmA, tmB, tmC, ep, max_ctas, st);
+  }
 }
