@@ -49,21 +49,28 @@ struct GemmEpi {
   int act;        // 0 none, 1 gelu(erf), 2 relu, 3 relu6
   int out_f32;    // 0: bf16 output, 1: fp32 output
   int row_mode;   // 0 identity, 1 row_map, 2 pixel-shuffle 2x2 (ConvTranspose2d k=2 s=2)
-  int dbg;        // perf-debug switches (env MMSAM_GEMM_DBG): 1 skip stores, 4 skip the epilogue math too
+  int dbg;        // perf-debug switches (env MMSAM_GEMM_DBG): 1 skip stores, 2 skip the residual, 4 skip the epilogue math,
+                  // 8 skip the MMA issue, 16 skip the TMA loads
   int ps_h, ps_w, ps_c;
 };
 
-template <int BN> struct GemmCfg {
+enum { V_BF16 = 0, V_BF16_GELU = 1, V_BF16_MAP = 2, V_F32 = 3, V_GENERIC = 4, V_BF16_RES = 5 };
+// Variants whose residual block is streamed into a third slab with cp.async (see epilogue_fast).
+__host__ __device__ constexpr bool var_async_res(int var) { return var == V_BF16_MAP || var == V_BF16_RES; }
+
+template <int BN, int VAR = V_BF16> struct GemmCfg {
   static constexpr int BM = 128;            // rows per CTA (the pair computes 256)
   static constexpr int BK = 64;
   static constexpr int BNH = BN / 2;        // weight rows staged per CTA
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BNH * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 5 : (BN == 128 ? 6 : 8);
+  static constexpr bool ASYNC_RES = var_async_res(VAR);
+  // 227 KB: 5 x 32 KB operand stages + 2 output slabs per warp, or (residual ring) 4 stages + 3 slabs per warp
+  static constexpr int STAGES = ASYNC_RES ? (BN == 256 ? 4 : (BN == 128 ? 5 : 6)) : (BN == 256 ? 5 : (BN == 128 ? 6 : 8));
   static constexpr int NUM_EPI_WARPS = 8;
   static constexpr int SLAB_BYTES = 32 * 128;   // 32 rows x 128 B
-  static constexpr int SLABS_PER_WARP = 2;
+  static constexpr int SLABS_PER_WARP = ASYNC_RES ? 3 : 2;
   static constexpr int STAGING_BYTES = NUM_EPI_WARPS * SLABS_PER_WARP * SLAB_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -143,8 +150,6 @@ __device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-enum { V_BF16 = 0, V_BF16_GELU = 1, V_BF16_MAP = 2, V_F32 = 3, V_GENERIC = 4 };
-
 __device__ __forceinline__ float4 ldg4_guard(const float* p, int col, int N) {   // N % 4 == 0 on the fast paths
   return col < N ? __ldg(reinterpret_cast<const float4*>(p + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
@@ -210,26 +215,53 @@ __device__ __forceinline__ void epilogue_generic(const GemmEpi& ep, uint32_t tme
   }
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* src, int src_bytes) {   // L2 -> smem, no L1 line
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
 // Fast epilogues. One warp = one TMEM lane quadrant (32 accumulator rows) x one half of the BN columns, walked
-// in 128-byte-wide panels (64 bf16 / 32 fp32 columns). The residual block of the NEXT panel (possibly of the
-// next tile: the tile sequence is static) is fetched into registers while the current panel is computed.
+// in 128-byte-wide panels (64 bf16 / 32 fp32 columns); the panel sequence of a warp is static, so the residual
+// block of the NEXT panel (possibly of a later tile) is always in flight while the current one is computed:
+//   * V_BF16_RES / V_BF16_MAP: cp.async.cg straight into a two-slab ring (no L1 line, no registers: with ~225 KB
+//     of the SM's 228 KB carved out as shared memory the L1 can track only a handful of outstanding LDG misses,
+//     measured 2 TB/s) + a third slab for the output;
+//   * V_BF16 (large K: the epilogue has time): LDG into registers, two in-place slabs, one more operand stage.
+// A whole tile ahead every lane also pulls the 128-byte residual line of its own row into L2.
 template <int BN, int VAR>
 __device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorMap* tmC, uint32_t tmem_base, uint32_t slab0,
                                               uint64_t* tfull, uint64_t* tempty, int warp, int lane, uint32_t rank, int pair,
                                               int num_pairs, int num_tiles, int num_n) {
   constexpr bool F32 = VAR == V_F32;
   constexpr bool MAPPED = VAR == V_BF16_MAP;
+  constexpr bool ASYNC = var_async_res(VAR);
+  constexpr uint32_t SLAB = GemmCfg<BN, VAR>::SLAB_BYTES;
   constexpr int PC = F32 ? 32 : 64;                      // columns per 128-byte panel row
   constexpr int CPH = (BN / 2 >= PC) ? BN / 2 : PC;      // columns per warp-half
   constexpr int NPAN = CPH / PC;
   constexpr int EPC = F32 ? 4 : 8;                       // elements per 16-byte chunk
   const int quad = warp & 3, half = warp >> 2;
-  const bool active = half * CPH < BN;                   // BN == 64 with bf16 output: the second half has no panel
-  const bool has_res = !F32 && ep.residual != nullptr;
+  const bool has_res = !F32 && ep.residual != nullptr && !(ep.dbg & 2);
   const int c = lane & 7, rsub = lane >> 3;
-
+  if (half * CPH >= BN) {
+    // BN == 64 with bf16 output: the second column half has no panel; only hand the accumulators back
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      mbar_wait(&tfull[it & 1], (it >> 1) & 1);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[it & 1]), 0));
+    }
+    return;
+  }
+  auto first_col = [&](int t) { return (t % num_n) * BN + half * CPH; };
+  // first tile at or after t in which this warp has a panel
+  auto next_valid = [&](int t) {
+    while (t < num_tiles && first_col(t) >= ep.N) t += num_pairs;
+    return t;
+  };
   // destination row of this thread's accumulator row in tile t (mode 2: row of the (dy,dx)=(0,0) sub-pixel)
   auto dst_of = [&](int t) -> int {
+    if (t >= num_tiles) return -1;
     const int row = (t / num_n) * 256 + (int)rank * 128 + quad * 32 + lane;
     if (row >= ep.M) return -1;
     if (!MAPPED) return row;
@@ -244,32 +276,59 @@ __device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorM
   };
   uint4 rv[8];
   // coalesced fetch of a 32 x 128 B residual block: 8 lanes per row, 4 rows per instruction
-  auto issue_res = [&](int dst, int col0) {
+  auto issue_res = [&](int dst, int col0, uint32_t ring_slab) {
     const int colc = col0 + c * 8;
     int dcolc = colc, sub = 0;
     if (MAPPED && ep.row_mode == 2) { sub = colc / ep.ps_c; dcolc = colc - sub * ep.ps_c; }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      int d = __shfl_sync(0xffffffffu, dst, i * 4 + rsub);
+      const int rl = i * 4 + rsub;
+      int d = __shfl_sync(0xffffffffu, dst, rl);
       if (MAPPED && ep.row_mode == 2 && d >= 0) d += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
-      rv[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (d >= 0 && colc < ep.N) rv[i] = __ldg(reinterpret_cast<const uint4*>(ep.residual + (long long)d * ep.ldr + dcolc));
+      const bool ok = d >= 0 && colc < ep.N;
+      const __nv_bfloat16* src = ok ? ep.residual + (long long)d * ep.ldr + dcolc : ep.residual;
+      if constexpr (ASYNC) {
+        cp_async16(ring_slab + swz128(rl, c), src, ok ? 16 : 0);
+      } else {
+        rv[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) rv[i] = __ldg(reinterpret_cast<const uint4*>(src));
+      }
+    }
+    if constexpr (ASYNC) asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto prefetch_res_l2 = [&](int dst, int t) {
+    if (dst < 0) return;
+#pragma unroll
+    for (int pi = 0; pi < NPAN; ++pi) {
+      const int col0 = first_col(t) + pi * PC;
+      if (col0 >= ep.N) break;
+      long long d = dst;
+      int dcol = col0;
+      if (MAPPED && ep.row_mode == 2) {
+        const int sub = col0 / ep.ps_c;
+        dcol = col0 - sub * ep.ps_c;
+        d += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
+      }
+      const __nv_bfloat16* p = ep.residual + d * ep.ldr + dcol;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      if (reinterpret_cast<uintptr_t>(p) & 127) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 63));
     }
   };
 
-  int slab_sel = 0, it = 0;
-  int tile = pair;
-  int my_dst = (active && tile < num_tiles) ? dst_of(tile) : -1;
-  if (has_res && active && tile < num_tiles) {
-    const int col0 = (tile % num_n) * BN + half * CPH;
-    if (col0 < ep.N) issue_res(my_dst, col0);
+  int sel = 0, it = 0;     // sel: non-ASYNC: which in-place slab; ASYNC: which ring slab holds the current residual block
+  if (has_res) {
+    const int t0 = next_valid(pair);
+    if (t0 < num_tiles) issue_res(dst_of(t0), first_col(t0), slab0);
   }
-  for (; tile < num_tiles; tile += num_pairs, ++it) {
+  for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
     const int mp = tile / num_n, n_blk = tile % num_n;
     const int acc = it & 1;
-    const int next_tile = tile + num_pairs;
-    // issued now, first used when the last panel of this tile prefetches the next tile's residual / stores
-    const int my_dst_next = (active && next_tile < num_tiles) ? dst_of(next_tile) : -1;
+    const int my_dst = (MAPPED || has_res) ? dst_of(tile) : -1;
+    // the next tile in which this warp has work: its residual rows go to L2 now, its first block is requested
+    // by the last panel of this tile
+    const int nt = next_valid(tile + num_pairs);
+    const int my_dst_nt = has_res ? dst_of(nt) : -1;
+    if (has_res && nt < num_tiles && !(ep.dbg & 32)) prefetch_res_l2(my_dst_nt, nt);
     mbar_wait(&tfull[acc], (it >> 1) & 1);
     tc_fence_after();
     const uint32_t tempty_addr = mapa_shared(smem_u32(&tempty[acc]), 0);
@@ -280,130 +339,146 @@ __device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorM
       if (lane == 0) mbar_arrive_cluster(tempty_addr);
       released = true;
     };
-    if (active) {
-      const int row0 = mp * 256 + (int)rank * 128 + quad * 32;
-      const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+    const int row0 = mp * 256 + (int)rank * 128 + quad * 32;
+    const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
 #pragma unroll
-      for (int pi = 0; pi < NPAN; ++pi) {
-        const int col_l = half * CPH + pi * PC;
-        const int col0 = n_blk * BN + col_l;
-        if (col0 >= ep.N) break;                            // warp-uniform
-        const uint32_t slab = slab0 + (uint32_t)slab_sel * GemmCfg<BN>::SLAB_BYTES;
-        slab_sel ^= 1;
+    for (int pi = 0; pi < NPAN; ++pi) {
+      const int col_l = half * CPH + pi * PC;
+      const int col0 = n_blk * BN + col_l;
+      if (col0 >= ep.N) break;                            // warp-uniform
+      const bool more_here = pi + 1 < NPAN && col0 + PC < ep.N;
+      const bool have_next = has_res && (more_here || nt < num_tiles);
+      // rslab: where this panel's residual block is (or, register path, will be put); oslab: where the output goes
+      const uint32_t rslab = slab0 + (uint32_t)sel * SLAB;
+      const uint32_t oslab = ASYNC ? slab0 + 2 * SLAB : rslab;
+      const uint32_t nslab = slab0 + (uint32_t)(sel ^ 1) * SLAB;
+      sel ^= 1;
+      if constexpr (!ASYNC) {
         // the TMA store that last read this slab (two panels ago) must have drained it
-        if (!MAPPED && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
         if (has_res) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) sts128(slab + swz128(i * 4 + rsub, c), rv[i]);
-          // prefetch the next panel's residual block (same tile, or the first panel of the next tile)
-          if (pi + 1 < NPAN && col0 + PC < ep.N) issue_res(my_dst, col0 + PC);
-          else if (next_tile < num_tiles) {
-            const int ncol0 = (next_tile % num_n) * BN + half * CPH;
-            if (ncol0 < ep.N) issue_res(my_dst_next, ncol0);
-          }
+          for (int i = 0; i < 8; ++i) sts128(rslab + swz128(i * 4 + rsub, c), rv[i]);
         }
-        uint32_t r[PC / 32][32];
+      } else {
+        __syncwarp();                                     // every lane is done with the ring slab being refilled
+      }
+      if (have_next) {
+        if (more_here) issue_res(my_dst, col0 + PC, nslab);
+        else issue_res(my_dst_nt, first_col(nt), nslab);
+      }
+      uint32_t r[PC / 32][32];
 #pragma unroll
-        for (int cc = 0; cc < PC / 32; ++cc) tmem_ld_32x32b_x32(tmem_acc + col_l + cc * 32, r[cc]);
-        tmem_ld_wait();
-        if (pi == NPAN - 1 || col0 + PC >= ep.N) release();
-        if (has_res) __syncwarp();                          // residual block visible to the row owners
-        if (ep.dbg & 4) continue;
+      for (int cc = 0; cc < PC / 32; ++cc) tmem_ld_32x32b_x32(tmem_acc + col_l + cc * 32, r[cc]);
+      tmem_ld_wait();
+      if (!more_here) release();
+      if (has_res) {
+        if constexpr (ASYNC) {
+          if (have_next) asm volatile("cp.async.wait_group 1;" ::: "memory");
+          else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();                                     // residual block visible to the row owners
+      }
+      if (ep.dbg & 4) continue;
 
-        uint4 pk[8];
+      uint4 pk[8];
 #pragma unroll
-        for (int cc = 0; cc < PC / 32; ++cc) {
-          const int col = col0 + cc * 32;
-          float v[32];
+      for (int cc = 0; cc < PC / 32; ++cc) {
+        const int col = col0 + cc * 32;
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[cc][j]);
-          if (ep.bias) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[cc][j]);
+        if (ep.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = ldg4_guard(ep.bias, col + j, ep.N);
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-          if (VAR == V_BF16_GELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          } else if (ep.act == 2) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (ep.act == 3) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
-          }
-          if (ep.scale) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 s = ldg4_guard(ep.scale, col + j, ep.N);
-              v[j] *= s.x; v[j + 1] *= s.y; v[j + 2] *= s.z; v[j + 3] *= s.w;
-            }
-          }
-          if (has_res) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float f[8];
-              unpack8(lds128(slab + swz128(lane, cc * 4 + j)), f);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) v[8 * j + k] += f[k];
-            }
-          }
-          if constexpr (F32) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              pk[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
-                                 __float_as_uint(v[4 * j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) pk[cc * 4 + j] = pack8(v + 8 * j);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = ldg4_guard(ep.bias, col + j, ep.N);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
         }
-        // own accumulator row -> swizzled slab (conflict-free 16-byte stores)
+        if (VAR == V_BF16_GELU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sts128(slab + swz128(lane, j), pk[j]);
-        if constexpr (!MAPPED) {
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && !(ep.dbg & 1)) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                             reinterpret_cast<uint64_t>(tmC)),
-                         "r"(slab), "r"(col0), "r"(row0)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (ep.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (ep.act == 3) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
+        }
+        if (ep.scale) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 s = ldg4_guard(ep.scale, col + j, ep.N);
+            v[j] *= s.x; v[j + 1] *= s.y; v[j + 2] *= s.z; v[j + 3] *= s.w;
           }
+        }
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f[8];
+            unpack8(lds128(rslab + swz128(lane, cc * 4 + j)), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[8 * j + k] += f[k];
+          }
+        }
+        if constexpr (F32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            pk[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                               __float_as_uint(v[4 * j + 3]));
         } else {
-          __syncwarp();
-          // coalesced row segments: 8 lanes write one 128-byte row piece, 4 rows per instruction
-          const int colc = col0 + c * EPC;
-          int dcolc = colc, sub = 0;
-          if (ep.row_mode == 2) { sub = colc / ep.ps_c; dcolc = colc - sub * ep.ps_c; }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rl = i * 4 + rsub;
-            int d = __shfl_sync(0xffffffffu, my_dst, rl);
-            if (ep.row_mode == 2 && d >= 0) d += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
-            const uint4 val = lds128(slab + swz128(rl, c));
-            if (d >= 0 && colc < ep.N && !(ep.dbg & 1))
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)d * ep.ldo + dcolc) = val;
-          }
+          for (int j = 0; j < 4; ++j) pk[cc * 4 + j] = pack8(v + 8 * j);
         }
+      }
+      if constexpr (ASYNC && !MAPPED) {
+        // single output slab: the previous panel's TMA store (issued a whole panel ago) must have read it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
+      // own accumulator row -> swizzled slab (conflict-free 16-byte stores)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sts128(oslab + swz128(lane, j), pk[j]);
+      if constexpr (!MAPPED) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && !(ep.dbg & 1)) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(tmC)),
+                       "r"(oslab), "r"(col0), "r"(row0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {
+        __syncwarp();
+        // coalesced row segments: 8 lanes write one 128-byte row piece, 4 rows per instruction
+        const int colc = col0 + c * EPC;
+        int dcolc = colc, sub = 0;
+        if (ep.row_mode == 2) { sub = colc / ep.ps_c; dcolc = colc - sub * ep.ps_c; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + rsub;
+          int d = __shfl_sync(0xffffffffu, my_dst, rl);
+          if (ep.row_mode == 2 && d >= 0) d += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
+          const uint4 val = lds128(oslab + swz128(rl, c));
+          if (d >= 0 && colc < ep.N && !(ep.dbg & 1))
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)d * ep.ldo + dcolc) = val;
+        }
+        __syncwarp();                                     // the output slab is rewritten by the next panel
       }
     }
     if (!released) release();
-    my_dst = my_dst_next;
   }
   if (!MAPPED && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's TMA stores are complete
   __syncwarp();
 }
 
 template <int BN, int VAR>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmCfg<BN>::THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmCfg<BN, VAR>::THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmEpi ep) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, VAR>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from the __shared__ array (so loads compile to LDS, not generic LD)
@@ -517,7 +592,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BN, int VAR>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmEpi& ep,
                        int max_ctas, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, VAR>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -596,14 +671,20 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
 
   int bn = block_n;
   if (bn != 64 && bn != 128 && bn != 256) {
-    // auto: widest tile that still gives every SM pair a tile, then prefer the least padded N
+    // auto: waves x per-k-step cost. Measured per k-step (64 deep) on a pair: BN=256 is MMA-bound (512 cycles),
+    // BN=128 / 64 are bound by the L2 -> SM operand traffic (~0.8 / ~0.7 of that), so narrower tiles only pay
+    // when they remove waves or padded columns.
     const long long num_mp = (M + 255) / 256;
-    const int pairs = kNumSMs / 2;
+    const long long pairs = kNumSMs / 2;
+    double best = 1e30;
+    const int cand[3] = {256, 128, 64};
+    const double tcost[3] = {1.0, 0.8, 0.7};
     bn = 256;
-    if (N <= 64) bn = 64;
-    else if (N <= 128) bn = 128;
-    else if (num_mp * ((N + 255) / 256) < pairs && num_mp * ((N + 127) / 128) >= num_mp * ((N + 255) / 256) * 2 - 1) bn = 128;
-    if (bn == 256 && (N % 256) != 0 && (N % 256) <= 128 && N < 1024) bn = 128;
+    for (int i = 0; i < 3; ++i) {
+      const long long tiles = num_mp * ((N + cand[i] - 1) / cand[i]);
+      const double cost = (double)((tiles + pairs - 1) / pairs) * tcost[i];
+      if (cost < best - 1e-9) { best = cost; bn = cand[i]; }
+    }
   }
   // epilogue variant: fast paths need 16-byte aligned rows and whole 16-byte chunks
   const int oelt = out_f32 ? 4 : 2;
@@ -613,7 +694,9 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
     var = V_GENERIC;
   else if (out_f32) var = V_F32;
   else if (row_mode != 0) var = V_BF16_MAP;
-  else var = act == 1 ? V_BF16_GELU : V_BF16;
+  else if (act == 1 && !residual) var = V_BF16_GELU;
+  else if (act == 1) var = V_GENERIC;
+  else var = (residual && K <= 2048) ? V_BF16_RES : V_BF16;   // long K: the epilogue has time, keep the 5th stage
   if (var == V_GENERIC) bn = 128;   // the general epilogue is instantiated for one tile width only
   CUtensorMap tmA, tmB;
   int rc = mmsam_host::make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64);
@@ -627,7 +710,7 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
   { const char* d = getenv("MMSAM_GEMM_DBG"); ep.dbg = d ? atoi(d) : 0; }
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tmC = tmA;
-  if (var == V_BF16 || var == V_BF16_GELU || var == V_F32) {
+  if (var == V_BF16 || var == V_BF16_GELU || var == V_F32 || var == V_BF16_RES) {
     // output tensor map for the per-warp TMA tensor stores: box = one 32-row x 128-byte slab
     mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
     cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
@@ -644,6 +727,7 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
     case V_BF16_GELU: return launch_gemm_bn<V_BF16_GELU>(bn, tmA, tmB, tmC, ep, max_ctas, st);
     case V_BF16_MAP: return launch_gemm_bn<V_BF16_MAP>(bn, tmA, tmB, tmC, ep, max_ctas, st);
     case V_F32: return launch_gemm_bn<V_F32>(bn, tmA, tmB, tmC, ep, max_ctas, st);
+    case V_BF16_RES: return launch_gemm_bn<V_BF16_RES>(bn, tmA, tmB, tmC, ep, max_ctas, st);
     default: return launch_gemm<128, V_GENERIC>(tmA, tmB, tmC, ep, max_ctas, st);
   }
 }

@@ -214,6 +214,63 @@ def test_gemm_pixel_shuffle():
     assert (out - ref).abs().max() < 2e-3
 
 
+@pytest.mark.parametrize("M,N,K,bn", [
+    (1000, 384, 1536, 256),    # last n-tile half empty: some epilogue warps have no panel in odd tiles
+    (700, 1024, 256, 0), (4173, 384, 64, 128), (300, 64, 128, 64), (520, 1024, 4096, 256), (33000, 384, 96, 0),
+    (20000, 1024, 512, 0),
+])
+def test_gemm_bf16_residual_paths(M, N, K, bn):
+    """bf16 output + bias + per-channel scale + residual through both residual pipelines (cp.async ring for
+    K <= 2048, register prefetch above), ragged M / N tiles, every tile width."""
+    k = _k()
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    scale = torch.rand(N, generator=g) + 0.5
+    res = torch.randn(M, N, generator=g).to(torch.bfloat16)
+    out = k.gemm(a.cuda(), w.cuda(), bias=bias.cuda(), scale=scale.cuda(), residual=res.cuda(), block_n=bn).cpu().double()
+    ref = _gemm_ref(a, w, bias, None, scale, res)
+    assert ((out - ref).abs() <= 0.008 * ref.abs() + 4e-3).all(), (out - ref).abs().max().item()
+
+
+def test_gemm_pixel_shuffle_bf16_residual():
+    """`up(c2) + c1` (..._new.py:324-325) as one GEMM: pixel-shuffle store with the residual read at the destination."""
+    k = _k()
+    B, H, W, Cin, Cout = 2, 16, 12, 128, 64
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(Cin, Cout, 2, 2, generator=g) / 8).to(torch.bfloat16)
+    bias = torch.randn(Cout, generator=g)
+    res = torch.randn(B * 4 * H * W, Cout, generator=g).to(torch.bfloat16)
+    ref = torch.nn.functional.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, stride=2)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, Cout).double() + res.double()
+    wg = wt.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).contiguous()
+    out = k.gemm(x.reshape(-1, Cin).cuda(), wg.cuda(), bias=bias.repeat(4).cuda(), residual=res.cuda(),
+                 pixel_shuffle=(H, W)).cpu().double()
+    assert ((out - ref).abs() <= 0.008 * ref.abs() + 4e-3).all()
+
+
+def test_gemm_row_map_big():
+    """Row-mapped store (c2|c3|c4 packing, window un-partition) over many tiles, with and without residual."""
+    k = _k()
+    M, N, K = 5000, 512, 192
+    g = torch.Generator().manual_seed(6)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    rm = torch.randperm(M + 300, generator=g)[:M].to(torch.int32)
+    rm[::11] = -1
+    res = torch.randn(M + 300, N, generator=g).to(torch.bfloat16)
+    ref = _gemm_ref(a, w)
+    for use_res in (False, True):
+        out = torch.full((M + 300, N), 3.0, dtype=torch.bfloat16, device="cuda")
+        k.gemm(a.cuda(), w.cuda(), residual=res.cuda() if use_res else None, out=out, row_map=rm.cuda())
+        exp = torch.full((M + 300, N), 3.0, dtype=torch.float64)
+        keep = rm >= 0
+        exp[rm[keep].long()] = ref[keep] + (res.double()[rm[keep].long()] if use_res else 0)
+        assert ((out.cpu().double() - exp).abs() <= 0.008 * exp.abs() + 4e-3).all()
+
+
 @pytest.mark.parametrize("Bp,nh,Kh,Kw,bias", [
     (2, 2, 14, 14, True),     # SAM window (196 keys, ragged 2nd key block)
     (1, 2, 16, 16, True),     # 256 tokens, two full key blocks

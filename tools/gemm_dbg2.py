@@ -8,6 +8,11 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     from mmsam_b200 import kernels as K
     shapes = ((32768, 3072, 1024, None, False), (32768, 4096, 1024, "gelu", False), (32768, 1024, 4096, None, True),
               (32768, 1536, 384, "gelu", False), (32768, 384, 1536, None, True))
+    if os.environ.get("SHAPES"):   # "M,N,K,act,res;..."
+        shapes = []
+        for t in os.environ["SHAPES"].split(";"):
+            m, n, k, act, res = t.split(",")
+            shapes.append((int(m), int(n), int(k), None if act in ("", "none") else act, res == "1"))
     bns = [int(x) for x in os.environ.get("BNS", "256,128").split(",")]
     for (M, N, Kd, act, res) in shapes:
         a = torch.randn(M, Kd, device="cuda").to(torch.bfloat16)
