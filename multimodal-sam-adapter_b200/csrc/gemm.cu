@@ -671,18 +671,33 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
 
   int bn = block_n;
   if (bn != 64 && bn != 128 && bn != 256) {
-    // auto: waves x per-k-step cost. Measured per k-step (64 deep) on a pair: BN=256 is MMA-bound (512 cycles),
-    // BN=128 / 64 are bound by the L2 -> SM operand traffic (~0.8 / ~0.7 of that), so narrower tiles only pay
-    // when they remove waves or padded columns.
+    // auto: per pair-tile cost = max(main loop, epilogue) summed over the n-tiles of a row block, times the wave
+    // quantisation. Units: one 64-deep k-step of a BN=256 tile (MMA-bound, 512 cycles). Narrower tiles are bound by
+    // the L2 -> SM operand traffic (~0.8 / ~0.7 of that per k-step); an epilogue panel (32 rows x 128 B per warp)
+    // costs ~3 units with GELU, ~2 with a residual, ~1.4 plain, and a ragged last n-tile leaves warps idle.
     const long long num_mp = (M + 255) / 256;
     const long long pairs = kNumSMs / 2;
+    const double kb = (double)((K + 63) / 64);
+    const double e = act == 1 ? 3.0 : (residual ? 2.0 : 1.4);
+    const int pc = out_f32 ? 32 : 64;
     double best = 1e30;
     const int cand[3] = {256, 128, 64};
     const double tcost[3] = {1.0, 0.8, 0.7};
     bn = 256;
     for (int i = 0; i < 3; ++i) {
-      const long long tiles = num_mp * ((N + cand[i] - 1) / cand[i]);
-      const double cost = (double)((tiles + pairs - 1) / pairs) * tcost[i];
+      const int nn = (N + cand[i] - 1) / cand[i];
+      const int cph = cand[i] / 2 >= pc ? cand[i] / 2 : pc;
+      double per_mp = 0;
+      for (int nb = 0; nb < nn; ++nb) {
+        int cols = N - nb * cand[i];
+        if (cols > cph) cols = cph;                  // columns of the busiest warp (half 0)
+        const double pan = (double)((cols + pc - 1) / pc);
+        const double ml = kb * tcost[i];
+        per_mp += ml > pan * e ? ml : pan * e;
+      }
+      const long long tiles = num_mp * nn;
+      const double quant = (double)((tiles + pairs - 1) / pairs) * (double)pairs / (double)tiles;
+      const double cost = per_mp * quant;
       if (cost < best - 1e-9) { best = cost; bn = cand[i]; }
     }
   }
