@@ -17,6 +17,8 @@
 //  * msda_generic_kernel - any D / dtype (incl. fp64), one thread per output element; used for the
 //    reference's own known-answer shapes (D = 2) and as the catch-all.
 #include "common.cuh"
+#include <cstdlib>
+#include <type_traits>
 
 namespace mmsam {
 
@@ -281,6 +283,115 @@ msda_fused_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shap
   Vec16<VT>::store(out + (row * M + m) * D + chunk * VEC, acc);
 }
 
+// Cooperative fused kernel for the hot shapes (bf16, D = 32, P = 4, L <= 4): a warp owns ONE query x 8 heads,
+// the 4 lanes of a head are (a) the 4 sampling points of a level while locations / softmax weights are computed
+// (one point per lane, softmax statistics by two width-4 shuffles) and (b) the 4 16-byte channel chunks while
+// gathering (each point's base index + 4 corner weights are broadcast inside the 4-lane group). Compared with
+// msda_fused_kernel (every lane recomputes all points of its head): the query-projection row is read as
+// contiguous 256 B / 128 B pieces (3 L1 wavefronts per level instead of ~70), 4x less address arithmetic, and
+// the gathers are branch-free (clamped indices, zero weights outside the map). The kernel then sits on the SM's
+// gather rate for 64-byte units (tools/micro/gather_bench.cu: ~1.6 cycles per unit, L1 hit or L2 hit alike).
+template <int MAXL>
+__global__ void __launch_bounds__(256)
+msda_fused_coop_kernel(const __nv_bfloat16* __restrict__ value, const int64_t* __restrict__ shapes,
+                       const int64_t* __restrict__ lsi, const float* __restrict__ qproj, long long ldq,
+                       const float* __restrict__ ref, __nv_bfloat16* __restrict__ out, int S, int M, int Lq, int L) {
+  constexpr int P = 4, D = 32;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, pl = lane & 3;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n = blockIdx.z;
+  const int m = blockIdx.y * 8 + g;
+  if (q >= Lq) return;                       // warp-uniform
+  const bool head_ok = m < M;
+  const int mc = head_ok ? m : M - 1;        // inactive head groups shadow the last head, their store is skipped
+  const long long row = (long long)n * Lq + q;
+  const float* offp = qproj + row * ldq + (long long)mc * L * P * 2;
+  const float* lgp = qproj + row * ldq + (long long)M * L * P * 2 + (long long)mc * L * P;
+  const float rx = __ldg(ref + 2 * q), ry = __ldg(ref + 2 * q + 1);
+  const long long rs = (long long)M * D;
+  const __nv_bfloat16* vbase = value + (long long)n * S * rs + (long long)mc * D + pl * 8;
+
+  // this lane's point of every level: logits -> softmax over the L*P points of the head
+  float lg[MAXL];
+  float2 of[MAXL];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int l = 0; l < MAXL; ++l) {
+    lg[l] = -INFINITY;
+    of[l] = make_float2(0.f, 0.f);
+    if (l < L) {
+      lg[l] = __ldg(lgp + l * P + pl);
+      of[l] = __ldg(reinterpret_cast<const float2*>(offp + (l * P + pl) * 2));
+      mx = fmaxf(mx, lg[l]);
+    }
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  float den = 0.f;
+#pragma unroll
+  for (int l = 0; l < MAXL; ++l) {
+    lg[l] = l < L ? __expf(lg[l] - mx) : 0.f;
+    den += lg[l];
+  }
+  den += __shfl_xor_sync(0xffffffffu, den, 1);
+  den += __shfl_xor_sync(0xffffffffu, den, 2);
+  const float inv = 1.f / den;
+
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int l = 0; l < MAXL; ++l) {
+    if (l < L) {
+      const int H = (int)__ldg(shapes + 2 * l), W = (int)__ldg(shapes + 2 * l + 1);
+      const __nv_bfloat16* vl = vbase + (long long)__ldg(lsi + l) * rs;
+      // my point: same arithmetic as the reference (loc = ref + off / (W, H); im = loc * size - 0.5)
+      const float h_im = (ry + of[l].y / H) * H - 0.5f, w_im = (rx + of[l].x / W) * W - 0.5f;
+      const bool inside = h_im > -1.f && w_im > -1.f && h_im < H && w_im < W;
+      const float hf = floorf(h_im), wf = floorf(w_im);
+      const int h0 = (int)hf, w0 = (int)wf;
+      const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+      const float aw = inside ? lg[l] * inv : 0.f;
+      const bool t0 = h0 >= 0, b0 = h0 + 1 <= H - 1, l0 = w0 >= 0, r0 = w0 + 1 <= W - 1;
+      float c1 = (t0 && l0) ? aw * hh * hw : 0.f, c2 = (t0 && r0) ? aw * hh * lw : 0.f;
+      float c3 = (b0 && l0) ? aw * lh * hw : 0.f, c4 = (b0 && r0) ? aw * lh * lw : 0.f;
+      // clamped corner indices: every gather reads valid memory, invalid corners carry a zero weight
+      const int h0c = min(max(h0, 0), H - 1), h1c = min(max(h0 + 1, 0), H - 1);
+      const int w0c = min(max(w0, 0), W - 1), w1c = min(max(w0 + 1, 0), W - 1);
+      int i00 = inside ? h0c * W + w0c : 0;
+      int dflag = inside ? ((w1c - w0c) | ((h1c - h0c) << 1)) : 0;
+#pragma unroll
+      for (int pp = 0; pp < P; ++pp) {
+        const int bi = __shfl_sync(0xffffffffu, i00, pp, 4);
+        const int bf = __shfl_sync(0xffffffffu, dflag, pp, 4);
+        const float k1 = __shfl_sync(0xffffffffu, c1, pp, 4), k2 = __shfl_sync(0xffffffffu, c2, pp, 4);
+        const float k3 = __shfl_sync(0xffffffffu, c3, pp, 4), k4 = __shfl_sync(0xffffffffu, c4, pp, 4);
+        const __nv_bfloat16* p00 = vl + (long long)bi * rs;
+        const long long dx = (bf & 1) ? rs : 0, dy = (bf & 2) ? (long long)W * rs : 0;
+        const uint4 u00 = __ldg(reinterpret_cast<const uint4*>(p00));
+        const uint4 u01 = __ldg(reinterpret_cast<const uint4*>(p00 + dx));
+        const uint4 u10 = __ldg(reinterpret_cast<const uint4*>(p00 + dy));
+        const uint4 u11 = __ldg(reinterpret_cast<const uint4*>(p00 + dy + dx));
+        float v[8];
+        unpack8(u00, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(k1, v[i], acc[i]);
+        unpack8(u01, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(k2, v[i], acc[i]);
+        unpack8(u10, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(k3, v[i], acc[i]);
+        unpack8(u11, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(k4, v[i], acc[i]);
+      }
+    }
+  }
+  if (head_ok) *reinterpret_cast<uint4*>(out + (row * M + m) * D + pl * 8) = pack8(acc);
+}
+
 template <typename VT, typename AT>
 static int launch_msda(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
                        const void* attw, void* out, int N, int S, int M, int D, int Lq, int L, int P,
@@ -358,6 +469,17 @@ MMSAM_API int mmsam_msda_fused_bf16(const void* value, const int64_t* spatial_sh
   if (!value || !spatial_shapes_dev || !level_start_index_dev || !qproj || !ref_xy || !out) return MMSAM_ERR_BAD_ARG;
   if ((D & 7) || D / 8 > 32 || P != 4 || (((uintptr_t)value | (uintptr_t)out) & 15) || (((uintptr_t)qproj) & 7) || (ldq & 1))
     return MMSAM_ERR_UNSUPPORTED;
+  if (D == 32 && L <= 4 && !getenv("MMSAM_MSDA_LEGACY")) {
+    dim3 grid((Lq + 7) / 8, (M + 7) / 8, N);
+    if (L <= 1)
+      msda_fused_coop_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)value, spatial_shapes_dev,
+          level_start_index_dev, qproj, ldq, ref_xy, (__nv_bfloat16*)out, S, M, Lq, L);
+    else
+      msda_fused_coop_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)value, spatial_shapes_dev,
+          level_start_index_dev, qproj, ldq, ref_xy, (__nv_bfloat16*)out, S, M, Lq, L);
+    MMSAM_LAUNCH_CHECK();
+    return MMSAM_OK;
+  }
   const int TPP = D / 8;
   int HB = (M % 2 == 0) ? 2 : 1;
   int QB = 256 / (HB * TPP);

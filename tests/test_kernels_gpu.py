@@ -88,6 +88,38 @@ def test_msda_unit_scale_and_small_scale():
             assert (out - ref).abs().max() < 1e-3
 
 
+@pytest.mark.parametrize("N,M,Lq,shapes,spread", [
+    (2, 16, 256, [(32, 32), (16, 16), (8, 8)], 3.0),      # injector-like: 3 levels
+    (2, 16, 1344, [(16, 16)], 3.0),                        # extractor-like: 1 level
+    (1, 12, 77, [(19, 25), (10, 13)], 6.0),                # ViT-B head count (not a multiple of 8), non-square, ragged
+    (1, 16, 50, [(9, 7)], 40.0),                           # most samples outside the map
+])
+def test_msda_fused_vs_oracle(N, M, Lq, shapes, spread):
+    """Fused entry point (softmax over L*P logits + loc = ref + off / (W, H) in the kernel,
+    ops/modules/ms_deform_attn.py:108-127) against the oracle fed the materialised locations / weights."""
+    from oracle.msda import ms_deform_attn_core
+    k = _k()
+    D, P = 32, 4
+    L = len(shapes)
+    g = torch.Generator().manual_seed(N * 1000 + M * 10 + Lq)
+    shapes_t = torch.as_tensor(shapes, dtype=torch.long)
+    S = int(shapes_t.prod(1).sum())
+    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+    value = torch.randn(N, S, M * D, generator=g).to(torch.bfloat16)
+    ref = torch.rand(Lq, 2, generator=g)
+    pad = 6                                                # qproj rows carry extra columns (ldq > M*L*P*3, even)
+    qproj = torch.randn(N * Lq, M * L * P * 3 + pad, generator=g)
+    qproj[:, :M * L * P * 2] *= spread
+    off = qproj[:, :M * L * P * 2].view(N, Lq, M, L, P, 2)
+    logits = qproj[:, M * L * P * 2:M * L * P * 3].view(N, Lq, M, L * P)
+    norm = torch.stack([shapes_t[:, 1], shapes_t[:, 0]], -1).float()          # (W, H)
+    loc = ref[None, :, None, None, None, :] + off / norm[None, None, None, :, None, :]
+    aw = torch.softmax(logits, -1).view(N, Lq, M, L, P)
+    exp = ms_deform_attn_core(value.float().view(N, S, M, D), shapes_t, loc, aw)
+    out = k.msda_fused(value.cuda(), shapes_t.cuda(), lsi.cuda(), qproj.cuda(), ref.cuda(), M, L, P).cpu().float()
+    assert (out - exp).abs().max() < 1e-3 + 0.008 * exp.abs().max()          # one bf16 rounding of the output
+
+
 def test_msda_empty():
     k = _k()
     shapes = torch.as_tensor([(4, 4)], dtype=torch.long).cuda()
