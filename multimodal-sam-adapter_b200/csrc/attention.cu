@@ -10,16 +10,18 @@
 // (Kh,Kw) = (14,14) — the zero-padded window tokens are ordinary keys (no masking, image_encoder.py
 // :504-526); global blocks with Bp = B, T = H*W.
 //
-// One CTA per SM, persistent over (batch', head, 128-query tile); 6 warps:
-//   warp 4  TMA producer: Q tile, K/V 128-key blocks (SWIZZLE_128B boxes straight out of the
+// One CTA per SM, persistent over (batch', head, 128-query tile); 10 warps:
+//   warp 8  TMA producer: Q tile, K/V 128-key blocks (SWIZZLE_128B boxes straight out of the
 //           [Bp,T,3,nh,64] qkv GEMM output through a 4-D tensor map), rel-pos tables once per CTA.
-//   warp 5  MMA issuer: G = Q.table^T (bias pre-products), S_j = Q.K_j^T into a double-buffered
-//           TMEM tile, O_j = P_j.V_j (V as an MN-major operand) into a third TMEM tile.
-//   warps 0-3  softmax: thread = query row (tcgen05.ld 32x32b). Scatter G into per-row bias rows in
-//           shared memory (Toeplitz gather), then per key block: t = S*scale + bias, online max /
-//           sum in base 2, P -> bf16 into the swizzled K-major smem tile for the PV MMA, and the
-//           running output is rescaled/accumulated in registers (no TMEM read-modify-write).
+//   warp 9  MMA issuer: G = Q.table^T (bias pre-products), S_j = Q.K_j^T into a double-buffered
+//           TMEM tile, O_half += P_j[:, half].V_j[half] (V as an MN-major operand) into two TMEM accumulators.
+//   warps 0-7  softmax: thread = query row (tcgen05.ld 32x32b), warps w / w+4 split each key block in halves
+//           with independent online-softmax state. Scatter G into per-row bias rows in shared memory (Toeplitz
+//           gather), then per key block: t = S*scale + bias, max / sum in base 2, P -> bf16 into the swizzled
+//           K-major smem panel of the half. The output accumulates in TMEM across key blocks and is rescaled
+//           only when a row maximum grows by more than 2^8 (lazy rescale); halves are merged per tile.
 #include "common.cuh"
+#include <type_traits>
 
 namespace mmsam {
 
@@ -46,18 +48,81 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-static constexpr int TM_S = 0;      // 2 x 128
-static constexpr int TM_PV = 256;   // 64
-static constexpr int TM_G = 320;    // 128
+static constexpr int TM_S = 0;      // 2 x 128: double-buffered score tile
+static constexpr int TM_O = 256;    // 2 x 64: output accumulators of the two key halves
+static constexpr int TM_G = 384;    // 128: bias pre-products
+static constexpr float kRescaleThreshold = 8.f;   // log2 units: P stays <= 256 with a stale row maximum
+
+// scale + bias + row maximum of this warp's 64 key columns [k0h, k0h + 64) of the score row
+template <int KW>
+__device__ __forceinline__ float add_bias_max(float (&t)[64], int k0h, const float* bh, const float* bw, bool has_bias,
+                                              float scale_log2, int Kh, int Kw) {
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  if (!has_bias) {
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+      t[c] *= scale_log2;
+      mx[c & 3] = fmaxf(mx[c & 3], t[c]);
+    }
+  } else if (KW == 64) {
+    const float bhv = bh[k0h >> 6];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+      t[c] = fmaf(t[c], scale_log2, bhv + bw[c]);
+      mx[c & 3] = fmaxf(mx[c & 3], t[c]);
+    }
+  } else if (KW == 32) {
+    const float b0 = bh[k0h >> 5], b1 = bh[(k0h >> 5) + 1];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+      t[c] = fmaf(t[c], scale_log2, (c < 32 ? b0 : b1) + bw[c & 31]);
+      mx[c & 3] = fmaxf(mx[c & 3], t[c]);
+    }
+  } else if (KW == 14) {
+    // SAM window (14 x 14 keys): k0h is 0, 64, 128 or 192 -> (kh, kw) of every column are compile-time constants
+    auto body = [&](auto k0c) {
+      constexpr int K0 = decltype(k0c)::value;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        constexpr int dummy = 0; (void)dummy;
+        const int key = K0 + c;
+        if (key < 196) {
+          t[c] = fmaf(t[c], scale_log2, bh[key / 14] + bw[key % 14]);
+          mx[c & 3] = fmaxf(mx[c & 3], t[c]);
+        }
+      }
+    };
+    switch (k0h >> 6) {
+      case 0: body(std::integral_constant<int, 0>{}); break;
+      case 1: body(std::integral_constant<int, 64>{}); break;
+      case 2: body(std::integral_constant<int, 128>{}); break;
+      default: body(std::integral_constant<int, 192>{}); break;
+    }
+  } else {
+    // generic grid: branch-free running (kh, kw)
+    int kh = k0h / Kw, kw = k0h - kh * Kw;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+      const int khc = kh < Kh ? kh : Kh - 1;
+      t[c] = fmaf(t[c], scale_log2, bh[khc] + bw[kw]);
+      mx[c & 3] = fmaxf(mx[c & 3], t[c]);
+      ++kw;
+      const bool wrap = kw == Kw;
+      kw = wrap ? 0 : kw;
+      kh += wrap ? 1 : 0;
+    }
+  }
+  return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+}
 
 template <int KW>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTabH,
                  const __grid_constant__ CUtensorMap tmTabW, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from the __shared__ array (so loads compile to LDS, not generic LD)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // layout: Q | KV stages | P (2 panels) | tables | bias rows | barriers
+  // layout: Q | KV stages | P (2 panels) | tables | bias rows | (m, l) exchange | barriers
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + TILE_BYTES;
   uint8_t* sP = sKV + p.kv_stages * 2 * TILE_BYTES;
@@ -67,7 +132,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   const int bh_stride = p.bh_stride, bw_stride = p.bw_stride;  // row-private rows, stride chosen odd
   float* sBh = sBias;
   float* sBw = sBias + ATT_BM * bh_stride;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBw + ((ATT_BM * bw_stride + 3) & ~3));
+  float* sML = sBw + ((ATT_BM * bw_stride + 3) & ~3);          // [2 halves][128 rows][m, l]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sML + 2 * ATT_BM * 2);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
   uint64_t* g_full = bars + 2;
@@ -88,22 +154,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   const int nch_h = has_bias ? (p.nh_pad + 127) / 128 : 0;
   const int nch_w = has_bias ? (p.nw_pad + 127) / 128 : 0;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
-    mbar_init(g_empty, 4);
-    mbar_init(p_full, 4);
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
+    mbar_init(g_empty, 8);
+    mbar_init(p_full, 8);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
     for (int i = 0; i < 3; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       if (has_bias) {
@@ -142,7 +208,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, ATT_BN, 0, 0);
@@ -154,7 +220,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       uint32_t g = 0;                     // global key-block counter (S buffer parity)
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t p_addr = smem_u32(sP);
-      auto issue_pv = [&](int stage) {
+      // O_half (+)= P[:, half] . V[half]: keys 0..63 of the block accumulate into O_a, keys 64..127 into O_b,
+      // across all key blocks of the tile (the first block overwrites)
+      auto issue_pv = [&](int stage, bool first) {
         mbar_wait(p_full, pph);
         pph ^= 1;
         tc_fence_after();
@@ -163,7 +231,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         for (int kk = 0; kk < ATT_BN / 16; ++kk) {
           const uint32_t a = p_addr + (kk >> 2) * TILE_BYTES + (kk & 3) * 32;
           const uint32_t b = v_addr + kk * 16 * 128;
-          umma_f16_ss(tmem + TM_PV, umma_desc_sw128(a), umma_desc_sw128(b), idesc_pv, kk != 0 ? 1u : 0u);
+          umma_f16_ss(tmem + TM_O + (kk >> 2) * ATT_D, umma_desc_sw128(a), umma_desc_sw128(b), idesc_pv,
+                      (first && (kk & 3) == 0) ? 0u : 1u);
         }
         umma_commit(pv_done);
         umma_commit(&kv_empty[stage]);
@@ -203,18 +272,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           if (j == nkb - 1) umma_commit(q_empty);
           if (++st == p.kv_stages) { st = 0; kph ^= 1; }
           if (j >= 1) {
-            issue_pv(st_pv);
+            issue_pv(st_pv, j == 1);
             if (++st_pv == p.kv_stages) st_pv = 0;
           }
         }
-        issue_pv(st_pv);
+        issue_pv(st_pv, nkb == 1);
         if (++st_pv == p.kv_stages) st_pv = 0;
       }
     }
   } else {
-    // =========================== softmax / output (warps 0..3) ===========================
-    const int row = warp * 32 + lane;  // TMEM lane == query row within the tile
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    // =========================== softmax / output (warps 0..7) ===========================
+    // Warps w and w+4 share TMEM lane quadrant w&3 (thread = query row) and split every 128-key block: half 0
+    // takes keys 0..63, half 1 keys 64..127, each as an INDEPENDENT online softmax with its own row maximum /
+    // sum and its own output accumulator in TMEM (O_a / O_b, accumulated by the tensor core across key blocks).
+    // The two halves are merged once per tile. Two softmax warps per scheduler hide each other's MUFU / TMEM /
+    // shared-memory latency; the accumulator is only touched when a row maximum grows by more than 2^8.
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;  // TMEM lane == query row within the tile
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     float* bh = sBh + row * bh_stride;
     float* bw = sBw + row * bw_stride;
     uint32_t gph = 0, pvph = 0;
@@ -225,7 +300,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       const int head = bhid % p.nh, bp = bhid / p.nh;
       const int q = qb * ATT_BM + row;
       const int qh = q / p.Kw, qw = q - qh * p.Kw;
-      // ---- scatter the bias pre-products into this row's bias rows (pre-scaled by log2 e) ----
+      // ---- scatter the bias pre-products into this row's bias rows (pre-scaled by log2 e); the two halves
+      //      take alternate 16-column groups ----
       for (int ci = 0; ci < nch_h + nch_w; ++ci) {
         const bool is_w = ci >= nch_h;
         const int c0 = (is_w ? ci - nch_h : ci) * 128;
@@ -237,7 +313,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         mbar_wait(g_full, gph);
         gph ^= 1;
         tc_fence_after();
-        for (int c = 0; c < n; c += 16) {
+        for (int c = half * 16; c < n; c += 32) {
           uint32_t r[16];
           __syncwarp();
           tmem_ld_32x32b_x16(lane_addr + TM_G + c, r);
@@ -252,150 +328,113 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(g_empty);
       }
-      float acc[ATT_D];
-#pragma unroll
-      for (int i = 0; i < ATT_D; ++i) acc[i] = 0.f;
-      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+      if (has_bias) asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // both halves' bias entries are in place
+      float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nkb; ++j, ++g) {
-        // ---- 1. scores of key block j ----
+        // ---- 1. this half's 64 score columns of key block j ----
         mbar_wait(&s_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
-        float t[ATT_BN];
-#pragma unroll
-        for (int c = 0; c < ATT_BN; c += 32) {
-          __syncwarp();
-          tmem_ld_32x32b_x32(lane_addr + TM_S + (g & 1) * ATT_BN + c, reinterpret_cast<uint32_t*>(t + c));
-        }
+        float t[64];
+        __syncwarp();
+        tmem_ld_32x32b_x32(lane_addr + TM_S + (g & 1) * ATT_BN + half * 64, reinterpret_cast<uint32_t*>(t));
+        tmem_ld_32x32b_x32(lane_addr + TM_S + (g & 1) * ATT_BN + half * 64 + 32, reinterpret_cast<uint32_t*>(t + 32));
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[g & 1]);
-        const int k0 = j * ATT_BN;
-        const int nvalid = p.T - k0 < ATT_BN ? p.T - k0 : ATT_BN;
-        // 4 independent max / sum chains: with one softmax warp per scheduler the dependent-issue
-        // latency is otherwise fully exposed.
-        float mx[4] = {m_run, -INFINITY, -INFINITY, -INFINITY};
-        if (!has_bias) {
+        const int k0h = j * ATT_BN + half * 64;
+        int nvalid = p.T - k0h;
+        nvalid = nvalid < 0 ? 0 : (nvalid > 64 ? 64 : nvalid);
+        float m_blk = add_bias_max<KW>(t, k0h, bh, bw, has_bias, p.scale_log2, p.Kh, p.Kw);
+        if (nvalid < 64) {  // ragged last key block: keys >= T do not exist
+          m_blk = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < ATT_BN; ++c) {
-            t[c] *= p.scale_log2;
-            mx[c & 3] = fmaxf(mx[c & 3], t[c]);
-          }
-        } else if (KW == 64 || KW == 32) {
-          // key grid width divides the key block: (kh, kw) of column c are compile-time constants
-          const int kh0 = k0 / KW;
-#pragma unroll
-          for (int seg = 0; seg < ATT_BN / (KW > 0 ? KW : ATT_BN); ++seg) {
-            const float bhv = bh[kh0 + seg];
-#pragma unroll
-            for (int i = 0; i < (KW > 0 ? KW : 1); ++i) {
-              const int c = seg * KW + i;
-              t[c] = fmaf(t[c], p.scale_log2, bhv + bw[i]);
-              mx[c & 3] = fmaxf(mx[c & 3], t[c]);
-            }
-          }
-        } else if (KW == 14) {
-          // SAM window: 196 keys = key block 0 (keys 0..127) + block 1 (keys 128..195)
-          if (j == 0) {
-#pragma unroll
-            for (int c = 0; c < ATT_BN; ++c) {
-              t[c] = fmaf(t[c], p.scale_log2, bh[c / 14] + bw[c % 14]);
-              mx[c & 3] = fmaxf(mx[c & 3], t[c]);
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 196 - ATT_BN; ++c) {
-              t[c] = fmaf(t[c], p.scale_log2, bh[(c + ATT_BN) / 14] + bw[(c + ATT_BN) % 14]);
-              mx[c & 3] = fmaxf(mx[c & 3], t[c]);
-            }
-          }
-        } else {
-          // generic grid: branch-free running (kh, kw)
-          int kh = k0 / p.Kw, kw = k0 - kh * p.Kw;
-#pragma unroll
-          for (int c = 0; c < ATT_BN; ++c) {
-            const int khc = kh < p.Kh ? kh : p.Kh - 1;
-            t[c] = fmaf(t[c], p.scale_log2, bh[khc] + bw[kw]);
-            mx[c & 3] = fmaxf(mx[c & 3], t[c]);
-            ++kw;
-            const bool wrap = kw == p.Kw;
-            kw = wrap ? 0 : kw;
-            kh += wrap ? 1 : 0;
-          }
-        }
-        if (nvalid < ATT_BN) {  // ragged last key block: keys >= T do not exist
-          mx[0] = m_run; mx[1] = mx[2] = mx[3] = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < ATT_BN; ++c) {
+          for (int c = 0; c < 64; ++c) {
             t[c] = c < nvalid ? t[c] : -INFINITY;
-            mx[c & 3] = fmaxf(mx[c & 3], t[c]);
+            m_blk = fmaxf(m_blk, t[c]);
           }
         }
-        const float m_new = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        const float alpha = ex2(m_run - m_new);
+        // lazy rescale: keep the stale reference maximum unless the block exceeds it by more than 2^8
+        float alpha = 1.f;
+        if (m_blk > m_ref + kRescaleThreshold) {
+          alpha = ex2(m_ref - m_blk);      // 0 on the first block (m_ref = -inf)
+          m_ref = m_blk;
+        }
+        const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t pk[ATT_BN / 2];
+        uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < ATT_BN; c += 2) {
-          const float p0 = ex2(t[c] - m_new), p1 = ex2(t[c + 1] - m_new);
+        for (int c = 0; c < 64; c += 2) {
+          const float p0 = ex2(t[c] - m_use), p1 = ex2(t[c + 1] - m_use);
           ls[(c >> 1) & 3] += p0 + p1;
           pk[c >> 1] = pack_bf16(p0, p1);
         }
         l_run = l_run * alpha + ((ls[0] + ls[1]) + (ls[2] + ls[3]));
-        m_run = m_new;
-        // ---- 2. fold in P_{j-1} V_{j-1} (the tensor core finished it while we did step 1) ----
+        // ---- 2. P_{j-1} V_{j-1} must be complete before P's shared-memory tile or the accumulator is touched ----
         if (j > 0) {
           mbar_wait(pv_done, pvph);
           pvph ^= 1;
           tc_fence_after();
-          uint32_t o[ATT_D];
-          __syncwarp();
-          tmem_ld_32x32b_x32(lane_addr + TM_PV, o);
-          tmem_ld_32x32b_x32(lane_addr + TM_PV + 32, o + 32);
-          tmem_ld_wait();
+          if (__any_sync(0xffffffffu, alpha != 1.f)) {
+            // rare: rescale this half's accumulator rows (alpha = 1 for the rows that kept their maximum)
 #pragma unroll
-          for (int i = 0; i < ATT_D; ++i) acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(o[i]));
+            for (int cc = 0; cc < ATT_D; cc += 32) {
+              uint32_t o[32];
+              tmem_ld_32x32b_x32(lane_addr + TM_O + half * ATT_D + cc, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x32b_x32(lane_addr + TM_O + half * ATT_D + cc, o);
+            }
+            tmem_st_wait();
+          }
           tc_fence_before();
         }
-        alpha_prev = alpha;
-        // ---- 3. P_j -> swizzled K-major bf16 smem tile, hand it to the MMA warp ----
+        // ---- 3. P_j -> this half's swizzled K-major bf16 panel, hand it to the MMA warp ----
 #pragma unroll
-        for (int c8 = 0; c8 < ATT_BN / 8; ++c8) {
+        for (int c8 = 0; c8 < 8; ++c8) {
           const uint4 v = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
-          const int panel = c8 >> 3, chunk = c8 & 7;
-          *reinterpret_cast<uint4*>(sP + panel * TILE_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+          *reinterpret_cast<uint4*>(sP + half * TILE_BYTES + row * 128 + ((c8 ^ (row & 7)) << 4)) = v;
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
       }
-      // ---- tile epilogue: last PV, normalise, store ----
+      // ---- tile epilogue: merge the two halves, normalise, store; this thread writes 32 of the 64 dims ----
       {
         mbar_wait(pv_done, pvph);
         pvph ^= 1;
         tc_fence_after();
-        uint32_t o[ATT_D];
+        sML[(half * ATT_BM + row) * 2] = m_ref;
+        sML[(half * ATT_BM + row) * 2 + 1] = l_run;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        const float m_o = sML[((half ^ 1) * ATT_BM + row) * 2], l_o = sML[((half ^ 1) * ATT_BM + row) * 2 + 1];
+        const float m = fmaxf(m_ref, m_o);
+        const float s_self = ex2(m_ref - m), s_oth = ex2(m_o - m);   // exp2(-inf) = 0 for a half without keys
+        const float inv = 1.f / (l_run * s_self + l_o * s_oth);
+        const float sa = (half == 0 ? s_self : s_oth) * inv, sb = (half == 0 ? s_oth : s_self) * inv;
+        uint32_t oa[32], ob[32];
         __syncwarp();
-        tmem_ld_32x32b_x32(lane_addr + TM_PV, o);
-        tmem_ld_32x32b_x32(lane_addr + TM_PV + 32, o + 32);
+        tmem_ld_32x32b_x32(lane_addr + TM_O + half * 32, oa);
+        tmem_ld_32x32b_x32(lane_addr + TM_O + ATT_D + half * 32, ob);
         tmem_ld_wait();
         tc_fence_before();
-        const float inv = 1.f / l_run;
+        float o[32];
 #pragma unroll
-        for (int i = 0; i < ATT_D; ++i) acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(o[i])) * inv;
+        for (int i = 0; i < 32; ++i) o[i] = sa * __uint_as_float(oa[i]) + sb * __uint_as_float(ob[i]);
         long long orow = (long long)bp * p.T + q;
         if (q < p.T && p.out_map) orow = p.out_map[orow];
         if (q < p.T && orow >= 0) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + orow * (p.nh * ATT_D) + head * ATT_D);
+          uint4* op = reinterpret_cast<uint4*>(p.out + orow * (p.nh * ATT_D) + head * ATT_D + half * 32);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) op[i] = pack8(acc + 8 * i);
+          for (int i = 0; i < 4; ++i) op[i] = pack8(o + 8 * i);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -430,7 +469,7 @@ MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const int* out_ro
   p.num_tiles = Bp * nh * p.nqb;
   const int tab_bytes = ((p.nh_pad + p.nw_pad) * 128 + 1023) & ~1023;
   const int bias_bytes = has_bias ? ATT_BM * ((Kh | 1) + (Kw | 1)) * 4 : ATT_BM * 2 * 4;
-  const int fixed = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*P*/ + tab_bytes + bias_bytes + 256 /*barriers*/ + 1024 /*align*/ + 64;
+  const int fixed = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*P*/ + tab_bytes + bias_bytes + 2 * ATT_BM * 2 * 4 /*(m,l)*/ + 256 /*barriers*/ + 1024 /*align*/ + 64;
   const int budget = 227 * 1024;
   p.kv_stages = 3;
   if (fixed + 3 * 2 * TILE_BYTES > budget) p.kv_stages = 2;
@@ -477,7 +516,7 @@ MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const int* out_ro
       if (e != cudaSuccess) return (int)e;                                                                      \
       configured = true;                                                                                        \
     }                                                                                                           \
-    attention_kernel<KWM><<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(tmQKV, tmH, tmW, p);                 \
+    attention_kernel<KWM><<<grid, 320, smem_bytes, (cudaStream_t)stream>>>(tmQKV, tmH, tmW, p);                 \
   } while (0)
   if (kw_mode == 64) ATT_LAUNCH(64);
   else if (kw_mode == 32) ATT_LAUNCH(32);
