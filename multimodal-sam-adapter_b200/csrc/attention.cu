@@ -53,43 +53,49 @@ static constexpr int TM_O = 256;    // 2 x 64: output accumulators of the two ke
 static constexpr int TM_G = 384;    // 128: bias pre-products
 static constexpr float kRescaleThreshold = 8.f;   // log2 units: P stays <= 256 with a stale row maximum
 
-// scale + bias + row maximum of this warp's 64 key columns [k0h, k0h + 64) of the score row
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2) and the 3-input maximum (FMNMX3): these halve the softmax's
+//      FMA-pipe instruction count ----
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ float max3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+
+// u = score * scale + bias (minus a per-segment constant kept in segb) for this warp's 64 key columns [k0h, k0h+64)
+// of the score row, as 32 fp32 pairs; returns the row maximum of the full logits. Segments: columns [0,32) / [32,64).
 template <int KW>
-__device__ __forceinline__ float add_bias_max(float (&t)[64], int k0h, const float* bh, const float* bw, bool has_bias,
-                                              float scale_log2, int Kh, int Kw) {
-  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+__device__ __forceinline__ float scores_to_logits(const uint32_t (&r)[64], u64 (&u)[32], float (&segb)[2], int k0h,
+                                                  const float* bh, const float* bw, bool has_bias, float scale_log2,
+                                                  int Kh, int Kw) {
+  const u64 sc2 = pack2(scale_log2, scale_log2);
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+  segb[0] = segb[1] = 0.f;
   if (!has_bias) {
 #pragma unroll
-    for (int c = 0; c < 64; ++c) {
-      t[c] *= scale_log2;
-      mx[c & 3] = fmaxf(mx[c & 3], t[c]);
-    }
-  } else if (KW == 64) {
-    const float bhv = bh[k0h >> 6];
+    for (int i = 0; i < 32; ++i) u[i] = mul2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2);
+  } else if (KW == 64 || KW == 32) {
+    // the key-row (kh) part of the bias is constant over a segment: it is folded into the exponent offset instead
+    // of being added to every element; the key-column part is a 64-bit shared-memory load per pair
+    if (KW == 64) { segb[0] = segb[1] = bh[k0h >> 6]; }
+    else { segb[0] = bh[k0h >> 5]; segb[1] = bh[(k0h >> 5) + 1]; }
 #pragma unroll
-    for (int c = 0; c < 64; ++c) {
-      t[c] = fmaf(t[c], scale_log2, bhv + bw[c]);
-      mx[c & 3] = fmaxf(mx[c & 3], t[c]);
-    }
-  } else if (KW == 32) {
-    const float b0 = bh[k0h >> 5], b1 = bh[(k0h >> 5) + 1];
-#pragma unroll
-    for (int c = 0; c < 64; ++c) {
-      t[c] = fmaf(t[c], scale_log2, (c < 32 ? b0 : b1) + bw[c & 31]);
-      mx[c & 3] = fmaxf(mx[c & 3], t[c]);
+    for (int i = 0; i < 32; ++i) {
+      const float2 b = *reinterpret_cast<const float2*>(bw + ((2 * i) & (KW - 1)));
+      u[i] = fma2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, pack2(b.x, b.y));
     }
   } else if (KW == 14) {
     // SAM window (14 x 14 keys): k0h is 0, 64, 128 or 192 -> (kh, kw) of every column are compile-time constants
     auto body = [&](auto k0c) {
       constexpr int K0 = decltype(k0c)::value;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
+      for (int i = 0; i < 32; ++i) {
         constexpr int dummy = 0; (void)dummy;
-        const int key = K0 + c;
-        if (key < 196) {
-          t[c] = fmaf(t[c], scale_log2, bh[key / 14] + bw[key % 14]);
-          mx[c & 3] = fmaxf(mx[c & 3], t[c]);
-        }
+        const int k0 = K0 + 2 * i, k1 = K0 + 2 * i + 1;
+        const float b0 = k0 < 196 ? bh[k0 / 14] + bw[k0 % 14] : 0.f;
+        const float b1 = k1 < 196 ? bh[k1 / 14] + bw[k1 % 14] : 0.f;
+        u[i] = fma2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, pack2(b0, b1));
       }
     };
     switch (k0h >> 6) {
@@ -101,18 +107,30 @@ __device__ __forceinline__ float add_bias_max(float (&t)[64], int k0h, const flo
   } else {
     // generic grid: branch-free running (kh, kw)
     int kh = k0h / Kw, kw = k0h - kh * Kw;
+    float bb[2];
 #pragma unroll
-    for (int c = 0; c < 64; ++c) {
-      const int khc = kh < Kh ? kh : Kh - 1;
-      t[c] = fmaf(t[c], scale_log2, bh[khc] + bw[kw]);
-      mx[c & 3] = fmaxf(mx[c & 3], t[c]);
-      ++kw;
-      const bool wrap = kw == Kw;
-      kw = wrap ? 0 : kw;
-      kh += wrap ? 1 : 0;
+    for (int i = 0; i < 32; ++i) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int khc = kh < Kh ? kh : Kh - 1;
+        bb[e] = bh[khc] + bw[kw];
+        ++kw;
+        const bool wrap = kw == Kw;
+        kw = wrap ? 0 : kw;
+        kh += wrap ? 1 : 0;
+      }
+      u[i] = fma2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, pack2(bb[0], bb[1]));
     }
   }
-  return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float a0, a1, c0, c1;
+    unpack2(u[i], a0, a1);
+    unpack2(u[16 + i], c0, c1);
+    mx0 = max3(mx0, a0, a1);
+    mx1 = max3(mx1, c0, c1);
+  }
+  return fmaxf(mx0 + segb[0], mx1 + segb[1]);
 }
 
 template <int KW>
@@ -129,7 +147,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint8_t* sTab = sP + 2 * TILE_BYTES;
   const int tab_bytes = (p.nh_pad + p.nw_pad) * 128;
   float* sBias = reinterpret_cast<float*>(sTab + ((tab_bytes + 1023) & ~1023));
-  const int bh_stride = p.bh_stride, bw_stride = p.bw_stride;  // row-private rows, stride chosen odd
+  const int bh_stride = p.bh_stride, bw_stride = p.bw_stride;  // row-private rows (strides: see the host code)
   float* sBh = sBias;
   float* sBw = sBias + ATT_BM * bh_stride;
   float* sML = sBw + ((ATT_BM * bw_stride + 3) & ~3);          // [2 halves][128 rows][m, l]
@@ -334,10 +352,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         // ---- 1. this half's 64 score columns of key block j ----
         mbar_wait(&s_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
-        float t[64];
+        uint32_t r[64];
         __syncwarp();
-        tmem_ld_32x32b_x32(lane_addr + TM_S + (g & 1) * ATT_BN + half * 64, reinterpret_cast<uint32_t*>(t));
-        tmem_ld_32x32b_x32(lane_addr + TM_S + (g & 1) * ATT_BN + half * 64 + 32, reinterpret_cast<uint32_t*>(t + 32));
+        tmem_ld_32x32b_x32(lane_addr + TM_S + (g & 1) * ATT_BN + half * 64, r);
+        tmem_ld_32x32b_x32(lane_addr + TM_S + (g & 1) * ATT_BN + half * 64 + 32, r + 32);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -345,13 +363,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         const int k0h = j * ATT_BN + half * 64;
         int nvalid = p.T - k0h;
         nvalid = nvalid < 0 ? 0 : (nvalid > 64 ? 64 : nvalid);
-        float m_blk = add_bias_max<KW>(t, k0h, bh, bw, has_bias, p.scale_log2, p.Kh, p.Kw);
+        u64 u[32];
+        float segb[2];
+        float m_blk = scores_to_logits<KW>(r, u, segb, k0h, bh, bw, has_bias, p.scale_log2, p.Kh, p.Kw);
         if (nvalid < 64) {  // ragged last key block: keys >= T do not exist
           m_blk = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            t[c] = c < nvalid ? t[c] : -INFINITY;
-            m_blk = fmaxf(m_blk, t[c]);
+          for (int i = 0; i < 32; ++i) {
+            float a0, a1;
+            unpack2(u[i], a0, a1);
+            a0 = 2 * i < nvalid ? a0 : -INFINITY;
+            a1 = 2 * i + 1 < nvalid ? a1 : -INFINITY;
+            u[i] = pack2(a0, a1);
+            m_blk = fmaxf(m_blk, fmaxf(a0, a1) + segb[i >> 4]);
           }
         }
         // lazy rescale: keep the stale reference maximum unless the block exceeds it by more than 2^8
@@ -361,14 +385,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           m_ref = m_blk;
         }
         const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        const float n0 = segb[0] - m_use, n1 = segb[1] - m_use;
+        const u64 neg[2] = {pack2(n0, n0), pack2(n1, n1)};
+        u64 ls2[2] = {0ull, 0ull};
         uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-          const float p0 = ex2(t[c] - m_use), p1 = ex2(t[c + 1] - m_use);
-          ls[(c >> 1) & 3] += p0 + p1;
-          pk[c >> 1] = pack_bf16(p0, p1);
+        for (int i = 0; i < 32; ++i) {
+          float a0, a1;
+          unpack2(add2(u[i], neg[i >> 4]), a0, a1);
+          const float p0 = ex2(a0), p1 = ex2(a1);
+          ls2[i & 1] = add2(ls2[i & 1], pack2(p0, p1));
+          pk[i] = pack_bf16(p0, p1);
         }
+        float ls[4];
+        unpack2(ls2[0], ls[0], ls[1]);
+        unpack2(ls2[1], ls[2], ls[3]);
         l_run = l_run * alpha + ((ls[0] + ls[1]) + (ls[2] + ls[3]));
         // ---- 2. P_{j-1} V_{j-1} must be complete before P's shared-memory tile or the accumulator is touched ----
         if (j > 0) {
@@ -468,15 +499,21 @@ MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const int* out_ro
   p.nqb = (T + ATT_BM - 1) / ATT_BM;
   p.num_tiles = Bp * nh * p.nqb;
   const int tab_bytes = ((p.nh_pad + p.nw_pad) * 128 + 1023) & ~1023;
-  const int bias_bytes = has_bias ? ATT_BM * ((Kh | 1) + (Kw | 1)) * 4 : ATT_BM * 2 * 4;
+  // per-row bias rows in shared memory: bh rows are read as scalars (odd stride), bw rows as 64-bit pairs (even
+  // stride with an odd number of pairs: conflict-free LDS.64 across the 32 rows of a warp)
+  p.bh_stride = has_bias ? (Kh | 1) : 1;
+  p.bw_stride = 2;
+  if (has_bias) {
+    p.bw_stride = (Kw + 1) & ~1;
+    if (((p.bw_stride >> 1) & 1) == 0) p.bw_stride += 2;
+  }
+  const int bias_bytes = ATT_BM * (p.bh_stride + p.bw_stride) * 4 + 16;
   const int fixed = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*P*/ + tab_bytes + bias_bytes + 2 * ATT_BM * 2 * 4 /*(m,l)*/ + 256 /*barriers*/ + 1024 /*align*/ + 64;
   const int budget = 227 * 1024;
   p.kv_stages = 3;
   if (fixed + 3 * 2 * TILE_BYTES > budget) p.kv_stages = 2;
   const int smem_bytes = fixed + p.kv_stages * 2 * TILE_BYTES;
   if (smem_bytes > budget) return MMSAM_ERR_UNSUPPORTED;
-  p.bh_stride = has_bias ? (Kh | 1) + ((Kh & 1) ? 0 : 0) : 1;
-  p.bw_stride = has_bias ? (Kw | 1) : 1;
   if (!has_bias) { p.Kh = 1; p.Kw = 1 << 30; }
 
   mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
