@@ -294,10 +294,13 @@ def main():
         "clocks": clk,
         "roofline": {"kernel": "gemm_bf16_kernel (tcgen05)", "bound": "tensor", "achieved": tf,
                      "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops_sustained"],
-                     "traffic": None, "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
+                     # ncu --set full, lin1 (32768x4096x1024, GELU) launch: dram__bytes_read + dram__bytes_write
+                     # (profiles/r01_gemm_ncu_summary.txt); algorithmic bytes of that launch: 343 MB
+                     "traffic": 291.6e6, "traffic_of": "lin1 GEMM launch (M=32768 N=4096 K=1024)",
+                     "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
                      "launches_per_step": gm["launches"], "ms_per_step": gm["ms"],
                      "share_of_step": gm["ms"] / (ms / args.steps)},
-        "roofline_msda": {"kernel": "msda_fused_kernel", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
+        "roofline_msda": {"kernel": "msda_fused_coop_kernel", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
                           "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None, "launches_per_step": md["launches"],
                           "ms_per_step": md["ms"], "peak_source": pk["source"]},
         "miou_check": {"pixels": int(conf_all.sum().item())},
