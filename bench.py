@@ -289,7 +289,7 @@ def main():
         "config": {"workload": WORKLOAD, "global_batch": world * B, "l2": "inputs (201 MB fp32 per step) exceed the 126 MB L2",
                    "parallelism": f"image-sharded x{world}, no data-path collective",
                    "launch": "eager" if args.no_graph else "cuda-graph replay"},
-        "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel()},
+        "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": world * x_host.numel() * 4, "d2h_bytes_per_step": world * out_host.numel()},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"kernel": "gemm_bf16_kernel (tcgen05)", "bound": "tensor", "achieved": tf,
