@@ -4,6 +4,7 @@
 // conv3x3.cu. Numerically sensitive reductions (HW-long Gram sums, LayerNorm-over-HW statistics) are
 // accumulated in fp32 per chunk and combined in fp64 / fp32 atomics.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace mmsam {
 
@@ -264,6 +265,9 @@ static inline unsigned nk_grid(long long total, int per_block = 256, int waves =
 
 }  // namespace mmsam
 
+int mmsam_gram_tc(const void* X, long long ld, int qoff, int koff, int n, int B, int HW, int blk, float* S, float* nq,
+                  float* nk, cudaStream_t st);   // gram_tc.cu
+
 MMSAM_API int mmsam_gram_bf16(const void* X, long long ld, int qoff, int koff, int n, int B, int HW, int blk,
                               float* S, float* nq, float* nk, void* stream) {
   using namespace mmsam;
@@ -271,6 +275,10 @@ MMSAM_API int mmsam_gram_bf16(const void* X, long long ld, int qoff, int koff, i
   if ((nq == nullptr) != (nk == nullptr)) return MMSAM_ERR_BAD_ARG;
   if (B == 0) return MMSAM_OK;
   if (!X || !S || (((uintptr_t)X) & 15)) return MMSAM_ERR_BAD_ARG;
+  if (!getenv("MMSAM_GRAM_SIMT")) {   // tensor-core path; shapes it does not take fall through to the SIMT kernel
+    const int rc = mmsam_gram_tc(X, ld, qoff, koff, n, B, HW, blk, S, nq, nk, (cudaStream_t)stream);
+    if (rc != MMSAM_ERR_UNSUPPORTED) return rc;
+  }
   const int nt = (n + 63) / 64;
   int nchunks = HW / 2048;
   if (nchunks < 1) nchunks = 1;

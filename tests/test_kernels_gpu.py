@@ -370,20 +370,27 @@ def test_conv3x3_grouped(B, H, W, Cin, groups):
     assert ((out - ref).abs() <= 0.01 * ref.abs() + 5e-3).all(), (out - ref).abs().max()
 
 
-@pytest.mark.parametrize("n,blk,HW", [(96, 12, 4096), (64, 0, 1000), (192, 0, 300), (768, 96, 256)])
-def test_gram(n, blk, HW):
+@pytest.mark.parametrize("n,blk,HW,norms", [
+    (96, 12, 4096, True), (64, 0, 1000, True), (192, 0, 300, True), (768, 96, 256, True),   # SIMT fallback when HW % 64 != 0
+    (192, 0, 8192, False), (384, 48, 2048, True), (384, 0, 1024, False), (1536, 0, 1024, False), (200, 0, 640, True),
+])
+def test_gram(n, blk, HW, norms):
+    """Gram over pixels (tcgen05 path with MN-major operands for HW % 64 == 0, SIMT kernel otherwise)."""
     k = _k()
     B, ld = 2, 3 * n
     g = torch.Generator().manual_seed(n + HW)
     x = torch.randn(B, HW, ld, generator=g).to(torch.bfloat16)
-    S, nq, nk = k.gram(x.reshape(-1, ld).cuda(), ld, 0, n, n, B, HW, blk=blk, norms=True)
+    r = k.gram(x.reshape(-1, ld).cuda(), ld, 0, n, n, B, HW, blk=blk, norms=norms)
+    S = r[0] if norms else r
     q, kk = x[..., :n].double(), x[..., n:2 * n].double()
     ref = q.transpose(1, 2) @ kk
     if blk:
         m = (torch.arange(n)[:, None] // blk) == (torch.arange(n)[None, :] // blk)
         ref = ref * m
     assert (S.cpu().double() - ref).abs().max() < 2e-3 * math.sqrt(HW)
-    assert torch.allclose(nq.cpu().double(), (q * q).sum(1), rtol=1e-4) and torch.allclose(nk.cpu().double(), (kk * kk).sum(1), rtol=1e-4)
+    if norms:
+        nq, nk = r[1], r[2]
+        assert torch.allclose(nq.cpu().double(), (q * q).sum(1), rtol=1e-4) and torch.allclose(nk.cpu().double(), (kk * kk).sum(1), rtol=1e-4)
 
 
 def test_colstats_gate_ln_dual():
