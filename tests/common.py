@@ -23,7 +23,7 @@ VITB_HEAD = dict(in_channels=[768] * 4, in_index=[0, 1, 2, 3], channels=512, dro
                  norm_cfg=dict(type="SyncBN", requires_grad=True), align_corners=False)
 
 
-def build_segmentor(bcfg, hcfg, seed=0, perturb_seed=1, test_cfg=None):
+def build_segmentor(bcfg, hcfg, seed=0, perturb_seed=1, test_cfg=None, btype="SAMAdapterbimodalMixModNewInTwinConvNEW"):
     """Deterministic CPU construction of our modules + the Appendix-D perturbation. Returns
     (segmentor module on CPU, state_dict of fp32 CPU tensors)."""
     import mmsam_b200  # noqa: F401
@@ -31,7 +31,7 @@ def build_segmentor(bcfg, hcfg, seed=0, perturb_seed=1, test_cfg=None):
     from mmsam_b200.registry import SEGMENTORS
     from oracle.perturb import perturb_state_dict
     torch.manual_seed(seed)
-    seg = SEGMENTORS.build(dict(type="EncoderDecoder", backbone=dict(type="SAMAdapterbimodalMixModNewInTwinConvNEW", **bcfg),
+    seg = SEGMENTORS.build(dict(type="EncoderDecoder", backbone=dict(type=btype, **bcfg),
                                 decode_head=dict(type="SegformerHead", **hcfg),
                                 test_cfg=test_cfg or dict(mode="whole")))
     sd = perturb_state_dict(seg.state_dict(), seed=perturb_seed)

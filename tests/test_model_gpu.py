@@ -164,6 +164,69 @@ def test_tiny_segmentor_labels_vs_oracle(tiny):
     assert rel_l2(lg, logits) < REL_TOL
 
 
+def _agreement(got, logits):
+    """(all-pixel agreement, agreement on the pixels the oracle decides by >= 5 % of the logit spread)."""
+    want = logits.softmax(1).argmax(1)
+    top2 = logits.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) / logits.std(dim=1) >= 0.05
+    ok = got == want
+    return ok.float().mean().item(), ok[decided].float().mean().item()
+
+
+def test_fmb_like_whole_dim_cut_vs_oracle():
+    """BASELINE config 4 in miniature (configs/FMB/...: registry name ...NEWwithcp, 14 classes, zero-padded square
+    input, logits cropped by whole_inference_dim_cut, encoder_decoder.py:364-391): a token grid that is NOT a
+    multiple of the 14-token window (10x10 -> padded to 14x14) and global blocks whose rel-pos tables are
+    interpolated (31 -> 19 rows, image_encoder.py:566-575)."""
+    import numpy as np
+    from oracle import model as om
+    from oracle.perturb import synthetic_batch
+    cfg = dict(TINY, img_size=160, conv_drop_path_rate=0.1)
+    head = dict(TINY_HEAD, num_classes=14)
+    tcfg = dict(mode="whole_dim_cut", rescale=True, dim=(160, 160), cut_dim=(160, 120))
+    seg, sd = build_segmentor(cfg, head, test_cfg=tcfg, btype="SAMAdapterbimodalMixModNewInTwinConvNEWwithcp")
+    x = synthetic_batch(2, 160, seed=11)
+    x[:, :, 120:] = 0                                   # the FMB pipeline pads 600 -> 800 rows with zeros
+    with torch.no_grad():
+        logits = om.segmentor_logits(sd, cfg, x, dict(dim=(160, 160), cut_dim=(160, 120)))
+    assert logits.shape == (2, 14, 120, 160)
+    got = torch.as_tensor(np.stack(seg.cuda().simple_test(x.cuda())))
+    assert got.shape == (2, 120, 160)
+    agree, agree_decided = _agreement(got, logits)
+    print(f"FMB-like whole_dim_cut: argmax agreement {agree * 100:.3f}% (decided pixels {agree_decided * 100:.4f}%)")
+    assert agree_decided >= 0.999 and agree >= 0.98
+
+
+def test_slide_inference_vs_oracle(tiny):
+    """BASELINE config 5 in miniature (MUSES: slide_inference, encoder_decoder.py:191-234): overlapping crops of the
+    network's input size, logits averaged by the overlap count, then argmax."""
+    import numpy as np
+    from oracle import model as om
+    from oracle.perturb import synthetic_batch
+    seg, sd = tiny
+    seg = seg.cuda()
+    old = dict(seg.test_cfg)
+    seg.test_cfg = dict(mode="slide", crop_size=(128, 128), stride=(64, 80))
+    try:
+        g = torch.Generator().manual_seed(21)
+        x = synthetic_batch(1, 128, seed=21)
+        x = torch.cat([x, synthetic_batch(1, 128, seed=22)], 3)[:, :, :, :208]      # 128 x 208 frame -> crops at x = 0, 80
+        preds = torch.zeros(1, 25, 128, 208)
+        count = torch.zeros(1, 1, 128, 208)
+        with torch.no_grad():
+            for x1 in (0, 80):
+                preds[:, :, :, x1:x1 + 128] += om.segmentor_logits(sd, TINY, x[:, :, :, x1:x1 + 128].contiguous())
+                count[:, :, :, x1:x1 + 128] += 1
+        logits = preds / count
+        got = torch.as_tensor(np.stack(seg.simple_test(x.cuda())))
+        assert got.shape == (1, 128, 208)
+        agree, agree_decided = _agreement(got, logits)
+        print(f"slide inference: argmax agreement {agree * 100:.3f}% (decided pixels {agree_decided * 100:.4f}%)")
+        assert agree_decided >= 0.999 and agree >= 0.98
+    finally:
+        seg.test_cfg = old
+
+
 @pytest.mark.timeout(900)
 def test_vitb512_config1_vs_reference_golden():
     """BASELINE config 1: ViT-B MM-adapter, one synthetic RGB+LiDAR 512x512 image."""
