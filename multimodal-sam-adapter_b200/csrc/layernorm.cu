@@ -6,92 +6,122 @@
 // 494-501, 527-532) and ConvNeXt LN2d (mmpretrain_custom/models/utils/norm.py:52-87), which in a
 // channels-last layout is the same row-wise operation.
 //
-// One warp per row, the row lives in registers (<= 8 x 16 B per lane), two-pass mean/variance in
+// One lane group (8 / 16 / 32 lanes) per row, the row lives in registers (<= 8 x 16 B per lane), two-pass mean/variance in
 // fp32 (biased variance, like F.layer_norm). An optional int32 row map scatters the output rows
 // (dst = map[src], -1 = drop): that is how norm1 writes straight into SAM's zero-padded 14x14
 // window layout (image_encoder.py:504-526) without a separate partition pass. A second scatter mode
 // writes each row into its slot of the 2x2-patchified matrix consumed by ConvNeXt's stride-2
 // downsample conv (LN2d -> Conv2d(k=2,s=2), twin_convnext.py:313-336), which is then a plain GEMM.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace mmsam {
 
-template <int NV>
+// G lanes share a row (G = 32: the classic warp-per-row; 16 / 8 for narrow rows such as ConvNeXt stage 0's C = 96,
+// where a full warp per row would leave 20 of 32 lanes idle: 25 % of HBM peak measured, two rows per warp ~2x), and
+// every lane group keeps R rows in flight (all loads issued before the first reduction): the per-row chain
+// load -> reduce -> reduce -> store is ~2-3 us of latency, and the mid-sized maps only give a warp 1-2 rows.
+template <int NV, int G, int R>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y2,
                  const int* __restrict__ row_map, long long rows, int C, long long ldx,
                  long long ldy, float eps, int ps_h, int ps_w) {
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / G;                                   // rows per warp (side by side)
+  const int lane = threadIdx.x & (G - 1);                        // lane within the row group
+  const int sub = (threadIdx.x & 31) / G;                        // row group within the warp
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long step = nwarps * RPW;
   const int nvec = C >> 3;
-  for (long long row = warp; row < rows; row += nwarps) {
-    long long dst = row;
-    long long dcol = 0;
-    if (row_map) {
-      dst = row_map[row];
-      if (dst < 0) continue;
-    } else if (ps_h > 0) {
-      // 2x2 patchify scatter for the stride-2 downsample conv: row (b,y,x) -> row (b,y/2,x/2),
-      // column block (y&1)*2 + (x&1)
-      const long long hw = (long long)ps_h * ps_w;
-      const long long b = row / hw;
-      const int r = (int)(row - b * hw);
-      const int yy = r / ps_w, xx = r - yy * ps_w;
-      dst = (b * (ps_h / 2) + yy / 2) * (ps_w / 2) + xx / 2;
-      dcol = ((yy & 1) * 2 + (xx & 1)) * C;
-    }
-    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
-    float f[NV][8];
-    float s = 0.f;
+  auto group_sum = [&](float v) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nvec) {
-        unpack8(__ldg(xr + v), f[i]);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+    return v;
+  };
+  for (long long row0 = warp * RPW + sub; row0 < rows; row0 += step * R) {
+    long long dst[R], dcol[R];
+    bool on[R];
+    float f[R][NV][8];
+    float s[R];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += f[i][j];
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r * step;
+      on[r] = row < rows;
+      dst[r] = row;
+      dcol[r] = 0;
+      if (on[r]) {
+        if (row_map) {
+          dst[r] = row_map[row];
+          on[r] = dst[r] >= 0;
+        } else if (ps_h > 0) {
+          // 2x2 patchify scatter for the stride-2 downsample conv: row (b,y,x) -> row (b,y/2,x/2),
+          // column block (y&1)*2 + (x&1)
+          const long long hw = (long long)ps_h * ps_w;
+          const long long b = row / hw;
+          const int rr = (int)(row - b * hw);
+          const int yy = rr / ps_w, xx = rr - yy * ps_w;
+          dst[r] = (b * (ps_h / 2) + yy / 2) * (ps_w / 2) + xx / 2;
+          dcol[r] = ((yy & 1) * 2 + (xx & 1)) * C;
+        }
       }
-    }
-    const float mean = warp_sum(s) / (float)C;
-    float s2 = 0.f;
+      s[r] = 0.f;
+      if (on[r]) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nvec) {
+        for (int i = 0; i < NV; ++i) {
+          const int v = lane + G * i;
+          if (v < nvec) {
+            unpack8(__ldg(xr + v), f[r][i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = f[i][j] - mean;
-          s2 += d * d;
+            for (int j = 0; j < 8; ++j) s[r] += f[r][i][j];
+          }
         }
       }
     }
-    const float rstd = rsqrtf(warp_sum(s2) / (float)C + eps);
-    uint4* yr = reinterpret_cast<uint4*>(y + dst * ldy + dcol);
-    uint4* yr2 = y2 ? reinterpret_cast<uint4*>(y2 + dst * ldy + dcol) : nullptr;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nvec) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v);
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v + 1);
-        float o[8];
-        o[0] = (f[i][0] - mean) * rstd * g0.x + b0.x;
-        o[1] = (f[i][1] - mean) * rstd * g0.y + b0.y;
-        o[2] = (f[i][2] - mean) * rstd * g0.z + b0.z;
-        o[3] = (f[i][3] - mean) * rstd * g0.w + b0.w;
-        o[4] = (f[i][4] - mean) * rstd * g1.x + b1.x;
-        o[5] = (f[i][5] - mean) * rstd * g1.y + b1.y;
-        o[6] = (f[i][6] - mean) * rstd * g1.z + b1.z;
-        o[7] = (f[i][7] - mean) * rstd * g1.w + b1.w;
-        yr[v] = pack8(o);
-        if (yr2) {  // second output: x + LN(x)  (GFE: x + attn(norm1(x)) keeps norm1(x) as a residual)
+    for (int r = 0; r < R; ++r) {
+      if (!on[r]) continue;                                      // uniform over the lane group
+      const float mean = group_sum(s[r]) / (float)C;
+      float s2 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += f[i][j];
-          yr2[v] = pack8(o);
+      for (int i = 0; i < NV; ++i) {
+        const int v = lane + G * i;
+        if (v < nvec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = f[r][i][j] - mean;
+            s2 += d * d;
+          }
+        }
+      }
+      const float rstd = rsqrtf(group_sum(s2) / (float)C + eps);
+      uint4* yr = reinterpret_cast<uint4*>(y + dst[r] * ldy + dcol[r]);
+      uint4* yr2 = y2 ? reinterpret_cast<uint4*>(y2 + dst[r] * ldy + dcol[r]) : nullptr;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = lane + G * i;
+        if (v < nvec) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v);
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v + 1);
+          float o[8];
+          o[0] = (f[r][i][0] - mean) * rstd * g0.x + b0.x;
+          o[1] = (f[r][i][1] - mean) * rstd * g0.y + b0.y;
+          o[2] = (f[r][i][2] - mean) * rstd * g0.z + b0.z;
+          o[3] = (f[r][i][3] - mean) * rstd * g0.w + b0.w;
+          o[4] = (f[r][i][4] - mean) * rstd * g1.x + b1.x;
+          o[5] = (f[r][i][5] - mean) * rstd * g1.y + b1.y;
+          o[6] = (f[r][i][6] - mean) * rstd * g1.z + b1.z;
+          o[7] = (f[r][i][7] - mean) * rstd * g1.w + b1.w;
+          yr[v] = pack8(o);
+          if (yr2) {  // second output: x + LN(x)  (GFE: x + attn(norm1(x)) keeps norm1(x) as a residual)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += f[r][i][j];
+            yr2[v] = pack8(o);
+          }
         }
       }
     }
@@ -111,22 +141,28 @@ MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const floa
   if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15)) return MMSAM_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = 8;
-  long long blocks = (rows + wpb - 1) / wpb;
-  const long long cap = (long long)kNumSMs * 16;
+  const int nvec = C / 8;
+  const int G = nvec > 16 ? 32 : (nvec > 8 ? 16 : 8);
+  const int rpw = 32 / G;
+  const int nv = (nvec + 31) / 32;
+  const int R = 1;   // rows in flight per lane group: 2 was measured SLOWER everywhere (registers -> occupancy)
+  long long blocks = (rows + (long long)wpb * rpw * R - 1) / ((long long)wpb * rpw * R);
+  const long long cap = (long long)kNumSMs * (getenv("MMSAM_LN_CAP") ? atoi(getenv("MMSAM_LN_CAP")) : 16);
   if (blocks > cap) blocks = cap;
   const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
   __nv_bfloat16* yo = (__nv_bfloat16*)y;
   __nv_bfloat16* yo2 = (__nv_bfloat16*)y2;
-  const int nv = (C / 8 + 31) / 32;
-#define LN_CASE(NV) \
-  layernorm_kernel<NV><<<(unsigned)blocks, wpb * 32, 0, st>>>(xi, gamma, beta, yo, yo2, row_map_dev, rows, C, ldx, ldy, eps, ps_h, ps_w)
-  switch (nv) {
-    case 1: LN_CASE(1); break;
-    case 2: LN_CASE(2); break;
-    case 3: LN_CASE(3); break;
-    case 4: LN_CASE(4); break;
-    case 5: case 6: LN_CASE(6); break;
-    default: LN_CASE(8); break;
+#define LN_CASE(NV, GG, RR) \
+  layernorm_kernel<NV, GG, RR><<<(unsigned)blocks, wpb * 32, 0, st>>>(xi, gamma, beta, yo, yo2, row_map_dev, rows, C, ldx, ldy, eps, ps_h, ps_w)
+  if (G == 8) LN_CASE(1, 8, 1);
+  else if (G == 16) LN_CASE(1, 16, 1);
+  else switch (nv) {
+    case 1: LN_CASE(1, 32, 1); break;
+    case 2: LN_CASE(2, 32, 1); break;
+    case 3: LN_CASE(3, 32, 1); break;
+    case 4: LN_CASE(4, 32, 1); break;
+    case 5: case 6: LN_CASE(6, 32, 1); break;
+    default: LN_CASE(8, 32, 1); break;
   }
 #undef LN_CASE
   MMSAM_LAUNCH_CHECK();

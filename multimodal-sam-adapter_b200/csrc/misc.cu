@@ -39,8 +39,20 @@ resize_add_affine_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloa
                          long long lds, long long ldb, float rh, float rw) {
   const int CV = C >> 3;
   const long long total = (long long)B * Ho * Wo * CV;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  // When the grid stride is a multiple of the channel-vector count a thread keeps ITS 8 channels for the whole loop:
+  // the BatchNorm scale / shift then live in registers. (Reading them per element as 16 scalar loads at a 32-byte
+  // lane stride cost 128 L1 wavefronts per warp against 20 for the data: 1.2 ms instead of 0.33 ms on the f1 map.)
+  const bool fixed_cv = scale != nullptr && (nthreads % CV) == 0;
+  float sc[8], sh[8];
+  if (fixed_cv) {
+    const int cv0 = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % CV);
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + cv0 * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + cv0 * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + cv0 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + cv0 * 8 + 4));
+    sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+    sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+  }
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
     const int cv = (int)(idx % CV);
     long long t = idx / CV;
     const int x = (int)(t % Wo); t /= Wo;
@@ -75,8 +87,14 @@ resize_add_affine_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloa
       for (int j = 0; j < 8; ++j) f[j] += g[j];
     }
     if (scale) {
+      if (!fixed_cv) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + cv * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + cv * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + cv * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + cv * 8 + 4));
+        sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+        sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+      }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = f[j] * __ldg(scale + cv * 8 + j) + __ldg(shift + cv * 8 + j);
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
     }
     *reinterpret_cast<uint4*>(out + b * out_bstride + ((long long)y * Wo + x) * ldo + cv * 8) = pack8(f);
   }
@@ -180,7 +198,7 @@ MMSAM_API int mmsam_resize_add_affine_bf16(const void* src, const void* base, co
   if ((scale == nullptr) != (shift == nullptr)) return MMSAM_ERR_BAD_ARG;
   if (B == 0) return MMSAM_OK;
   if (!src || !out) return MMSAM_ERR_BAD_ARG;
-  if ((((uintptr_t)src | (uintptr_t)out | (uintptr_t)base) & 15)) return MMSAM_ERR_BAD_ARG;
+  if ((((uintptr_t)src | (uintptr_t)out | (uintptr_t)base | (uintptr_t)scale | (uintptr_t)shift) & 15)) return MMSAM_ERR_BAD_ARG;
   const long long total = (long long)B * Ho * Wo * (C / 8);
   resize_add_affine_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)src, (const __nv_bfloat16*)base, scale, shift, (__nv_bfloat16*)out, B, Hs, Ws, Ho, Wo, C,

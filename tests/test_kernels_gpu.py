@@ -393,6 +393,31 @@ def test_gram(n, blk, HW, norms):
         assert torch.allclose(nq.cpu().double(), (q * q).sum(1), rtol=1e-4) and torch.allclose(nk.cpu().double(), (kk * kk).sum(1), rtol=1e-4)
 
 
+@pytest.mark.parametrize("B,C,hs,ws,ho,wo", [
+    (2, 1024, 8, 8, 32, 32),     # x4 up (f1 fusion), channel vectors divide the grid stride: scale/shift in registers
+    (2, 96, 16, 12, 8, 6),       # x0.5 down, 12 channel vectors: in-loop scale/shift path
+    (1, 64, 5, 7, 5, 7),         # same size (f3: plain add + BatchNorm)
+    (3, 512, 4, 4, 16, 16),
+])
+def test_resize_add_affine(B, C, hs, ws, ho, wo):
+    """(base + bilinear(src)) * scale + shift, channels-last, against F.interpolate(align_corners=False) + eval-BN
+    folded to scale/shift (backbone tail ..._new.py:326-337, head resize segformer_head.py:55-61)."""
+    k = _k()
+    g = torch.Generator().manual_seed(B * C + hs)
+    src = torch.randn(B, hs, ws, C, generator=g).to(torch.bfloat16)
+    base = torch.randn(B, ho, wo, C, generator=g).to(torch.bfloat16)
+    scale = torch.rand(C, generator=g) + 0.5
+    shift = torch.randn(C, generator=g)
+    up = torch.nn.functional.interpolate(src.float().permute(0, 3, 1, 2), size=(ho, wo), mode="bilinear",
+                                         align_corners=False).permute(0, 2, 3, 1)
+    ref = (up + base.float()) * scale + shift
+    out = k.resize_add_affine(src.cuda(), (hs, ws), (ho, wo), B, C, base=base.cuda(), scale=scale.cuda(),
+                              shift=shift.cuda()).cpu().float()
+    assert ((out - ref).abs() <= 0.008 * ref.abs() + 4e-3).all()
+    out2 = k.resize_add_affine(src.cuda(), (hs, ws), (ho, wo), B, C).cpu().float()       # plain resize
+    assert ((out2 - up).abs() <= 0.008 * up.abs() + 4e-3).all()
+
+
 def test_colstats_gate_ln_dual():
     k = _k()
     B, HW, C = 2, 1500, 192

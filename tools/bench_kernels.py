@@ -102,3 +102,6 @@ if __name__ == "__main__":
         bench_ln(B * 4096, 1024)
         bench_ln(B * 21504, 1024)
         bench_ln(B * 65536, 96)
+        bench_ln(B * 16384, 192)
+        bench_ln(B * 4096, 384)
+        bench_ln(B * 1024, 768)
