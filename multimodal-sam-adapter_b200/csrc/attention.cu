@@ -65,9 +65,14 @@ __device__ __forceinline__ float max3(float a, float b, float c) { float r; asm(
 
 // u = score * scale + bias (minus a per-segment constant kept in segb) for this warp's 64 key columns [k0h, k0h+64)
 // of the score row, as 32 fp32 pairs; returns the row maximum of the full logits. Segments: columns [0,32) / [32,64).
-template <int KW>
+__device__ __forceinline__ float ldb(const float* p) { return *p; }
+__device__ __forceinline__ float ldb(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void stb(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stb(__half* p, float v) { *p = __float2half_rn(v); }
+
+template <int KW, typename BT>
 __device__ __forceinline__ float scores_to_logits(const uint32_t (&r)[64], u64 (&u)[32], float (&segb)[2], int k0h,
-                                                  const float* bh, const float* bw, bool has_bias, float scale_log2,
+                                                  const BT* bh, const BT* bw, bool has_bias, float scale_log2,
                                                   int Kh, int Kw) {
   const u64 sc2 = pack2(scale_log2, scale_log2);
   float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -75,14 +80,14 @@ __device__ __forceinline__ float scores_to_logits(const uint32_t (&r)[64], u64 (
   if (!has_bias) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) u[i] = mul2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2);
-  } else if (KW == 64 || KW == 32) {
+  } else if ((KW == 64 || KW == 32) && std::is_same<BT, float>::value) {
     // the key-row (kh) part of the bias is constant over a segment: it is folded into the exponent offset instead
     // of being added to every element; the key-column part is a 64-bit shared-memory load per pair
-    if (KW == 64) { segb[0] = segb[1] = bh[k0h >> 6]; }
-    else { segb[0] = bh[k0h >> 5]; segb[1] = bh[(k0h >> 5) + 1]; }
+    if (KW == 64) { segb[0] = segb[1] = ldb(bh + (k0h >> 6)); }
+    else { segb[0] = ldb(bh + (k0h >> 5)); segb[1] = ldb(bh + (k0h >> 5) + 1); }
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const float2 b = *reinterpret_cast<const float2*>(bw + ((2 * i) & (KW - 1)));
+      const float2 b = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(bw) + ((2 * i) & (KW - 1)));
       u[i] = fma2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, pack2(b.x, b.y));
     }
   } else if (KW == 14) {
@@ -93,8 +98,8 @@ __device__ __forceinline__ float scores_to_logits(const uint32_t (&r)[64], u64 (
       for (int i = 0; i < 32; ++i) {
         constexpr int dummy = 0; (void)dummy;
         const int k0 = K0 + 2 * i, k1 = K0 + 2 * i + 1;
-        const float b0 = k0 < 196 ? bh[k0 / 14] + bw[k0 % 14] : 0.f;
-        const float b1 = k1 < 196 ? bh[k1 / 14] + bw[k1 % 14] : 0.f;
+        const float b0 = k0 < 196 ? ldb(bh + k0 / 14) + ldb(bw + k0 % 14) : 0.f;
+        const float b1 = k1 < 196 ? ldb(bh + k1 / 14) + ldb(bw + k1 % 14) : 0.f;
         u[i] = fma2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, pack2(b0, b1));
       }
     };
@@ -113,7 +118,7 @@ __device__ __forceinline__ float scores_to_logits(const uint32_t (&r)[64], u64 (
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int khc = kh < Kh ? kh : Kh - 1;
-        bb[e] = bh[khc] + bw[kw];
+        bb[e] = ldb(bh + khc) + ldb(bw + kw);
         ++kw;
         const bool wrap = kw == Kw;
         kw = wrap ? 0 : kw;
@@ -133,7 +138,9 @@ __device__ __forceinline__ float scores_to_logits(const uint32_t (&r)[64], u64 (
   return fmaxf(mx0 + segb[0], mx1 + segb[1]);
 }
 
-template <int KW>
+// BT: element type of the per-row bias rows in shared memory (float; __half for key grids whose fp32 rows would not
+// fit beside the K/V ring, e.g. a whole 1088 x 1920 MUSES frame = 68 x 120 tokens).
+template <int KW, typename BT>
 __global__ void __launch_bounds__(320, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTabH,
                  const __grid_constant__ CUtensorMap tmTabW, const AttnParams p) {
@@ -148,9 +155,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   const int tab_bytes = (p.nh_pad + p.nw_pad) * 128;
   float* sBias = reinterpret_cast<float*>(sTab + ((tab_bytes + 1023) & ~1023));
   const int bh_stride = p.bh_stride, bw_stride = p.bw_stride;  // row-private rows (strides: see the host code)
-  float* sBh = sBias;
-  float* sBw = sBias + ATT_BM * bh_stride;
-  float* sML = sBw + ((ATT_BM * bw_stride + 3) & ~3);          // [2 halves][128 rows][m, l]
+  BT* sBh = reinterpret_cast<BT*>(sBias);
+  BT* sBw = sBh + ATT_BM * bh_stride;
+  float* sML = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sBw + ATT_BM * bw_stride) + 15) & ~(uintptr_t)15);   // [2 halves][128 rows][m, l]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sML + 2 * ATT_BM * 2);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
@@ -308,8 +315,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const int quad = warp & 3, half = warp >> 2;
     const int row = quad * 32 + lane;  // TMEM lane == query row within the tile
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    float* bh = sBh + row * bh_stride;
-    float* bw = sBw + row * bw_stride;
+    BT* bh = sBh + row * bh_stride;
+    BT* bw = sBw + row * bw_stride;
     uint32_t gph = 0, pvph = 0;
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -327,7 +334,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         const int n = npad - c0 < 128 ? npad - c0 : 128;
         const int K1 = is_w ? p.Kw : p.Kh;
         const int qpos = is_w ? qw : qh;
-        float* dst = is_w ? bw : bh;
+        BT* dst = is_w ? bw : bh;
         mbar_wait(g_full, gph);
         gph ^= 1;
         tc_fence_after();
@@ -339,7 +346,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int kpos = qpos + K1 - 1 - (c0 + c + i);  // table row r = qpos - kpos + K1 - 1
-            if (kpos >= 0 && kpos < K1) dst[kpos] = __uint_as_float(r[i]) * kLog2e;
+            if (kpos >= 0 && kpos < K1) stb(dst + kpos, __uint_as_float(r[i]) * kLog2e);
           }
         }
         tc_fence_before();
@@ -365,7 +372,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         nvalid = nvalid < 0 ? 0 : (nvalid > 64 ? 64 : nvalid);
         u64 u[32];
         float segb[2];
-        float m_blk = scores_to_logits<KW>(r, u, segb, k0h, bh, bw, has_bias, p.scale_log2, p.Kh, p.Kw);
+        float m_blk = scores_to_logits<KW, BT>(r, u, segb, k0h, bh, bw, has_bias, p.scale_log2, p.Kh, p.Kw);
         if (nvalid < 64) {  // ragged last key block: keys >= T do not exist
           m_blk = -INFINITY;
 #pragma unroll
@@ -507,9 +514,21 @@ MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const int* out_ro
     p.bw_stride = (Kw + 1) & ~1;
     if (((p.bw_stride >> 1) & 1) == 0) p.bw_stride += 2;
   }
-  const int bias_bytes = ATT_BM * (p.bh_stride + p.bw_stride) * 4 + 16;
-  const int fixed = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*P*/ + tab_bytes + bias_bytes + 2 * ATT_BM * 2 * 4 /*(m,l)*/ + 256 /*barriers*/ + 1024 /*align*/ + 64;
+  int bias_elt = 4;
+  int bias_bytes = ATT_BM * (p.bh_stride + p.bw_stride) * bias_elt + 32;
+  int fixed = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*P*/ + tab_bytes + bias_bytes + 2 * ATT_BM * 2 * 4 /*(m,l)*/ + 256 /*barriers*/ + 1024 /*align*/ + 64;
   const int budget = 227 * 1024;
+  int kw_mode = 0;
+  if (has_bias && Kw == 64 && T % ATT_BN == 0) kw_mode = 64;
+  else if (has_bias && Kw == 32 && T % ATT_BN == 0) kw_mode = 32;
+  else if (has_bias && Kw == 14 && Kh == 14) kw_mode = 14;
+  if (kw_mode == 0 && fixed + 2 * 2 * TILE_BYTES > budget) {
+    // large generic key grid: half-precision bias rows (|bias| is O(1): 2^-11 relative, below the bf16 rounding of P)
+    bias_elt = 2;
+    fixed -= bias_bytes;
+    bias_bytes = ATT_BM * (p.bh_stride + p.bw_stride) * bias_elt + 32;
+    fixed += bias_bytes;
+  }
   p.kv_stages = 3;
   if (fixed + 3 * 2 * TILE_BYTES > budget) p.kv_stages = 2;
   const int smem_bytes = fixed + p.kv_stages * 2 * TILE_BYTES;
@@ -541,24 +560,21 @@ MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const int* out_ro
   }
   if (max_ctas <= 0 || max_ctas > kNumSMs) max_ctas = kNumSMs;
   const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
-  int kw_mode = 0;
-  if (has_bias && Kw == 64 && T % ATT_BN == 0) kw_mode = 64;
-  else if (has_bias && Kw == 32 && T % ATT_BN == 0) kw_mode = 32;
-  else if (has_bias && Kw == 14 && Kh == 14) kw_mode = 14;
-#define ATT_LAUNCH(KWM)                                                                                         \
+#define ATT_LAUNCH(KWM, BTY)                                                                                         \
   do {                                                                                                          \
     static bool configured = false;                                                                             \
     if (!configured) {                                                                                          \
-      cudaError_t e = cudaFuncSetAttribute(attention_kernel<KWM>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget); \
+      cudaError_t e = cudaFuncSetAttribute(attention_kernel<KWM, BTY>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget); \
       if (e != cudaSuccess) return (int)e;                                                                      \
       configured = true;                                                                                        \
     }                                                                                                           \
-    attention_kernel<KWM><<<grid, 320, smem_bytes, (cudaStream_t)stream>>>(tmQKV, tmH, tmW, p);                 \
+    attention_kernel<KWM, BTY><<<grid, 320, smem_bytes, (cudaStream_t)stream>>>(tmQKV, tmH, tmW, p);                 \
   } while (0)
-  if (kw_mode == 64) ATT_LAUNCH(64);
-  else if (kw_mode == 32) ATT_LAUNCH(32);
-  else if (kw_mode == 14) ATT_LAUNCH(14);
-  else ATT_LAUNCH(0);
+  if (kw_mode == 64) ATT_LAUNCH(64, float);
+  else if (kw_mode == 32) ATT_LAUNCH(32, float);
+  else if (kw_mode == 14) ATT_LAUNCH(14, float);
+  else if (bias_elt == 4) ATT_LAUNCH(0, float);
+  else ATT_LAUNCH(0, __half);
 #undef ATT_LAUNCH
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;

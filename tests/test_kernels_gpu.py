@@ -311,6 +311,7 @@ def test_gemm_row_map_big():
     (2, 3, 19, 25, True),     # non-square grid (475 tokens, ragged)
     (50, 16, 14, 14, True),   # many windows: exercises the persistent tile loop (2 images x 25 windows)
     (1, 16, 64, 64, True),    # ViT-L/1024 global: 4096 tokens, 127-row tables, two G chunks
+    (1, 2, 68, 120, True),    # MUSES whole frame 1088x1920 (BASELINE config 5b): 8160 tokens, half-precision bias rows
 ])
 def test_attention_vs_oracle(Bp, nh, Kh, Kw, bias):
     from oracle.model import attention_core
@@ -326,8 +327,9 @@ def test_attention_vs_oracle(Bp, nh, Kh, Kw, bias):
     out = k.attention(qkv.view(Bp, T, -1).cuda(), nh, (Kh, Kw), th, tw).cpu().float()
     q, kk, v = qkv.float().permute(2, 0, 3, 1, 4).reshape(3, Bp * nh, T, 64).unbind(0)
     nchk = min(Bp * nh, 48)
-    ref = attention_core(q[:nchk].double(), kk[:nchk].double(), v[:nchk].double(), Kh, Kw,
-                         rph.double() if bias else None, rpw.double() if bias else None).float()
+    dt = torch.float64 if T <= 4096 else torch.float32      # the 8160-token score matrix is 0.5 GB in double
+    ref = attention_core(q[:nchk].to(dt), kk[:nchk].to(dt), v[:nchk].to(dt), Kh, Kw,
+                         rph.to(dt) if bias else None, rpw.to(dt) if bias else None).float()
     got = out.view(Bp, T, nh, 64).permute(0, 2, 1, 3).reshape(Bp * nh, T, 64)[:nchk]
     err = (got - ref).abs().max().item()
     rel = ((got - ref).norm() / ref.norm()).item()
@@ -416,6 +418,36 @@ def test_resize_add_affine(B, C, hs, ws, ho, wo):
     assert ((out - ref).abs() <= 0.008 * ref.abs() + 4e-3).all()
     out2 = k.resize_add_affine(src.cuda(), (hs, ws), (ho, wo), B, C).cpu().float()       # plain resize
     assert ((out2 - up).abs() <= 0.008 * up.abs() + 4e-3).all()
+
+
+@pytest.mark.parametrize("K,B,C,grids,act", [
+    (7, 2, 96, [(37, 50)], None),                       # ConvNeXt 7x7, ragged tiles, 1.5 channel groups
+    (7, 3, 384, [(16, 16)], None),                      # many (channel group, image, tile) items per persistent CTA
+    (3, 2, 256, [(32, 32), (16, 16), (8, 8)], "gelu"),  # ConvFFN DWConv: three token grids, shared weights, fused GELU
+    (3, 1, 192, [(19, 25)], "relu6"),                   # MobileNetV2 block of the fusion neck
+])
+def test_dwconv_vs_torch(K, B, C, grids, act):
+    """Depthwise KxK (twin_convnext.py:98-101, adapter_modules_...new.py:456-471, :281-295) against F.conv2d(groups=C)."""
+    k = _k()
+    g = torch.Generator().manual_seed(K * 100 + C)
+    S = sum(h * w for h, w in grids)
+    x = torch.randn(B, S, C, generator=g).to(torch.bfloat16)
+    wt = torch.randn(C, 1, K, K, generator=g) / K
+    bias = torch.randn(C, generator=g)
+    w_tap = wt.reshape(C, K * K).t().contiguous()        # [K*K, C] tap-major
+    out = k.dwconv(x.cuda(), w_tap.cuda(), bias.cuda(), K, grids, B, C, S * C, S * C, act=act).cpu().float()
+    refs, o = [], 0
+    for (h, w) in grids:
+        xi = x[:, o:o + h * w].float().reshape(B, h, w, C).permute(0, 3, 1, 2)
+        y = torch.nn.functional.conv2d(xi, wt, bias, padding=K // 2, groups=C)
+        if act == "gelu":
+            y = torch.nn.functional.gelu(y)
+        elif act == "relu6":
+            y = torch.clamp(y, 0, 6)
+        refs.append(y.permute(0, 2, 3, 1).reshape(B, h * w, C))
+        o += h * w
+    ref = torch.cat(refs, 1)
+    assert ((out - ref).abs() <= 0.008 * ref.abs() + 4e-3).all(), (out - ref).abs().max().item()
 
 
 def test_colstats_gate_ln_dual():
