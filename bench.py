@@ -140,10 +140,10 @@ def instrumented_pass(eng, x):
         rec["gemm"].append((s, e, 2.0 * a.shape[0] * w.shape[0] * a.shape[1]))
         return r
 
-    def msda(value, shapes, lsi, qproj, ref, n_heads, n_levels, n_points=4, out=None):
+    def msda(value, shapes, lsi, qproj, ref, n_heads, n_levels, n_points=4, out=None, geom=None):
         s, e = ev(), ev()
         s.record()
-        r = om_(value, shapes, lsi, qproj, ref, n_heads, n_levels, n_points, out)
+        r = om_(value, shapes, lsi, qproj, ref, n_heads, n_levels, n_points, out, geom=geom)
         e.record()
         N, S, MD = value.shape
         Lq = ref.shape[0]

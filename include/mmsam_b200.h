@@ -90,6 +90,23 @@ int mmsam_msda_fused_bf16(const void* value, const int64_t* spatial_shapes_dev,
                           const float* ref_xy, void* out, int N, int S, int M, int D, int Lq, int L, int P,
                           void* stream);
 
+/* Same contract as mmsam_msda_fused_bf16, for callers that know the geometry on the host (the backbone does:
+ * deform_inputs, adapter_modules_...new.py:397-431): the value windows are staged in shared memory by TMA and
+ * gathered from there (~3x the L1 gather rate). level_hw_host [L][2] = (H_l, W_l), levels packed back to back in
+ * value (sum = S); qgrid_hw_host [n_qgrids][2]: the queries are n_qgrids <= 3 row-major grids back to back
+ * (sum = Lq) whose reference points are the cell centres; a CTA owns one head of a tile_h x tile_w tile of the
+ * anchor_h x anchor_w anchor grid (a partition of the normalised plane) and serves every query whose cell centre
+ * falls inside. prior_min_host [L][M][2] = per level/head minimum over the P points of the sampling_offsets bias
+ * (x, y; ops/modules/ms_deform_attn.py:64-74), prior_ext_host [L][2] = max over heads of (max - min): they only
+ * place and size the staged boxes; a sample that leaves its box is gathered from global memory, so results do not
+ * depend on them. Returns MMSAM_ERR_UNSUPPORTED (-3) when the boxes do not fit shared memory or M > 16, D != 32,
+ * P != 4, L > 4: call mmsam_msda_fused_bf16 instead. *_host arrays are HOST pointers read before the call returns. */
+int mmsam_msda_fused_staged_bf16(const void* value, const int* level_hw_host, const float* qproj, long long ldq,
+                                 const float* ref_xy, void* out, int N, int S, int M, int D, int Lq, int L, int P,
+                                 int n_qgrids, const int* qgrid_hw_host, int anchor_h, int anchor_w, int tile_h,
+                                 int tile_w, const float* prior_min_host, const float* prior_ext_host, int margin,
+                                 void* stream);
+
 /* Depthwise k x k conv (k = 3 or 7, stride 1, zero "same" padding) on channels-last bf16 maps, fp32
  * weights given tap-major [k*k][C], optional bias[C], act 0 none / 1 exact GELU / 3 ReLU6.
  * Up to 3 grids per batch item share the weights (ConvFFN DWConv over the 128^2|64^2|32^2 token

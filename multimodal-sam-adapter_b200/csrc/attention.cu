@@ -53,16 +53,6 @@ static constexpr int TM_O = 256;    // 2 x 64: output accumulators of the two ke
 static constexpr int TM_G = 384;    // 128: bias pre-products
 static constexpr float kRescaleThreshold = 8.f;   // log2 units: P stays <= 256 with a stale row maximum
 
-// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2) and the 3-input maximum (FMNMX3): these halve the softmax's
-//      FMA-pipe instruction count ----
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pack2(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void unpack2(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ float max3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
-
 // u = score * scale + bias (minus a per-segment constant kept in segb) for this warp's 64 key columns [k0h, k0h+64)
 // of the score row, as 32 fp32 pairs; returns the row maximum of the full logits. Segments: columns [0,32) / [32,64).
 __device__ __forceinline__ float ldb(const float* p) { return *p; }

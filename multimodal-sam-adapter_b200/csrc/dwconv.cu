@@ -76,37 +76,35 @@ dwconv_kernel(const DwParams p) {
   const int cp = threadIdx.x & 31;
   const int xg = threadIdx.x >> 5;
   const int c = c0 + cp * 2;
-  float acc[TH][XO][2];
+  // packed fp32x2 accumulators: .x = channel c, .y = channel c + 1 (one FFMA2 per tap and output instead of two FFMA;
+  // three-register FFMA issues every 2 cycles per scheduler, FFMA2 every 3 for twice the work)
+  u64 acc[TH][XO];
   {
     float b0 = 0.f, b1 = 0.f;
     if (p.bias && cp * 2 < cvalid) { b0 = p.bias[c]; b1 = p.bias[c + 1]; }
 #pragma unroll
     for (int r = 0; r < TH; ++r)
 #pragma unroll
-      for (int xo = 0; xo < XO; ++xo) { acc[r][xo][0] = b0; acc[r][xo][1] = b1; }
+      for (int xo = 0; xo < XO; ++xo) acc[r][xo] = pack2(b0, b1);
   }
   const uint32_t* s_in32 = reinterpret_cast<const uint32_t*>(s_in);
 #pragma unroll
   for (int ky = 0; ky < K; ++ky) {
-    float2 w[K];
+    u64 w[K];
 #pragma unroll
-    for (int kx = 0; kx < K; ++kx) w[kx] = *reinterpret_cast<const float2*>(&s_w[(ky * K + kx) * CB + cp * 2]);
+    for (int kx = 0; kx < K; ++kx) w[kx] = *reinterpret_cast<const u64*>(&s_w[(ky * K + kx) * CB + cp * 2]);
 #pragma unroll
     for (int r = 0; r < TH; ++r) {
-      float in0[XO + K - 1], in1[XO + K - 1];
+      u64 in[XO + K - 1];
 #pragma unroll
       for (int i = 0; i < XO + K - 1; ++i) {
         const uint32_t v = s_in32[((r + ky) * IW + xg * XO + i) * (CB / 2) + cp];
-        in0[i] = bf16lo(v);
-        in1[i] = bf16hi(v);
+        in[i] = pack2(bf16lo(v), bf16hi(v));
       }
 #pragma unroll
       for (int xo = 0; xo < XO; ++xo)
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          acc[r][xo][0] = fmaf(in0[xo + kx], w[kx].x, acc[r][xo][0]);
-          acc[r][xo][1] = fmaf(in1[xo + kx], w[kx].y, acc[r][xo][1]);
-        }
+        for (int kx = 0; kx < K; ++kx) acc[r][xo] = fma2(in[xo + kx], w[kx], acc[r][xo]);
     }
   }
   if (cp * 2 >= cvalid) return;
@@ -118,7 +116,8 @@ dwconv_kernel(const DwParams p) {
     for (int xo = 0; xo < XO; ++xo) {
       const int ox = x0 + xg * XO + xo;
       if (ox >= W) continue;
-      float a0 = acc[r][xo][0], a1 = acc[r][xo][1];
+      float a0, a1;
+      unpack2(acc[r][xo], a0, a1);
       if (p.act == 1) { a0 = gelu_erf(a0); a1 = gelu_erf(a1); }
       else if (p.act == 3) { a0 = fminf(fmaxf(a0, 0.f), 6.f); a1 = fminf(fmaxf(a1, 0.f), 6.f); }
       *reinterpret_cast<uint32_t*>(yout + ((long long)oy * W + ox) * p.C + c) = pack_bf16(a0, a1);

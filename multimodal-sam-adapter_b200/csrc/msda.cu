@@ -18,6 +18,8 @@
 //    reference's own known-answer shapes (D = 2) and as the catch-all.
 #include "common.cuh"
 #include <cstdlib>
+#include <cstring>
+#include <cmath>
 #include <type_traits>
 
 namespace mmsam {
@@ -392,6 +394,233 @@ msda_fused_coop_kernel(const __nv_bfloat16* __restrict__ value, const int64_t* _
   if (head_ok) *reinterpret_cast<uint4*>(out + (row * M + m) * D + pl * 8) = pack8(acc);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Shared-memory staged fused kernel (bf16, D = 32, P = 4, L <= 4, M <= 16).
+//
+// The cooperative kernel above is capped by the L1 gather rate (~1.6 cycles per 64-byte unit). Shared memory serves
+// the same unit in ~0.54 cycles when the two 4-lane groups of a quarter warp read opposite bank halves
+// (tools/micro/gather_bench.cu mode 9). So: a CTA owns ONE head of a REGION of the normalised plane (a tile of an
+// anchor grid given by the host) and
+//   * stages, with one TMA box per level, the window of that head's value map the region's queries are expected to
+//     sample: origin = region corner (in level pixels) + the head's prior offset (min over points of the
+//     sampling_offsets bias, ops/modules/ms_deform_attn.py:64-74) - margin. The box is dense [y][x][32 ch] = 64 B per
+//     pixel, so horizontally adjacent pixels alternate bank halves, and out-of-map pixels are zero-filled by the
+//     TMA unit — exactly the reference's zero padding (ms_deform_im2col_cuda.cuh:33-84);
+//   * handles every query of every query grid whose reference point falls inside the region (extractor: the 128^2,
+//     64^2 and 32^2 token grids all sample the same 64^2 map, so one staged window serves all three).
+// 8 lanes own a query: first lane j computes points j and j+8 (location, softmax weight, bilinear factors, byte offset
+// in the box), then for each point lanes 0-3 / 4-7 gather the left / right corner column (16 B channel chunks, top and
+// bottom row) — the left and right pixels sit in opposite bank halves, so every LDS.128 phase is conflict-free.
+// A sample whose corners leave the staged box (offsets far from the prior) is gathered from global memory with the
+// reference's bounds logic: correctness never depends on the prior, only speed does.
+struct MsdaStagedParams {
+  const __nv_bfloat16* value;
+  const float* qproj;
+  const float* ref;
+  __nv_bfloat16* out;
+  long long ldq;
+  int S, M, Lq, L, margin;
+  int H[4], W[4], lsi[4], BW[4], BH[4], box_off[4];
+  float pmin[4][16][2];                  // prior minimum offset (x, y), level pixels, per level and head
+  int AH, AW, TAH, TAW, tiles_x, NG;     // anchor grid, region tile (anchor cells), query grids
+  int gh[3], gw[3], gstart[3];
+  unsigned tx_bytes, bar_off;
+  unsigned qoff_off, qlg_off, qref_off, qidx_off;   // per-query staging areas: offsets, logits, ref point, query index
+  int dbg;                               // perf-debug switches (MMSAM_MSDA_DBG): 1 = no TMA staging, 2 = no gather
+};
+struct MsdaMaps { CUtensorMap m[4]; };
+
+__device__ __forceinline__ int cdiv_pos(int num, int den) { return (num + den - 1) / den; }   // num >= 1 - den
+__device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_ca8(void* smem_dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int MAXL>
+__global__ void __launch_bounds__(512)
+msda_staged_kernel(const __grid_constant__ MsdaMaps maps, const MsdaStagedParams p) {
+  constexpr int NK = MAXL > 2 ? 2 : 1;   // points per lane (lane j: points j, j + 8)
+  // [box level 0 | box level 1 | ... | per-query offsets | logits | ref points | query indices | mbarrier]
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  uint64_t& bar = *reinterpret_cast<uint64_t*>(st_smem + p.bar_off);
+  const int lane = threadIdx.x & 31, sub = lane & 7, side = sub >> 2, ch = sub & 3;
+  const int grp = threadIdx.x >> 3, ngrp = blockDim.x >> 3;
+  const int m = blockIdx.y, n = blockIdx.z;
+  const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
+  const int X0 = tx * p.TAW, X1 = min(X0 + p.TAW, p.AW), Y0 = ty * p.TAH, Y1 = min(Y0 + p.TAH, p.AH);
+  const float fx0 = (float)X0 / (float)p.AW, fy0 = (float)Y0 / (float)p.AH;
+
+  if (threadIdx.x == 0 && !(p.dbg & 1)) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(&bar, p.tx_bytes);
+    for (int l = 0; l < p.L; ++l) {
+      const int ox = (int)floorf(fx0 * p.W[l] - 0.5f + p.pmin[l][m][0]) - p.margin;
+      const int oy = (int)floorf(fy0 * p.H[l] - 0.5f + p.pmin[l][m][1]) - p.margin;
+      tma_load_4d(st_smem + p.box_off[l], &maps.m[l], &bar, m * 32, ox, oy, n);
+    }
+  }
+
+  // the region's rectangle of every query grid: queries whose cell centre (i + 0.5) / g lies in [X0, X1) / AW
+  int cnt[3], qx0[3], qy0[3], qw[3], total = 0;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    cnt[g] = 0; qx0[g] = qy0[g] = 0; qw[g] = 1;
+    if (g < p.NG) {
+      const int ix0 = cdiv_pos(2 * X0 * p.gw[g] - p.AW, 2 * p.AW), ix1 = cdiv_pos(2 * X1 * p.gw[g] - p.AW, 2 * p.AW);
+      const int iy0 = cdiv_pos(2 * Y0 * p.gh[g] - p.AH, 2 * p.AH), iy1 = cdiv_pos(2 * Y1 * p.gh[g] - p.AH, 2 * p.AH);
+      qx0[g] = ix0; qy0[g] = iy0; qw[g] = max(ix1 - ix0, 1);
+      cnt[g] = (ix1 - ix0) * (iy1 - iy0);
+      total += cnt[g];
+    }
+  }
+
+  const int LP = p.L * 4;
+  // stage this head's slice of every query's projection row (LP float2 offsets, LP logits), its reference point and
+  // its index with asynchronous copies: all of them are in flight at once, none holds a register
+  float2* s_off = reinterpret_cast<float2*>(st_smem + p.qoff_off);
+  float* s_lg = reinterpret_cast<float*>(st_smem + p.qlg_off);
+  float2* s_ref = reinterpret_cast<float2*>(st_smem + p.qref_off);
+  int* s_q = reinterpret_cast<int*>(st_smem + p.qidx_off);
+  for (int j = threadIdx.x; j < total; j += blockDim.x) {
+    int r = j, q = 0;
+    bool found = false;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      if (!found) {
+        if (r < cnt[g]) {
+          const int iy = r / qw[g], ix = r - iy * qw[g];
+          q = p.gstart[g] + (qy0[g] + iy) * p.gw[g] + qx0[g] + ix;
+          found = true;
+        } else {
+          r -= cnt[g];
+        }
+      }
+    }
+    const long long row = (long long)n * p.Lq + q;
+    const float* offp = p.qproj + row * p.ldq + (long long)m * LP * 2;
+    const float* lgp = p.qproj + row * p.ldq + (long long)p.M * LP * 2 + (long long)m * LP;
+    for (int c = 0; c < LP / 2; ++c) cp_async_cg16(s_off + j * LP + 2 * c, offp + 4 * c);
+    for (int c = 0; c < LP / 4; ++c) cp_async_cg16(s_lg + j * LP + 4 * c, lgp + 4 * c);
+    cp_async_ca8(s_ref + j, p.ref + 2 * q);
+    s_q[j] = q;
+  }
+  cp_async_wait_all();
+  __syncthreads();        // staged query data visible to every thread; the mbarrier init too
+  if (!(p.dbg & 1)) mbar_wait(&bar, 0);
+
+  const long long vrow = (long long)p.M * 32;
+  const __nv_bfloat16* vimg = p.value + (long long)n * p.S * vrow + (long long)m * 32 + ch * 8;
+
+  for (int base = 0; base < total; base += ngrp) {     // warp-uniform trip count: the shuffles below use the full mask
+    const bool valid = base + grp < total;
+    const int j = min(base + grp, total - 1);
+    const int q = s_q[j];
+    const long long row = (long long)n * p.Lq + q;
+    const float2 rf = s_ref[j];
+    const float rx = rf.x, ry = rf.y;
+    float lg[NK];
+    float2 of[NK];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const int pi = sub + 8 * k;
+      lg[k] = -INFINITY;
+      of[k] = make_float2(0.f, 0.f);
+      if (pi < LP) {
+        lg[k] = s_lg[j * LP + pi];
+        of[k] = s_off[j * LP + pi];
+        mx = fmaxf(mx, lg[k]);
+      }
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      lg[k] = (sub + 8 * k < LP) ? __expf(lg[k] - mx) : 0.f;
+      den += lg[k];
+    }
+    den += __shfl_xor_sync(0xffffffffu, den, 1);
+    den += __shfl_xor_sync(0xffffffffu, den, 2);
+    den += __shfl_xor_sync(0xffffffffu, den, 4);
+    const float inv = 1.f / den;
+
+    // my points: bilinear factors and the byte offset of the top-left corner inside the staged box (-1: not staged)
+    int soff[NK], xy[NK];
+    float plw[NK], ptop[NK], pbot[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const int pi = sub + 8 * k;
+      const int l = min(pi >> 2, p.L - 1);
+      const int H = p.H[l], W = p.W[l];
+      // same arithmetic as the reference: loc = ref + off / (W, H); im = loc * size - 0.5
+      const float h_im = (ry + of[k].y / H) * H - 0.5f, w_im = (rx + of[k].x / W) * W - 0.5f;
+      const bool inside = (pi < LP) && h_im > -1.f && w_im > -1.f && h_im < H && w_im < W;
+      const float hf = floorf(h_im), wf = floorf(w_im);
+      const int y0 = inside ? (int)hf : 0, x0 = inside ? (int)wf : 0;
+      const float lh = h_im - hf;
+      const float aw = inside ? lg[k] * inv : 0.f;
+      plw[k] = inside ? w_im - wf : 0.f;
+      ptop[k] = aw * (1.f - lh);
+      pbot[k] = aw * lh;
+      const int ox = (int)floorf(fx0 * W - 0.5f + p.pmin[l][m][0]) - p.margin;
+      const int oy = (int)floorf(fy0 * H - 0.5f + p.pmin[l][m][1]) - p.margin;
+      const int bx = x0 - ox, by = y0 - oy;
+      const bool inbox = bx >= 0 && bx <= p.BW[l] - 2 && by >= 0 && by <= p.BH[l] - 2 && !(p.dbg & 4);
+      soff[k] = inside ? (inbox ? p.box_off[l] + (by * p.BW[l] + bx) * 64 : -1) : 0;   // outside the map: weight 0
+      xy[k] = (y0 * 65536) | (x0 & 0xffff);
+    }
+
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < MAXL * 4; ++pp) {
+      if (pp < LP && !(p.dbg & 2)) {
+        const int k = pp >> 3, src = pp & 7, l = pp >> 2;
+        const int so = __shfl_sync(0xffffffffu, soff[k], src, 8);
+        const int pxy = __shfl_sync(0xffffffffu, xy[k], src, 8);
+        const float lw = __shfl_sync(0xffffffffu, plw[k], src, 8);
+        const float at = __shfl_sync(0xffffffffu, ptop[k], src, 8);
+        const float ab = __shfl_sync(0xffffffffu, pbot[k], src, 8);
+        const float wx = side ? lw : 1.f - lw;
+        const float kt = at * wx, kb = ab * wx;
+        uint4 ut, ub;
+        if (so >= 0) {
+          const uint8_t* a = st_smem + so + side * 64 + ch * 16;
+          ut = *reinterpret_cast<const uint4*>(a);
+          ub = *reinterpret_cast<const uint4*>(a + p.BW[l] * 64);
+        } else {
+          const int H = p.H[l], W = p.W[l];
+          const int x = (int)(short)(pxy & 0xffff) + side, y = pxy >> 16;
+          const __nv_bfloat16* vl = vimg + (long long)p.lsi[l] * vrow;
+          ut = ub = make_uint4(0, 0, 0, 0);
+          if (x >= 0 && x < W) {
+            if (y >= 0 && y < H) ut = __ldg(reinterpret_cast<const uint4*>(vl + ((long long)y * W + x) * vrow));
+            if (y + 1 >= 0 && y + 1 < H) ub = __ldg(reinterpret_cast<const uint4*>(vl + ((long long)(y + 1) * W + x) * vrow));
+          }
+        }
+        float v[8];
+        unpack8(ut, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(kt, v[i], acc[i]);
+        unpack8(ub, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(kb, v[i], acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
+    if (valid && side == 0) *reinterpret_cast<uint4*>(p.out + (row * p.M + m) * 32 + ch * 8) = pack8(acc);
+  }
+}
+
 template <typename VT, typename AT>
 static int launch_msda(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
                        const void* attw, void* out, int N, int S, int M, int D, int Lq, int L, int P,
@@ -489,6 +718,112 @@ MMSAM_API int mmsam_msda_fused_bf16(const void* value, const int64_t* spatial_sh
   msda_fused_kernel<__nv_bfloat16, 4><<<grid, block, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)value, spatial_shapes_dev, level_start_index_dev, qproj, ldq, ref_xy,
       (__nv_bfloat16*)out, S, M, D, Lq, L, HB, TPP);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+// Staged variant of mmsam_msda_fused_bf16 (see msda_staged_kernel and include/mmsam_b200.h). All *_host arrays are
+// HOST pointers read before the call returns.
+MMSAM_API int mmsam_msda_fused_staged_bf16(const void* value, const int* level_hw_host, const float* qproj,
+                                           long long ldq, const float* ref_xy, void* out, int N, int S, int M, int D,
+                                           int Lq, int L, int P, int n_qgrids, const int* qgrid_hw_host, int anchor_h,
+                                           int anchor_w, int tile_h, int tile_w, const float* prior_min_host,
+                                           const float* prior_ext_host, int margin, void* stream) {
+  using namespace mmsam;
+  if (N < 0 || S < 0 || M <= 0 || D <= 0 || Lq < 0 || L <= 0 || margin < 0) return MMSAM_ERR_BAD_ARG;
+  if (N == 0 || Lq == 0) return MMSAM_OK;
+  if (!value || !level_hw_host || !qproj || !ref_xy || !out || !qgrid_hw_host || !prior_min_host || !prior_ext_host)
+    return MMSAM_ERR_BAD_ARG;
+  if (D != 32 || P != 4 || L > 4 || M > 16 || n_qgrids < 1 || n_qgrids > 3 || N > 65535 || anchor_h <= 0 ||
+      anchor_w <= 0 || tile_h <= 0 || tile_w <= 0 || (((uintptr_t)value | (uintptr_t)out) & 15) ||
+      (((uintptr_t)qproj) & 15) || (ldq & 3) || (((uintptr_t)ref_xy) & 7))
+    return MMSAM_ERR_UNSUPPORTED;
+  MsdaStagedParams p;
+  memset(&p, 0, sizeof(p));
+  p.value = (const __nv_bfloat16*)value; p.qproj = qproj; p.ref = ref_xy; p.out = (__nv_bfloat16*)out;
+  p.ldq = ldq; p.S = S; p.M = M; p.Lq = Lq; p.L = L; p.margin = margin;
+  p.AH = anchor_h; p.AW = anchor_w; p.TAH = tile_h; p.TAW = tile_w; p.NG = n_qgrids;
+  long long s_sum = 0, q_sum = 0;
+  unsigned off = 0;
+  for (int l = 0; l < L; ++l) {
+    p.H[l] = level_hw_host[2 * l]; p.W[l] = level_hw_host[2 * l + 1];
+    if (p.H[l] <= 0 || p.W[l] <= 0 || p.H[l] > 32767 || p.W[l] > 32767) return MMSAM_ERR_BAD_ARG;
+    p.lsi[l] = (int)s_sum;
+    s_sum += (long long)p.H[l] * p.W[l];
+    const int span_x = (tile_w * p.W[l] + anchor_w - 1) / anchor_w, span_y = (tile_h * p.H[l] + anchor_h - 1) / anchor_h;
+    p.BW[l] = span_x + (int)ceilf(prior_ext_host[2 * l]) + 2 * margin + 2;
+    p.BH[l] = span_y + (int)ceilf(prior_ext_host[2 * l + 1]) + 2 * margin + 2;
+    if (p.BW[l] > 256 || p.BH[l] > 256) return MMSAM_ERR_UNSUPPORTED;
+    p.box_off[l] = (int)off;
+    off += (unsigned)(p.BW[l] * p.BH[l] * 64);
+    off = (off + 127u) & ~127u;
+    for (int m = 0; m < M; ++m) {
+      p.pmin[l][m][0] = prior_min_host[(l * M + m) * 2];
+      p.pmin[l][m][1] = prior_min_host[(l * M + m) * 2 + 1];
+    }
+  }
+  p.tx_bytes = 0;
+  for (int l = 0; l < L; ++l) p.tx_bytes += (unsigned)(p.BW[l] * p.BH[l] * 64);
+  for (int g = 0; g < n_qgrids; ++g) {
+    p.gh[g] = qgrid_hw_host[2 * g]; p.gw[g] = qgrid_hw_host[2 * g + 1];
+    if (p.gh[g] <= 0 || p.gw[g] <= 0 || p.gh[g] > 16384 || p.gw[g] > 16384) return MMSAM_ERR_BAD_ARG;
+    p.gstart[g] = (int)q_sum;
+    q_sum += (long long)p.gh[g] * p.gw[g];
+  }
+  if (s_sum != S || q_sum != Lq) return MMSAM_ERR_BAD_ARG;
+  // the most queries a region serves: same cell-centre assignment as the kernel, per axis
+  auto max_cells = [](int anchor, int tile, int g) {
+    int best = 0;
+    for (int a0 = 0; a0 < anchor; a0 += tile) {
+      const int a1 = a0 + tile < anchor ? a0 + tile : anchor;
+      const int i0 = (2 * a0 * g - anchor + 2 * anchor - 1) / (2 * anchor), i1 = (2 * a1 * g - anchor + 2 * anchor - 1) / (2 * anchor);
+      if (i1 - i0 > best) best = i1 - i0;
+    }
+    return best;
+  };
+  unsigned qmax = 0;
+  for (int g = 0; g < n_qgrids; ++g)
+    qmax += (unsigned)(max_cells(anchor_w, tile_w, p.gw[g]) * max_cells(anchor_h, tile_h, p.gh[g]));
+  const unsigned LP = (unsigned)L * 4;
+  p.qoff_off = off; off += qmax * LP * 8;
+  p.qlg_off = off; off += qmax * LP * 4;
+  p.qref_off = off; off += qmax * 8;
+  p.qidx_off = off; off += qmax * 4;
+  off = (off + 15u) & ~15u;
+  p.bar_off = off;
+  { const char* e = getenv("MMSAM_MSDA_DBG"); p.dbg = e ? atoi(e) : 0; }
+  const unsigned smem = off + 16;
+  if (smem > 226u * 1024u) return MMSAM_ERR_UNSUPPORTED;
+  p.tiles_x = (anchor_w + tile_w - 1) / tile_w;
+  const int tiles_y = (anchor_h + tile_h - 1) / tile_h;
+
+  MsdaMaps maps;
+  mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
+  if (!enc) return MMSAM_ERR_DRIVER;
+  for (int l = 0; l < 4; ++l) {
+    const int ll = l < L ? l : 0;
+    cuuint64_t dims[4] = {(cuuint64_t)M * 32, (cuuint64_t)p.W[ll], (cuuint64_t)p.H[ll], (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)M * 64, (cuuint64_t)p.W[ll] * M * 64, (cuuint64_t)S * M * 64};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.BW[ll], (cuuint32_t)p.BH[ll], 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    void* base = (void*)((const __nv_bfloat16*)value + (long long)p.lsi[ll] * M * 32);
+    if (enc(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MMSAM_ERR_DRIVER;
+  }
+  dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)M, (unsigned)N);
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(msda_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(msda_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  // 8 lanes per query: one pass over the region's queries when there are few (injector), 256 threads otherwise
+  const unsigned threads = qmax <= 64 ? 512 : 256;
+  if (L <= 2) msda_staged_kernel<2><<<grid, threads, smem, st>>>(maps, p);
+  else msda_staged_kernel<4><<<grid, threads, smem, st>>>(maps, p);
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }

@@ -11,6 +11,7 @@ image_encoder_adapter_bimodal_mix_mod_new_in_twin_convnext_new.py:161-349) step 
 line ranges are given at each stage below.
 """
 import math
+import os
 
 import torch
 
@@ -57,6 +58,11 @@ def _pad_rows(w, n):
     return out
 
 
+# The shared-memory staged MSDeformAttn kernel is correct (tests/test_kernels_gpu.py::test_msda_staged_vs_oracle) but
+# issue-bound and slower than the L1-gather kernel at the bench shapes (profiles/r01_msda_notes.md): opt-in only.
+MSDA_STAGED = os.environ.get("MMSAM_MSDA_STAGED", "0") == "1"
+
+
 class _MSDA:
     """Packed MSDeformAttn weights: one fused query projection (offsets | logits) with fp32 output."""
 
@@ -67,6 +73,20 @@ class _MSDA:
         bq = torch.cat((m.sampling_offsets.bias.detach(), m.attention_weights.bias.detach()), 0)
         self.qproj = _Lin(wq, bq, dev)
         self.out = _Lin(m.output_proj.weight, m.output_proj.bias, dev)
+        self.off_bias = m.sampling_offsets.bias.detach().float().cpu()
+        self._geoms = {}
+
+    def geom(self, kind, sc):
+        """Staged-gather geometry (K.MsdaGeometry): injector = ViT-token queries over the 3 c-levels, extractor =
+        the 3 c-grids as queries over the ViT-token map; regions are 8 x 8 (injector: three boxes per CTA) / 8 x 16 (extractor) tiles of the ViT token grid."""
+        key = (kind, tuple(sc["s1"]), tuple(sc["s3"]))
+        g = self._geoms.get(key)
+        if g is None:
+            levels, qgrids = (sc["s3"], sc["s1"]) if kind == "inj" else (sc["s1"], sc["s3"])
+            g = K.MsdaGeometry(levels, qgrids, sc["s1"][0], (8, 8) if kind == "inj" else (8, 16), self.off_bias, self.n_heads, self.n_levels,
+                               self.n_points, margin=int(os.environ.get("MMSAM_MSDA_MARGIN", "2")))
+            self._geoms[key] = g
+        return g
 
 
 def pack_block(blk, dev):
@@ -130,7 +150,7 @@ def deform_geometry(B, Hi, Wi, dev):
         lsi = torch.cat((t.new_zeros((1,)), t.prod(1).cumsum(0)[:-1]))
         return t.to(dev), lsi.to(dev)
 
-    sc = dict(ref1=ref(s1), ref2=ref(s3), lv3=lv(s3), lv1=lv(s1), s3=s3, S3=sum(h * w for h, w in s3))
+    sc = dict(ref1=ref(s1), ref2=ref(s3), lv3=lv(s3), lv1=lv(s1), s1=s1, s3=s3, S3=sum(h * w for h, w in s3))
     offs, o = [], 0
     for (h, w) in s3:
         n = h * w
@@ -150,12 +170,12 @@ class _Ops:
     def _ln(self, x, ln, **kw):
         return K.layernorm(x, ln.w, ln.b, ln.eps, **kw)
 
-    def _msda(self, pk, query_n, feat_n, ref, lv, B):
+    def _msda(self, pk, query_n, feat_n, ref, lv, B, geom=None):
         """MSDeformAttn.forward up to (not including) output_proj (ops/modules/ms_deform_attn.py:83-127)."""
         value = self._gemm(feat_n, pk.value)                                   # [B*S, M*D]
         qp = self._gemm(query_n, pk.qproj, out_dtype=torch.float32)            # [B*Lq, M*L*P*3]
         S = feat_n.shape[0] // B
-        return K.msda_fused(value.view(B, S, -1), lv[0], lv[1], qp, ref, pk.n_heads, pk.n_levels, pk.n_points)
+        return K.msda_fused(value.view(B, S, -1), lv[0], lv[1], qp, ref, pk.n_heads, pk.n_levels, pk.n_points, geom=geom)
 
     def _block(self, x, blk, sc, tabs, B, out=None):
         """Block.forward (base/image_encoder.py:382-423). x [B*T, C] is updated in place unless out is given."""
@@ -184,7 +204,7 @@ class _Ops:
         is one of the saved ViT outputs `outs` and must stay intact)."""
         qn = self._ln(x, inj["qn"])
         fn = self._ln(c, inj["fn"])
-        o = self._msda(inj["attn"], qn, fn, sc["ref1"], sc["lv3"], B)
+        o = self._msda(inj["attn"], qn, fn, sc["ref1"], sc["lv3"], B, inj["attn"].geom("inj", sc) if MSDA_STAGED else None)
         return K.gemm(o.view(-1, o.shape[-1]), inj["attn"].out.w, bias=inj["attn"].out.b, scale=inj["gamma"],
                       residual=x, out=torch.empty_like(x))
 
@@ -192,7 +212,7 @@ class _Ops:
         """Extractor.forward (adapter_modules_...new.py:490-511); c [B*S3, C] updated in place."""
         qn = self._ln(c, e["qn"])
         fn = self._ln(x, e["fn"])
-        o = self._msda(e["attn"], qn, fn, sc["ref2"], sc["lv1"], B)
+        o = self._msda(e["attn"], qn, fn, sc["ref2"], sc["lv1"], B, e["attn"].geom("ext", sc) if MSDA_STAGED else None)
         self._gemm(o.view(-1, o.shape[-1]), e["attn"].out, residual=c, out=c)
         f = e["ffn"]
         if f is not None:

@@ -3,6 +3,8 @@
 torch is used for device memory and the current CUDA stream only; every op below launches one of
 this repo's sm_100a kernels and raises if the tensors are not on a CUDA device.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -146,8 +148,35 @@ def attention(qkv, num_heads, hw, tab_h=None, tab_w=None, out=None, max_ctas=0, 
     return out
 
 
-def msda_fused(value, spatial_shapes, level_start_index, qproj, ref_xy, n_heads, n_levels, n_points=4, out=None):
-    """value bf16 [N,S,M*D]; qproj fp32 [N*Lq, >= M*L*P*3] (offsets | logits); ref_xy fp32 [Lq,2]."""
+class MsdaGeometry:
+    """Host-side geometry for the shared-memory staged MSDeformAttn kernel (mmsam_msda_fused_staged_bf16): level
+    shapes, query grids (row-major, reference points = cell centres, adapter_modules_...new.py:397-431), the anchor
+    grid / tile that partitions the normalised plane into CTA regions, and the per-level / per-head prior of the
+    sampling offsets taken from the sampling_offsets bias [M, L, P, 2] (ops/modules/ms_deform_attn.py:64-74)."""
+
+    def __init__(self, level_shapes, qgrid_shapes, anchor, tile, offset_bias, n_heads, n_levels, n_points=4, margin=2):
+        import ctypes
+        L, M = n_levels, n_heads
+        assert len(level_shapes) == L
+        b = offset_bias.detach().float().cpu().view(M, L, n_points, 2)
+        pmin = b.min(2)[0].permute(1, 0, 2).contiguous()                    # [L, M, 2]
+        ext = (b.max(2)[0] - b.min(2)[0]).max(0)[0].contiguous()            # [L, 2]: max over heads
+        self.levels = (ctypes.c_int * (2 * L))(*[int(v) for hw in level_shapes for v in hw])
+        self.qgrids = (ctypes.c_int * (2 * len(qgrid_shapes)))(*[int(v) for hw in qgrid_shapes for v in hw])
+        self.n_qgrids = len(qgrid_shapes)
+        self.pmin = (ctypes.c_float * (L * M * 2))(*pmin.view(-1).tolist())
+        self.ext = (ctypes.c_float * (L * 2))(*ext.view(-1).tolist())
+        self.anchor, self.tile, self.margin = (int(anchor[0]), int(anchor[1])), (int(tile[0]), int(tile[1])), int(margin)
+        self.S = sum(h * w for h, w in level_shapes)
+        self.Lq = sum(h * w for h, w in qgrid_shapes)
+        self.unsupported = False
+
+
+def msda_fused(value, spatial_shapes, level_start_index, qproj, ref_xy, n_heads, n_levels, n_points=4, out=None,
+               geom=None):
+    """value bf16 [N,S,M*D]; qproj fp32 [N*Lq, >= M*L*P*3] (offsets | logits); ref_xy fp32 [Lq,2].
+    geom (MsdaGeometry, optional): use the shared-memory staged kernel when the configuration supports it."""
+    import ctypes
     _need_cuda(value, spatial_shapes, level_start_index, qproj, ref_xy)
     N, S, MD = value.shape
     D = MD // n_heads
@@ -155,6 +184,18 @@ def msda_fused(value, spatial_shapes, level_start_index, qproj, ref_xy, n_heads,
     assert qproj.shape[0] == N * Lq and qproj.dtype == torch.float32 and qproj.stride(1) == 1
     if out is None:
         out = torch.empty((N, Lq, MD), dtype=value.dtype, device=value.device)
+    if geom is not None and not geom.unsupported and os.environ.get("MMSAM_MSDA_STAGED", "1") != "0":
+        assert geom.S == S and geom.Lq == Lq
+        rc = _lib.load().mmsam_msda_fused_staged_bf16(
+            _ptr(value), ctypes.cast(geom.levels, ctypes.c_void_p), _ptr(qproj), qproj.stride(0), _ptr(ref_xy), _ptr(out),
+            N, S, n_heads, D, Lq, n_levels, n_points, geom.n_qgrids, ctypes.cast(geom.qgrids, ctypes.c_void_p),
+            geom.anchor[0], geom.anchor[1], geom.tile[0], geom.tile[1], ctypes.cast(geom.pmin, ctypes.c_void_p),
+            ctypes.cast(geom.ext, ctypes.c_void_p), geom.margin, _stream())
+        if rc != -3:                              # MMSAM_ERR_UNSUPPORTED: fall through to the L1-gather kernel
+            _lib.check(rc, "mmsam_msda_fused_staged_bf16")
+            _count()
+            return out
+        geom.unsupported = True
     rc = _lib.load().mmsam_msda_fused_bf16(
         _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(qproj), qproj.stride(0), _ptr(ref_xy),
         _ptr(out), N, S, n_heads, D, Lq, n_levels, n_points, _stream())

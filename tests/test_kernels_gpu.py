@@ -120,6 +120,65 @@ def test_msda_fused_vs_oracle(N, M, Lq, shapes, spread):
     assert (out - exp).abs().max() < 1e-3 + 0.008 * exp.abs().max()          # one bf16 rounding of the output
 
 
+def _grid_refs(qgrids):
+    refs = []
+    for (h, w) in qgrids:
+        ys = torch.linspace(0.5, h - 0.5, h) / h
+        xs = torch.linspace(0.5, w - 0.5, w) / w
+        yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+        refs.append(torch.stack((xx.reshape(-1), yy.reshape(-1)), -1))
+    return torch.cat(refs).float().contiguous()
+
+
+@pytest.mark.parametrize("N,M,levels,qgrids,anchor,tile,noise,margin", [
+    (2, 16, [(32, 32), (16, 16), (8, 8)], [(16, 16)], (16, 16), (8, 16), 0.3, 2),        # injector-like
+    (2, 16, [(16, 16)], [(32, 32), (16, 16), (8, 8)], (16, 16), (8, 16), 0.3, 2),        # extractor-like
+    (1, 12, [(40, 56), (20, 28), (10, 14)], [(20, 28)], (20, 28), (8, 16), 0.5, 2),      # 320x448 geometry, ViT-B heads, ragged tiles
+    (1, 12, [(20, 28)], [(40, 56), (20, 28), (10, 14)], (20, 28), (8, 16), 0.5, 2),
+    (1, 16, [(25, 25)], [(50, 50), (25, 25), (12, 12)], (25, 25), (8, 16), 0.3, 1),      # FMB-like: 12 = 100 // 8, non-integer grid ratios
+    (1, 16, [(16, 16), (8, 8)], [(16, 16)], (16, 16), (4, 4), 6.0, 1),                   # offsets far from the prior: global fall-back path
+    (1, 16, [(9, 7)], [(9, 7)], (9, 7), (8, 16), 40.0, 0),                               # most samples outside the map
+])
+def test_msda_staged_vs_oracle(N, M, levels, qgrids, anchor, tile, noise, margin):
+    """Shared-memory staged kernel (TMA boxes placed by the sampling_offsets-bias prior, global fall-back for samples
+    that leave their box) against the oracle fed the materialised locations / weights."""
+    from oracle.msda import ms_deform_attn_core
+    k = _k()
+    D, P = 32, 4
+    L = len(levels)
+    g = torch.Generator().manual_seed(N * 1000 + M * 10 + L)
+    shapes_t = torch.as_tensor(levels, dtype=torch.long)
+    S = int(shapes_t.prod(1).sum())
+    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+    ref = _grid_refs(qgrids)
+    Lq = ref.shape[0]
+    value = torch.randn(N, S, M * D, generator=g).to(torch.bfloat16)
+    # MSDeformAttn._reset_parameters: head direction x (p + 1) pixels (ops/modules/ms_deform_attn.py:64-74)
+    th = torch.arange(M).float() * (2 * math.pi / M)
+    gi = torch.stack([th.cos(), th.sin()], -1)
+    gi = gi / gi.abs().max(-1, keepdim=True)[0]
+    bias = (gi.view(M, 1, 1, 2) * torch.arange(1, P + 1).view(1, 1, P, 1).float()).expand(M, L, P, 2).contiguous()
+    pad = 8                                                # the staged kernel copies 16-byte pieces: ldq % 4 == 0
+    qproj = torch.randn(N * Lq, M * L * P * 3 + pad, generator=g)
+    qproj[:, :M * L * P * 2] = qproj[:, :M * L * P * 2] * noise + bias.reshape(-1)
+    off = qproj[:, :M * L * P * 2].view(N, Lq, M, L, P, 2)
+    logits = qproj[:, M * L * P * 2:M * L * P * 3].view(N, Lq, M, L * P)
+    norm = torch.stack([shapes_t[:, 1], shapes_t[:, 0]], -1).float()
+    loc = ref[None, :, None, None, None, :] + off / norm[None, None, None, :, None, :]
+    aw = torch.softmax(logits, -1).view(N, Lq, M, L, P)
+    exp = ms_deform_attn_core(value.float().view(N, S, M, D), shapes_t, loc, aw)
+    geom = k.MsdaGeometry(levels, qgrids, anchor, tile, bias, M, L, P, margin=margin)
+    out = torch.full((N, Lq, M * D), float("nan"), dtype=torch.bfloat16, device="cuda")   # every query must be written
+    k.msda_fused(value.cuda(), shapes_t.cuda(), lsi.cuda(), qproj.cuda(), ref.cuda(), M, L, P, out=out, geom=geom)
+    assert not geom.unsupported
+    out = out.cpu().float()
+    assert torch.isfinite(out).all()
+    assert (out - exp).abs().max() < 1e-3 + 0.008 * exp.abs().max()
+    # and the staged kernel agrees with the L1-gather kernel to fp32 summation order
+    out2 = k.msda_fused(value.cuda(), shapes_t.cuda(), lsi.cuda(), qproj.cuda(), ref.cuda(), M, L, P).cpu().float()
+    assert (out - out2).abs().max() <= 0.008 * exp.abs().max() + 1e-6
+
+
 def test_msda_empty():
     k = _k()
     shapes = torch.as_tensor([(4, 4)], dtype=torch.long).cuda()
