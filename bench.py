@@ -251,18 +251,22 @@ def main():
     value = world * B * args.steps / (ms / 1e3)
 
     # ---------------- e2e: public API, pinned host input -> H2D -> forward -> D2H labels ----------------
+    # EncoderDecoder.stream_labels is the test-loop call: one host batch in, one host label map out, per step; the
+    # copy of step i+1 overlaps the forward of step i (copy stream), every step's H2D and D2H is inside the timed region
     seg.use_cuda_graph = not args.no_graph
-    for _ in range(max(min(W, 2), 1)):
-        seg.encode_decode_labels(x_host.cuda(non_blocking=True), (1024, 1024)).cpu()
+
+    def host_batches(n):
+        for _ in range(n):
+            yield x_host
+
+    for lab in seg.stream_labels(host_batches(max(min(W, 2), 1)), (1024, 1024)):
+        pass
     barrier()
-    out_host = torch.empty((B, 1024, 1024), dtype=torch.uint8).pin_memory()
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s2.record()
-    for _ in range(args.steps):
-        xd = x_host.cuda(non_blocking=True)
-        lab = seg.encode_decode_labels(xd, (1024, 1024))
-        out_host.copy_(lab, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    d2h = 0
+    for lab in seg.stream_labels(host_batches(args.steps), (1024, 1024)):
+        d2h = lab.numel()                    # uint8 labels in pinned host memory
     e2.record()
     barrier()
     ms2 = s2.elapsed_time(e2)
@@ -289,7 +293,8 @@ def main():
         "config": {"workload": WORKLOAD, "global_batch": world * B, "l2": "inputs (201 MB fp32 per step) exceed the 126 MB L2",
                    "parallelism": f"image-sharded x{world}, no data-path collective",
                    "launch": "eager" if args.no_graph else "cuda-graph replay"},
-        "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": world * x_host.numel() * 4, "d2h_bytes_per_step": world * out_host.numel()},
+        "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": world * x_host.numel() * 4, "d2h_bytes_per_step": world * d2h,
+                "api": "EncoderDecoder.stream_labels (H2D of step i+1 overlaps the forward of step i)"},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"kernel": "gemm_bf16_kernel (tcgen05)", "bound": "tensor", "achieved": tf,

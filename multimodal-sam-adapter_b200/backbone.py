@@ -209,6 +209,65 @@ class EncoderDecoder(nn.Module):
         return self._engine().segment(img, out_hw, crop_hw)
 
     @torch.no_grad()
+    def stream_labels(self, batches, out_hw=None, crop_hw=None):
+        """Whole-image inference over an iterable of HOST batches [B, C, H, W] (the test loop of
+        mmseg_custom/apis/test_bs.py:91-163 feeds one DataLoader batch at a time): yields one uint8 [B, H, W]
+        label tensor in pinned host memory per batch, in order. The host->device copy of batch i+1 runs on a copy
+        stream while batch i is computed, and the labels of batch i are read back asynchronously, so a step costs
+        max(copy, compute) instead of their sum. Pass pinned tensors (tensor.pin_memory()); pageable ones still work
+        but their copies are synchronous. A yielded tensor is valid until the generator has been advanced twice."""
+        dev = next(self.parameters()).device
+        comp = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._stage = [None, None]
+            self._out_host = [None, None]
+        copy = self._copy_stream
+        free_ev = [None, None]
+
+        def upload(x, slot):
+            buf = self._stage[slot]
+            if buf is None or buf.shape != x.shape or buf.dtype != x.dtype:
+                buf = self._stage[slot] = torch.empty(x.shape, dtype=x.dtype, device=dev)   # allocated on comp
+                copy.wait_stream(comp)
+            with torch.cuda.stream(copy):
+                if free_ev[slot] is not None:
+                    copy.wait_event(free_ev[slot])          # the forward that read this slot has consumed it
+                buf.copy_(x, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return buf, ev
+
+        it = iter(batches)
+        try:
+            nxt = upload(next(it), 0)
+        except StopIteration:
+            return
+        prev, i = None, 0
+        while nxt is not None:
+            (buf, ev), slot = nxt, i % 2
+            try:
+                nxt = upload(next(it), (i + 1) % 2)
+            except StopIteration:
+                nxt = None
+            comp.wait_event(ev)
+            lab = self.encode_decode_labels(buf, out_hw, crop_hw)
+            free_ev[slot] = torch.cuda.Event()
+            free_ev[slot].record(comp)
+            out = self._out_host[slot]
+            if out is None or out.shape != lab.shape:
+                out = self._out_host[slot] = torch.empty(lab.shape, dtype=lab.dtype).pin_memory()
+            out.copy_(lab, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(comp)
+            if prev is not None:
+                prev[1].synchronize()
+                yield prev[0]
+            prev, i = (out, done), i + 1
+        prev[1].synchronize()
+        yield prev[0]
+
+    @torch.no_grad()
     def encode_decode(self, img, img_metas=None):
         """Logits at image size (bilinear, align_corners=False): [B, num_classes, H, W] fp32."""
         eng = self._engine()

@@ -32,6 +32,7 @@ struct AttnParams {
   int nh_rows, nw_rows;        // table rows (2K-1), 0 = no relative position bias
   int nh_pad, nw_pad;          // padded to a multiple of 16
   int kv_stages;               // 2 or 3
+  int q_bufs;                  // 1 or 2 Q tiles in shared memory (2: next tile's prologue overlaps this tile's tail)
   int bh_stride, bw_stride;    // floats per bias row in shared memory
   float scale_log2;            // scale * log2(e)
   int num_tiles, nqb;
@@ -137,9 +138,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from the __shared__ array (so loads compile to LDS, not generic LD)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // layout: Q | KV stages | P (2 panels) | tables | bias rows | (m, l) exchange | barriers
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + TILE_BYTES;
+  // layout: Q (2 buffers) | KV stages | P (2 panels) | tables | bias rows | (m, l) exchange | barriers
+  uint8_t* sQ = smem;                       // q_bufs tiles: Q of the CTA's i-th tile lives in buffer i % q_bufs
+  uint8_t* sKV = sQ + p.q_bufs * TILE_BYTES;
   uint8_t* sP = sKV + p.kv_stages * 2 * TILE_BYTES;
   uint8_t* sTab = sP + 2 * TILE_BYTES;
   const int tab_bytes = (p.nh_pad + p.nw_pad) * 128;
@@ -149,8 +150,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   BT* sBw = sBh + ATT_BM * bh_stride;
   float* sML = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sBw + ATT_BM * bw_stride) + 15) & ~(uintptr_t)15);   // [2 halves][128 rows][m, l]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sML + 2 * ATT_BM * 2);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
+  uint64_t* q_full = bars + 0;    // [2] at bars + 0, bars + 17
+  uint64_t* q_empty = bars + 1;   // [2] at bars + 1, bars + 18
   uint64_t* g_full = bars + 2;
   uint64_t* g_empty = bars + 3;
   uint64_t* p_full = bars + 4;
@@ -160,7 +161,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint64_t* s_empty = bars + 9;   // [2]
   uint64_t* kv_full = bars + 11;  // [3]
   uint64_t* kv_empty = bars + 14; // [3]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool has_bias = p.nh_rows > 0;
@@ -168,10 +169,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   // G chunks of <= 128 table rows each: first the h table, then the w table
   const int nch_h = has_bias ? (p.nh_pad + 127) / 128 : 0;
   const int nch_w = has_bias ? (p.nw_pad + 127) / 128 : 0;
+  const bool g_merged = has_bias && p.nh_pad + p.nw_pad <= 128;
+  const int ng_chunks = g_merged ? 1 : nch_h + nch_w;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    mbar_init(bars + 17, 1);
+    mbar_init(bars + 18, 1);
     mbar_init(g_empty, 8);
     mbar_init(p_full, 8);
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
@@ -192,19 +197,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         tma_load_2d(sTab, &tmTabH, tab_full, 0, 0);
         tma_load_2d(sTab + p.nh_pad * 128, &tmTabW, tab_full, 0, 0);
       }
-      int st = 0; uint32_t kph = 0; uint32_t qph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int st = 0; uint32_t kph = 0; uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int qb = tile % p.nqb;
         const int bh = tile / p.nqb;
         const int head = bh % p.nh, bp = bh / p.nh;
-        mbar_wait(q_empty, qph ^ 1);
-        mbar_arrive_expect_tx(q_full, TILE_BYTES);
+        const uint32_t qi = p.q_bufs == 2 ? (it & 1) : 0, qph = p.q_bufs == 2 ? ((it >> 1) & 1) : (it & 1);
+        uint64_t* qf = q_full + qi * 17;
+        mbar_wait(q_empty + qi * 17, qph ^ 1);
+        mbar_arrive_expect_tx(qf, TILE_BYTES);
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-            ::"r"(smem_u32(sQ)), "l"(reinterpret_cast<uint64_t>(&tmQKV)), "r"(smem_u32(q_full)), "r"(0),
+            ::"r"(smem_u32(sQ + qi * TILE_BYTES)), "l"(reinterpret_cast<uint64_t>(&tmQKV)), "r"(smem_u32(qf)), "r"(0),
             "r"(head), "r"(qb * ATT_BM), "r"(bp)
             : "memory");
-        qph ^= 1;
         for (int j = 0; j < nkb; ++j) {
           mbar_wait(&kv_empty[st], kph ^ 1);
           mbar_arrive_expect_tx(&kv_full[st], 2 * TILE_BYTES);
@@ -231,9 +237,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       if (has_bias) { mbar_wait(tab_full, 0); }
       int st = 0; uint32_t kph = 0;       // kv ring (QK side)
       int st_pv = 0;                      // kv ring (PV side)
-      uint32_t qph = 0, gph = 0, pph = 0;
+      uint32_t gph = 0, pph = 0;
       uint32_t g = 0;                     // global key-block counter (S buffer parity)
-      const uint32_t q_addr = smem_u32(sQ);
+      uint32_t q_addr = smem_u32(sQ);     // Q buffer of the tile whose S / G products are being issued
       const uint32_t p_addr = smem_u32(sP);
       // O_half (+)= P[:, half] . V[half]: keys 0..63 of the block accumulate into O_a, keys 64..127 into O_b,
       // across all key blocks of the tile (the first block overwrites)
@@ -252,15 +258,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         umma_commit(pv_done);
         umma_commit(&kv_empty[stage]);
       };
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(q_full, qph);
-        qph ^= 1;
+      // S_j = Q . K_j^T into the double-buffered score tile
+      auto issue_qk = [&]() {
+        mbar_wait(&kv_full[st], kph);
+        mbar_wait(&s_empty[g & 1], ((g >> 1) & 1) ^ 1);
         tc_fence_after();
-        // ---- bias pre-products G = Q . table^T, chunk by chunk through TM_G ----
-        for (int ci = 0; ci < nch_h + nch_w; ++ci) {
-          const bool is_w = ci >= nch_h;
-          const int c0 = (is_w ? ci - nch_h : ci) * 128;
-          const int npad = is_w ? p.nw_pad : p.nh_pad;
+        const uint32_t k_addr = smem_u32(sKV + st * 2 * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tmem + TM_S + (g & 1) * ATT_BN, umma_desc_sw128(q_addr + k * 32),
+                      umma_desc_sw128(k_addr + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[g & 1]);
+        if (++st == p.kv_stages) { st = 0; kph ^= 1; }
+        ++g;
+      };
+      // Tile prologue: wait for Q, then S_0 (needs only Q and the first key block) and the bias pre-products
+      // G = Q . table^T through TM_G — one chunk when both tables fit its 128 columns (SAM windows: 32 + 32 rows; the
+      // tables sit back to back in shared memory), else <= 128 rows at a time. It is issued BEFORE the previous tile's
+      // last P.V, so these products (and their hand-shakes with the softmax warps) overlap the previous tile's tail.
+      auto prologue = [&](uint32_t it) {
+        const uint32_t qi = p.q_bufs == 2 ? (it & 1) : 0, qph = p.q_bufs == 2 ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(q_full + qi * 17, qph);
+        tc_fence_after();
+        q_addr = smem_u32(sQ + qi * TILE_BYTES);
+        issue_qk();
+        for (int ci = 0; ci < ng_chunks; ++ci) {
+          const bool is_w = !g_merged && ci >= nch_h;
+          const int c0 = g_merged ? 0 : (is_w ? ci - nch_h : ci) * 128;
+          const int npad = g_merged ? p.nh_pad + p.nw_pad : (is_w ? p.nw_pad : p.nh_pad);
           const int n = npad - c0 < 128 ? npad - c0 : 128;
           mbar_wait(g_empty, gph ^ 1);
           tc_fence_after();
@@ -273,26 +298,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           umma_commit(g_full);
           gph ^= 1;
         }
+        if (nkb == 1) umma_commit(q_empty + qi * 17);   // every MMA that reads this Q has been issued
+      };
+      uint32_t it = 0;
+      if ((int)blockIdx.x < p.num_tiles) prologue(0);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         // ---- main loop: QK_j issued ahead of PV_{j-1} ----
-        for (int j = 0; j < nkb; ++j, ++g) {
-          mbar_wait(&kv_full[st], kph);
-          mbar_wait(&s_empty[g & 1], ((g >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t k_addr = smem_u32(sKV + st * 2 * TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ss(tmem + TM_S + (g & 1) * ATT_BN, umma_desc_sw128(q_addr + k * 32),
-                        umma_desc_sw128(k_addr + k * 32), idesc_qk, k != 0 ? 1u : 0u);
-          umma_commit(&s_full[g & 1]);
-          if (j == nkb - 1) umma_commit(q_empty);
-          if (++st == p.kv_stages) { st = 0; kph ^= 1; }
-          if (j >= 1) {
-            issue_pv(st_pv, j == 1);
-            if (++st_pv == p.kv_stages) st_pv = 0;
-          }
+        for (int j = 1; j < nkb; ++j) {
+          issue_qk();
+          if (j == nkb - 1) umma_commit(q_empty + (p.q_bufs == 2 ? (it & 1) : 0) * 17);
+          issue_pv(st_pv, j == 1);
+          if (++st_pv == p.kv_stages) st_pv = 0;
         }
+        const bool more = tile + (int)gridDim.x < p.num_tiles;
+        if (more && p.q_bufs == 2) prologue(it + 1);      // with one Q buffer the wait for Q would stall the last P.V
         issue_pv(st_pv, nkb == 1);
         if (++st_pv == p.kv_stages) st_pv = 0;
+        if (more && p.q_bufs == 1) prologue(it + 1);
       }
     }
   } else {
@@ -317,25 +339,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       const int qh = q / p.Kw, qw = q - qh * p.Kw;
       // ---- scatter the bias pre-products into this row's bias rows (pre-scaled by log2 e); the two halves
       //      take alternate 16-column groups ----
-      for (int ci = 0; ci < nch_h + nch_w; ++ci) {
-        const bool is_w = ci >= nch_h;
-        const int c0 = (is_w ? ci - nch_h : ci) * 128;
-        const int npad = is_w ? p.nw_pad : p.nh_pad;
+      for (int ci = 0; ci < ng_chunks; ++ci) {
+        const bool chunk_w = !g_merged && ci >= nch_h;
+        const int c0 = g_merged ? 0 : (chunk_w ? ci - nch_h : ci) * 128;
+        const int npad = g_merged ? p.nh_pad + p.nw_pad : (chunk_w ? p.nw_pad : p.nh_pad);
         const int n = npad - c0 < 128 ? npad - c0 : 128;
-        const int K1 = is_w ? p.Kw : p.Kh;
-        const int qpos = is_w ? qw : qh;
-        BT* dst = is_w ? bw : bh;
         mbar_wait(g_full, gph);
         gph ^= 1;
         tc_fence_after();
         for (int c = half * 16; c < n; c += 32) {
+          // a 16-column group belongs to one table (both are padded to multiples of 16 rows)
+          const bool is_w = g_merged ? c >= p.nh_pad : chunk_w;
+          const int cl = g_merged && is_w ? c - p.nh_pad : c;
+          const int K1 = is_w ? p.Kw : p.Kh;
+          const int qpos = is_w ? qw : qh;
+          BT* dst = is_w ? bw : bh;
           uint32_t r[16];
           __syncwarp();
           tmem_ld_32x32b_x16(lane_addr + TM_G + c, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int kpos = qpos + K1 - 1 - (c0 + c + i);  // table row r = qpos - kpos + K1 - 1
+            const int kpos = qpos + K1 - 1 - (c0 + cl + i);  // table row r = qpos - kpos + K1 - 1
             if (kpos >= 0 && kpos < K1) stb(dst + kpos, __uint_as_float(r[i]) * kLog2e);
           }
         }
@@ -521,8 +546,10 @@ MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const int* out_ro
   }
   p.kv_stages = 3;
   if (fixed + 3 * 2 * TILE_BYTES > budget) p.kv_stages = 2;
-  const int smem_bytes = fixed + p.kv_stages * 2 * TILE_BYTES;
+  int smem_bytes = fixed + p.kv_stages * 2 * TILE_BYTES;
   if (smem_bytes > budget) return MMSAM_ERR_UNSUPPORTED;
+  p.q_bufs = 1;
+  if (smem_bytes + TILE_BYTES <= budget) { p.q_bufs = 2; smem_bytes += TILE_BYTES; }
   if (!has_bias) { p.Kh = 1; p.Kw = 1 << 30; }
 
   mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
