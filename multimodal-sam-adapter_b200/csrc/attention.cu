@@ -21,6 +21,7 @@
 //           K-major smem panel of the half. The output accumulates in TMEM across key blocks and is rescaled
 //           only when a row maximum grows by more than 2^8 (lazy rescale); halves are merged per tile.
 #include "common.cuh"
+#include <cstdlib>
 #include <type_traits>
 
 namespace mmsam {
@@ -32,6 +33,7 @@ struct AttnParams {
   int nh_rows, nw_rows;        // table rows (2K-1), 0 = no relative position bias
   int nh_pad, nw_pad;          // padded to a multiple of 16
   int kv_stages;               // 2 or 3
+  int dbg;                     // perf-debug switches (MMSAM_ATT_DBG): 1 no bias scatter, 2 no bias add, 4 no pair barrier
   int q_bufs;                  // 1 or 2 Q tiles in shared memory (2: next tile's prologue overlaps this tile's tail)
   int bh_stride, bw_stride;    // floats per bias row in shared memory
   float scale_log2;            // scale * log2(e)
@@ -82,16 +84,23 @@ __device__ __forceinline__ float scores_to_logits(const uint32_t (&r)[64], u64 (
       u[i] = fma2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, pack2(b.x, b.y));
     }
   } else if (KW == 14) {
-    // SAM window (14 x 14 keys): k0h is 0, 64, 128 or 192 -> (kh, kw) of every column are compile-time constants
+    // SAM window (14 x 14 keys): k0h is 0, 64, 128 or 192 -> (kh, kw) of every column are compile-time constants.
+    // The 7 key-column pairs of the row's bw entries are read once as 64-bit words, the <= 6 key-row entries this
+    // half touches once as scalars; a column pair never straddles a key row (14 is even), so its bias is ONE packed
+    // add of two registers instead of two shared-memory reads and two scalar adds per element.
     auto body = [&](auto k0c) {
       constexpr int K0 = decltype(k0c)::value;
+      constexpr int KH0 = K0 / 14, KH1 = (K0 + 63) / 14 < 13 ? (K0 + 63) / 14 : 13;
+      u64 bw2[7], bh2[KH1 - KH0 + 1];
+#pragma unroll
+      for (int t = 0; t < 7; ++t) bw2[t] = *(reinterpret_cast<const u64*>(bw) + t);
+#pragma unroll
+      for (int t = 0; t <= KH1 - KH0; ++t) { const float v = ldb(bh + KH0 + t); bh2[t] = pack2(v, v); }
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        constexpr int dummy = 0; (void)dummy;
-        const int k0 = K0 + 2 * i, k1 = K0 + 2 * i + 1;
-        const float b0 = k0 < 196 ? ldb(bh + k0 / 14) + ldb(bw + k0 % 14) : 0.f;
-        const float b1 = k1 < 196 ? ldb(bh + k1 / 14) + ldb(bw + k1 % 14) : 0.f;
-        u[i] = fma2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, pack2(b0, b1));
+        const int k0 = K0 + 2 * i;
+        const u64 b2 = k0 < 196 ? add2(bw2[(k0 % 14) >> 1], bh2[(k0 / 14 < KH1 ? k0 / 14 : KH1) - KH0]) : 0ull;
+        u[i] = fma2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, b2);
       }
     };
     switch (k0h >> 6) {
@@ -354,6 +363,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           const int K1 = is_w ? p.Kw : p.Kh;
           const int qpos = is_w ? qw : qh;
           BT* dst = is_w ? bw : bh;
+          if (p.dbg & 1) continue;
           uint32_t r[16];
           __syncwarp();
           tmem_ld_32x32b_x16(lane_addr + TM_G + c, r);
@@ -368,7 +378,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(g_empty);
       }
-      if (has_bias) asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // both halves' bias entries are in place
+      if (has_bias && !(p.dbg & 4)) asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // both halves' bias entries are in place
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nkb; ++j, ++g) {
         // ---- 1. this half's 64 score columns of key block j ----
@@ -387,7 +397,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         nvalid = nvalid < 0 ? 0 : (nvalid > 64 ? 64 : nvalid);
         u64 u[32];
         float segb[2];
-        float m_blk = scores_to_logits<KW, BT>(r, u, segb, k0h, bh, bw, has_bias, p.scale_log2, p.Kh, p.Kw);
+        float m_blk = scores_to_logits<KW, BT>(r, u, segb, k0h, bh, bw, has_bias && !(p.dbg & 2), p.scale_log2, p.Kh, p.Kw);
         if (nvalid < 64) {  // ragged last key block: keys >= T do not exist
           m_blk = -INFINITY;
 #pragma unroll
@@ -549,6 +559,7 @@ MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const int* out_ro
   int smem_bytes = fixed + p.kv_stages * 2 * TILE_BYTES;
   if (smem_bytes > budget) return MMSAM_ERR_UNSUPPORTED;
   p.q_bufs = 1;
+  { const char* e = getenv("MMSAM_ATT_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (smem_bytes + TILE_BYTES <= budget) { p.q_bufs = 2; smem_bytes += TILE_BYTES; }
   if (!has_bias) { p.Kh = 1; p.Kw = 1 << 30; }
 

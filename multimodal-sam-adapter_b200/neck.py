@@ -16,6 +16,8 @@ Everything that touches a pixel is one of this repo's kernels. The O(B*C^2)-size
 (softmax of the [ch, ch] / [ci, ci] matrices, folding proj into Weff, the FFRM / CA vectors: a few kFLOP
 per image) is done with torch tensor ops on the device, in fp32/fp64.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -45,6 +47,7 @@ class NeckB200:
     def __init__(self, m, dev):
         self.dev = dev
         self.levels = []
+        self._side = []
         for i, C in enumerate(m.in_channels):
             ci = C // 2
             lv = dict(C=C, ci=ci)
@@ -166,4 +169,26 @@ class NeckB200:
     @torch.no_grad()
     def __call__(self, fx, fy, B):
         """fx / fy: per level (tokens bf16 [B*h*w, ci], h, w) -> list of fused tokens bf16 [B*h*w, C]."""
-        return [self._level(lv, tx, ty, B, h, w) for lv, (tx, h, w), (ty, _, _) in zip(self.levels, fx, fy)]
+        items = list(zip(self.levels, fx, fy))
+        if os.environ.get("MMSAM_NECK_STREAMS", "1") == "0" or len(items) < 2:
+            return [self._level(lv, tx, ty, B, h, w) for lv, (tx, h, w), (ty, _, _) in items]
+        # The four pyramid levels are independent until the backbone consumes them, and the kernels of the small levels
+        # (32^2 / 64^2 / 128^2 maps: a handful of CTAs each, plus the O(B*C^2) glue) leave most of the GPU idle: they
+        # run on side streams next to the 256^2 level (fork / join on the current stream; inside a CUDA graph capture
+        # this records parallel branches). Every tensor a side stream allocates is either freed on that stream or
+        # returned and consumed after the join, and the next call forks again before reusing the side pools.
+        main = torch.cuda.current_stream()
+        if len(self._side) < len(items) - 1:
+            self._side = [torch.cuda.Stream(device=self.dev) for _ in range(len(items) - 1)]
+        outs = [None] * len(items)
+        for i in range(1, len(items)):
+            lv, (tx, h, w), (ty, _, _) = items[i]
+            side = self._side[i - 1]
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                outs[i] = self._level(lv, tx, ty, B, h, w)
+        lv, (tx, h, w), (ty, _, _) = items[0]
+        outs[0] = self._level(lv, tx, ty, B, h, w)
+        for side in self._side[: len(items) - 1]:
+            main.wait_stream(side)
+        return outs
