@@ -306,7 +306,13 @@ def main():
                      "launches_per_step": gm["launches"], "ms_per_step": gm["ms"],
                      "share_of_step": gm["ms"] / (ms / args.steps)},
         "roofline_msda": {"kernel": "msda_fused_coop_kernel", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
-                          "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None, "launches_per_step": md["launches"],
+                          "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                          # ncu --set full inside a forward (profiles/r01_msda_ncu_summary.txt): dram read + write per
+                          # launch, injector 280.1 MB / extractor 302.2 MB, averaged over the step's 4 + 6 launches
+                          "traffic": (4 * 280.1e6 + 6 * 302.2e6) / 10, "traffic_of": "average msda launch of the step",
+                          "ceiling": "SM load path, not HBM: gathered bytes are 8.2x the algorithmic bytes and L1 gathers "
+                                     "peak at 11.5 TB/s chip-wide (tools/micro/gather_bench.cu) -> 22 % of HBM peak",
+                          "launches_per_step": md["launches"],
                           "ms_per_step": md["ms"], "peak_source": pk["source"]},
         "miou_check": {"pixels": int(conf_all.sum().item())},
     }
