@@ -132,6 +132,14 @@ int mmsam_resize_add_affine_bf16(const void* src, const void* base, const float*
                                  long long lds, long long base_bstride, long long ldb, long long out_bstride,
                                  long long ldo, void* stream);
 
+/* out[b,y,x,:] = act((base[b,y,x,:] + sum_k bilinear(src_k[b] (Hs_k x Ws_k) -> Ho x Wo)[y,x,:]) * scale + shift),
+ * dense channels-last bf16, nsrc <= 3 sources (src_hw_host [nsrc][2], HOST pointer), base / scale / shift optional,
+ * relu != 0 applies ReLU. The Segformer head's concat + fusion conv + BN + ReLU (decode_heads/segformer_head.py:55-64)
+ * with the fusion weight applied per level BEFORE the (linear) resize. */
+int mmsam_resize_sum_affine_bf16(const void* base, int nsrc, const void* src0, const void* src1, const void* src2,
+                                 const int* src_hw_host, const float* scale, const float* shift, int relu, void* out,
+                                 int B, int Ho, int Wo, int C, void* stream);
+
 /* labels_u8[b, y<Hc, x<Wc] = argmax_c bilinear(logits[b] (hs x ws x ldl fp32, ncls valid) -> Ho x Wo):
  * resize + softmax + argmax (+ crop) of segmentors/encoder_decoder.py:96-117, 329-414, 449, 477. */
 int mmsam_upsample_argmax_f32(const float* logits, void* labels_u8, int B, int hs, int ws, int ldl, int ncls,

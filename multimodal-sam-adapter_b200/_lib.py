@@ -26,6 +26,7 @@ SIGNATURES = {
     "mmsam_dwconv_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _ll, _i, _vp],
     "mmsam_patchify_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_resize_add_affine_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _vp],
+    "mmsam_resize_sum_affine_bf16": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],
     "mmsam_upsample_argmax_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_confusion_u8": [_vp, _vp, _vp, _ll, _i, _i, _vp],
     "mmsam_conv3x3_kblocks": [_i, _i, _i],

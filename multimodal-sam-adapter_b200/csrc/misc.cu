@@ -8,14 +8,44 @@ namespace mmsam {
 // NCHW fp32 image -> patch-major bf16 rows [(b, py, px), (c, ky, kx)]: turns the non-overlapping
 // strided convs (ViT patch embed 16x16/s16, image_encoder.py:662-671; ConvNeXt stem 4x4/s4,
 // twin_convnext.py:295-312) into GEMMs against the flattened conv weight [Cout, C*p*p].
+// A thread owns one (patch, channel, patch row): p contiguous floats in, p contiguous bf16 out (16-byte loads, 8/16-byte
+// stores); consecutive threads walk (c, ky) of one patch, so a warp writes one contiguous span of the output row and reads
+// 16/64-byte pieces that neighbouring patches complete to full sectors. (One element per thread scattered 2-byte stores
+// over 8 sectors per warp instruction: 208 us per launch against a 25 us HBM floor.)
+template <int P>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int Ctot, int c_off,
-                int C, int H, int W, int p) {
+                int C, int H, int W) {
+  const int PW = W / P, PH = H / P;
+  const long long total = (long long)B * PH * PW * C * P;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ky = (int)(idx % P);
+    long long t = idx / P;
+    const int c = (int)(t % C); t /= C;
+    const int px = (int)(t % PW); t /= PW;
+    const int py = (int)(t % PH);
+    const int b = (int)(t / PH);
+    const float4* src = reinterpret_cast<const float4*>(img + (((long long)b * Ctot + c_off + c) * H + py * P + ky) * W + px * P);
+    __nv_bfloat16* dst = out + (((long long)b * PH + py) * PW + px) * (C * P * P) + (c * P + ky) * P;
+#pragma unroll
+    for (int j = 0; j < P / 4; ++j) {
+      const float4 v = __ldg(src + j);
+      uint2 o;
+      o.x = pack_bf16(v.x, v.y);
+      o.y = pack_bf16(v.z, v.w);
+      *reinterpret_cast<uint2*>(dst + 4 * j) = o;
+    }
+  }
+}
+// any patch size / alignment: one element per thread
+__global__ void __launch_bounds__(256)
+patchify_generic_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int Ctot, int c_off,
+                        int C, int H, int W, int p) {
   const int PW = W / p, PH = H / p;
   const long long total = (long long)B * PH * PW * C * p * p;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    // consecutive threads walk kx fastest within a row of the patch: coalesced p-float reads
     const int kx = (int)(idx % p);
     long long t = idx / p;
     const int px = (int)(t % PW); t /= PW;
@@ -97,6 +127,85 @@ resize_add_affine_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloa
       for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
     }
     *reinterpret_cast<uint4*>(out + b * out_bstride + ((long long)y * Wo + x) * ldo + cv * 8) = pack8(f);
+  }
+}
+
+// out[b,y,x,:] = act((base[b,y,x,:] + sum_k bilinear(src_k[b])[y,x,:]) * scale + shift), dense NHWC bf16, up to 3 sources
+// of different resolutions. The Segformer head's fusion conv is linear and so is the bilinear resize in front of it:
+//   fusion(concat_i resize(y_i)) = sum_i resize(W_i y_i)      (decode_heads/segformer_head.py:55-64)
+// so each level's slice of the fusion weight is applied at the level's OWN resolution and this kernel adds the
+// up-sampled partial sums, the folded BatchNorm shift and the ReLU: the [B, H/4 * W/4, 4 * 512] concat is never built.
+struct ResizeSumParams {
+  const __nv_bfloat16* base;
+  const __nv_bfloat16* src[3];
+  int Hs[3], Ws[3];
+  float rh[3], rw[3];
+  int nsrc;
+  const float* scale;
+  const float* shift;
+  __nv_bfloat16* out;
+  int B, Ho, Wo, C, relu;
+};
+__global__ void __launch_bounds__(256)
+resize_sum_affine_kernel(const ResizeSumParams p) {
+  const int CV = p.C >> 3;
+  const long long total = (long long)p.B * p.Ho * p.Wo * CV;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const bool fixed_cv = (nthreads % CV) == 0;     // a thread then keeps its 8 channels: scale / shift stay in registers
+  float sc[8], sh[8];
+  auto load_affine = [&](int cv) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
+    if (p.scale) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.scale + cv * 8)), a1 = __ldg(reinterpret_cast<const float4*>(p.scale + cv * 8 + 4));
+      sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+    }
+    if (p.shift) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.shift + cv * 8)), b1 = __ldg(reinterpret_cast<const float4*>(p.shift + cv * 8 + 4));
+      sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+    }
+  };
+  if (fixed_cv) load_affine((int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % CV));
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+    const int cv = (int)(idx % CV);
+    long long t = idx / CV;
+    const int x = (int)(t % p.Wo); t /= p.Wo;
+    const int y = (int)(t % p.Ho);
+    const int b = (int)(t / p.Ho);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    if (p.base) unpack8(__ldg(reinterpret_cast<const uint4*>(p.base + (((long long)b * p.Ho + y) * p.Wo + x) * p.C + cv * 8)), f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < p.nsrc) {
+        const int Hs = p.Hs[k], Ws = p.Ws[k];
+        float sy = (y + 0.5f) * p.rh[k] - 0.5f, sx = (x + 0.5f) * p.rw[k] - 0.5f;
+        sy = sy < 0.f ? 0.f : sy;
+        sx = sx < 0.f ? 0.f : sx;
+        int y0 = (int)sy, x0 = (int)sx;
+        y0 = y0 > Hs - 1 ? Hs - 1 : y0;
+        x0 = x0 > Ws - 1 ? Ws - 1 : x0;
+        const int y1 = y0 < Hs - 1 ? y0 + 1 : y0, x1 = x0 < Ws - 1 ? x0 + 1 : x0;
+        const float ly = sy - y0, lx = sx - x0;
+        const __nv_bfloat16* sb = p.src[k] + (long long)b * Hs * Ws * p.C + cv * 8;
+        float a[8], c[8], d[8], e[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(sb + ((long long)y0 * Ws + x0) * p.C)), a);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(sb + ((long long)y0 * Ws + x1) * p.C)), c);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(sb + ((long long)y1 * Ws + x0) * p.C)), d);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(sb + ((long long)y1 * Ws + x1) * p.C)), e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          f[j] += (1.f - ly) * ((1.f - lx) * a[j] + lx * c[j]) + ly * ((1.f - lx) * d[j] + lx * e[j]);
+      }
+    }
+    if (!fixed_cv) load_affine(cv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (p.relu) f[j] = fmaxf(f[j], 0.f);
+    }
+    *reinterpret_cast<uint4*>(p.out + (((long long)b * p.Ho + y) * p.Wo + x) * p.C + cv * 8) = pack8(f);
   }
 }
 
@@ -183,7 +292,11 @@ MMSAM_API int mmsam_patchify_f32(const float* img, void* out, int B, int Ctot, i
   if (B == 0) return MMSAM_OK;
   if (!img || !out) return MMSAM_ERR_BAD_ARG;
   const long long total = (long long)B * C * H * W;
-  patchify_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)out, B, Ctot, c_off, C, H, W, p);
+  const bool vec = (((uintptr_t)img) & 15) == 0 && (((uintptr_t)out) & 7) == 0 && (W & 3) == 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec && p == 4) patchify_kernel<4><<<grid_for(total / 4), 256, 0, st>>>(img, (__nv_bfloat16*)out, B, Ctot, c_off, C, H, W);
+  else if (vec && p == 16) patchify_kernel<16><<<grid_for(total / 16), 256, 0, st>>>(img, (__nv_bfloat16*)out, B, Ctot, c_off, C, H, W);
+  else patchify_generic_kernel<<<grid_for(total), 256, 0, st>>>(img, (__nv_bfloat16*)out, B, Ctot, c_off, C, H, W, p);
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }
@@ -203,6 +316,37 @@ MMSAM_API int mmsam_resize_add_affine_bf16(const void* src, const void* base, co
   resize_add_affine_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)src, (const __nv_bfloat16*)base, scale, shift, (__nv_bfloat16*)out, B, Hs, Ws, Ho, Wo, C,
       src_bstride, base_bstride, out_bstride, ldo, lds, ldb, (float)Hs / (float)Ho, (float)Ws / (float)Wo);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+MMSAM_API int mmsam_resize_sum_affine_bf16(const void* base, int nsrc, const void* src0, const void* src1,
+                                           const void* src2, const int* src_hw_host, const float* scale,
+                                           const float* shift, int relu, void* out, int B, int Ho, int Wo, int C,
+                                           void* stream) {
+  using namespace mmsam;
+  if (B < 0 || C <= 0 || (C & 7) || Ho <= 0 || Wo <= 0 || nsrc < 0 || nsrc > 3) return MMSAM_ERR_BAD_ARG;
+  if (B == 0) return MMSAM_OK;
+  if (!out || (nsrc > 0 && !src_hw_host) || (!base && nsrc == 0)) return MMSAM_ERR_BAD_ARG;
+  const void* srcs[3] = {src0, src1, src2};
+  ResizeSumParams p;
+  p.base = (const __nv_bfloat16*)base; p.nsrc = nsrc; p.scale = scale; p.shift = shift; p.out = (__nv_bfloat16*)out;
+  p.B = B; p.Ho = Ho; p.Wo = Wo; p.C = C; p.relu = relu;
+  uintptr_t align = (uintptr_t)base | (uintptr_t)out | (uintptr_t)scale | (uintptr_t)shift;
+  for (int k = 0; k < 3; ++k) {
+    p.src[k] = nullptr; p.Hs[k] = p.Ws[k] = 1; p.rh[k] = p.rw[k] = 1.f;
+    if (k < nsrc) {
+      if (!srcs[k]) return MMSAM_ERR_BAD_ARG;
+      p.src[k] = (const __nv_bfloat16*)srcs[k];
+      p.Hs[k] = src_hw_host[2 * k]; p.Ws[k] = src_hw_host[2 * k + 1];
+      if (p.Hs[k] <= 0 || p.Ws[k] <= 0) return MMSAM_ERR_BAD_ARG;
+      p.rh[k] = (float)p.Hs[k] / (float)Ho; p.rw[k] = (float)p.Ws[k] / (float)Wo;
+      align |= (uintptr_t)srcs[k];
+    }
+  }
+  if (align & 15) return MMSAM_ERR_BAD_ARG;
+  const long long total = (long long)B * Ho * Wo * (C / 8);
+  resize_sum_affine_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(p);
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }

@@ -352,7 +352,9 @@ class EncoderEngine(_Ops):
             hd["convs"].append(_Lin(w, t, dev))
         s, t = _bn_fold(h.fusion_conv.bn, dev)
         w = h.fusion_conv.conv.weight.detach().float().reshape(h.fusion_conv.conv.weight.shape[0], -1).to(dev) * s[:, None]
-        hd["fusion"] = _Lin(w, t, dev)
+        chn = w.shape[0]
+        hd["fusion_w"] = [w[:, i * chn:(i + 1) * chn].to(torch.bfloat16).contiguous() for i in range(len(h.convs))]
+        hd["fusion_shift"] = t.float().contiguous()
         ncls = h.conv_seg.weight.shape[0]
         npad = (ncls + 31) // 32 * 32
         hd["cls"] = _Lin(_pad_rows(h.conv_seg.weight.detach().float().reshape(ncls, -1), npad),
@@ -487,17 +489,18 @@ class EncoderEngine(_Ops):
         hd = self.head
         B, h0, w0, _ = feats[0].shape
         ch = hd["channels"]
-        n = len(feats)
-        cat = torch.empty((B * h0 * w0, n * ch), dtype=torch.bfloat16, device=self.dev)
+        # fusion(concat_i resize(y_i)) = sum_i resize(W_i y_i): every level's slice of the (BN-scaled) fusion weight is
+        # applied at the level's own resolution; one kernel adds the up-sampled partial sums, the BN shift and the ReLU
+        zs, hws = [], []
         for i, f in enumerate(feats):
             _, h, w, Cf = f.shape
-            if i == 0:
-                self._gemm(f.view(-1, Cf), hd["convs"][i], act="relu", out=cat[:, :ch])
-            else:
-                t = self._gemm(f.view(-1, Cf), hd["convs"][i], act="relu")
-                K.resize_add_affine(t, (h, w), (h0, w0), B, ch, out=cat[:, i * ch:], ldo=n * ch,
-                                    out_bstride=h0 * w0 * n * ch)
-        o = self._gemm(cat, hd["fusion"], act="relu")
+            y = self._gemm(f.view(-1, Cf), hd["convs"][i], act="relu")
+            zs.append(K.gemm(y, hd["fusion_w"][i]))
+            hws.append((h, w))
+        if len(zs) <= 4:
+            o = K.resize_sum_affine(zs[0], zs[1:], hws[1:], (h0, w0), B, ch, shift=hd["fusion_shift"], relu=True)
+        else:
+            raise NotImplementedError("SegformerHead with more than 4 input levels")
         return self._gemm(o, hd["cls"], out_dtype=torch.float32), (h0, w0)
 
     @torch.no_grad()

@@ -265,6 +265,24 @@ def resize_add_affine(src, src_hw, out_hw, B, C, base=None, scale=None, shift=No
     return out
 
 
+def resize_sum_affine(base, srcs, src_hws, out_hw, B, C, scale=None, shift=None, relu=False, out=None):
+    """Dense channels-last bf16: out = act((base + sum_k bilinear(srcs[k])) * scale + shift); <= 3 sources."""
+    import ctypes
+    _need_cuda(base, scale, shift, out, *srcs)
+    Ho, Wo = out_hw
+    assert len(srcs) == len(src_hws) <= 3
+    hw = (ctypes.c_int * max(2 * len(srcs), 2))(*[int(v) for s in src_hws for v in s])
+    ptrs = [_ptr(s) for s in srcs] + [0] * (3 - len(srcs))
+    if out is None:
+        out = torch.empty((B * Ho * Wo, C), dtype=torch.bfloat16, device=(base if base is not None else srcs[0]).device)
+    rc = _lib.load().mmsam_resize_sum_affine_bf16(_ptr(base), len(srcs), ptrs[0], ptrs[1], ptrs[2],
+                                                  ctypes.cast(hw, ctypes.c_void_p), _ptr(scale), _ptr(shift),
+                                                  1 if relu else 0, _ptr(out), B, Ho, Wo, C, _stream())
+    _lib.check(rc, "mmsam_resize_sum_affine_bf16")
+    _count()
+    return out
+
+
 def upsample_argmax(logits, B, hw, ncls, out_hw, crop_hw=None, out=None):
     """logits fp32 [B*h*w, ldl] -> uint8 labels [B, Hc, Wc] (bilinear to out_hw, argmax, crop)."""
     _need_cuda(logits)

@@ -479,6 +479,45 @@ def test_resize_add_affine(B, C, hs, ws, ho, wo):
     assert ((out2 - up).abs() <= 0.008 * up.abs() + 4e-3).all()
 
 
+@pytest.mark.parametrize("B,C,ho,wo,srcs,relu", [
+    (2, 64, 32, 32, [(16, 16), (8, 8), (4, 4)], True),      # Segformer head: 3 coarser levels added to the 1/4 level
+    (1, 24, 25, 19, [(13, 10), (25, 19)], False),           # ragged, one source already at the output size
+    (2, 8, 12, 12, [], True),                               # base only
+])
+def test_resize_sum_affine(B, C, ho, wo, srcs, relu):
+    """act((base + sum_k bilinear(src_k)) * scale + shift) against F.interpolate(align_corners=False); with the fusion
+    weight applied per level this equals concat + 1x1 fusion conv + BN + ReLU (decode_heads/segformer_head.py:55-64)."""
+    k = _k()
+    g = torch.Generator().manual_seed(B * C + ho)
+    base = torch.randn(B, ho, wo, C, generator=g).to(torch.bfloat16)
+    ss = [torch.randn(B, h, w, C, generator=g).to(torch.bfloat16) for h, w in srcs]
+    scale = torch.rand(C, generator=g) + 0.5
+    shift = torch.randn(C, generator=g)
+    ref = base.float()
+    for t_ in ss:
+        ref = ref + torch.nn.functional.interpolate(t_.float().permute(0, 3, 1, 2), size=(ho, wo), mode="bilinear",
+                                                    align_corners=False).permute(0, 2, 3, 1)
+    ref = ref * scale + shift
+    if relu:
+        ref = ref.clamp_min(0)
+    out = k.resize_sum_affine(base.cuda(), [t_.cuda() for t_ in ss], srcs, (ho, wo), B, C, scale=scale.cuda(),
+                              shift=shift.cuda(), relu=relu).cpu().float().view(B, ho, wo, C)
+    assert ((out - ref).abs() <= 0.008 * ref.abs() + 6e-3).all()
+
+
+@pytest.mark.parametrize("p,C,c_off,H,W", [(4, 3, 0, 32, 48), (4, 3, 3, 32, 48), (16, 3, 0, 64, 32), (2, 3, 1, 8, 12)])
+def test_patchify_vs_unfold(p, C, c_off, H, W):
+    """NCHW fp32 channels [c_off, c_off+C) -> bf16 rows [(b,py,px), (c,ky,kx)] (PatchEmbed / ConvNeXt stem im2col,
+    base/image_encoder.py:662-671, base/twin_convnext.py:295-312): vector kernels (p = 4, 16) and the generic one."""
+    k = _k()
+    g = torch.Generator().manual_seed(p * 100 + H)
+    img = torch.randn(2, 6, H, W, generator=g)
+    ref = torch.nn.functional.unfold(img[:, c_off:c_off + C], kernel_size=p, stride=p)          # [B, C*p*p, L]
+    ref = ref.transpose(1, 2).reshape(-1, C * p * p).to(torch.bfloat16)
+    out = k.patchify(img.cuda(), c_off, C, p).cpu()
+    assert torch.equal(out.view(ref.shape), ref)
+
+
 @pytest.mark.parametrize("K,B,C,grids,act", [
     (7, 2, 96, [(37, 50)], None),                       # ConvNeXt 7x7, ragged tiles, 1.5 channel groups
     (7, 3, 384, [(16, 16)], None),                      # many (channel group, image, tile) items per persistent CTA
