@@ -152,10 +152,14 @@ int mmsam_confusion_u8(const void* pred_u8, const void* gt_u8, void* conf_u64, l
 
 /* Grouped 3x3 conv (stride 1, pad 1, no bias) on channels-last bf16 as a tcgen05 implicit GEMM.
  * Replaces AttentionBase.qkv2 and Mlp.dwconv of the fusion neck (adapter_modules_...new.py:84, 118-119).
- * w_packed: bf16 [(ceil(Cout/64) * 9 * KC) * 64, 64], KC = mmsam_conv3x3_kblocks(Cin, Cout, groups); block
- * (n-tile, tap, k-block) = W[co, ci, tap] for co in the tile, ci in the 64-channel window starting at
- * (((n-tile*64) / (Cout/groups)) * (Cin/groups) & ~7) + k-block*64, zero outside co's group. */
+ * w_packed: bf16 [(ceil(Cout/NS) * 9 * KC) * 64, 64], NS = mmsam_conv3x3_nstride(Cin, Cout, groups) output channels
+ * per n-tile, KC = mmsam_conv3x3_kblocks(Cin, Cout, groups); block (n-tile, tap, k-block) = W[co, ci, tap] for the
+ * tile's co (rows >= NS zero), ci in the 64-channel window starting at
+ * (((n-tile*NS) / (Cout/groups)) * (Cin/groups) & ~7) + k-block*64, zero outside co's group. */
 int mmsam_conv3x3_kblocks(int Cin, int Cout, int groups);
+/* Output channels per n-tile (<= 64) the kernel and the weight packing use for this grouping: the stride that
+ * minimises (n-tiles x k-blocks), i.e. the kernel's L2 -> shared-memory traffic. */
+int mmsam_conv3x3_nstride(int Cin, int Cout, int groups);
 int mmsam_conv3x3_bf16(const void* x, const void* w_packed, void* out, int B, int H, int W, int Cin, int Cout,
                        int groups, int max_ctas, void* stream);
 

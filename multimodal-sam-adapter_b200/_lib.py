@@ -30,6 +30,7 @@ SIGNATURES = {
     "mmsam_upsample_argmax_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_confusion_u8": [_vp, _vp, _vp, _ll, _i, _i, _vp],
     "mmsam_conv3x3_kblocks": [_i, _i, _i],
+    "mmsam_conv3x3_nstride": [_i, _i, _i],
     "mmsam_conv3x3_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_gram_bf16": [_vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "mmsam_colstats_chunks": [_i],

@@ -15,6 +15,7 @@
 // (n-tile, tap, k-block) with zeros outside each group. Same warp specialisation as gemm.cu
 // (TMA producer warp, one MMA-issuer lane, 8 epilogue warps, 2 TMEM accumulators).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace mmsam {
 
@@ -23,13 +24,15 @@ struct ConvParams {
   int B, H, W, Cin, Cout;
   int cg_in, cg_out;   // channels per group
   int KC;              // 64-channel k-blocks per tap
+  int NS;              // output channels per n-tile (<= 64; the MMA tile stays 64 wide, the tail columns carry zero weights)
   int tiles_x, tiles_y, num_n, num_tiles;
 };
 
 static constexpr int CV_BN = 64, CV_STAGES = 8;
 static constexpr int CV_A_BYTES = 128 * 64 * 2, CV_B_BYTES = CV_BN * 64 * 2;
 static constexpr int CV_STAGE_BYTES = CV_A_BYTES + CV_B_BYTES;
-static constexpr int CV_SMEM = CV_STAGES * CV_STAGE_BYTES + 1024 + 256;
+static constexpr int CV_EPI_PITCH = 80;   // bytes per staged row (64 B of data): 16-byte stores of a quarter warp hit distinct banks
+static constexpr int CV_SMEM = CV_STAGES * CV_STAGE_BYTES + 1024 + 256 + 8 * 32 * CV_EPI_PITCH;
 
 __global__ void __launch_bounds__(320, 1)
 conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
@@ -75,7 +78,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         decode(tile, nt, x0, y0, b);
         // first input channel of the first group touched, aligned down to 8 channels: a TMA box must start on
         // a 16-byte boundary of the innermost dimension
-        const int kwin = (((nt * CV_BN) / p.cg_out) * p.cg_in) & ~7;
+        const int kwin = (((nt * p.NS) / p.cg_out) * p.cg_in) & ~7;
         for (int kb = 0; kb < num_k; ++kb) {
           const int tap = kb / p.KC, kc = kb - tap * p.KC;
           const int dy = tap / 3, dx = tap - dy * 3;
@@ -133,23 +136,54 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      const int rr = quad * 32 + lane;
-      const int y = y0 + (rr >> 4), x = x0 + (rr & 15);
-      const int col = nt * CV_BN + half * 32;
-      if (y < p.H && x < p.W && col < p.Cout) {
-        __nv_bfloat16* op = p.out + (((long long)b * p.H + y) * p.W + x) * p.Cout + col;
-        if (col + 32 <= p.Cout) {
+      // Unaligned / partial tiles: row-per-thread scalar stores cost one L1 wavefront per row and instruction; instead the warp parks its 32 rows
+      // x 32 columns in a private shared-memory slab and writes them back two rows per instruction (16 lanes x 4 B
+      // each), whatever the alignment of the tile's first channel (NS = 54 or 36 starts rows on odd 4-byte words).
+      const int col = nt * p.NS + half * 32;
+      // this warp's columns [col, col + nval): inside the tile's NS channels and inside the map
+      int nval = p.NS - half * 32;
+      nval = nval > 32 ? 32 : nval;
+      nval = col + nval > p.Cout ? p.Cout - col : nval;
+      if (nval == 32 && (col & 7) == 0) {
+        // aligned full tile (NS = 64): four 16-byte stores per thread are cheaper than the slab round trip
+        const int rr = quad * 32 + lane;
+        const int y = y0 + (rr >> 4), x = x0 + (rr & 15);
+        if (y < p.H && x < p.W) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          uint4* op = reinterpret_cast<uint4*>(p.out + (((long long)b * p.H + y) * p.W + x) * p.Cout + col);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(op)[j] = pack8(v + 8 * j);
-        } else {
+          for (int j = 0; j < 4; ++j) op[j] = pack8(v + 8 * j);
+        }
+        continue;
+      }
+      uint8_t* slab = smem + CV_STAGES * CV_STAGE_BYTES + 256 + warp * 32 * CV_EPI_PITCH;
+      {
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col + j < p.Cout) op[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(slab + lane * CV_EPI_PITCH + j * 16) = pack8(v + 8 * j);
+      }
+      __syncwarp();
+      const int sub = lane & 15, rsel = lane >> 4;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int rl = 2 * i + rsel;                 // row of this warp's 32
+        const int rr = quad * 32 + rl;
+        const int y = y0 + (rr >> 4), x = x0 + (rr & 15);
+        if (y < p.H && x < p.W && 2 * sub < nval) {
+          const uint32_t w2 = *reinterpret_cast<const uint32_t*>(slab + rl * CV_EPI_PITCH + sub * 4);
+          __nv_bfloat16* op = p.out + (((long long)b * p.H + y) * p.W + x) * p.Cout + col + 2 * sub;
+          if (2 * sub + 1 < nval && ((col & 1) == 0)) *reinterpret_cast<uint32_t*>(op) = w2;
+          else {
+            op[0] = __ushort_as_bfloat16((unsigned short)(w2 & 0xffffu));
+            if (2 * sub + 1 < nval) op[1] = __ushort_as_bfloat16((unsigned short)(w2 >> 16));
+          }
         }
       }
+      __syncwarp();     // the slab is rewritten by the next tile
     }
   }
   tc_fence_before();
@@ -162,13 +196,14 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
 }  // namespace mmsam
 
-// Number of 64-channel k-blocks per tap for a given grouping (host helper, also used by the weight packer).
-MMSAM_API int mmsam_conv3x3_kblocks(int Cin, int Cout, int groups) {
-  if (groups <= 0 || Cin % groups || Cout % groups) return -1;
+namespace mmsam {
+// 64-channel k-blocks per tap when the output channels are tiled NS at a time: the widest input-channel window
+// (first channel rounded down to a 16-byte boundary) any tile's groups span.
+static int conv3x3_kblocks_for(int Cin, int Cout, int groups, int NS) {
   const int cgi = Cin / groups, cgo = Cout / groups;
   int kc = 1;
-  for (int n0 = 0; n0 < Cout; n0 += 64) {
-    const int n1 = (n0 + 64 < Cout ? n0 + 64 : Cout) - 1;
+  for (int n0 = 0; n0 < Cout; n0 += NS) {
+    const int n1 = (n0 + NS < Cout ? n0 + NS : Cout) - 1;
     const int g0 = n0 / cgo, g1 = n1 / cgo;
     const int len = (g1 + 1) * cgi - ((g0 * cgi) & ~7);
     const int need = (len + 63) / 64;
@@ -176,10 +211,36 @@ MMSAM_API int mmsam_conv3x3_kblocks(int Cin, int Cout, int groups) {
   }
   return kc;
 }
+}  // namespace mmsam
 
-// x [B,H,W,Cin] bf16, w_packed bf16 [(ceil(Cout/64) * 9 * KC) * 64, 64]: block (nt, tap, kc) holds
-// W[co = nt*64 + r, ci = kwin(nt) + kc*64 + c, tap] (0 outside co's group), kwin(nt) = first input channel of the
-// first group the tile touches rounded down to 8; out [B,H,W,Cout] bf16.
+// Output channels per n-tile. The kernel is bound by the L2 -> shared-memory fill (9 taps x KC blocks of 24 KB per
+// tile), so the stride that minimises (number of n-tiles) x KC wins: e.g. 9 channels per group (qkv2 of the 256^2
+// level) -> 54 = 6 whole groups whose window fits ONE 64-channel block, instead of 64 outputs spanning 72 inputs.
+MMSAM_API int mmsam_conv3x3_nstride(int Cin, int Cout, int groups) {
+  if (groups <= 0 || Cin <= 0 || Cout <= 0 || Cin % groups || Cout % groups) return -1;
+  if (const char* e = getenv("MMSAM_CONV3X3_NS")) {          // perf-debug: force the n-tile stride (64 = the old tiling)
+    const int v = atoi(e);
+    if (v >= 16 && v <= 64 && !(v & 1)) return v;
+  }
+  int best = 64;
+  long long best_cost = -1;
+  for (int ns = 64; ns >= 16; ns -= 2) {
+    const long long cost = (long long)((Cout + ns - 1) / ns) * mmsam::conv3x3_kblocks_for(Cin, Cout, groups, ns);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ns; }
+  }
+  return best;
+}
+
+// Number of 64-channel k-blocks per tap for a given grouping (host helper, also used by the weight packer).
+MMSAM_API int mmsam_conv3x3_kblocks(int Cin, int Cout, int groups) {
+  const int ns = mmsam_conv3x3_nstride(Cin, Cout, groups);
+  if (ns < 0) return -1;
+  return mmsam::conv3x3_kblocks_for(Cin, Cout, groups, ns);
+}
+
+// x [B,H,W,Cin] bf16, w_packed bf16 [(ceil(Cout/NS) * 9 * KC) * 64, 64] with NS = mmsam_conv3x3_nstride(): block
+// (nt, tap, kc) holds W[co = nt*NS + r, ci = kwin(nt) + kc*64 + c, tap] (0 outside co's group and for r >= NS),
+// kwin(nt) = first input channel of the first group the tile touches rounded down to 8; out [B,H,W,Cout] bf16.
 MMSAM_API int mmsam_conv3x3_bf16(const void* x, const void* w_packed, void* out, int B, int H, int W, int Cin,
                                  int Cout, int groups, int max_ctas, void* stream) {
   using namespace mmsam;
@@ -191,7 +252,8 @@ MMSAM_API int mmsam_conv3x3_bf16(const void* x, const void* w_packed, void* out,
   ConvParams p;
   p.out = (__nv_bfloat16*)out;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.cg_in = Cin / groups; p.cg_out = Cout / groups; p.KC = KC;
-  p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 7) / 8; p.num_n = (Cout + 63) / 64;
+  p.NS = mmsam_conv3x3_nstride(Cin, Cout, groups);
+  p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 7) / 8; p.num_n = (Cout + p.NS - 1) / p.NS;
   p.num_tiles = p.num_n * p.tiles_x * p.tiles_y * B;
   mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
   if (!enc) return MMSAM_ERR_DRIVER;

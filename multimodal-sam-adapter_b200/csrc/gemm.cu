@@ -398,7 +398,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorM
         }
         if (VAR == V_BF16_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
         } else if (ep.act == 2) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);

@@ -317,12 +317,13 @@ def pack_conv3x3_weight(w, groups):
     Cin = cgi * groups
     cgo = Cout // groups
     KC = _lib.load().mmsam_conv3x3_kblocks(Cin, Cout, groups)
-    nn = (Cout + 63) // 64
+    NS = _lib.load().mmsam_conv3x3_nstride(Cin, Cout, groups)      # output channels per n-tile (<= 64)
+    nn = (Cout + NS - 1) // NS
     wf = w.detach().float().cpu().reshape(Cout, cgi, 9)
     out = torch.zeros((nn, 9, KC, 64, 64), dtype=torch.float32)
     co = torch.arange(Cout)
-    nt, r = co // 64, co % 64
-    kwin = (((nt * 64) // cgo) * cgi) // 8 * 8      # first input channel of the tile's window (16-byte aligned)
+    nt, r = co // NS, co % NS
+    kwin = (((nt * NS) // cgo) * cgi) // 8 * 8      # first input channel of the tile's window (16-byte aligned)
     base = (co // cgo) * cgi - kwin                 # window column of each output channel's group start
     for ci in range(cgi):
         col = base + ci

@@ -414,7 +414,9 @@ def test_attention_relpos_interpolated_table():
 
 
 @pytest.mark.parametrize("B,H,W,Cin,groups", [
-    (2, 16, 16, 288, 32),   # GFE qkv2 at level 0 (cg = 9, two k-blocks)
+    (2, 16, 16, 288, 32),   # GFE qkv2 at level 0 (cg = 9: 54-channel n-tiles, one k-block)
+    (1, 16, 16, 576, 32),   # level 1 (cg = 18: 54-channel n-tiles)
+    (1, 8, 16, 1152, 32),   # level 2 (cg = 36: 36-channel n-tiles)
     (1, 8, 24, 64, 32),     # cg = 2 (Mlp dwconv style), one k-block
     (1, 4, 4, 192, 96),     # map smaller than the 8x16 tile, 2 ch / group
     (1, 13, 9, 2304, 32),   # cg = 72, three k-blocks, ragged map
