@@ -14,6 +14,11 @@
 // 9 taps x KC 64-channel blocks of that window, against weight blocks pre-packed per
 // (n-tile, tap, k-block) with zeros outside each group. Same warp specialisation as gemm.cu
 // (TMA producer warp, one MMA-issuer lane, 8 epilogue warps, 2 TMEM accumulators).
+//
+// Measured (tools/bench_conv3x3.py, batch 8): ~0.33 us per k-block (one 16 KB shifted input box + one 8 KB weight block
+// + four 128x64x16 MMAs) whatever the grouping, i.e. ~600 cycles per 128-row box: the per-row request rate of the 4-D
+// box loads, not bytes or FLOPs, bounds the kernel. Halving the k-blocks per tile (n-tile stride below) pays in full;
+// keeping the weights resident in shared memory (tried: n-tile-major ranges, 72 KB of tap blocks) does not.
 #include "common.cuh"
 #include <cstdlib>
 
