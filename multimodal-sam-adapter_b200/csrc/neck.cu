@@ -93,7 +93,7 @@ gram_kernel(const __nv_bfloat16* __restrict__ X, long long ld, int qoff, int kof
 
 // ------------------------------------------------------------------------------------------------
 // Per-chunk column statistics of o [B, HW, C] for GFFM's LayerNorm over the spatial axis (:262-264):
-// part[chunk, b, c, {sum o, sum o^2, sum o*w[pix]}] in fp32 (chunks <= 1024 px; combined in fp64 later).
+// part[chunk, b, c, {sum o, sum o^2, sum o*w[pix]}] in fp32 (chunks of 64 or 512 px; combined in fp64 later).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colstats_kernel(const __nv_bfloat16* __restrict__ o, const float* __restrict__ wpix, float* __restrict__ part,
@@ -293,7 +293,10 @@ MMSAM_API int mmsam_gram_bf16(const void* X, long long ld, int qoff, int koff, i
 }
 
 // part must hold mmsam_colstats_chunks(HW) * B * C * 3 floats
-MMSAM_API int mmsam_colstats_chunks(int HW) { return (HW + 511) / 512; }
+// pixels per chunk: small maps (the 32^2 / 64^2 levels carry 768 - 1536 channels, i.e. 1 - 2 pixel lanes per CTA) get short
+// chunks so that the launch still fills the GPU (16 CTAs walking 512 pixels each took 205 us for 25 MB)
+static inline int colstats_chunk_px(int HW) { return HW >= 16384 ? 512 : 64; }
+MMSAM_API int mmsam_colstats_chunks(int HW) { const int c = colstats_chunk_px(HW); return (HW + c - 1) / c; }
 
 MMSAM_API int mmsam_colstats_bf16(const void* o, const float* wpix, float* part, int B, int HW, int C, void* stream) {
   using namespace mmsam;
@@ -304,7 +307,7 @@ MMSAM_API int mmsam_colstats_bf16(const void* o, const float* wpix, float* part,
   if (CV > 256) return MMSAM_ERR_UNSUPPORTED;
   const int PL = 256 / CV;
   dim3 grid(mmsam_colstats_chunks(HW), B);
-  colstats_kernel<<<grid, CV * PL, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)o, wpix, part, B, HW, C, 512);
+  colstats_kernel<<<grid, CV * PL, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)o, wpix, part, B, HW, C, colstats_chunk_px(HW));
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }

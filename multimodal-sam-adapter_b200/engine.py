@@ -432,8 +432,21 @@ class EncoderEngine(_Ops):
         sc = self._shape(B, Hi, Wi)
         H, W, T, C, S3 = sc["H"], sc["W"], sc["T"], self.C, sc["S3"]
         # --- SPM (adapter_modules_...new.py:929-964): twin ConvNeXt -> fusion neck -> fc1..4 ---
-        fx = self._convnext_branch(img, 0, self.cnx["x"], B, Hi, Wi)
-        fy = self._convnext_branch(img, self.cin, self.cnx["y"], B, Hi, Wi)
+        # The two modality towers are independent until the fusion neck: the second one runs on a side stream (a parallel
+        # branch of the CUDA graph), so each kernel's partially filled last wave is covered by the other tower's work.
+        if os.environ.get("MMSAM_TOWER_STREAMS", "1") != "0":
+            main = torch.cuda.current_stream()
+            if getattr(self, "_tower_stream", None) is None:
+                self._tower_stream = torch.cuda.Stream(device=self.dev)
+            side = self._tower_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                fy = self._convnext_branch(img, self.cin, self.cnx["y"], B, Hi, Wi)
+            fx = self._convnext_branch(img, 0, self.cnx["x"], B, Hi, Wi)
+            main.wait_stream(side)
+        else:
+            fx = self._convnext_branch(img, 0, self.cnx["x"], B, Hi, Wi)
+            fy = self._convnext_branch(img, self.cin, self.cnx["y"], B, Hi, Wi)
         fused = self.neck(fx, fy, B)                                    # 4 x [B*h*w, 2*Ci] bf16
         if debug is not None:
             debug.update(fx=[(t.clone(), h, w) for t, h, w in fx], fy=[(t.clone(), h, w) for t, h, w in fy], fused=[t.clone() for t in fused])
