@@ -123,45 +123,96 @@ class ClockSampler:
 
 
 def instrumented_pass(eng, x):
-    """One extra forward with CUDA events around every launch of the two kernels the roofline is reported
-    for: the tcgen05 GEMM (by FLOPs) and the fused MSDeformAttn gather (by algorithmic bytes)."""
+    """Kernel-only timings of the two kernels the roofline is reported for, taken live with CUDA events on the
+    launching stream. One extra single-stream forward records every GEMM / fused MSDeformAttn call and its arguments.
+    The 470 GEMM launches are short (12 - 230 us) and an eager launch from Python takes ~10 us, so an event pair
+    around each one in the forward would mostly time the host; instead every distinct GEMM (and MSDeformAttn)
+    configuration of the forward is replayed 8 times back to back on the tensors it ran on (event pair around the 8) and weighted by how
+    often the step launches it: sum(count x per-launch time) = the GEMM time of a step as the graph replay runs it."""
     from mmsam_b200 import kernels as K
-    rec = dict(gemm=[], msda=[])
+    calls, mcalls = {}, {}
     og, om_ = K.gemm, K.msda_fused
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
-    def gemm(a, w, *args, **kw):
-        s, e = ev(), ev()
-        s.record()
-        r = og(a, w, *args, **kw)
-        e.record()
-        rec["gemm"].append((s, e, 2.0 * a.shape[0] * w.shape[0] * a.shape[1]))
+    def gemm(a, w, **kw):
+        r = og(a, w, **kw)
+        key = (a.shape[0], w.shape[0], a.shape[1], a.stride(0), r.stride(0), kw.get("act"), kw.get("bias") is not None,
+               kw.get("scale") is not None, kw.get("residual") is not None, kw.get("row_map") is not None,
+               kw.get("pixel_shuffle") is not None, str(r.dtype))
+        ent = calls.get(key)
+        if ent is None:
+            kw2 = dict(kw)
+            kw2["out"] = r
+            calls[key] = [1, a, w, kw2]
+        else:
+            ent[0] += 1
         return r
 
     def msda(value, shapes, lsi, qproj, ref, n_heads, n_levels, n_points=4, out=None, geom=None):
-        s, e = ev(), ev()
-        s.record()
         r = om_(value, shapes, lsi, qproj, ref, n_heads, n_levels, n_points, out, geom=geom)
-        e.record()
         N, S, MD = value.shape
         Lq = ref.shape[0]
         # SURVEY.md §8(d): value + locations(fp32 x2) + weights(fp32) + output, bf16 value/out
         by = N * (S * MD * 2 + Lq * n_heads * n_levels * n_points * 3 * 4 + Lq * MD * 2)
-        rec["msda"].append((s, e, by))
+        key = (N, S, MD, Lq, n_levels)
+        ent = mcalls.get(key)
+        if ent is None:
+            mcalls[key] = [1, by, (value, shapes, lsi, qproj, ref, n_heads, n_levels, n_points, r), geom]
+        else:
+            ent[0] += 1
         return r
 
-    K.gemm, K.msda_fused = gemm, msda
+    # single-stream for this pass: on the parallel graph branches (ConvNeXt towers, neck levels) two kernels share the
+    # GPU and an event pair would charge each with the other's time
+    saved = {k: os.environ.get(k) for k in ("MMSAM_TOWER_STREAMS", "MMSAM_NECK_STREAMS")}
+    os.environ.update(MMSAM_TOWER_STREAMS="0", MMSAM_NECK_STREAMS="0")
+    import mmsam_b200.engine as E
+    import mmsam_b200.neck as NK
+    mods = [K, E.K, NK.K]
+    for m in mods:
+        m.gemm, m.msda_fused = gemm, msda
     try:
         eng.segment(x)
         torch.cuda.synchronize()
     finally:
-        K.gemm, K.msda_fused = og, om_
+        for m in mods:
+            m.gemm, m.msda_fused = og, om_
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     out = {}
-    for k, lst in rec.items():
-        ms = sum(s.elapsed_time(e) for s, e, _ in lst)
-        out[k] = dict(ms=ms, work=sum(w for _, _, w in lst), launches=len(lst))
+    reps, m_ms, m_work, m_n = 8, 0.0, 0.0, 0
+    for cnt, by, margs, geom in mcalls.values():
+        for _ in range(2):
+            om_(*margs, geom=geom)
+        s, e = ev(), ev()
+        s.record()
+        for _ in range(reps):
+            om_(*margs, geom=geom)
+        e.record()
+        torch.cuda.synchronize()
+        m_ms += cnt * s.elapsed_time(e) / reps
+        m_work += cnt * by
+        m_n += cnt
+    out["msda"] = dict(ms=m_ms, work=m_work, launches=m_n)
+    reps, g_ms, g_work, g_n = 8, 0.0, 0.0, 0
+    for cnt, a, w, kw in calls.values():
+        for _ in range(2):
+            og(a, w, **kw)
+        s, e = ev(), ev()
+        s.record()
+        for _ in range(reps):
+            og(a, w, **kw)
+        e.record()
+        torch.cuda.synchronize()
+        g_ms += cnt * s.elapsed_time(e) / reps
+        g_work += cnt * 2.0 * a.shape[0] * w.shape[0] * a.shape[1]
+        g_n += cnt
+    out["gemm"] = dict(ms=g_ms, work=g_work, launches=g_n, configs=len(calls))
     return out
 
 
@@ -303,7 +354,8 @@ def main():
                      # (profiles/r01_gemm_ncu_summary.txt); algorithmic bytes of that launch: 343 MB
                      "traffic": 291.6e6, "traffic_of": "lin1 GEMM launch (M=32768 N=4096 K=1024)",
                      "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
-                     "launches_per_step": gm["launches"], "ms_per_step": gm["ms"],
+                     "launches_per_step": gm["launches"], "distinct_configs": gm["configs"], "ms_per_step": gm["ms"],
+                     "timing": "every distinct GEMM configuration of the step replayed 8x back to back (CUDA events), weighted by its launch count",
                      "share_of_step": gm["ms"] / (ms / args.steps)},
         "roofline_msda": {"kernel": "msda_fused_coop_kernel", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
                           "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
