@@ -271,6 +271,53 @@ def test_vitb512_config1_vs_reference_golden():
         assert abs(f.float().norm().item() - nrm) / nrm < 2e-2
 
 
+@pytest.mark.timeout(1500)
+def test_vitl1024_config2_full_size_vs_oracle_and_properties():
+    """BASELINE config 2 at its full size (ViT-L MM-adapter + Segformer head, DeLiVER-shaped RGB+LiDAR 1024x1024):
+    (a) features and logits of one image against the fp32 CPU oracle (a few seconds per image on the GPU box's cores),
+    (b) size-independent properties on a batch: an image's result does not depend on what else is in the batch or on
+    its position, CUDA-graph replay = eager launches, labels are valid class ids."""
+    import bench
+    from oracle import model as om
+    from oracle.perturb import synthetic_batch
+    seg, sd = build_segmentor(bench.VITL, bench.VITL_HEAD, test_cfg=dict(mode="whole_dim", rescale=True, dim=(1024, 1024)))
+    seg = seg.cuda()
+    x = synthetic_batch(2, 1024, seed=77)
+    xc = x.cuda()
+    # ---- (a) parity with the oracle, image 0 ----
+    torch.set_num_threads(max(os.cpu_count() or 1, 1))
+    with torch.no_grad():
+        ref_feats = om.backbone_forward(sd, bench.VITL, x[:1], prefix="backbone.")
+        ref_logits = om.segformer_head(sd, ref_feats)
+    feats, _ = seg.backbone(xc[:1])
+    for i, (f, r) in enumerate(zip(feats, ref_feats)):
+        rl, c = _report(f"ViT-L/1024 f{i + 1} vs oracle", f.float().cpu(), r)
+        assert rl < REL_TOL and c > COS_TOL
+    lg = seg.encode_decode(xc[:1]).float().cpu()
+    want = torch.nn.functional.interpolate(ref_logits, size=(1024, 1024), mode="bilinear", align_corners=False)
+    rl, c = _report("ViT-L/1024 logits vs oracle", lg, want)
+    assert rl < REL_TOL and c > COS_TOL
+    margin = want.topk(2, dim=1).values
+    decided = (margin[:, 0] - margin[:, 1]) / want.std(dim=1) >= 0.05
+    seg.use_cuda_graph = False
+    lab1 = seg.encode_decode_labels(xc[:1], (1024, 1024)).cpu()
+    agree = (lab1.long() == want.argmax(1))[decided].float().mean().item()
+    print(f"ViT-L/1024 argmax agreement on decided pixels ({decided.float().mean().item() * 100:.1f}% of all): {agree * 100:.4f}%")
+    assert agree >= 0.999
+    # ---- (b) properties ----
+    lab2 = seg.encode_decode_labels(xc, (1024, 1024)).cpu()
+    assert lab2.dtype == torch.uint8 and int(lab2.max()) < 25
+    same = lambda a, b: (a == b).float().mean().item()      # noqa: E731
+    floor = min(same(seg.encode_decode_labels(xc[:1], (1024, 1024)).cpu(), lab1), 0.999) - 0.003   # run-to-run (fp32 atomics)
+    assert same(lab2[:1], lab1) >= floor                                  # batch-composition invariance
+    lab_sw = seg.encode_decode_labels(xc.flip(0).contiguous(), (1024, 1024)).cpu()
+    assert same(lab_sw.flip(0), lab2) >= floor                            # position in the batch
+    seg.use_cuda_graph = True
+    lab_g = seg.encode_decode_labels(xc, (1024, 1024)).cpu()
+    assert same(lab_g, lab2) >= floor                                     # graph replay = eager
+    assert same(lab2[0], lab2[1]) < 0.9                                   # and the two images really differ
+
+
 def test_confusion_matrix_kernel():
     import mmsam_b200  # noqa
     from mmsam_b200 import kernels as K
