@@ -80,6 +80,20 @@ int mmsam_attention_bf16(const void* qkv, void* out, const int* out_row_map_dev,
                          const void* tab_w, int Bp, int T, int nh, int Kh, int Kw, float scale, int max_ctas,
                          void* stream);
 
+/* stats[row] = (mean, 1 / sqrt(var + eps)) fp32 pairs of the rows of a bf16 [rows, C] matrix (row stride ldx), the
+ * statistics nn.LayerNorm would use (biased variance). C % 8 == 0, C <= 2048. */
+int mmsam_rowstats_bf16(const void* x, float* stats, long long rows, int C, long long ldx, float eps, void* stream);
+
+/* LayerNorm -> Linear folded into one GEMM (Injector / Extractor query_norm / feat_norm / ffn_norm feeding
+ * sampling_offsets | attention_weights, value_proj and ffn.fc1, adapter_modules_...new.py:490-542):
+ *   out = act(rowstat[m].rstd * (A W^T - rowstat[m].mean * colsum[n]) + bias[n]) (+ residual)
+ * with W = bf16(gamma (.) W_linear), colsum[n] = sum_k W[n,k], bias[n] = sum_k beta[k] W_linear[n,k] + b_linear[n],
+ * rowstat from mmsam_rowstats_bf16 on A. Same layouts / restrictions as mmsam_gemm_bf16 (identity row mode). */
+int mmsam_gemm_ln_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                       const float* colsum, const float* rowstat, const void* residual, long long ldr, void* out,
+                       long long ldo, int M, int N, int K, int act, int out_f32, int block_n, int max_ctas,
+                       void* stream);
+
 /* MSDeformAttn core fused with its front end (bf16 value/out): reads the raw fp32 output of the
  * query projection (columns [M*L*P*2 sampling offsets | M*L*P attention logits], row stride ldq;
  * ops/modules/ms_deform_attn.py:108-113) and the per-query reference point ref_xy [Lq,2] (broadcast

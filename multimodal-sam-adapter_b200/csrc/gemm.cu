@@ -41,6 +41,7 @@ namespace mmsam {
 struct GemmEpi {
   const float* bias;               // [N] or null
   const float* scale;              // [N] or null, applied after the activation
+  const float2* rowstat;           // [M] (mean, rstd) or null: LayerNorm folded in, acc -> rstd * (acc - mean * scale[n]) + bias[n]
   const __nv_bfloat16* residual;   // indexed at the destination row, or null
   void* out;
   const int* row_map;              // row_mode 1: dst row of each source row (-1 = drop)
@@ -203,9 +204,12 @@ __device__ __forceinline__ void epilogue_generic(const GemmEpi& ep, uint32_t tme
             drow += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
           }
           float x = __uint_as_float(r[j]);
-          if (ep.bias) x += ep.bias[cj];
+          if (ep.rowstat) {
+            const float2 rs = ep.rowstat[row];
+            x = fmaf(rs.y, fmaf(-rs.x, ep.scale[cj], x), ep.bias[cj]);
+          } else if (ep.bias) x += ep.bias[cj];
           x = apply_act(x, ep.act);
-          if (ep.scale) x *= ep.scale[cj];
+          if (ep.scale && !ep.rowstat) x *= ep.scale[cj];
           if (ep.residual) x += __bfloat162float(ep.residual[drow * ep.ldr + dcol]);
           if (ep.out_f32) reinterpret_cast<float*>(ep.out)[drow * ep.ldo + dcol] = x;
           else reinterpret_cast<__nv_bfloat16*>(ep.out)[drow * ep.ldo + dcol] = __float2bfloat16_rn(x);
@@ -341,6 +345,8 @@ __device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorM
     };
     const int row0 = mp * 256 + (int)rank * 128 + quad * 32;
     const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+    float2 rs = make_float2(0.f, 1.f);          // this thread's accumulator row: (mean, rstd) of the folded LayerNorm
+    if (ep.rowstat && row0 + lane < ep.M) rs = __ldg(ep.rowstat + row0 + lane);
 #pragma unroll
     for (int pi = 0; pi < NPAN; ++pi) {
       const int col_l = half * CPH + pi * PC;
@@ -389,7 +395,18 @@ __device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorM
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[cc][j]);
-        if (ep.bias) {
+        if (ep.rowstat) {
+          const float nm = -rs.x;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sc = ldg4_guard(ep.scale, col + j, ep.N);
+            const float4 b = ldg4_guard(ep.bias, col + j, ep.N);
+            v[j] = fmaf(rs.y, fmaf(nm, sc.x, v[j]), b.x);
+            v[j + 1] = fmaf(rs.y, fmaf(nm, sc.y, v[j + 1]), b.y);
+            v[j + 2] = fmaf(rs.y, fmaf(nm, sc.z, v[j + 2]), b.z);
+            v[j + 3] = fmaf(rs.y, fmaf(nm, sc.w, v[j + 3]), b.w);
+          }
+        } else if (ep.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b = ldg4_guard(ep.bias, col + j, ep.N);
@@ -406,7 +423,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorM
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
         }
-        if (ep.scale) {
+        if (ep.scale && !ep.rowstat) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 s = ldg4_guard(ep.scale, col + j, ep.N);
@@ -646,12 +663,13 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 }  // namespace mmsam_host
 
 // See include/mmsam_b200.h for the contract.
-MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
-                              const float* scale, const void* residual, long long ldr, void* out,
-                              long long ldo, int M, int N, int K, int act, int out_f32, int row_mode,
-                              const int* row_map_dev, int ps_h, int ps_w, int ps_c, int block_n,
-                              int max_ctas, void* stream) {
+static int gemm_impl(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                     const float* scale, const float* rowstat, const void* residual, long long ldr, void* out,
+                     long long ldo, int M, int N, int K, int act, int out_f32, int row_mode,
+                     const int* row_map_dev, int ps_h, int ps_w, int ps_c, int block_n,
+                     int max_ctas, void* stream) {
   using namespace mmsam;
+  if (rowstat && (!bias || !scale || (((uintptr_t)rowstat) & 7))) return MMSAM_ERR_BAD_ARG;
   if (M < 0 || N < 0 || K <= 0) return MMSAM_ERR_BAD_ARG;
   if (M == 0 || N == 0) return MMSAM_OK;
   if (!A || !W || !out) return MMSAM_ERR_BAD_ARG;
@@ -719,7 +737,7 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
   rc = mmsam_host::make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(bn / 2), 64);
   if (rc) return rc;
   GemmEpi ep;
-  ep.bias = bias; ep.scale = scale; ep.residual = (const __nv_bfloat16*)residual; ep.out = out;
+  ep.bias = bias; ep.scale = scale; ep.rowstat = (const float2*)rowstat; ep.residual = (const __nv_bfloat16*)residual; ep.out = out;
   ep.row_map = row_map_dev; ep.ldo = ldo; ep.ldr = ldr; ep.M = M; ep.N = N; ep.K = K; ep.act = act;
   ep.out_f32 = out_f32; ep.row_mode = row_mode; ep.ps_h = ps_h; ep.ps_w = ps_w; ep.ps_c = ps_c;
   { const char* d = getenv("MMSAM_GEMM_DBG"); ep.dbg = d ? atoi(d) : 0; }
@@ -745,4 +763,24 @@ MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long 
     case V_BF16_RES: return launch_gemm_bn<V_BF16_RES>(bn, tmA, tmB, tmC, ep, max_ctas, st);
     default: return launch_gemm<128, V_GENERIC>(tmA, tmB, tmC, ep, max_ctas, st);
   }
+}
+
+// See include/mmsam_b200.h for the contract.
+MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                              const float* scale, const void* residual, long long ldr, void* out,
+                              long long ldo, int M, int N, int K, int act, int out_f32, int row_mode,
+                              const int* row_map_dev, int ps_h, int ps_w, int ps_c, int block_n,
+                              int max_ctas, void* stream) {
+  return gemm_impl(A, lda, W, ldw, bias, scale, nullptr, residual, ldr, out, ldo, M, N, K, act, out_f32, row_mode,
+                   row_map_dev, ps_h, ps_w, ps_c, block_n, max_ctas, stream);
+}
+
+// LayerNorm folded into the GEMM: out = epilogue(rstd[m] * (A W^T - mean[m] * colsum[n]) + bias[n]); see the header.
+MMSAM_API int mmsam_gemm_ln_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                                 const float* colsum, const float* rowstat, const void* residual, long long ldr,
+                                 void* out, long long ldo, int M, int N, int K, int act, int out_f32, int block_n,
+                                 int max_ctas, void* stream) {
+  if (!rowstat || !bias || !colsum) return MMSAM_ERR_BAD_ARG;
+  return gemm_impl(A, lda, W, ldw, bias, colsum, rowstat, residual, ldr, out, ldo, M, N, K, act, out_f32, 0, nullptr,
+                   0, 0, 0, block_n, max_ctas, stream);
 }

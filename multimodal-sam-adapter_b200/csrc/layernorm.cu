@@ -143,6 +143,46 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
   }
 }
 
+
+// Row statistics only: stats[row] = (mean, 1 / sqrt(var + eps)) in fp32, same two-pass arithmetic as layernorm_kernel.
+// For LayerNorm -> Linear pairs folded into the GEMM (mmsam_gemm_ln_bf16): LN(x) W^T + b
+//   = rstd * (x (g (.) W)^T - mean * s) + c,  s_n = sum_k g_k W_nk,  c_n = sum_k beta_k W_nk + b_n,
+// so the normalised copy of x is never written or re-read: this pass costs half of the LayerNorm's HBM traffic.
+// Warp per row, C % 8 == 0, C <= 2048.
+__global__ void __launch_bounds__(256)
+rowstats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats, long long rows, int C, long long ldx,
+                float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nvec = C >> 3;
+  for (long long row = warp; row < rows; row += nwarps) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+    float f[8][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        unpack8(__ldg(xr + v), f[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += f[i][j];
+      }
+    }
+    const float mean = warp_sum(sum) / (float)C;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; var = fmaf(d, d, var); }
+      }
+    }
+    var = warp_sum(var) / (float)C;
+    if (lane == 0) stats[row] = make_float2(mean, rsqrtf(var + eps));
+  }
+}
+
 }  // namespace mmsam
 
 MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* y, void* y2,
@@ -180,6 +220,18 @@ MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const floa
     default: LN_CASE(8, 32, 1); break;
   }
 #undef LN_CASE
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+MMSAM_API int mmsam_rowstats_bf16(const void* x, float* stats, long long rows, int C, long long ldx, float eps, void* stream) {
+  using namespace mmsam;
+  if (rows < 0 || C <= 0 || (C & 7) || C > 2048 || ldx < C || (ldx & 7)) return MMSAM_ERR_BAD_ARG;
+  if (rows == 0) return MMSAM_OK;
+  if (!x || !stats || (((uintptr_t)x) & 15) || (((uintptr_t)stats) & 7)) return MMSAM_ERR_BAD_ARG;
+  long long blocks = (rows + 7) / 8;
+  if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+  rowstats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)stats, rows, C, ldx, eps);
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }

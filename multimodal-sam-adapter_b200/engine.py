@@ -44,6 +44,28 @@ class _LN:
         self.eps = m.eps if eps is None else eps
 
 
+class _LinLN:
+    """LayerNorm -> Linear folded for K.gemm_ln: w = bf16(gamma (.) W), colsum[n] = sum_k w[n,k] (of the ROUNDED weight,
+    so that a constant row maps to exactly `b`), b = W beta + bias; the GEMM epilogue applies the row statistics."""
+
+    def __init__(self, lin_w, lin_b, ln, dev):
+        W = lin_w.detach().float().reshape(lin_w.shape[0], -1)
+        g, beta = ln.weight.detach().float(), ln.bias.detach().float()
+        self.w = _bf(W * g[None, :], dev)
+        self.colsum = self.w.float().sum(1).contiguous()
+        b = W @ beta
+        if lin_b is not None:
+            b = b + lin_b.detach().float()
+        self.b = _f32(b, dev)
+        self.eps = ln.eps
+        self.n, self.k = self.w.shape
+
+
+# LayerNorm folded into the consumer GEMM (row statistics + column sums) for the adapter's LN -> Linear pairs; set
+# MMSAM_LN_FOLD=0 to run the separate LayerNorm kernel + plain GEMM instead.
+LN_FOLD = os.environ.get("MMSAM_LN_FOLD", "1") != "0"
+
+
 def _bn_fold(bn, dev):
     s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
     t = bn.bias.detach().float() - bn.running_mean.detach().float() * s
@@ -66,12 +88,15 @@ MSDA_STAGED = os.environ.get("MMSAM_MSDA_STAGED", "0") == "1"
 class _MSDA:
     """Packed MSDeformAttn weights: one fused query projection (offsets | logits) with fp32 output."""
 
-    def __init__(self, m, dev):
+    def __init__(self, m, dev, query_norm=None, feat_norm=None):
         self.n_heads, self.n_levels, self.n_points = m.n_heads, m.n_levels, m.n_points
         self.value = _Lin(m.value_proj.weight, m.value_proj.bias, dev)
         wq = torch.cat((m.sampling_offsets.weight.detach(), m.attention_weights.weight.detach()), 0)
         bq = torch.cat((m.sampling_offsets.bias.detach(), m.attention_weights.bias.detach()), 0)
         self.qproj = _Lin(wq, bq, dev)
+        # the Injector / Extractor feed both projections straight from a LayerNorm: fold it into the GEMMs
+        self.value_ln = _LinLN(m.value_proj.weight, m.value_proj.bias, feat_norm, dev) if feat_norm is not None else None
+        self.qproj_ln = _LinLN(wq, bq, query_norm, dev) if query_norm is not None else None
         self.out = _Lin(m.output_proj.weight, m.output_proj.bias, dev)
         self.off_bias = m.sampling_offsets.bias.detach().float().cpu()
         self._geoms = {}
@@ -101,14 +126,17 @@ def pack_block(blk, dev):
 
 def pack_interaction(it, dev):
     d = dict(inj=dict(qn=_LN(it.injector.query_norm, dev), fn=_LN(it.injector.feat_norm, dev),
-                      attn=_MSDA(it.injector.attn, dev), gamma=_f32(it.injector.gamma, dev)))
+                      attn=_MSDA(it.injector.attn, dev, it.injector.query_norm, it.injector.feat_norm),
+                      gamma=_f32(it.injector.gamma, dev)))
     exts = [it.extractor] + (list(it.extra_extractors) if it.extra_extractors is not None else [])
     d["ext"] = []
     for ex in exts:
-        e = dict(qn=_LN(ex.query_norm, dev), fn=_LN(ex.feat_norm, dev), attn=_MSDA(ex.attn, dev), ffn=None)
+        e = dict(qn=_LN(ex.query_norm, dev), fn=_LN(ex.feat_norm, dev),
+                 attn=_MSDA(ex.attn, dev, ex.query_norm, ex.feat_norm), ffn=None)
         if ex.with_cffn:
             hc = ex.ffn.fc1.weight.shape[0]
             e["ffn"] = dict(norm=_LN(ex.ffn_norm, dev), fc1=_Lin(ex.ffn.fc1.weight, ex.ffn.fc1.bias, dev),
+                            fc1_ln=_LinLN(ex.ffn.fc1.weight, ex.ffn.fc1.bias, ex.ffn_norm, dev),
                             dw_w=_f32(ex.ffn.dwconv.dwconv.weight.detach().reshape(hc, 9).t(), dev),
                             dw_b=_f32(ex.ffn.dwconv.dwconv.bias, dev),
                             fc2=_Lin(ex.ffn.fc2.weight, ex.ffn.fc2.bias, dev))
@@ -170,11 +198,21 @@ class _Ops:
     def _ln(self, x, ln, **kw):
         return K.layernorm(x, ln.w, ln.b, ln.eps, **kw)
 
-    def _msda(self, pk, query_n, feat_n, ref, lv, B, geom=None):
-        """MSDeformAttn.forward up to (not including) output_proj (ops/modules/ms_deform_attn.py:83-127)."""
-        value = self._gemm(feat_n, pk.value)                                   # [B*S, M*D]
-        qp = self._gemm(query_n, pk.qproj, out_dtype=torch.float32)            # [B*Lq, M*L*P*3]
-        S = feat_n.shape[0] // B
+    def _gemm_ln(self, x, lnlin, **kw):
+        """lnlin(LayerNorm(x)) with the LayerNorm folded into the GEMM: one statistics pass over x (half the traffic of
+        the LayerNorm kernel), no normalised copy of x."""
+        return K.gemm_ln(x, lnlin.w, lnlin.b, lnlin.colsum, K.rowstats(x, lnlin.eps), **kw)
+
+    def _msda(self, pk, query, feat, ref, lv, B, geom=None, qn=None, fn=None):
+        """MSDeformAttn.forward up to (not including) output_proj (ops/modules/ms_deform_attn.py:83-127) on
+        query_norm(query) / feat_norm(feat) (adapter_modules_...new.py:494-501, 527-532)."""
+        if LN_FOLD and pk.value_ln is not None and pk.qproj_ln is not None:
+            value = self._gemm_ln(feat, pk.value_ln)                             # [B*S, M*D]
+            qp = self._gemm_ln(query, pk.qproj_ln, out_dtype=torch.float32)      # [B*Lq, M*L*P*3]
+        else:
+            value = self._gemm(self._ln(feat, fn), pk.value)
+            qp = self._gemm(self._ln(query, qn), pk.qproj, out_dtype=torch.float32)
+        S = feat.shape[0] // B
         return K.msda_fused(value.view(B, S, -1), lv[0], lv[1], qp, ref, pk.n_heads, pk.n_levels, pk.n_points, geom=geom)
 
     def _block(self, x, blk, sc, tabs, B, out=None):
@@ -202,22 +240,19 @@ class _Ops:
     def _injector(self, x, c, inj, sc, B):
         """Injector.forward (adapter_modules_...new.py:525-542); returns a NEW [B*T, C] buffer (the input
         is one of the saved ViT outputs `outs` and must stay intact)."""
-        qn = self._ln(x, inj["qn"])
-        fn = self._ln(c, inj["fn"])
-        o = self._msda(inj["attn"], qn, fn, sc["ref1"], sc["lv3"], B, inj["attn"].geom("inj", sc) if MSDA_STAGED else None)
+        o = self._msda(inj["attn"], x, c, sc["ref1"], sc["lv3"], B, inj["attn"].geom("inj", sc) if MSDA_STAGED else None,
+                       qn=inj["qn"], fn=inj["fn"])
         return K.gemm(o.view(-1, o.shape[-1]), inj["attn"].out.w, bias=inj["attn"].out.b, scale=inj["gamma"],
                       residual=x, out=torch.empty_like(x))
 
     def _extractor(self, c, x, e, sc, B):
         """Extractor.forward (adapter_modules_...new.py:490-511); c [B*S3, C] updated in place."""
-        qn = self._ln(c, e["qn"])
-        fn = self._ln(x, e["fn"])
-        o = self._msda(e["attn"], qn, fn, sc["ref2"], sc["lv1"], B, e["attn"].geom("ext", sc) if MSDA_STAGED else None)
+        o = self._msda(e["attn"], c, x, sc["ref2"], sc["lv1"], B, e["attn"].geom("ext", sc) if MSDA_STAGED else None,
+                       qn=e["qn"], fn=e["fn"])
         self._gemm(o.view(-1, o.shape[-1]), e["attn"].out, residual=c, out=c)
         f = e["ffn"]
         if f is not None:
-            y = self._ln(c, f["norm"])
-            h = self._gemm(y, f["fc1"])
+            h = self._gemm_ln(c, f["fc1_ln"]) if LN_FOLD else self._gemm(self._ln(c, f["norm"]), f["fc1"])
             hc = h.shape[1]
             h2 = K.dwconv(h, f["dw_w"], f["dw_b"], 3, sc["s3"], B, hc, sc["S3"] * hc, sc["S3"] * hc, act="gelu")
             self._gemm(h2, f["fc2"], residual=c, out=c)

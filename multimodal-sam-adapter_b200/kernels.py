@@ -114,6 +114,37 @@ def gemm(a, w, bias=None, act=None, scale=None, residual=None, out=None, out_dty
     return out
 
 
+def rowstats(x, eps, out=None):
+    """x bf16 [rows, C] (rows contiguous) -> fp32 [rows, 2] = (mean, rstd) of every row (LayerNorm statistics)."""
+    _need_cuda(x)
+    rows, C = x.shape
+    if out is None:
+        out = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+    rc = _lib.load().mmsam_rowstats_bf16(_ptr(x), _ptr(out), rows, C, x.stride(0), float(eps), _stream())
+    _lib.check(rc, "mmsam_rowstats_bf16")
+    _count()
+    return out
+
+
+def gemm_ln(a, w, bias, colsum, rowstat, act=None, residual=None, out=None, out_dtype=torch.bfloat16, block_n=0,
+            max_ctas=0):
+    """LayerNorm folded into the GEMM: out = act(rstd * (a @ w^T - mean * colsum) + bias) (+ residual);
+    w = bf16(gamma * W), colsum = w.sum(1), bias = W @ beta + b (see include/mmsam_b200.h)."""
+    _need_cuda(a, w, bias, colsum, rowstat, residual, out)
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1 and rowstat.shape[0] == M
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    rc = _lib.load().mmsam_gemm_ln_bf16(
+        _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(colsum), _ptr(rowstat), _ptr(residual),
+        residual.stride(0) if residual is not None else 0, _ptr(out), out.stride(0), M, N, K, ACT[act],
+        1 if out.dtype == torch.float32 else 0, block_n, max_ctas, _stream())
+    _lib.check(rc, "mmsam_gemm_ln_bf16")
+    _count()
+    return out
+
+
 def relpos_table(rel_pos, size):
     """SAM get_rel_pos for q_size == k_size == size (base/image_encoder.py:554-584): linear
     interpolation of the [L, 64] table to 2*size-1 rows when L differs; row r = q - k + size - 1.

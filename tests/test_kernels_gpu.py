@@ -4,6 +4,8 @@ import math
 import pytest
 import torch
 
+from common import rel_l2  # noqa: E402
+
 pytestmark = pytest.mark.gpu
 
 
@@ -479,6 +481,33 @@ def test_resize_add_affine(B, C, hs, ws, ho, wo):
     assert ((out - ref).abs() <= 0.008 * ref.abs() + 4e-3).all()
     out2 = k.resize_add_affine(src.cuda(), (hs, ws), (ho, wo), B, C).cpu().float()       # plain resize
     assert ((out2 - up).abs() <= 0.008 * up.abs() + 4e-3).all()
+
+
+@pytest.mark.parametrize("M,N,K,f32,act", [(1000, 192, 1024, True, None), (4096, 512, 1024, False, None),
+                                             (777, 256, 1024, False, "gelu"), (300, 72, 256, True, None)])
+def test_gemm_with_folded_layernorm(M, N, K, f32, act):
+    """rowstats + gemm_ln (LayerNorm folded into the GEMM through row statistics and the weight's column sums) against
+    F.layer_norm -> F.linear in fp32, on inputs with a large common offset (the term the fold has to cancel)."""
+    k = _k()
+    g = torch.Generator().manual_seed(M + N)
+    x = (torch.randn(M, K, generator=g) * (0.5 + torch.rand(M, 1, generator=g) * 3) + torch.randn(M, 1, generator=g) * 4).to(torch.bfloat16)
+    gamma, beta = 1 + 0.3 * torch.randn(K, generator=g), 0.2 * torch.randn(K, generator=g)
+    W, b = torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    eps = 1e-6
+    ref = torch.nn.functional.linear(torch.nn.functional.layer_norm(x.float(), (K,), gamma, beta, eps), W, b)
+    if act == "gelu":
+        ref = torch.nn.functional.gelu(ref)
+    st = k.rowstats(x.cuda(), eps)
+    mu, var = x.float().mean(1), x.float().var(1, unbiased=False)
+    assert torch.allclose(st[:, 0].cpu(), mu, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(st[:, 1].cpu(), 1 / torch.sqrt(var + eps), rtol=1e-3)
+    wf = (W * gamma[None, :]).to(torch.bfloat16)
+    out = k.gemm_ln(x.cuda(), wf.cuda(), (W @ beta + b).cuda(), wf.float().sum(1).cuda(), st, act=act,
+                    out_dtype=torch.float32 if f32 else torch.bfloat16).cpu().float()
+    assert out.shape == ref.shape
+    err = (out - ref).abs()
+    assert (err <= 2e-2 * ref.abs() + 3e-2).all(), err.max()
+    assert rel_l2(out, ref) < 8e-3
 
 
 @pytest.mark.parametrize("B,C,ho,wo,srcs,relu", [
