@@ -278,8 +278,10 @@ class EncoderDecoder(nn.Module):
         return torch.nn.functional.interpolate(lg, size=img.shape[2:], mode="bilinear", align_corners=False)
 
     @torch.no_grad()
-    def slide_labels(self, img):
-        """slide_inference (encoder_decoder.py:191-234): overlapping crops, logits averaged by count."""
+    def slide_labels(self, img, crop_batch=8):
+        """slide_inference (encoder_decoder.py:191-234): overlapping crops, logits averaged by count. The crops of a frame
+        are independent, so they go through the network `crop_batch` at a time (one forward for the 6 crops of a MUSES
+        frame) instead of one by one; the overlap-add / count normalisation is unchanged."""
         h_stride, w_stride = self.test_cfg["stride"]
         h_crop, w_crop = self.test_cfg["crop_size"]
         B, _, h_img, w_img = img.shape
@@ -287,13 +289,26 @@ class EncoderDecoder(nn.Module):
         w_grids = max(w_img - w_crop + w_stride - 1, 0) // w_stride + 1
         preds = img.new_zeros((B, self.num_classes, h_img, w_img))
         count = img.new_zeros((B, 1, h_img, w_img))
+        boxes = []
         for hi in range(h_grids):
             for wi in range(w_grids):
                 y1, x1 = hi * h_stride, wi * w_stride
                 y2, x2 = min(y1 + h_crop, h_img), min(x1 + w_crop, w_img)
-                y1, x1 = max(y2 - h_crop, 0), max(x2 - w_crop, 0)
-                preds[:, :, y1:y2, x1:x2] += self.encode_decode(img[:, :, y1:y2, x1:x2].contiguous())
-                count[:, :, y1:y2, x1:x2] += 1
+                boxes.append((max(y2 - h_crop, 0), max(x2 - w_crop, 0), y2, x2))
+        per = max(crop_batch // B, 1)                      # crop positions per forward (each contributes B crops)
+        for i in range(0, len(boxes), per):
+            grp = boxes[i:i + per]
+            same = len({(y2 - y1, x2 - x1) for y1, x1, y2, x2 in grp}) == 1
+            if same and len(grp) > 1:
+                crops = torch.cat([img[:, :, y1:y2, x1:x2] for y1, x1, y2, x2 in grp], 0).contiguous()
+                lg = self.encode_decode(crops)
+                for j, (y1, x1, y2, x2) in enumerate(grp):
+                    preds[:, :, y1:y2, x1:x2] += lg[j * B:(j + 1) * B]
+                    count[:, :, y1:y2, x1:x2] += 1
+            else:
+                for y1, x1, y2, x2 in grp:
+                    preds[:, :, y1:y2, x1:x2] += self.encode_decode(img[:, :, y1:y2, x1:x2].contiguous())
+                    count[:, :, y1:y2, x1:x2] += 1
         return (preds / count).argmax(1).to(torch.uint8)
 
     @torch.no_grad()

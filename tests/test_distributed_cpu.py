@@ -71,3 +71,26 @@ def test_sharded_confusion_allgather_equals_single_process():
     assert torch.equal(u2.float(), ap + al - inter)
     mt = metrics_from_confusion(want)
     assert abs(mt["mIoU"] - torch.nanmean(inter / (ap + al - inter)).item()) < 1e-6   # fp32 vs fp64 division
+
+
+def test_deliver_keys_and_bucket_metrics_host_logic():
+    """Per-condition bucketing (datasets/DELIVER.py:261-615): path -> (weather, case) keys; bucket matrices add up to
+    the global one; metrics per bucket follow total_area_to_metrics."""
+    sys.path.insert(0, ROOT)
+    import mmsam_b200  # noqa
+    from mmsam_b200 import evalmetrics as em
+    assert em.deliver_keys("data/DELIVER/img/cloud/test/MAP_10_point102/045050_rgb_front.png") == ("cloud", None)
+    assert em.deliver_keys("data/DELIVER/lists/test_motionblur/img/night/test/MAP_1/000001_rgb_front.png") == ("night", "motionblur")
+    pred, gt = _data(n=6)
+    keys = [("cloud", "ordinary"), ("fog",), ("cloud",), (), ("sun", "lidarjitter"), ("cloud", "unknown-key")]
+    bc = em.BucketedConfusion(25, em.DELIVER_WEATHERS + em.DELIVER_CASES, "cpu")
+    for i in range(pred.shape[0]):                       # CPU stand-in for the device kernel: same counts
+        c = _conf_cpu(pred[i], gt[i], 25)
+        for k in ["global"] + [k for k in keys[i] if k in bc.index]:
+            bc.conf[bc.index[k]] += c
+    assert torch.equal(bc.conf[0], _conf_cpu(pred, gt, 25))
+    assert torch.equal(bc.conf[bc.index["cloud"]], _conf_cpu(pred[[0, 2, 5]], gt[[0, 2, 5]], 25))
+    assert int(bc.conf[bc.index["rain"]].sum()) == 0
+    m = bc.metrics()
+    assert set(m) == set(bc.keys) and abs(m["global"]["mIoU"] - em.metrics_from_confusion(bc.conf[0])["mIoU"]) < 1e-12
+    assert torch.equal(bc.gather(), bc.conf)             # no process group: identity

@@ -329,3 +329,27 @@ def test_confusion_matrix_kernel():
     m = gt != 255
     want = torch.bincount(gt[m].long() * 25 + pred[m].long(), minlength=625).view(25, 25)
     assert torch.equal(conf, want)
+
+
+def test_bucketed_confusion_on_device():
+    """BucketedConfusion.add (confusion kernel once per image and bucket) against bincount on the host."""
+    import mmsam_b200  # noqa
+    from mmsam_b200 import evalmetrics as em
+    g = torch.Generator().manual_seed(3)
+    pred = torch.randint(0, 25, (4, 130, 70), generator=g, dtype=torch.uint8)
+    gt = torch.randint(0, 25, (4, 130, 70), generator=g, dtype=torch.uint8)
+    gt[torch.rand(gt.shape, generator=g) < 0.02] = 255
+    keys = [("cloud", "ordinary"), ("fog", "ordinary"), ("cloud", "motionblur"), None]
+    bc = em.BucketedConfusion(25, em.DELIVER_WEATHERS + em.DELIVER_CASES, "cuda")
+    bc.add(pred.cuda(), gt.cuda(), [k if k is not None else () for k in keys])
+
+    def ref(idx):
+        m = gt[idx] != 255
+        return torch.bincount(gt[idx][m].long() * 25 + pred[idx][m].long(), minlength=625).view(25, 25)
+    conf = bc.conf.cpu()
+    assert torch.equal(conf[bc.index["global"]], ref([0, 1, 2, 3]))
+    assert torch.equal(conf[bc.index["cloud"]], ref([0, 2]))
+    assert torch.equal(conf[bc.index["ordinary"]], ref([0, 1]))
+    assert torch.equal(conf[bc.index["motionblur"]], ref([2]))
+    assert int(conf[bc.index["night"]].sum()) == 0
+    assert abs(bc.metrics()["cloud"]["mIoU"] - em.metrics_from_confusion(ref([0, 2]))["mIoU"]) < 1e-12
