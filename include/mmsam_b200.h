@@ -132,6 +132,12 @@ int mmsam_dwconv_bf16(const void* x, void* y, const float* w_tap_major, const fl
                       const long long* grid_out_off_host, long long in_bstride, long long out_bstride, int act,
                       void* stream);
 
+/* One modality's decoded image, HWC uint8 [B, H, W, C] (C <= 4, W % 4 == 0) -> channels [c_off, c_off + C) of the fp32
+ * NCHW network input [B, Ctot, H, W]: out = (v * prescale - mean[c]) / std[c] (Normalize_multimodal with norm_by_max:
+ * prescale = 1/255, pipelines/transform.py:2796-2806; + ImageToTensor's HWC -> CHW). mean / std are HOST pointers. */
+int mmsam_normalize_u8(const void* img_hwc_u8, float* out_nchw, int B, int H, int W, int C, int Ctot, int c_off,
+                       const float* mean_host, const float* std_host, float prescale, void* stream);
+
 /* NCHW fp32 image channels [c_off, c_off+C) -> bf16 rows [(b,py,px), (c,ky,kx)] for p x p / stride p
  * convs as GEMMs (patch embed base/image_encoder.py:662-671; ConvNeXt stem twin_convnext.py:295-312). */
 int mmsam_patchify_f32(const float* img, void* out, int B, int Ctot, int c_off, int C, int H, int W, int p,

@@ -26,6 +26,7 @@ SIGNATURES = {
     "mmsam_msda_fused_staged_bf16": [_vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i,
                                      _vp, _vp, _i, _vp],
     "mmsam_dwconv_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _ll, _i, _vp],
+    "mmsam_normalize_u8": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp],
     "mmsam_patchify_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_resize_add_affine_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _vp],
     "mmsam_resize_sum_affine_bf16": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],

@@ -58,6 +58,33 @@ patchify_generic_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict
   }
 }
 
+// The step before the path (pipelines/transform.py:2796-2806 Normalize_multimodal + formatting.py ImageToTensor): one
+// modality's decoded image, HWC uint8, -> (v * inv255 - mean[c]) / std[c] written as channels [c_off, c_off + C) of the
+// fp32 NCHW network input. A thread owns 4 consecutive pixels of a row: 4 * C byte loads, one float4 store per channel.
+__global__ void __launch_bounds__(256)
+normalize_u8_kernel(const uint8_t* __restrict__ img, float* __restrict__ out, int B, int H, int W, int C, int Ctot,
+                    int c_off, float m0, float m1, float m2, float m3, float r0, float r1, float r2, float r3, float pre) {
+  const float mean[4] = {m0, m1, m2, m3}, rstd[4] = {r0, r1, r2, r3};
+  const int W4 = W >> 2;
+  const long long total = (long long)B * H * W4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x4 = (int)(idx % W4);
+    long long t = idx / W4;
+    const int y = (int)(t % H);
+    const int b = (int)(t / H);
+    const uint8_t* src = img + (((long long)b * H + y) * W + x4 * 4) * C;
+    for (int c = 0; c < C; ++c) {
+      float4 v;
+      v.x = ((float)src[c] * pre - mean[c]) * rstd[c];
+      v.y = ((float)src[C + c] * pre - mean[c]) * rstd[c];
+      v.z = ((float)src[2 * C + c] * pre - mean[c]) * rstd[c];
+      v.w = ((float)src[3 * C + c] * pre - mean[c]) * rstd[c];
+      *reinterpret_cast<float4*>(out + (((long long)b * Ctot + c_off + c) * H + y) * W + x4 * 4) = v;
+    }
+  }
+}
+
 // out[b,y,x,c] = (base[b,y,x,c] + bilinear(src[b])[y,x,c]) * scale[c] + shift[c]   (NHWC bf16)
 // PyTorch bilinear, align_corners=False. Serves the ViT-feature fusion + eval BatchNorm at the end of
 // the backbone (..._new.py:326-337) and the head's resize-into-concat (segformer_head.py:55-61).
@@ -297,6 +324,25 @@ MMSAM_API int mmsam_patchify_f32(const float* img, void* out, int B, int Ctot, i
   if (vec && p == 4) patchify_kernel<4><<<grid_for(total / 4), 256, 0, st>>>(img, (__nv_bfloat16*)out, B, Ctot, c_off, C, H, W);
   else if (vec && p == 16) patchify_kernel<16><<<grid_for(total / 16), 256, 0, st>>>(img, (__nv_bfloat16*)out, B, Ctot, c_off, C, H, W);
   else patchify_generic_kernel<<<grid_for(total), 256, 0, st>>>(img, (__nv_bfloat16*)out, B, Ctot, c_off, C, H, W, p);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+MMSAM_API int mmsam_normalize_u8(const void* img_hwc_u8, float* out_nchw, int B, int H, int W, int C, int Ctot, int c_off,
+                                 const float* mean_host, const float* std_host, float prescale, void* stream) {
+  using namespace mmsam;
+  if (B < 0 || H <= 0 || W <= 0 || C <= 0 || C > 4 || (W & 3) || c_off < 0 || c_off + C > Ctot) return MMSAM_ERR_BAD_ARG;
+  if (B == 0) return MMSAM_OK;
+  if (!img_hwc_u8 || !out_nchw || !mean_host || !std_host || (((uintptr_t)out_nchw) & 15)) return MMSAM_ERR_BAD_ARG;
+  float m[4] = {0, 0, 0, 0}, r[4] = {1, 1, 1, 1};
+  for (int c = 0; c < C; ++c) {
+    if (std_host[c] == 0.f) return MMSAM_ERR_BAD_ARG;
+    m[c] = mean_host[c];
+    r[c] = 1.f / std_host[c];
+  }
+  const long long total = (long long)B * H * (W / 4);
+  normalize_u8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)img_hwc_u8, out_nchw, B, H, W, C, Ctot, c_off,
+                                                                       m[0], m[1], m[2], m[3], r[0], r[1], r[2], r[3], prescale);
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }

@@ -261,6 +261,22 @@ def dwconv(x, w_tap_major, bias, ksize, grids, B, C, in_bstride, out_bstride, ac
     return out
 
 
+def normalize_u8(img_u8, out, c_off, mean, std, prescale=1.0 / 255.0):
+    """img_u8 uint8 [B, H, W, C] (HWC, CUDA) -> out[:, c_off:c_off+C] of the fp32 NCHW input: (v * prescale - mean) / std."""
+    import ctypes
+    _need_cuda(img_u8, out)
+    assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous() and out.dtype == torch.float32 and out.is_contiguous()
+    B, H, W, C = img_u8.shape
+    assert out.shape[0] == B and tuple(out.shape[2:]) == (H, W)
+    m = (ctypes.c_float * C)(*[float(v) for v in mean])
+    sd = (ctypes.c_float * C)(*[float(v) for v in std])
+    rc = _lib.load().mmsam_normalize_u8(_ptr(img_u8), _ptr(out), B, H, W, C, out.shape[1], c_off, ctypes.cast(m, ctypes.c_void_p),
+                                        ctypes.cast(sd, ctypes.c_void_p), float(prescale), _stream())
+    _lib.check(rc, "mmsam_normalize_u8")
+    _count()
+    return out
+
+
 def patchify(img, c_off, C, p, out=None):
     """img fp32 NCHW [B, Ctot, H, W] -> bf16 [B*(H/p)*(W/p), C*p*p]."""
     _need_cuda(img)

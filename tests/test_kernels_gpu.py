@@ -536,6 +536,21 @@ def test_resize_sum_affine(B, C, ho, wo, srcs, relu):
     assert ((out - ref).abs() <= 0.008 * ref.abs() + 6e-3).all()
 
 
+def test_normalize_u8_matches_reference_pipeline():
+    """HWC uint8 -> normalised fp32 NCHW channels (Normalize_multimodal with norm_by_max + ImageToTensor,
+    pipelines/transform.py:2796-2806): RGB with the ImageNet statistics, LiDAR with mean 0 / std 1."""
+    k = _k()
+    g = torch.Generator().manual_seed(5)
+    rgb = torch.randint(0, 256, (2, 24, 36, 3), generator=g, dtype=torch.uint8)
+    aux = torch.randint(0, 256, (2, 24, 36, 3), generator=g, dtype=torch.uint8)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    out = torch.full((2, 6, 24, 36), float("nan"), device="cuda")
+    k.normalize_u8(rgb.cuda(), out, 0, mean, std)
+    k.normalize_u8(aux.cuda(), out, 3, [0, 0, 0], [1, 1, 1])
+    ref = torch.cat((((rgb.float() / 255.0) - torch.tensor(mean)) / torch.tensor(std), aux.float() / 255.0), -1).permute(0, 3, 1, 2)
+    assert torch.allclose(out.cpu(), ref, atol=2e-6, rtol=1e-6)
+
+
 @pytest.mark.parametrize("p,C,c_off,H,W", [(4, 3, 0, 32, 48), (4, 3, 3, 32, 48), (16, 3, 0, 64, 32), (2, 3, 1, 8, 12)])
 def test_patchify_vs_unfold(p, C, c_off, H, W):
     """NCHW fp32 channels [c_off, c_off+C) -> bf16 rows [(b,py,px), (c,ky,kx)] (PatchEmbed / ConvNeXt stem im2col,
