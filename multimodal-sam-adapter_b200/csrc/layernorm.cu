@@ -149,6 +149,10 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
 //   = rstd * (x (g (.) W)^T - mean * s) + c,  s_n = sum_k g_k W_nk,  c_n = sum_k beta_k W_nk + b_n,
 // so the normalised copy of x is never written or re-read: this pass costs half of the LayerNorm's HBM traffic.
 // Warp per row, C % 8 == 0, C <= 2048.
+// NV = 16-byte chunks per lane (C <= 256 * NV): the row lives in 8 * NV registers; every warp keeps TWO rows in flight
+// (both rows' loads are issued before the first reduction) and the register budget leaves 5+ CTAs per SM, which is what
+// a read-only streaming pass needs to reach HBM speed (a first version with a fixed 64-register row ran at 3.3 TB/s).
+template <int NV>
 __global__ void __launch_bounds__(256)
 rowstats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats, long long rows, int C, long long ldx,
                 float eps) {
@@ -156,30 +160,41 @@ rowstats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats,
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = C >> 3;
-  for (long long row = warp; row < rows; row += nwarps) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
-    float f[8][8];
-    float sum = 0.f;
+  const float invC = 1.f / (float)C;
+  for (long long row = warp * 2; row < rows; row += nwarps * 2) {
+    uint4 raw[2][NV];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nvec) {
-        unpack8(__ldg(xr + v), f[i]);
+    for (int r = 0; r < 2; ++r) {
+      const long long rr = row + r < rows ? row + r : row;
+      const uint4* xr = reinterpret_cast<const uint4*>(x + rr * ldx);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = lane + 32 * i;
+        raw[r][i] = v < nvec ? __ldg(xr + v) : make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float f[NV][8];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        unpack8(raw[r][i], f[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) sum += f[i][j];
       }
-    }
-    const float mean = warp_sum(sum) / (float)C;
-    float var = 0.f;
+      const float mean = warp_sum(sum) * invC;      // lanes past the row end contributed zeros
+      float var = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (lane + 32 * i < nvec) {
+      for (int i = 0; i < NV; ++i) {
+        if (lane + 32 * i < nvec) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; var = fmaf(d, d, var); }
+          for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; var = fmaf(d, d, var); }
+        }
       }
+      var = warp_sum(var) * invC;
+      if (lane == 0 && row + r < rows) stats[row + r] = make_float2(mean, rsqrtf(var + eps));
     }
-    var = warp_sum(var) / (float)C;
-    if (lane == 0) stats[row] = make_float2(mean, rsqrtf(var + eps));
   }
 }
 
@@ -229,9 +244,16 @@ MMSAM_API int mmsam_rowstats_bf16(const void* x, float* stats, long long rows, i
   if (rows < 0 || C <= 0 || (C & 7) || C > 2048 || ldx < C || (ldx & 7)) return MMSAM_ERR_BAD_ARG;
   if (rows == 0) return MMSAM_OK;
   if (!x || !stats || (((uintptr_t)x) & 15) || (((uintptr_t)stats) & 7)) return MMSAM_ERR_BAD_ARG;
-  long long blocks = (rows + 7) / 8;
+  long long blocks = (rows + 15) / 16;
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
-  rowstats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)stats, rows, C, ldx, eps);
+  const int nv = (C / 8 + 31) / 32;
+  cudaStream_t st = (cudaStream_t)stream;
+#define ROWSTATS(NVV) rowstats_kernel<NVV><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (float2*)stats, rows, C, ldx, eps)
+  if (nv <= 1) ROWSTATS(1);
+  else if (nv <= 2) ROWSTATS(2);
+  else if (nv <= 4) ROWSTATS(4);
+  else ROWSTATS(8);
+#undef ROWSTATS
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }
