@@ -512,6 +512,8 @@ def test_gemm_with_folded_layernorm(M, N, K, f32, act):
 
 @pytest.mark.parametrize("B,C,ho,wo,srcs,relu", [
     (2, 64, 32, 32, [(16, 16), (8, 8), (4, 4)], True),      # Segformer head: 3 coarser levels added to the 1/4 level
+    (1, 16, 27, 40, [(12, 20), (7, 9), (27, 40)], False),   # ragged row blocks, non-integer ratios, same-size source
+    (1, 8, 6, 6, [(1, 1), (2, 3)], True),                   # degenerate sources (all corners clamp to one pixel)
     (1, 24, 25, 19, [(13, 10), (25, 19)], False),           # ragged, one source already at the output size
     (2, 8, 12, 12, [], True),                               # base only
 ])
