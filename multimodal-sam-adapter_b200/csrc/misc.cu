@@ -88,72 +88,76 @@ normalize_u8_kernel(const uint8_t* __restrict__ img, float* __restrict__ out, in
 // out[b,y,x,c] = (base[b,y,x,c] + bilinear(src[b])[y,x,c]) * scale[c] + shift[c]   (NHWC bf16)
 // PyTorch bilinear, align_corners=False. Serves the ViT-feature fusion + eval BatchNorm at the end of
 // the backbone (..._new.py:326-337) and the head's resize-into-concat (segformer_head.py:55-61).
+// Grid = (x * channel-vector chunks, blocks of RA_YB rows, batch): a thread keeps its (x, 8 channels) for RA_YB consecutive
+// output rows — one 32-bit division per thread instead of three 64-bit ones per element, horizontal corners / weights and
+// the BatchNorm scale / shift (registers) computed once per RA_YB outputs (see resize_sum_affine_kernel).
+static constexpr int RA_YB = 8;
 __global__ void __launch_bounds__(256)
 resize_add_affine_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ base,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          __nv_bfloat16* __restrict__ out, int B, int Hs, int Ws, int Ho, int Wo, int C,
                          long long src_bstride, long long base_bstride, long long out_bstride, long long ldo,
                          long long lds, long long ldb, float rh, float rw) {
-  const int CV = C >> 3;
-  const long long total = (long long)B * Ho * Wo * CV;
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
-  // When the grid stride is a multiple of the channel-vector count a thread keeps ITS 8 channels for the whole loop:
-  // the BatchNorm scale / shift then live in registers. (Reading them per element as 16 scalar loads at a 32-byte
-  // lane stride cost 128 L1 wavefronts per warp against 20 for the data: 1.2 ms instead of 0.33 ms on the f1 map.)
-  const bool fixed_cv = scale != nullptr && (nthreads % CV) == 0;
+  const uint32_t CV = (uint32_t)C >> 3;
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= (uint32_t)Wo * CV) return;
+  const uint32_t x = i / CV, cv = i - x * CV;
+  const int b = blockIdx.z;
+  const int y_begin = blockIdx.y * RA_YB, y_end = min(y_begin + RA_YB, Ho);
   float sc[8], sh[8];
-  if (fixed_cv) {
-    const int cv0 = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % CV);
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + cv0 * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + cv0 * 8 + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + cv0 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + cv0 * 8 + 4));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
+  if (scale) {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + cv * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + cv * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + cv * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + cv * 8 + 4));
     sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
     sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
   }
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
-    const int cv = (int)(idx % CV);
-    long long t = idx / CV;
-    const int x = (int)(t % Wo); t /= Wo;
-    const int y = (int)(t % Ho);
-    const int b = (int)(t / Ho);
+  const bool same = Hs == Ho && Ws == Wo;
+  float sx = (x + 0.5f) * rw - 0.5f;
+  sx = sx < 0.f ? 0.f : sx;
+  int x0 = same ? (int)x : (int)sx;
+  x0 = x0 > Ws - 1 ? Ws - 1 : x0;
+  const int x1 = x0 < Ws - 1 ? x0 + 1 : x0;
+  const float lx = same ? 0.f : sx - x0;
+  const __nv_bfloat16* sb = src + b * src_bstride + cv * 8;
+  const long long so0 = (long long)x0 * lds, so1 = (long long)x1 * lds;
+  const __nv_bfloat16* bp = base ? base + b * base_bstride + ((long long)y_begin * Wo + x) * ldb + cv * 8 : nullptr;
+  __nv_bfloat16* op = out + b * out_bstride + ((long long)y_begin * Wo + x) * ldo + cv * 8;
+  for (int y = y_begin; y < y_end; ++y, op += (long long)Wo * ldo) {
     float f[8];
-    if (Hs == Ho && Ws == Wo) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(src + b * src_bstride + ((long long)y * Ws + x) * lds + cv * 8)), f);
+    if (same) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(sb + (long long)y * Ws * lds + so0)), f);
     } else {
-      float sy = (y + 0.5f) * rh - 0.5f, sx = (x + 0.5f) * rw - 0.5f;
+      float sy = (y + 0.5f) * rh - 0.5f;
       sy = sy < 0.f ? 0.f : sy;
-      sx = sx < 0.f ? 0.f : sx;
-      int y0 = (int)sy, x0 = (int)sx;
+      int y0 = (int)sy;
       y0 = y0 > Hs - 1 ? Hs - 1 : y0;
-      x0 = x0 > Ws - 1 ? Ws - 1 : x0;
-      const int y1 = y0 < Hs - 1 ? y0 + 1 : y0, x1 = x0 < Ws - 1 ? x0 + 1 : x0;
-      const float ly = sy - y0, lx = sx - x0;
-      const __nv_bfloat16* sb = src + b * src_bstride + cv * 8;
+      const int y1 = y0 < Hs - 1 ? y0 + 1 : y0;
+      const float ly = sy - y0;
+      const __nv_bfloat16* r0 = sb + (long long)y0 * Ws * lds;
+      const __nv_bfloat16* r1 = sb + (long long)y1 * Ws * lds;
       float a[8], c[8], d[8], e[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(sb + ((long long)y0 * Ws + x0) * lds)), a);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(sb + ((long long)y0 * Ws + x1) * lds)), c);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(sb + ((long long)y1 * Ws + x0) * lds)), d);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(sb + ((long long)y1 * Ws + x1) * lds)), e);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(r0 + so0)), a);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(r0 + so1)), c);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(r1 + so0)), d);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(r1 + so1)), e);
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        f[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * c[j]) + ly * ((1.f - lx) * d[j] + lx * e[j]);
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(w00, a[j], fmaf(w01, c[j], fmaf(w10, d[j], w11 * e[j])));
     }
-    if (base) {
+    if (bp) {
       float g[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(base + b * base_bstride + ((long long)y * Wo + x) * ldb + cv * 8)), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(bp)), g);
+      bp += (long long)Wo * ldb;
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] += g[j];
     }
     if (scale) {
-      if (!fixed_cv) {
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + cv * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + cv * 8 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + cv * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + cv * 8 + 4));
-        sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
-        sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
-      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
     }
-    *reinterpret_cast<uint4*>(out + b * out_bstride + ((long long)y * Wo + x) * ldo + cv * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(op) = pack8(f);
   }
 }
 
@@ -392,8 +396,9 @@ MMSAM_API int mmsam_resize_add_affine_bf16(const void* src, const void* base, co
   if (B == 0) return MMSAM_OK;
   if (!src || !out) return MMSAM_ERR_BAD_ARG;
   if ((((uintptr_t)src | (uintptr_t)out | (uintptr_t)base | (uintptr_t)scale | (uintptr_t)shift) & 15)) return MMSAM_ERR_BAD_ARG;
-  const long long total = (long long)B * Ho * Wo * (C / 8);
-  resize_add_affine_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+  if (B > 65535 || (Ho + RA_YB - 1) / RA_YB > 65535 || (long long)Wo * (C / 8) > (1ll << 31) - 256) return MMSAM_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)(((long long)Wo * (C / 8) + 255) / 256), (unsigned)((Ho + RA_YB - 1) / RA_YB), (unsigned)B);
+  resize_add_affine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)src, (const __nv_bfloat16*)base, scale, shift, (__nv_bfloat16*)out, B, Hs, Ws, Ho, Wo, C,
       src_bstride, base_bstride, out_bstride, ldo, lds, ldb, (float)Hs / (float)Ho, (float)Ws / (float)Wo);
   MMSAM_LAUNCH_CHECK();
