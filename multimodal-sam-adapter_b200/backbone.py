@@ -61,9 +61,8 @@ class ImageEncoderViT(nn.Module):
 
     def init_weights(self, pretrained=None):
         if isinstance(pretrained, str):
-            sd = torch.load(pretrained, map_location="cpu")
-            sd = sd.get("state_dict", sd.get("model", sd))
-            self.load_state_dict(sd, strict=False)
+            from .checkpoint import load_checkpoint        # mmcv-style: unwrap, strip 'module.', non-strict
+            load_checkpoint(self, pretrained, strict=False)
 
 
 @BACKBONES.register_module(force=True)

@@ -193,3 +193,39 @@ def test_msdeformattn_module_contract():
     assert m.value_proj.weight.shape == (32, 64) and m.output_proj.weight.shape == (64, 32)
     with pytest.raises(ValueError):
         MSDeformAttn(d_model=65, n_heads=4)
+
+
+def test_checkpoint_ingestion_rules():
+    """mmcv-style unwrap / module. strip, the SAM image-encoder conversion
+    (tools/SAM_checkpoint_convert.py:15-33) and the twin-ConvNeXt key surgery (base/twin_convnext.py:399-443)."""
+    import mmsam_b200  # noqa: F401
+    from mmsam_b200 import checkpoint as ck
+    from mmsam_b200 import nn_modules as M
+    torch.manual_seed(0)
+    # (a) SAM: image_encoder.* minus neck.* -> ImageEncoderViT keys
+    sam = {"image_encoder.pos_embed": torch.zeros(1), "image_encoder.blocks.0.norm1.weight": torch.ones(2),
+           "image_encoder.neck.0.weight": torch.ones(3), "prompt_encoder.x": torch.ones(1), "mask_decoder.y": torch.ones(1)}
+    assert list(ck.convert_sam_image_encoder(sam)) == ["pos_embed", "blocks.0.norm1.weight"]
+    # (b) twin ConvNeXt from a single-tower checkpoint (wrapped + 'backbone.' prefix)
+    twin = M.TwinConvNeXt(arch=dict(depths=[1, 1, 1, 1], channels=[8, 16, 32, 64]))
+    single = {}
+    for k, v in twin.state_dict().items():
+        if "_x" in k.split(".")[0]:
+            single["backbone." + k.replace("_x", "", 1)] = torch.randn_like(v)
+    single["backbone.norm0.weight"] = torch.randn(8)          # per-stage output norms: norm{i} -> norm{i}_x ... see below
+    left = ck.load_twin_convnext(twin, {"state_dict": single})
+    sd = twin.state_dict()
+    for k, v in single.items():
+        k = k[len("backbone."):]
+        dot = k.find(".")
+        kx, ky = k[:dot] + "_x" + k[dot:], k[:dot] + "_y" + k[dot:]
+        if kx in sd:
+            assert torch.equal(sd[kx], v) and torch.equal(sd[ky], v)   # both towers got the same tensor
+        else:
+            assert kx in left                                           # e.g. norm0_x: the reference's own naming quirk
+    # (c) mmcv-style load of a DataParallel-wrapped segmentor checkpoint
+    lin = torch.nn.Linear(3, 2)
+    wrapped = {"state_dict": {"module." + k: v + 1 for k, v in lin.state_dict().items()}, "meta": {}}
+    missing, unexpected = ck.load_checkpoint(lin, wrapped)
+    assert missing == [] and unexpected == []
+    assert torch.equal(lin.weight.data, wrapped["state_dict"]["module.weight"])
