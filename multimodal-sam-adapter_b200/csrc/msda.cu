@@ -340,9 +340,10 @@ msda_fused_coop_kernel(const __nv_bfloat16* __restrict__ value, const int64_t* _
   den += __shfl_xor_sync(0xffffffffu, den, 2);
   const float inv = 1.f / den;
 
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  // packed fp32x2 accumulators (channel pairs): one FFMA2 per corner and pair instead of two FFMA — the kernel issues at
+  // 68 - 82 % of its slots (ncu), so instructions, not only L1 wavefronts, are on the critical path
+  u64 acc2[4] = {0ull, 0ull, 0ull, 0ull};
+  const uint32_t rs32 = (uint32_t)rs;
 #pragma unroll
   for (int l = 0; l < MAXL; ++l) {
     if (l < L) {
@@ -369,28 +370,31 @@ msda_fused_coop_kernel(const __nv_bfloat16* __restrict__ value, const int64_t* _
         const int bf = __shfl_sync(0xffffffffu, dflag, pp, 4);
         const float k1 = __shfl_sync(0xffffffffu, c1, pp, 4), k2 = __shfl_sync(0xffffffffu, c2, pp, 4);
         const float k3 = __shfl_sync(0xffffffffu, c3, pp, 4), k4 = __shfl_sync(0xffffffffu, c4, pp, 4);
-        const __nv_bfloat16* p00 = vl + (long long)bi * rs;
-        const long long dx = (bf & 1) ? rs : 0, dy = (bf & 2) ? (long long)W * rs : 0;
-        const uint4 u00 = __ldg(reinterpret_cast<const uint4*>(p00));
-        const uint4 u01 = __ldg(reinterpret_cast<const uint4*>(p00 + dx));
-        const uint4 u10 = __ldg(reinterpret_cast<const uint4*>(p00 + dy));
-        const uint4 u11 = __ldg(reinterpret_cast<const uint4*>(p00 + dy + dx));
-        float v[8];
-        unpack8(u00, v);
+        // 32-bit element offsets inside the level (a level of one image is far below 2^31 elements)
+        const uint32_t o00 = (uint32_t)bi * rs32;
+        const uint32_t dx = (bf & 1) ? rs32 : 0u, dy = (bf & 2) ? (uint32_t)W * rs32 : 0u;
+        const uint4 u00 = __ldg(reinterpret_cast<const uint4*>(vl + o00));
+        const uint4 u01 = __ldg(reinterpret_cast<const uint4*>(vl + (o00 + dx)));
+        const uint4 u10 = __ldg(reinterpret_cast<const uint4*>(vl + (o00 + dy)));
+        const uint4 u11 = __ldg(reinterpret_cast<const uint4*>(vl + (o00 + dy + dx)));
+        const u64 w1 = pack2(k1, k1), w2 = pack2(k2, k2), w3 = pack2(k3, k3), w4 = pack2(k4, k4);
+        const uint32_t* c00 = reinterpret_cast<const uint32_t*>(&u00);
+        const uint32_t* c01 = reinterpret_cast<const uint32_t*>(&u01);
+        const uint32_t* c10 = reinterpret_cast<const uint32_t*>(&u10);
+        const uint32_t* c11 = reinterpret_cast<const uint32_t*>(&u11);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(k1, v[i], acc[i]);
-        unpack8(u01, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(k2, v[i], acc[i]);
-        unpack8(u10, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(k3, v[i], acc[i]);
-        unpack8(u11, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(k4, v[i], acc[i]);
+        for (int i = 0; i < 4; ++i) {
+          acc2[i] = fma2(pack2(bf16lo(c00[i]), bf16hi(c00[i])), w1, acc2[i]);
+          acc2[i] = fma2(pack2(bf16lo(c01[i]), bf16hi(c01[i])), w2, acc2[i]);
+          acc2[i] = fma2(pack2(bf16lo(c10[i]), bf16hi(c10[i])), w3, acc2[i]);
+          acc2[i] = fma2(pack2(bf16lo(c11[i]), bf16hi(c11[i])), w4, acc2[i]);
+        }
       }
     }
   }
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) unpack2(acc2[i], acc[2 * i], acc[2 * i + 1]);
   if (head_ok) *reinterpret_cast<uint4*>(out + (row * M + m) * D + pl * 8) = pack8(acc);
 }
 
