@@ -212,7 +212,9 @@ MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const floa
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = 8;
   const int nvec = C / 8;
-  const int G = nvec > 16 ? 32 : (nvec > 8 ? 16 : 8);
+  // C = 96 (12 chunks, ConvNeXt stage 0 at 1/4 resolution): 16 lanes per row leave 4 idle; 4 lanes x 3 chunks use them all
+  const bool g4 = nvec == 12 && !getenv("MMSAM_LN_NO_G4");
+  const int G = g4 ? 4 : (nvec > 16 ? 32 : (nvec > 8 ? 16 : 8));
   const int rpw = 32 / G;
   const int nv = (nvec + 31) / 32;
   const int R = 1;   // rows in flight per lane group: 2 was measured SLOWER everywhere (registers -> occupancy)
@@ -224,7 +226,8 @@ MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const floa
   __nv_bfloat16* yo2 = (__nv_bfloat16*)y2;
 #define LN_CASE(NV, GG, RR) \
   layernorm_kernel<NV, GG, RR><<<(unsigned)blocks, wpb * 32, 0, st>>>(xi, gamma, beta, yo, yo2, row_map_dev, rows, C, ldx, ldy, eps, ps_h, ps_w)
-  if (G == 8) LN_CASE(1, 8, 1);
+  if (G == 4) LN_CASE(3, 4, 1);
+  else if (G == 8) LN_CASE(1, 8, 1);
   else if (G == 16) LN_CASE(1, 16, 1);
   else switch (nv) {
     case 1: LN_CASE(1, 32, 1); break;
