@@ -213,8 +213,10 @@ MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const floa
   const int wpb = 8;
   const int nvec = C / 8;
   // C = 96 (12 chunks, ConvNeXt stage 0 at 1/4 resolution): 16 lanes per row leave 4 idle; 4 lanes x 3 chunks use them all
-  const bool g4 = nvec == 12 && !getenv("MMSAM_LN_NO_G4");
-  const int G = g4 ? 4 : (nvec > 16 ? 32 : (nvec > 8 ? 16 : 8));
+  // likewise C = 192 (24 chunks) = 8 lanes x 3 and C = 384 (48 chunks) = 16 lanes x 3 instead of 24 / 48 of 32 / 64 slots
+  const bool narrow = !getenv("MMSAM_LN_NO_G4");
+  const int G = (narrow && nvec == 12) ? 4 : (narrow && nvec == 24) ? 8 : (narrow && nvec == 48) ? 16
+                : (nvec > 16 ? 32 : (nvec > 8 ? 16 : 8));
   const int rpw = 32 / G;
   const int nv = (nvec + 31) / 32;
   const int R = 1;   // rows in flight per lane group: 2 was measured SLOWER everywhere (registers -> occupancy)
@@ -227,7 +229,9 @@ MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const floa
 #define LN_CASE(NV, GG, RR) \
   layernorm_kernel<NV, GG, RR><<<(unsigned)blocks, wpb * 32, 0, st>>>(xi, gamma, beta, yo, yo2, row_map_dev, rows, C, ldx, ldy, eps, ps_h, ps_w)
   if (G == 4) LN_CASE(3, 4, 1);
+  else if (G == 8 && nvec == 24) LN_CASE(3, 8, 1);
   else if (G == 8) LN_CASE(1, 8, 1);
+  else if (G == 16 && nvec == 48) LN_CASE(3, 16, 1);
   else if (G == 16) LN_CASE(1, 16, 1);
   else switch (nv) {
     case 1: LN_CASE(1, 32, 1); break;

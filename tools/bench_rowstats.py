@@ -19,7 +19,7 @@ def t(fn, n=10):
     return s.elapsed_time(e) / n * 1e3
 
 
-for rows, C in ((172032, 1024), (32768, 1024), (524288, 96)):
+for rows, C in ((172032, 1024), (32768, 1024), (524288, 96), (131072, 192), (32768, 384), (8192, 768)):
     x = torch.randn(rows, C, device="cuda").to(torch.bfloat16)
     g, b = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
     st = torch.empty(rows, 2, device="cuda")
