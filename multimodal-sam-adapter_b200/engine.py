@@ -198,17 +198,29 @@ class _Ops:
     def _ln(self, x, ln, **kw):
         return K.layernorm(x, ln.w, ln.b, ln.eps, **kw)
 
-    def _gemm_ln(self, x, lnlin, **kw):
+    def _gemm_ln(self, x, lnlin, stats_of=None, **kw):
         """lnlin(LayerNorm(x)) with the LayerNorm folded into the GEMM: one statistics pass over x (half the traffic of
-        the LayerNorm kernel), no normalised copy of x."""
-        return K.gemm_ln(x, lnlin.w, lnlin.b, lnlin.colsum, K.rowstats(x, lnlin.eps), **kw)
+        the LayerNorm kernel), no normalised copy of x. stats_of: the shape-cache dict when x is the adapter's token
+        buffer `c`: its row statistics are kept there until `c` is written again — the Injector's feat_norm and the
+        following Extractor's query_norm normalise the SAME c (only the affine part differs), one pass serves both."""
+        st = None
+        if stats_of is not None:
+            ent = stats_of.get("c_stats")
+            if ent is not None and ent[0] == x.data_ptr() and ent[1] == lnlin.eps:
+                st = ent[2]
+        if st is None:
+            st = K.rowstats(x, lnlin.eps)
+            if stats_of is not None:
+                stats_of["c_stats"] = (x.data_ptr(), lnlin.eps, st)
+        return K.gemm_ln(x, lnlin.w, lnlin.b, lnlin.colsum, st, **kw)
 
-    def _msda(self, pk, query, feat, ref, lv, B, geom=None, qn=None, fn=None):
+    def _msda(self, pk, query, feat, ref, lv, B, geom=None, qn=None, fn=None, c_is=None, sc=None):
         """MSDeformAttn.forward up to (not including) output_proj (ops/modules/ms_deform_attn.py:83-127) on
-        query_norm(query) / feat_norm(feat) (adapter_modules_...new.py:494-501, 527-532)."""
+        query_norm(query) / feat_norm(feat) (adapter_modules_...new.py:494-501, 527-532). c_is: "feat" / "query" tells
+        which operand is the adapter's token buffer c (row statistics cached in sc)."""
         if LN_FOLD and pk.value_ln is not None and pk.qproj_ln is not None:
-            value = self._gemm_ln(feat, pk.value_ln)                             # [B*S, M*D]
-            qp = self._gemm_ln(query, pk.qproj_ln, out_dtype=torch.float32)      # [B*Lq, M*L*P*3]
+            value = self._gemm_ln(feat, pk.value_ln, stats_of=sc if c_is == "feat" else None)                      # [B*S, M*D]
+            qp = self._gemm_ln(query, pk.qproj_ln, stats_of=sc if c_is == "query" else None, out_dtype=torch.float32)  # [B*Lq, M*L*P*3]
         else:
             value = self._gemm(self._ln(feat, fn), pk.value)
             qp = self._gemm(self._ln(query, qn), pk.qproj, out_dtype=torch.float32)
@@ -241,14 +253,15 @@ class _Ops:
         """Injector.forward (adapter_modules_...new.py:525-542); returns a NEW [B*T, C] buffer (the input
         is one of the saved ViT outputs `outs` and must stay intact)."""
         o = self._msda(inj["attn"], x, c, sc["ref1"], sc["lv3"], B, inj["attn"].geom("inj", sc) if MSDA_STAGED else None,
-                       qn=inj["qn"], fn=inj["fn"])
+                       qn=inj["qn"], fn=inj["fn"], c_is="feat", sc=sc)
         return K.gemm(o.view(-1, o.shape[-1]), inj["attn"].out.w, bias=inj["attn"].out.b, scale=inj["gamma"],
                       residual=x, out=torch.empty_like(x))
 
     def _extractor(self, c, x, e, sc, B):
         """Extractor.forward (adapter_modules_...new.py:490-511); c [B*S3, C] updated in place."""
         o = self._msda(e["attn"], c, x, sc["ref2"], sc["lv1"], B, e["attn"].geom("ext", sc) if MSDA_STAGED else None,
-                       qn=e["qn"], fn=e["fn"])
+                       qn=e["qn"], fn=e["fn"], c_is="query", sc=sc)
+        sc["c_stats"] = None                                   # c is about to change
         self._gemm(o.view(-1, o.shape[-1]), e["attn"].out, residual=c, out=c)
         f = e["ffn"]
         if f is not None:
@@ -487,6 +500,7 @@ class EncoderEngine(_Ops):
             debug.update(fx=[(t.clone(), h, w) for t, h, w in fx], fy=[(t.clone(), h, w) for t, h, w in fy], fused=[t.clone() for t in fused])
         c1 = self._gemm(fused[0], self.fc[0])                            # [B*16T, C]
         c = torch.empty((B * S3, C), dtype=torch.bfloat16, device=self.dev)
+        sc["c_stats"] = None                                    # row statistics of c cached by _gemm_ln: none yet
         for i in range(3):
             self._gemm(fused[i + 1], self.fc[i + 1], out=c, row_map=sc["c_rowmaps"][i], out_rows=B * S3)
         # --- patch embed + pos embed (image_encoder.py:662-671, ..._new.py:268-278) ---
