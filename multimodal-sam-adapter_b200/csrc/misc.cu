@@ -1,5 +1,7 @@
 // Small HBM-bound layout / resampling kernels around the GEMMs.
 #include "common.cuh"
+#include <cmath>
+#include <cstdlib>
 
 MMSAM_API int mmsam_arch(void) { return 100; }
 
@@ -322,6 +324,74 @@ upsample_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ l
   }
 }
 
+// Same result, source window staged in shared memory. The flat kernel above is bound by L1 wavefronts: every one of its
+// 28 16-byte loads per pixel touches ~9 distinct source pixels per warp. Here a CTA owns UA_RY output rows x 256 output
+// columns, copies the few source rows / columns they interpolate from (coalesced, pixel pitch padded to 144 B so that the
+// ~9 source pixels a warp reads side by side fall into different banks) and every thread walks its column down the rows.
+static constexpr int UA_RY = 4, UA_PITCH = 36;   // floats per staged pixel (32 logits + 4 pad)
+__global__ void __launch_bounds__(256)
+upsample_argmax_staged_kernel(const float* __restrict__ logits, uint8_t* __restrict__ labels, int hs, int ws, int ldl,
+                              int ncls, int Hc, int Wc, float rh, float rw, int cols_s, int rows_s) {
+  extern __shared__ __align__(16) float ua_s[];     // [rows_s][cols_s][UA_PITCH]
+  const int b = blockIdx.z;
+  const int y_begin = blockIdx.y * UA_RY, y_end = min(y_begin + UA_RY, Hc);
+  const int x_begin = blockIdx.x * 256;
+  // first source row / column any pixel of the tile reads (the clamped floor of its source coordinate)
+  float fy = (y_begin + 0.5f) * rh - 0.5f, fx = (x_begin + 0.5f) * rw - 0.5f;
+  fy = fy < 0.f ? 0.f : fy;
+  fx = fx < 0.f ? 0.f : fx;
+  const int ys0 = min((int)fy, hs - 1), xs0 = min((int)fx, ws - 1);
+  const int nvec = ldl >> 2;                         // float4 per source pixel (ldl <= 32)
+  const float* lb = logits + (long long)b * hs * ws * ldl;
+  for (int i = threadIdx.x; i < rows_s * cols_s * nvec; i += 256) {
+    const int v = i % nvec, px = i / nvec;
+    const int cx = px % cols_s, cy = px / cols_s;
+    const int sy = min(ys0 + cy, hs - 1), sx = min(xs0 + cx, ws - 1);
+    *reinterpret_cast<float4*>(ua_s + (cy * cols_s + cx) * UA_PITCH + v * 4) =
+        __ldg(reinterpret_cast<const float4*>(lb + ((long long)sy * ws + sx) * ldl) + v);
+  }
+  __syncthreads();
+  const int x = x_begin + threadIdx.x;
+  if (x >= Wc) return;
+  float sxf = (x + 0.5f) * rw - 0.5f;
+  sxf = sxf < 0.f ? 0.f : sxf;
+  int x0 = (int)sxf;
+  x0 = x0 > ws - 1 ? ws - 1 : x0;
+  const int x1 = x0 < ws - 1 ? x0 + 1 : x0;
+  const float lx = sxf - x0;
+  const int cx0 = x0 - xs0, cx1 = x1 - xs0;
+  for (int y = y_begin; y < y_end; ++y) {
+    float syf = (y + 0.5f) * rh - 0.5f;
+    syf = syf < 0.f ? 0.f : syf;
+    int y0 = (int)syf;
+    y0 = y0 > hs - 1 ? hs - 1 : y0;
+    const int y1 = y0 < hs - 1 ? y0 + 1 : y0;
+    const float ly = syf - y0;
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const float* p00 = ua_s + ((y0 - ys0) * cols_s + cx0) * UA_PITCH;
+    const float* p01 = ua_s + ((y0 - ys0) * cols_s + cx1) * UA_PITCH;
+    const float* p10 = ua_s + ((y1 - ys0) * cols_s + cx0) * UA_PITCH;
+    const float* p11 = ua_s + ((y1 - ys0) * cols_s + cx1) * UA_PITCH;
+    float best = -INFINITY;
+    int arg = 0;
+    for (int c = 0; c < ncls; c += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(p00 + c);
+      const float4 bq = *reinterpret_cast<const float4*>(p01 + c);
+      const float4 cq = *reinterpret_cast<const float4*>(p10 + c);
+      const float4 d = *reinterpret_cast<const float4*>(p11 + c);
+      const float v0 = w00 * a.x + w01 * bq.x + w10 * cq.x + w11 * d.x;
+      const float v1 = w00 * a.y + w01 * bq.y + w10 * cq.y + w11 * d.y;
+      const float v2 = w00 * a.z + w01 * bq.z + w10 * cq.z + w11 * d.z;
+      const float v3 = w00 * a.w + w01 * bq.w + w10 * cq.w + w11 * d.w;
+      if (v0 > best) { best = v0; arg = c; }
+      if (c + 1 < ncls && v1 > best) { best = v1; arg = c + 1; }
+      if (c + 2 < ncls && v2 > best) { best = v2; arg = c + 2; }
+      if (c + 3 < ncls && v3 > best) { best = v3; arg = c + 3; }
+    }
+    labels[((long long)b * Hc + y) * Wc + x] = (uint8_t)arg;
+  }
+}
+
 // confusion[gt, pred] += 1 over all pixels with gt != ignore (the device-side form of
 // intersect_and_union, mmseg_custom/apis/evaluation/metrics_micro.py:26-86).
 __global__ void __launch_bounds__(256)
@@ -448,8 +518,18 @@ MMSAM_API int mmsam_upsample_argmax_f32(const float* logits, void* labels_u8, in
   if (B == 0) return MMSAM_OK;
   if (!logits || !labels_u8 || (((uintptr_t)logits) & 15)) return MMSAM_ERR_BAD_ARG;
   const long long total = (long long)B * Hc * Wc;
-  upsample_argmax_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
-      logits, (uint8_t*)labels_u8, B, hs, ws, ldl, ncls, Ho, Wo, Hc, Wc, (float)hs / (float)Ho, (float)ws / (float)Wo);
+  const float rh = (float)hs / (float)Ho, rw = (float)ws / (float)Wo;
+  // staged variant: the source window of a (UA_RY rows x 256 columns) output tile must fit 48 KB of shared memory
+  const int cols_s = (int)ceilf(256.f * rw) + 2, rows_s = (int)ceilf((float)UA_RY * rh) + 2;
+  const size_t smem = (size_t)cols_s * rows_s * UA_PITCH * sizeof(float);
+  if (ldl <= 32 && smem <= 48 * 1024 && B <= 65535 && (Hc + UA_RY - 1) / UA_RY <= 65535 && !getenv("MMSAM_ARGMAX_FLAT")) {
+    dim3 grid((unsigned)((Wc + 255) / 256), (unsigned)((Hc + UA_RY - 1) / UA_RY), (unsigned)B);
+    upsample_argmax_staged_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(logits, (uint8_t*)labels_u8, hs, ws, ldl, ncls, Hc,
+                                                                            Wc, rh, rw, cols_s, rows_s);
+  } else {
+    upsample_argmax_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+        logits, (uint8_t*)labels_u8, B, hs, ws, ldl, ncls, Ho, Wo, Hc, Wc, rh, rw);
+  }
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }

@@ -553,6 +553,29 @@ def test_normalize_u8_matches_reference_pipeline():
     assert torch.allclose(out.cpu(), ref, atol=2e-6, rtol=1e-6)
 
 
+@pytest.mark.parametrize("B,hs,ws,ncls,Ho,Wo,crop", [
+    (2, 64, 64, 25, 256, 256, None),        # the bench shape's 4x up-sampling (staged kernel)
+    (1, 50, 50, 14, 200, 200, (150, 200)),   # FMB-like: crop of whole_dim_cut
+    (1, 17, 23, 19, 40, 61, None),           # non-integer ratios, ragged tiles
+    (1, 48, 48, 25, 48, 48, None),           # same size: source window too large to stage -> flat kernel
+])
+def test_upsample_argmax_vs_torch(B, hs, ws, ncls, Ho, Wo, crop):
+    """resize(logits -> image size) + softmax + argmax (+ crop) of encoder_decoder.py:96-117, 329-414 against
+    F.interpolate(bilinear, align_corners=False).argmax on the pixels whose top-2 margin is above fp32 noise."""
+    k = _k()
+    g = torch.Generator().manual_seed(hs * Wo)
+    npad = (ncls + 31) // 32 * 32
+    lg = torch.randn(B, hs, ws, npad, generator=g)
+    up = torch.nn.functional.interpolate(lg[..., :ncls].permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear", align_corners=False)
+    if crop is not None:
+        up = up[:, :, :crop[0], :crop[1]]
+    top2 = up.topk(2, dim=1).values
+    sure = (top2[:, 0] - top2[:, 1]) > 1e-4
+    got = k.upsample_argmax(lg.view(-1, npad).cuda(), B, (hs, ws), ncls, (Ho, Wo), crop).cpu().long()
+    assert got.shape == up.argmax(1).shape and int(got.max()) < ncls
+    assert torch.equal(got[sure], up.argmax(1)[sure])
+
+
 @pytest.mark.parametrize("p,C,c_off,H,W", [(4, 3, 0, 32, 48), (4, 3, 3, 32, 48), (16, 3, 0, 64, 32), (2, 3, 1, 8, 12)])
 def test_patchify_vs_unfold(p, C, c_off, H, W):
     """NCHW fp32 channels [c_off, c_off+C) -> bf16 rows [(b,py,px), (c,ky,kx)] (PatchEmbed / ConvNeXt stem im2col,
