@@ -146,6 +146,25 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert _lib.load().mmsam_arch() == 100
+    # the ctypes stub must agree with every prototype: parameter count and the C type class of each parameter
+    kind = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_longlong: "ll", ctypes.c_float: "float"}
+    for name, params in re.findall(r"^int\s+(mmsam_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.M | re.S):
+        plist = [q.strip() for q in params.replace("\n", " ").split(",")]
+        if plist == ["void"]:
+            plist = []
+        want = []
+        for q in plist:
+            if "*" in q:
+                want.append("ptr")
+            elif re.match(r"^(const\s+)?long long\b", q):
+                want.append("ll")
+            elif re.match(r"^(const\s+)?float\b", q):
+                want.append("float")
+            else:
+                assert re.match(r"^(const\s+)?int\b", q), (name, q)
+                want.append("int")
+        got = [kind[t] for t in _lib.SIGNATURES[name]]
+        assert got == want, (name, got, want)
 
 
 def test_no_cpu_fallback():
