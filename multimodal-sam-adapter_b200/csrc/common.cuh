@@ -6,6 +6,9 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+// the public C ABI: including it here makes the compiler check every MMSAM_API definition against its declaration
+#include "../../include/mmsam_b200.h"
+
 #ifndef MMSAM_API
 #define MMSAM_API extern "C" __attribute__((visibility("default")))
 #endif
