@@ -430,6 +430,68 @@ def segmentor_logits(sd, cfg, img, test_cfg=None):
     return logits
 
 
-def simple_test(sd, cfg, img, test_cfg=None):
-    """E:417-508: softmax then argmax -> int64 labels [B,H,W]."""
+def encode_decode(sd, cfg, img):
+    """E:85-95 / 96-117: head logits resized (bilinear, align_corners=False) to the input size."""
+    feats = backbone_forward(sd, cfg, img, prefix="backbone.")
+    return F.interpolate(segformer_head(sd, feats), size=img.shape[2:], mode="bilinear", align_corners=False)
+
+
+def slide_inference(sd, cfg, img, test_cfg, rescale=False, ori_shape=None):
+    """E:191-234: overlapping crops of the network input size, zero-padded logits summed and divided by the count."""
+    h_stride, w_stride = test_cfg["stride"]
+    h_crop, w_crop = test_cfg["crop_size"]
+    B, _, h_img, w_img = img.shape
+    h_grids = max(h_img - h_crop + h_stride - 1, 0) // h_stride + 1
+    w_grids = max(w_img - w_crop + w_stride - 1, 0) // w_stride + 1
+    preds = count = None
+    for hi in range(h_grids):
+        for wi in range(w_grids):
+            y1, x1 = hi * h_stride, wi * w_stride
+            y2, x2 = min(y1 + h_crop, h_img), min(x1 + w_crop, w_img)
+            y1, x1 = max(y2 - h_crop, 0), max(x2 - w_crop, 0)
+            lg = encode_decode(sd, cfg, img[:, :, y1:y2, x1:x2])
+            if preds is None:
+                preds = img.new_zeros((B, lg.shape[1], h_img, w_img))
+                count = img.new_zeros((B, 1, h_img, w_img))
+            preds = preds + F.pad(lg, (x1, w_img - x2, y1, h_img - y2))
+            count[:, :, y1:y2, x1:x2] += 1
+    preds = preds / count
+    if rescale:
+        preds = F.interpolate(preds, size=tuple(ori_shape[:2]), mode="bilinear", align_corners=False)
+    return preds
+
+
+def inference(sd, cfg, img, test_cfg, rescale=True, ori_shape=None, flip=False, flip_direction="horizontal"):
+    """E:417-469: mode dispatch (slide / whole / whole_dim / whole_dim_cut), softmax, flip. Returns probabilities."""
+    mode = test_cfg.get("mode", "whole")
+    ori_shape = tuple(img.shape[2:]) if ori_shape is None else tuple(ori_shape)
+    if mode == "slide":
+        lg = slide_inference(sd, cfg, img, test_cfg, rescale, ori_shape)
+    else:
+        lg = encode_decode(sd, cfg, img)
+        if mode == "whole":                      # E:310-327
+            if rescale:
+                lg = F.interpolate(lg, size=ori_shape[:2], mode="bilinear", align_corners=False)
+        elif mode == "whole_dim":                # E:329-362 (returns nothing when rescale is False)
+            if not rescale:
+                raise ValueError("whole_inference_dim returns None with rescale=False (encoder_decoder.py:333-362)")
+            lg = F.interpolate(lg, size=tuple(test_cfg["dim"]), mode="bilinear", align_corners=False)
+        elif mode == "whole_dim_cut":            # E:364-391: the backbone returns (feats, None) -> the tuple branch
+            if rescale:
+                lg = F.interpolate(lg, size=tuple(test_cfg["dim"]), mode="bilinear", align_corners=False)
+            cw, ch = test_cfg["cut_dim"]
+            lg = lg[:, :, :ch, :cw]
+        else:
+            raise ValueError(mode)
+    out = F.softmax(lg, dim=1)
+    if flip:
+        out = out.flip(dims=(3,)) if flip_direction == "horizontal" else out.flip(dims=(2,))
+    return out
+
+
+def simple_test(sd, cfg, img, test_cfg=None, rescale=True, ori_shape=None, flip=False, flip_direction="horizontal"):
+    """E:471-508: softmax then argmax -> int64 labels [B,H,W]. With test_cfg=None / no "mode": the whole_dim(_cut) logits
+    of segmentor_logits (kept for the earlier tests)."""
+    if test_cfg is not None and "mode" in test_cfg:
+        return inference(sd, cfg, img, test_cfg, rescale, ori_shape, flip, flip_direction).argmax(dim=1)
     return F.softmax(segmentor_logits(sd, cfg, img, test_cfg), dim=1).argmax(dim=1)

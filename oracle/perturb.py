@@ -37,6 +37,10 @@ def perturb_state_dict(sd, seed=1, head_std=0.5):
             pass  # keep the reference's directional grid init
         elif k.endswith("injector.gamma"):
             v = 0.3 + rn(v.shape, 0.1)
+        elif "twin_conv.stages_" in k and last == "gamma":
+            # ConvNeXt layer scale (twin_convnext.py:58-61, init 1e-6): pretrained values are O(0.1-1); at 1e-6 the whole
+            # residual branch (7x7 dwconv, LN, pw1 + GELU, pw2) would be invisible to every parity test
+            v = 0.3 + rn(v.shape, 0.1)
         elif k.endswith("gammax.scale") or k.endswith("gammay.scale"):
             v = torch.tensor(0.1) + rn((), 0.02)
         elif "local_feature_encoder" in k and last == "scale":

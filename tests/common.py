@@ -17,6 +17,18 @@ VITB = dict(img_size=512, modalities_name=["rgb", "lidar"], modalities_ch=[3, 3]
             cffn_ratio=0.25, deform_ratio=0.5, with_cp=True, interaction_indexes=[[0, 2], [3, 5], [6, 8], [9, 11]],
             global_attn_indexes=[2, 5, 8, 11], window_size=14, arch="small", checkpoint="none")
 
+# BASELINE.json config 4 (configs/FMB/Segformer_MMSAM_adapter_large_FMB_800x800_ss_RGBTHERM.py:26-62): registry name
+# ...NEWwithcp, 800 x 800 zero-padded input, 14 classes, logits cropped to 600 x 800 (the test loop calls with rescale=False
+# for this config: mmseg_custom/apis/test_bs.py:241-244 with evaluation.resize_dim=(800, 600))
+FMB = dict(img_size=800, modalities_name=["rgb", "therm"], modalities_ch=[3, 3], init_values=1e-6, gamma_init_values=1e-6,
+           patch_size=16, embed_dim=1024, depth=24, num_heads=16, mlp_ratio=4, drop_path_rate=0.3, drop_multimodal_path=0,
+           conv_inplane=48, n_points=4, deform_num_heads=16, cffn_ratio=0.25, deform_ratio=0.5, with_cp=True,
+           interaction_indexes=[[0, 5], [6, 11], [12, 17], [18, 23]], global_attn_indexes=[5, 11, 17, 23], window_size=14,
+           arch="small", checkpoint="none")
+FMB_HEAD = dict(in_channels=[1024] * 4, in_index=[0, 1, 2, 3], channels=512, dropout_ratio=0.1, num_classes=14,
+                norm_cfg=dict(type="SyncBN", requires_grad=True), align_corners=False)
+FMB_TEST_CFG = dict(mode="whole_dim_cut", rescale=False, dim=(600, 800), cut_dim=(800, 600))
+
 TINY_HEAD = dict(in_channels=[128] * 4, in_index=[0, 1, 2, 3], channels=64, dropout_ratio=0.1, num_classes=25,
                  norm_cfg=dict(type="SyncBN", requires_grad=True), align_corners=False)
 VITB_HEAD = dict(in_channels=[768] * 4, in_index=[0, 1, 2, 3], channels=512, dropout_ratio=0.1, num_classes=25,

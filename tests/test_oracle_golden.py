@@ -248,3 +248,135 @@ def test_checkpoint_ingestion_rules():
     missing, unexpected = ck.load_checkpoint(lin, wrapped)
     assert missing == [] and unexpected == []
     assert torch.equal(lin.weight.data, wrapped["state_dict"]["module.weight"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Head / segmentor pin and the full-size configs: goldens produced by the reference's own
+# SegformerHead.forward / EncoderDecoder.simple_test (tools/make_golden.py, tools/ref_shim.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def _frame():
+    from oracle.perturb import synthetic_batch
+    return torch.cat([synthetic_batch(1, 128, seed=21), synthetic_batch(1, 128, seed=22)], 3)[:, :, :, :208]
+
+
+def test_oracle_head_and_inference_modes_match_reference_segmentor():
+    """decode_heads/segformer_head.py:48-66 + segmentors/encoder_decoder.py:191-234, 310-414, 417-508 on the TINY config."""
+    from oracle import model as om
+    from oracle.perturb import synthetic_batch
+    rec = torch.load(os.path.join(GOLD, "segmentor_tiny.pt"))
+    _, sd = build_segmentor(TINY, TINY_HEAD)
+    assert sd_digest(sd) == rec["digest"]
+    x = synthetic_batch(2, 128, seed=5)
+    with torch.no_grad():
+        feats = om.backbone_forward(sd, TINY, x, prefix="backbone.")
+        hl = om.segformer_head(sd, feats)
+        assert rel_l2(hl, rec["head_logits"]) < 1e-5
+        assert rel_l2(om.encode_decode(sd, TINY, x).reshape(-1)[rec["logits_img_idx"]], rec["logits_img_vals"]) < 1e-5
+        tc = dict(mode="slide", crop_size=(128, 128), stride=(64, 80))
+        assert rel_l2(om.slide_inference(sd, TINY, _frame(), tc).reshape(-1)[rec["slide_idx"]], rec["slide_vals"]) < 1e-5
+        for name, c in rec["cases"].items():
+            img = _frame() if name.startswith("slide") else x
+            got = om.simple_test(sd, TINY, img, c["test_cfg"], c["rescale"], c["ori_shape"], c["flip"], c["direction"])
+            assert got.shape == c["labels"].shape, name
+            agree = (got == c["labels"].long()).float().mean().item()
+            assert agree >= 0.9995, (name, agree)      # fp32 summation-order ties only
+
+
+def test_oracle_head_vitl_matches_reference_head():
+    """The reference SegformerHead.forward at the ViT-L head size (4 x 1024 -> 512 -> fusion 2048 -> 512 -> 25)."""
+    import bench
+    from oracle import model as om
+    from oracle.perturb import perturb_state_dict
+    import mmsam_b200  # noqa
+    from mmsam_b200.backbone import SegformerHead
+    rec = torch.load(os.path.join(GOLD, "head_vitl.pt"))
+    torch.manual_seed(31)
+    sd = perturb_state_dict(SegformerHead(**bench.VITL_HEAD).state_dict(), seed=6)
+    assert sd_digest(sd) == rec["digest"]
+    g = torch.Generator().manual_seed(rec["seed"])
+    feats = [torch.randn(2, 1024, 64 >> i, 64 >> i, generator=g) for i in range(4)]
+    with torch.no_grad():
+        out = om.segformer_head(sd, feats, prefix="")
+    assert rel_l2(out, rec["out"]) < 1e-5
+
+
+def test_oracle_blocks_68x120_match_reference():
+    """BASELINE config 5b: Block (window: 68x120 -> 70x126 padded; global: 8160 tokens, tables interpolated 127 -> 135 / 239
+    rows) and InteractionBlock(extra_extractor=True) on the 1088 x 1920 geometry."""
+    from oracle import model as om
+    from oracle.perturb import perturb_state_dict
+    import mmsam_b200  # noqa
+    from mmsam_b200 import nn_modules as M
+    from mmsam_b200.ops.modules import MSDeformAttn
+    rec = torch.load(os.path.join(GOLD, "blocks_68x120.pt"))
+    H, W, dim, nh = rec["H"], rec["W"], rec["dim"], rec["nh"]
+    x = torch.randn(1, H * W, dim, generator=torch.Generator().manual_seed(rec["x_seed"]))
+    for name, ws in (("window", 14), ("global", 0)):
+        torch.manual_seed(42)
+        sd = perturb_state_dict(M.Block(dim, nh, 4.0, True, True, ws, (64, 64)).state_dict(), seed=7)
+        r = rec[name]
+        assert sd_digest(sd) == r["digest"]
+        with torch.no_grad():
+            out = om.vit_block(x, om.SD(sd), H, W, ws, nh)
+        assert rel_l2(out.reshape(-1)[r["idx"]], r["vals"]) < 1e-5 and abs(out.norm().item() - r["norm"]) / r["norm"] < 1e-5
+    r = rec["interaction"]
+    torch.manual_seed(44)
+    sd = perturb_state_dict(M.InteractionBlock(dim, nh, 4, True, 0.25, 0.5, 0.5, True, MSDeformAttn).state_dict(), seed=8)
+    assert sd_digest(sd) == r["digest"]
+    g = torch.Generator().manual_seed(r["seed"])
+    xq = torch.randn(1, H * W, dim, generator=g)
+    c = torch.randn(1, r["S3"], dim, generator=g)
+    s = om.SD(sd)
+    (ref1, sh1), (ref2, sh2) = om.deform_inputs(r["Hi"], r["Wi"], torch.float32)
+    with torch.no_grad():
+        xo = om.injector(xq, c, ref1, sh1, s.sub("injector"), nh, 4)
+        co = om.extractor(c, xo, ref2, sh2, s.sub("extractor"), nh, 4, H, W)
+        for j in range(2):
+            co = om.extractor(co, xo, ref2, sh2, s.sub(f"extra_extractors.{j}"), nh, 4, H, W)
+    assert rel_l2(xo.reshape(-1)[r["idx_x"]], r["vals_x"]) < 1e-5
+    assert rel_l2(co.reshape(-1)[r["idx_c"]], r["vals_c"]) < 1e-5
+
+
+def _full_size_oracle_check(rec, bcfg, hcfg, size, kind, btype, zero_rows_from=None):
+    from oracle import model as om
+    from oracle.perturb import synthetic_batch
+    _, sd = build_segmentor(bcfg, hcfg, btype=btype)
+    assert sd_digest(sd) == rec["digest"]
+    x = synthetic_batch(1, size, kind=kind)
+    if zero_rows_from is not None:
+        x[:, :, zero_rows_from:] = 0
+    torch.set_num_threads(max(os.cpu_count() or 1, 1))
+    with torch.no_grad():
+        feats = om.backbone_forward(sd, bcfg, x, prefix="backbone.")
+        hl = om.segformer_head(sd, feats)
+        lg = torch.nn.functional.interpolate(hl, size=x.shape[2:], mode="bilinear", align_corners=False)
+        tc = rec["test_cfg"]
+        if tc["mode"] == "whole_dim" or (tc["mode"] == "whole_dim_cut" and rec["rescale"]):
+            lg = torch.nn.functional.interpolate(lg, size=tuple(tc["dim"]), mode="bilinear", align_corners=False)
+        if tc["mode"] == "whole_dim_cut":
+            lg = lg[:, :, :tc["cut_dim"][1], :tc["cut_dim"][0]]
+        labels = lg.softmax(1).argmax(1)
+    for f, idx, vals, nrm in zip(feats, rec["idx"], rec["vals"], rec["norms"]):
+        assert rel_l2(f.reshape(-1)[idx], vals) < 1e-4
+        assert abs(f.norm().item() - nrm) / nrm < 1e-4
+    assert rel_l2(hl.reshape(-1)[rec["head_idx"]], rec["head_vals"]) < 1e-4
+    agree = (labels == rec["labels"].long()).float().mean().item()
+    print(f"oracle vs reference labels: {agree * 100:.4f}% of {labels.numel()} pixels")
+    assert labels.shape == rec["labels"].shape and agree >= 0.9995
+
+
+@pytest.mark.timeout(900)
+def test_oracle_fmb800_config4_matches_reference():
+    """BASELINE config 4 at full size: ...NEWwithcp ViT-L, 800 x 800 (tokens 50 x 50 -> windows padded to 56, rel-pos 127 ->
+    99 rows), 14 classes, whole_dim_cut with rescale=False -> [600, 800] labels."""
+    from common import FMB, FMB_HEAD
+    rec = torch.load(os.path.join(GOLD, "fmb800_samples.pt"))
+    _full_size_oracle_check(rec, FMB, FMB_HEAD, 800, "thermal", "SAMAdapterbimodalMixModNewInTwinConvNEWwithcp", 600)
+
+
+@pytest.mark.timeout(900)
+def test_oracle_vitl1024_config2_matches_reference():
+    """BASELINE config 2 at full size (one image): ViT-L 1024 x 1024, 25 classes, whole_dim."""
+    import bench
+    rec = torch.load(os.path.join(GOLD, "vitl1024_samples.pt"))
+    _full_size_oracle_check(rec, bench.VITL, bench.VITL_HEAD, 1024, "lidar", "SAMAdapterbimodalMixModNewInTwinConvNEW")
