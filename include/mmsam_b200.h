@@ -42,7 +42,8 @@ int mmsam_msda_forward(const void* value, const int64_t* spatial_shapes_dev,
                        const void* attn_weight, void* out, int N, int S, int M, int D, int Lq, int L,
                        int P, int value_dtype, int aux_dtype, void* stream);
 
-/* Row LayerNorm over the last dim of a bf16 [rows, C] matrix, fp32 affine, biased variance.
+/* Row LayerNorm over the last dim of a [rows, C] matrix, fp32 affine, biased variance. x_dtype / y_dtype: MMSAM_BF16 or
+ * MMSAM_F32 (bf16 -> bf16, fp32 -> bf16, fp32 -> fp32; the fp32 forms serve the fp32 residual streams).
  * Replaces nn.LayerNorm / LayerNorm2d calls on the path (base/image_encoder.py:398,421;
  * adapter_modules_...new.py:494-501,527-532; mmpretrain_custom/models/utils/norm.py:52-87).
  * row_map_dev (optional int32[rows]): destination row of each source row, -1 = drop.
@@ -50,23 +51,32 @@ int mmsam_msda_forward(const void* value, const int64_t* spatial_shapes_dev,
  * block (y&1)*2+(x&1) of a [rows/4, 4C] matrix = the 2x2 patchify of ConvNeXt's LN2d -> Conv2d(k2,s2)
  * downsample (base/twin_convnext.py:313-336).
  * y2 (optional): second output x + LN(x) with the same row mapping (GFE residual, adapter_modules_...new.py:143). */
-int mmsam_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* y, void* y2,
-                         const int* row_map_dev, long long rows, int C, long long ldx, long long ldy,
-                         float eps, int ps_h, int ps_w, void* stream);
+int mmsam_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_dtype, void* y2,
+                    const int* row_map_dev, long long rows, int C, long long ldx, long long ldy,
+                    float eps, int ps_h, int ps_w, void* stream);
 
 /* out = epilogue(A[M,K] . W[N,K]^T): bf16 operands, fp32 accumulation on tcgen05 tensor cores.
  * Replaces every nn.Linear / 1x1 conv / patchified conv on the path (see csrc/gemm.cu header).
  *   epilogue: (+bias[N]) -> act (0 none, 1 exact GELU, 2 ReLU, 3 ReLU6) -> (*scale[N]) ->
  *             (+residual[dst_row, col]) -> store bf16 (out_f32=0) or fp32 (out_f32=1)
+ *             residual is bf16, or fp32 when res_f32 != 0 (then out_f32 must be set: the fp32 residual streams)
  *   row_mode 0: dst_row = row; 1: dst_row = row_map_dev[row] (-1 drops the row);
  *            2: 2x2 pixel shuffle of a ConvTranspose2d(k=2,s=2): rows are (b, y<ps_h, x<ps_w),
  *               columns (dy, dx, c<ps_c) -> dst_row (b, 2y+dy, 2x+dx), dst col c.
  *   block_n: 64/128/256 tile width, 0 = auto. max_ctas: 0 = all SMs. */
 int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
-                    const float* scale, const void* residual, long long ldr, void* out,
+                    const float* scale, const void* residual, int res_f32, long long ldr, void* out,
                     long long ldo, int M, int N, int K, int act, int out_f32, int row_mode,
                     const int* row_map_dev, int ps_h, int ps_w, int ps_c, int block_n, int max_ctas,
                     void* stream);
+
+/* Grouped form of mmsam_gemm_bf16 for per-image weights: rows [g * rows_per_group, (g+1) * rows_per_group) of A use the
+ * weight matrix W[g] of W [G * N, K], G = M / rows_per_group; bias / scale [N] are shared; bf16 output, identity rows.
+ * rows_per_group % 256 == 0 (a 256-row tile never straddles two groups). The fusion neck's per-image channel-attention
+ * and cross-modal attention products (adapter_modules_...new.py:104-107, 255-259) in one launch per batch. */
+int mmsam_gemm_grouped_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                            const float* scale, const void* residual, long long ldr, void* out, long long ldo, int M,
+                            int N, int K, int rows_per_group, int act, int block_n, int max_ctas, void* stream);
 
 /* Fused multi-head attention (head_dim 64) with SAM's decomposed relative-position bias.
  * Replaces Attention.forward + add_decomposed_rel_pos (base/image_encoder.py:483-501, 587-623).
@@ -121,13 +131,14 @@ int mmsam_msda_fused_staged_bf16(const void* value, const int* level_hw_host, co
                                  int tile_w, const float* prior_min_host, const float* prior_ext_host, int margin,
                                  void* stream);
 
-/* Depthwise k x k conv (k = 3 or 7, stride 1, zero "same" padding) on channels-last bf16 maps, fp32
+/* Depthwise k x k conv (k = 3 or 7, stride 1, zero "same" padding) on channels-last maps (input bf16, or fp32 for k = 7:
+ * x_dtype; output bf16), fp32
  * weights given tap-major [k*k][C], optional bias[C], act 0 none / 1 exact GELU / 3 ReLU6.
  * Up to 3 grids per batch item share the weights (ConvFFN DWConv over the 128^2|64^2|32^2 token
  * grids, adapter_modules_...new.py:456-471); grid i starts grid_*_off_host[i] elements into a batch
  * item of in_bstride / out_bstride elements. Also ConvNeXt's 7x7 (base/twin_convnext.py:98-101).
  * The *_host arrays are HOST pointers read before the call returns. */
-int mmsam_dwconv_bf16(const void* x, void* y, const float* w_tap_major, const float* bias, int B, int C,
+int mmsam_dwconv(const void* x, int x_dtype, void* y, const float* w_tap_major, const float* bias, int B, int C,
                       int ksize, int ngrids, const int* grid_hw_host, const long long* grid_in_off_host,
                       const long long* grid_out_off_host, long long in_bstride, long long out_bstride, int act,
                       void* stream);
@@ -143,11 +154,12 @@ int mmsam_normalize_u8(const void* img_hwc_u8, float* out_nchw, int B, int H, in
 int mmsam_patchify_f32(const float* img, void* out, int B, int Ctot, int c_off, int C, int H, int W, int p,
                        void* stream);
 
-/* out[b,y,x,:] = (base[b,y,x,:] + bilinear(src[b])[y,x,:]) * scale + shift on channels-last bf16
+/* out[b,y,x,:] = (base[b,y,x,:] + bilinear(src[b])[y,x,:]) * scale + shift on channels-last maps (src bf16 or fp32:
+ * src_dtype; base / out bf16
  * (align_corners=False; base and scale/shift optional; ld* = elements between pixels, *_bstride =
  * elements between batch items). Backbone tail (..._new.py:326-337) and head resize-into-concat
  * (decode_heads/segformer_head.py:55-61). */
-int mmsam_resize_add_affine_bf16(const void* src, const void* base, const float* scale, const float* shift,
+int mmsam_resize_add_affine(const void* src, int src_dtype, const void* base, const float* scale, const float* shift,
                                  void* out, int B, int Hs, int Ws, int Ho, int Wo, int C, long long src_bstride,
                                  long long lds, long long base_bstride, long long ldb, long long out_bstride,
                                  long long ldo, void* stream);
@@ -183,11 +195,43 @@ int mmsam_conv3x3_nstride(int Cin, int Cout, int groups);
 int mmsam_conv3x3_bf16(const void* x, const void* w_packed, void* out, int B, int H, int W, int Cin, int Cout,
                        int groups, int max_ctas, void* stream);
 
-/* S[b,i,j] += sum_pix X[b,pix,qoff+i] * X[b,pix,koff+j] (fp32, caller zeroes S), optional squared row norms
- * nq/nk [B,n]; blk > 0 restricts to the block diagonal (per-head). AttentionBase q@k^T / F.normalize
- * (adapter_modules_...new.py:98-103) and GFFM energies (:250-254). X is [B, HW, ld] bf16. */
-int mmsam_gram_bf16(const void* X, long long ld, int qoff, int koff, int n, int B, int HW, int blk, float* S,
-                    float* nq, float* nk, void* stream);
+/* Gram matrix over pixels, as per-pixel-chunk partial sums (no floating-point atomics: the consumers add the chunks in a
+ * fixed order, so results are bit-reproducible):
+ *   S_part[c, b, i, j] = sum_{pix in chunk c} X[b,pix,qoff+i] * X[b,pix,koff+j]      fp32 [nchunks, B, n, n]
+ *   nq_part / nk_part [nchunks, B, n]: partial squared norms of the q / k columns (optional, both or neither)
+ * with nchunks = mmsam_gram_chunks(n, B, HW, norms). blk > 0: only the block-diagonal (per-head) elements are written,
+ * the rest of S_part is left untouched. AttentionBase q@k^T / F.normalize (adapter_modules_...new.py:98-103) and GFFM
+ * energies (:250-254). X is [B, HW, ld] bf16. */
+int mmsam_gram_chunks(int n, int B, int HW, int norms);
+int mmsam_gram_bf16(const void* X, long long ld, int qoff, int koff, int n, int B, int HW, int blk, float* S_part,
+                    float* nq_part, float* nk_part, void* stream);
+
+/* AttentionBase after the Gram pass (adapter_modules_...new.py:100-107): att = softmax(cos(q_a, k_j) * temperature[h])
+ * per head from the chunk partials, with `proj` and scale2 folded in:
+ *   weff[b, i, h*ch + j] = scale2 * sum_a wproj[i, h*ch + a] * att[b, h, a, j]        bf16 [B, ci, ci]
+ * so that (attn @ v) -> proj is one GEMM over the pixels with weff[b] as the weight. temperature fp32 [heads],
+ * wproj fp32 [ci, ci] (proj.weight), scale2 fp32 [1] (device). */
+int mmsam_gfe_weff_bf16(const float* S_part, const float* nq_part, const float* nk_part, int nchunks, int B, int ci,
+                        int heads, const float* temperature, const float* wproj, const float* scale2, void* weff,
+                        void* stream);
+
+/* GFFM attention maps (:250-259) from the partials of the cross-modal energy E [B, ci, ci]:
+ * ax[b,i,:] = softmax_j E[b,i,j], ay[b,j,:] = softmax_i E[b,i,j]; bf16 [B, ci, ci] each. ci <= 1024. */
+int mmsam_gffm_softmax_bf16(const float* E_part, int nchunks, int B, int ci, void* ax, void* ay, void* stream);
+
+/* GFFM LayerNorm-over-HW statistics + FFRM gate (:262-264, 148-162) from the mmsam_colstats_bf16 partials:
+ * mu, rstd fp32 [B, C]; gate[b, c] = 1 + sigmoid(relu(GroupNorm_groups(wffrm . GAP(LN_HW(o)))[c])); sum_w = sum of the
+ * LayerNorm weight over the HW positions, mean_b = mean of its bias. wffrm fp32 [C, C] (1x1 conv, no bias). */
+int mmsam_ffrm_gate_f32(const float* colstats_part, int nchunks, int B, int HW, int C, double sum_w, double mean_b,
+                        float ln_eps, const float* wffrm, const float* gn_weight, const float* gn_bias, int groups,
+                        float gn_eps, float* mu, float* rstd, float* gate, void* stream);
+
+/* CoordinateAttention vectors (:187-215) from the pools of mmsam_combine_pool_bf16: per row y / column x the pooled mean
+ * [C] -> conv1 (C -> mip) -> eval BN (scale, shift) -> h_swish -> conv_h | conv_w (mip -> C) -> sigmoid:
+ * ah fp32 [B, H, C], aw fp32 [B, W, C]. w1 [mip, C], wh / ww [C, mip]. */
+int mmsam_ca_vectors_f32(const float* ph, const float* pw_part, int nstrips, int B, int H, int W, int C, int mip,
+                         const float* w1, const float* b1, const float* bn_scale, const float* bn_shift, const float* wh,
+                         const float* bh, const float* ww, const float* bw, float* ah, float* aw, void* stream);
 
 /* Per-512-pixel-chunk column statistics {sum o, sum o^2, sum o*w[pix]} of o [B,HW,C] bf16 for GFFM's
  * LayerNorm over the spatial axis (:262-264): part fp32 [mmsam_colstats_chunks(HW), B, C, 3]. */

@@ -17,18 +17,19 @@ _vp, _i, _ll, _f = _c.c_void_p, _c.c_int, _c.c_longlong, _c.c_float
 SIGNATURES = {
     "mmsam_arch": [],
     "mmsam_msda_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "mmsam_layernorm_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _ll, _ll, _f, _i, _i, _vp],
-    "mmsam_gemm_bf16": [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp,
+    "mmsam_layernorm": [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _ll, _i, _ll, _ll, _f, _i, _i, _vp],
+    "mmsam_gemm_bf16": [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _i, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp,
                         _i, _i, _i, _i, _i, _vp],
+    "mmsam_gemm_grouped_bf16": [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_rowstats_bf16": [_vp, _vp, _ll, _i, _ll, _f, _vp],
     "mmsam_gemm_ln_bf16": [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_msda_fused_bf16": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_msda_fused_staged_bf16": [_vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i,
                                      _vp, _vp, _i, _vp],
-    "mmsam_dwconv_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _ll, _i, _vp],
+    "mmsam_dwconv": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _ll, _i, _vp],
     "mmsam_normalize_u8": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp],
     "mmsam_patchify_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "mmsam_resize_add_affine_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _vp],
+    "mmsam_resize_add_affine": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _vp],
     "mmsam_resize_sum_affine_bf16": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],
     "mmsam_upsample_argmax_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_confusion_u8": [_vp, _vp, _vp, _ll, _i, _i, _vp],
@@ -36,6 +37,11 @@ SIGNATURES = {
     "mmsam_conv3x3_nstride": [_i, _i, _i],
     "mmsam_conv3x3_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_gram_bf16": [_vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "mmsam_gram_chunks": [_i, _i, _i, _i],
+    "mmsam_gfe_weff_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "mmsam_gffm_softmax_bf16": [_vp, _i, _i, _i, _vp, _vp, _vp],
+    "mmsam_ffrm_gate_f32": [_vp, _i, _i, _i, _i, _c.c_double, _c.c_double, _f, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp],
+    "mmsam_ca_vectors_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mmsam_colstats_chunks": [_i],
     "mmsam_colstats_bf16": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "mmsam_gate_bf16": [_vp, _vp, _ll, _i, _vp],

@@ -43,8 +43,8 @@ class ImageEncoderViT(nn.Module):
                  with_cp=False, pretrained_size=1024, fix=False):
         super().__init__()
         if embed_dim % num_heads or embed_dim // num_heads != 64:
-            raise ValueError("the B200 attention kernel is built for head_dim 64 (SAM ViT-B/L/H); got "
-                             f"embed_dim={embed_dim}, num_heads={num_heads}")
+            raise ValueError("the B200 attention kernel is built for head_dim 64 (SAM ViT-B / ViT-L; ViT-H has head_dim 80); "
+                             f"got embed_dim={embed_dim}, num_heads={num_heads}")
         self.img_size, self.embed_dim, self.num_heads, self.patch_size = img_size, embed_dim, num_heads, patch_size
         self.patch_embed = M.PatchEmbed((patch_size, patch_size), (patch_size, patch_size), in_chans, embed_dim)
         self.pos_embed = None
@@ -108,27 +108,39 @@ class _AdapterBase(ImageEncoderViT):
             if isinstance(m, MSDeformAttn):
                 m._reset_parameters()
         nn.init.normal_(self.level_embed)
-        self._engine = None
+        self._engines = {}
+        self._stamp_tensors = {}
 
     # ------------------------------------------------------------------
+    def _weights_stamp(self, head):
+        """Changes whenever a parameter / buffer of the backbone or head is written in place (load_state_dict, mmcv's
+        load_checkpoint via _load_from_state_dict, optimizer steps ...): the sum of the tensors' version counters. The
+        tensor list is cached per head (cleared by invalidate(); module surgery after the first forward needs that call)."""
+        ts = self._stamp_tensors.get(id(head))
+        if ts is None:
+            ts = [t for m in (self, head) if m is not None for t in list(m.parameters()) + list(m.buffers())]
+            self._stamp_tensors[id(head)] = ts
+        return sum(t._version for t in ts)
+
     def engine(self, head=None):
+        """Packed weights + captured graphs, one per (device, head): `backbone.forward` (no head) and the segmentor's label
+        paths (with the decode head) keep separate engines instead of rebuilding each other's. An engine is rebuilt
+        when any weight of the backbone / head has changed since it was packed."""
         dev = next(self.parameters()).device
-        if self._engine is None or self._engine[0] != (str(dev), id(head)):
-            self._engine = ((str(dev), id(head)), EncoderEngine(self, head, dev))
-        return self._engine[1]
+        key = (str(dev), id(head))
+        stamp = self._weights_stamp(head)
+        ent = self._engines.get(key)
+        if ent is None or ent[0] != stamp:
+            for k in [k for k in self._engines if k[0] != str(dev)]:
+                del self._engines[k]
+            ent = (stamp, EncoderEngine(self, head, dev))
+            self._engines[key] = ent
+        return ent[1]
 
     def invalidate(self):
-        """Call after changing weights in place (load_state_dict does it automatically)."""
-        self._engine = None
-
-    def load_state_dict(self, *a, **k):
-        r = super().load_state_dict(*a, **k)
-        self._engine = None
-        return r
-
-    def _apply(self, fn, *a, **k):
-        self._engine = None
-        return super()._apply(fn, *a, **k)
+        """Drop the packed weights (they are also re-packed automatically when a weight changes)."""
+        self._engines = {}
+        self._stamp_tensors = {}
 
     @torch.no_grad()
     def forward(self, x):
@@ -191,11 +203,6 @@ class EncoderDecoder(nn.Module):
 
     def _engine(self):
         return self.backbone.engine(self.decode_head)
-
-    def load_state_dict(self, *a, **k):
-        r = super().load_state_dict(*a, **k)
-        self.backbone.invalidate()
-        return r
 
     use_cuda_graph = True
 

@@ -590,12 +590,7 @@ MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const int* out_ro
   const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
 #define ATT_LAUNCH(KWM, BTY)                                                                                         \
   do {                                                                                                          \
-    static bool configured = false;                                                                             \
-    if (!configured) {                                                                                          \
-      cudaError_t e = cudaFuncSetAttribute(attention_kernel<KWM, BTY>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget); \
-      if (e != cudaSuccess) return (int)e;                                                                      \
-      configured = true;                                                                                        \
-    }                                                                                                           \
+    MMSAM_SET_SMEM_ONCE((attention_kernel<KWM, BTY>), budget);                                                   \
     attention_kernel<KWM, BTY><<<grid, 320, smem_bytes, (cudaStream_t)stream>>>(tmQKV, tmH, tmW, p);                 \
   } while (0)
   if (kw_mode == 64) ATT_LAUNCH(64, float);

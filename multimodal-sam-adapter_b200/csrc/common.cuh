@@ -32,6 +32,21 @@
     if (e__ != cudaSuccess) return (int)e__;        \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: opt in once per (kernel, device) —
+// a process-wide flag would leave the second GPU a process touches (MMDataParallel, a model moved to cuda:1) at the
+// 48 KB default. Use inside a function returning an int error code; one static table per expansion site.
+#define MMSAM_SET_SMEM_ONCE(kernel, bytes)                                                              \
+  do {                                                                                                  \
+    static bool configured__[64] = {};                                                                  \
+    int dev__ = 0;                                                                                      \
+    if (cudaGetDevice(&dev__) != cudaSuccess || dev__ < 0 || dev__ >= 64) return MMSAM_ERR_DRIVER;      \
+    if (!configured__[dev__]) {                                                                         \
+      cudaError_t e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+      if (e__ != cudaSuccess) return (int)e__;                                                          \
+      configured__[dev__] = true;                                                                       \
+    }                                                                                                   \
+  } while (0)
+
 namespace mmsam {
 
 static constexpr int kNumSMs = 148;

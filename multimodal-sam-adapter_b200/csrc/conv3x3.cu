@@ -275,12 +275,7 @@ MMSAM_API int mmsam_conv3x3_bf16(const void* x, const void* w_packed, void* out,
   }
   int rc = mmsam_host::make_tmap_2d_bf16(&tmW, w_packed, (uint64_t)p.num_n * 9 * KC * 64, 64, 64, 64, 64);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  MMSAM_SET_SMEM_ONCE(conv3x3_kernel, CV_SMEM);
   if (max_ctas <= 0 || max_ctas > kNumSMs) max_ctas = kNumSMs;
   const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
   conv3x3_kernel<<<grid, 320, CV_SMEM, (cudaStream_t)stream>>>(tmX, tmW, p);

@@ -21,7 +21,8 @@ struct DwGrid {
   int H, W;
 };
 struct DwParams {
-  const __nv_bfloat16* x;
+  const void* x;      // bf16, or fp32 (XF32: the ConvNeXt towers keep their residual stream in fp32; it is rounded to bf16 once,
+                      // while being staged)
   __nv_bfloat16* y;
   const float* w;     // [K*K][C] fp32 (tap-major)
   const float* bias;  // [C] or null
@@ -31,7 +32,7 @@ struct DwParams {
   int tiles_x[3], tiles_y[3], tile_start[4];
 };
 
-template <int K, int TH, int TW>
+template <int K, int TH, int TW, bool XF32>
 __global__ void __launch_bounds__(256, 2)
 dwconv_kernel(const DwParams p) {
   constexpr int R = K / 2;
@@ -51,7 +52,7 @@ dwconv_kernel(const DwParams p) {
   const int H = p.g[gi].H, W = p.g[gi].W;
   const int c0 = blockIdx.y * CB;
   const int b = blockIdx.z;
-  const __nv_bfloat16* xin = p.x + (long long)b * p.in_bstride + p.g[gi].in_off;
+  const long long xoff = (long long)b * p.in_bstride + p.g[gi].in_off;
   __nv_bfloat16* yout = p.y + (long long)b * p.out_bstride + p.g[gi].out_off;
   const int y0 = ty * TH, x0 = tx * TW;
   const int cvalid = p.C - c0 < CB ? p.C - c0 : CB;  // multiple of 8
@@ -66,8 +67,16 @@ dwconv_kernel(const DwParams p) {
     const int pix = i / (CB / 8);
     const int iy = y0 + pix / IW - R, ix = x0 + pix % IW - R;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W && cv * 8 < cvalid)
-      v = __ldg(reinterpret_cast<const uint4*>(xin + ((long long)iy * W + ix) * p.C + c0 + cv * 8));
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W && cv * 8 < cvalid) {
+      const long long e = xoff + ((long long)iy * W + ix) * p.C + c0 + cv * 8;
+      if constexpr (XF32) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + e));
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + e + 4));
+        v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c4.x, c4.y), pack_bf16(c4.z, c4.w));
+      } else {
+        v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + e));
+      }
+    }
     *reinterpret_cast<uint4*>(&s_in[(pix * CB) + cv * 8]) = v;
   }
   __syncthreads();
@@ -125,16 +134,11 @@ dwconv_kernel(const DwParams p) {
   }
 }
 
-template <int K, int TH, int TW>
+template <int K, int TH, int TW, bool XF32>
 static int launch_dw(const DwParams& p, dim3 grid, cudaStream_t st) {
   constexpr int smem = (TH + K - 1) * (TW + K - 1) * 64 * 2 + K * K * 64 * 4;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv_kernel<K, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
-  dwconv_kernel<K, TH, TW><<<grid, 256, smem, st>>>(p);
+  MMSAM_SET_SMEM_ONCE((dwconv_kernel<K, TH, TW, XF32>), smem);
+  dwconv_kernel<K, TH, TW, XF32><<<grid, 256, smem, st>>>(p);
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }
@@ -142,19 +146,21 @@ static int launch_dw(const DwParams& p, dim3 grid, cudaStream_t st) {
 }  // namespace mmsam
 
 // See include/mmsam_b200.h for the contract.
-MMSAM_API int mmsam_dwconv_bf16(const void* x, void* y, const float* w_tap_major, const float* bias, int B,
+MMSAM_API int mmsam_dwconv(const void* x, int x_dtype, void* y, const float* w_tap_major, const float* bias, int B,
                                 int C, int ksize, int ngrids, const int* grid_hw_host,
                                 const long long* grid_in_off_host, const long long* grid_out_off_host,
                                 long long in_bstride, long long out_bstride, int act, void* stream) {
   using namespace mmsam;
   if (B < 0 || C <= 0 || (C & 7) || ngrids < 1 || ngrids > 3) return MMSAM_ERR_BAD_ARG;
   if (ksize != 3 && ksize != 7) return MMSAM_ERR_UNSUPPORTED;
+  if (x_dtype != MMSAM_BF16 && x_dtype != MMSAM_F32) return MMSAM_ERR_BAD_DTYPE;
+  if (x_dtype == MMSAM_F32 && ksize != 7) return MMSAM_ERR_UNSUPPORTED;    // fp32 input: the ConvNeXt 7x7 only
   if (act != 0 && act != 1 && act != 3) return MMSAM_ERR_BAD_ARG;
   if (B == 0) return MMSAM_OK;
   if (!x || !y || !w_tap_major || !grid_hw_host) return MMSAM_ERR_BAD_ARG;
   if ((((uintptr_t)x | (uintptr_t)y) & 15) || (in_bstride & 7) || (out_bstride & 7)) return MMSAM_ERR_BAD_ARG;
   DwParams p;
-  p.x = (const __nv_bfloat16*)x; p.y = (__nv_bfloat16*)y; p.w = w_tap_major; p.bias = bias;
+  p.x = x; p.y = (__nv_bfloat16*)y; p.w = w_tap_major; p.bias = bias;
   p.in_bstride = in_bstride; p.out_bstride = out_bstride; p.C = C; p.B = B; p.ngrids = ngrids; p.act = act;
   const int TH = ksize == 7 ? 4 : 8, TW = 32;
   int total = 0;
@@ -175,6 +181,6 @@ MMSAM_API int mmsam_dwconv_bf16(const void* x, void* y, const float* w_tap_major
   p.tile_start[3] = total;
   dim3 grid(total, (C + 63) / 64, B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (ksize == 7) return launch_dw<7, 4, 32>(p, grid, st);
-  return launch_dw<3, 8, 32>(p, grid, st);
+  if (ksize == 7) return x_dtype == MMSAM_F32 ? launch_dw<7, 4, 32, true>(p, grid, st) : launch_dw<7, 4, 32, false>(p, grid, st);
+  return launch_dw<3, 8, 32, false>(p, grid, st);
 }

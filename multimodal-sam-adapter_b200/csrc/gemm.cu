@@ -42,7 +42,7 @@ struct GemmEpi {
   const float* bias;               // [N] or null
   const float* scale;              // [N] or null, applied after the activation
   const float2* rowstat;           // [M] (mean, rstd) or null: LayerNorm folded in, acc -> rstd * (acc - mean * scale[n]) + bias[n]
-  const __nv_bfloat16* residual;   // indexed at the destination row, or null
+  const void* residual;            // indexed at the destination row, or null; bf16, or fp32 in the V_F32_RES variant
   void* out;
   const int* row_map;              // row_mode 1: dst row of each source row (-1 = drop)
   long long ldo, ldr;
@@ -53,9 +53,12 @@ struct GemmEpi {
   int dbg;        // perf-debug switches (env MMSAM_GEMM_DBG): 1 skip stores, 2 skip the residual, 4 skip the epilogue math,
                   // 8 skip the MMA issue, 16 skip the TMA loads
   int ps_h, ps_w, ps_c;
+  int res_f32;        // the residual is fp32 (generic epilogue / V_F32_RES)
+  int w_group_rows;   // > 0: grouped GEMM, rows [g * w_group_rows, (g + 1) * w_group_rows) of A use weight rows [g * N, (g + 1) * N)
 };
 
-enum { V_BF16 = 0, V_BF16_GELU = 1, V_BF16_MAP = 2, V_F32 = 3, V_GENERIC = 4, V_BF16_RES = 5 };
+// V_F32_RES: fp32 output + fp32 residual (in place on the fp32 residual streams: ViT tokens, ConvNeXt feature maps)
+enum { V_BF16 = 0, V_BF16_GELU = 1, V_BF16_MAP = 2, V_F32 = 3, V_GENERIC = 4, V_BF16_RES = 5, V_F32_RES = 6 };
 // Variants whose residual block is streamed into a third slab with cp.async (see epilogue_fast).
 __host__ __device__ constexpr bool var_async_res(int var) { return var == V_BF16_MAP || var == V_BF16_RES; }
 
@@ -210,7 +213,8 @@ __device__ __forceinline__ void epilogue_generic(const GemmEpi& ep, uint32_t tme
           } else if (ep.bias) x += ep.bias[cj];
           x = apply_act(x, ep.act);
           if (ep.scale && !ep.rowstat) x *= ep.scale[cj];
-          if (ep.residual) x += __bfloat162float(ep.residual[drow * ep.ldr + dcol]);
+          if (ep.residual) x += ep.res_f32 ? reinterpret_cast<const float*>(ep.residual)[drow * ep.ldr + dcol]
+                                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ep.residual)[drow * ep.ldr + dcol]);
           if (ep.out_f32) reinterpret_cast<float*>(ep.out)[drow * ep.ldo + dcol] = x;
           else reinterpret_cast<__nv_bfloat16*>(ep.out)[drow * ep.ldo + dcol] = __float2bfloat16_rn(x);
         }
@@ -235,7 +239,7 @@ template <int BN, int VAR>
 __device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorMap* tmC, uint32_t tmem_base, uint32_t slab0,
                                               uint64_t* tfull, uint64_t* tempty, int warp, int lane, uint32_t rank, int pair,
                                               int num_pairs, int num_tiles, int num_n) {
-  constexpr bool F32 = VAR == V_F32;
+  constexpr bool F32 = VAR == V_F32 || VAR == V_F32_RES;
   constexpr bool MAPPED = VAR == V_BF16_MAP;
   constexpr bool ASYNC = var_async_res(VAR);
   constexpr uint32_t SLAB = GemmCfg<BN, VAR>::SLAB_BYTES;
@@ -244,7 +248,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorM
   constexpr int NPAN = CPH / PC;
   constexpr int EPC = F32 ? 4 : 8;                       // elements per 16-byte chunk
   const int quad = warp & 3, half = warp >> 2;
-  const bool has_res = !F32 && ep.residual != nullptr && !(ep.dbg & 2);
+  const bool has_res = VAR != V_F32 && ep.residual != nullptr && !(ep.dbg & 2);
   const int c = lane & 7, rsub = lane >> 3;
   if (half * CPH >= BN) {
     // BN == 64 with bf16 output: the second column half has no panel; only hand the accumulators back
@@ -281,7 +285,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorM
   uint4 rv[8];
   // coalesced fetch of a 32 x 128 B residual block: 8 lanes per row, 4 rows per instruction
   auto issue_res = [&](int dst, int col0, uint32_t ring_slab) {
-    const int colc = col0 + c * 8;
+    const int colc = col0 + c * EPC;
     int dcolc = colc, sub = 0;
     if (MAPPED && ep.row_mode == 2) { sub = colc / ep.ps_c; dcolc = colc - sub * ep.ps_c; }
 #pragma unroll
@@ -290,7 +294,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorM
       int d = __shfl_sync(0xffffffffu, dst, rl);
       if (MAPPED && ep.row_mode == 2 && d >= 0) d += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
       const bool ok = d >= 0 && colc < ep.N;
-      const __nv_bfloat16* src = ok ? ep.residual + (long long)d * ep.ldr + dcolc : ep.residual;
+      const char* src = reinterpret_cast<const char*>(ep.residual) + (ok ? ((long long)d * ep.ldr + dcolc) * (F32 ? 4 : 2) : 0);
       if constexpr (ASYNC) {
         cp_async16(ring_slab + swz128(rl, c), src, ok ? 16 : 0);
       } else {
@@ -313,9 +317,9 @@ __device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorM
         dcol = col0 - sub * ep.ps_c;
         d += (sub >> 1) * (2 * ep.ps_w) + (sub & 1);
       }
-      const __nv_bfloat16* p = ep.residual + d * ep.ldr + dcol;
+      const char* p = reinterpret_cast<const char*>(ep.residual) + (d * ep.ldr + dcol) * (F32 ? 4 : 2);
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-      if (reinterpret_cast<uintptr_t>(p) & 127) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 63));
+      if (reinterpret_cast<uintptr_t>(p) & 127) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 126));
     }
   };
 
@@ -431,12 +435,21 @@ __device__ __forceinline__ void epilogue_fast(const GemmEpi& ep, const CUtensorM
           }
         }
         if (has_res) {
+          if constexpr (F32) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float f[8];
-            unpack8(lds128(rslab + swz128(lane, cc * 4 + j)), f);
+            for (int j = 0; j < 8; ++j) {
+              const uint4 q = lds128(rslab + swz128(lane, j));
+              v[4 * j] += __uint_as_float(q.x); v[4 * j + 1] += __uint_as_float(q.y);
+              v[4 * j + 2] += __uint_as_float(q.z); v[4 * j + 3] += __uint_as_float(q.w);
+            }
+          } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[8 * j + k] += f[k];
+            for (int j = 0; j < 4; ++j) {
+              float f[8];
+              unpack8(lds128(rslab + swz128(lane, cc * 4 + j)), f);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[8 * j + k] += f[k];
+            }
           }
         }
         if constexpr (F32) {
@@ -540,7 +553,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int mp = tile / num_n, n_blk = tile % num_n;
         const int m0 = mp * (2 * Cfg::BM) + (int)rank * Cfg::BM;
-        const int nb0 = n_blk * BN + (int)rank * Cfg::BNH;
+        // grouped GEMM (per-image weights): the 256-row block lies inside one group (w_group_rows % 256 == 0)
+        const int nb0 = n_blk * BN + (int)rank * Cfg::BNH + (ep.w_group_rows > 0 ? (mp * (2 * Cfg::BM) / ep.w_group_rows) * ep.N : 0);
         for (int kb = 0; kb < num_k; ++kb) {
           if (ep.dbg & 16) continue;
           mbar_wait(&empty[s], ph ^ 1);
@@ -610,12 +624,7 @@ template <int BN, int VAR>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmEpi& ep,
                        int max_ctas, cudaStream_t st) {
   using Cfg = GemmCfg<BN, VAR>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  MMSAM_SET_SMEM_ONCE((gemm_bf16_kernel<BN, VAR>), Cfg::SMEM_BYTES);
   const int num_tiles = ((ep.M + 255) / 256) * ((ep.N + BN - 1) / BN);
   int pairs = max_ctas / 2;
   if (num_tiles < pairs) pairs = num_tiles;
@@ -663,12 +672,19 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 }  // namespace mmsam_host
 
 // See include/mmsam_b200.h for the contract.
+static int gemm_dbg_flags() {
+  static const int v = [] { const char* d = getenv("MMSAM_GEMM_DBG"); return d ? atoi(d) : 0; }();   // read once
+  return v;
+}
+
 static int gemm_impl(const void* A, long long lda, const void* W, long long ldw, const float* bias,
                      const float* scale, const float* rowstat, const void* residual, long long ldr, void* out,
                      long long ldo, int M, int N, int K, int act, int out_f32, int row_mode,
                      const int* row_map_dev, int ps_h, int ps_w, int ps_c, int block_n,
-                     int max_ctas, void* stream) {
+                     int max_ctas, void* stream, int group_rows = 0, int res_f32 = 0) {
   using namespace mmsam;
+  if (group_rows < 0 || (group_rows > 0 && ((group_rows & 255) || M % group_rows))) return MMSAM_ERR_BAD_ARG;
+  const int groups = group_rows > 0 ? M / group_rows : 1;
   if (rowstat && (!bias || !scale || (((uintptr_t)rowstat) & 7))) return MMSAM_ERR_BAD_ARG;
   if (M < 0 || N < 0 || K <= 0) return MMSAM_ERR_BAD_ARG;
   if (M == 0 || N == 0) return MMSAM_OK;
@@ -683,6 +699,7 @@ static int gemm_impl(const void* A, long long lda, const void* W, long long ldw,
   int vec_ok = 1;
   if ((((uintptr_t)out) & 15) || ((ldo * (out_f32 ? 4 : 2)) & 15)) vec_ok = 0;
   if (residual && ((((uintptr_t)residual) & 15) || (ldr & 7))) vec_ok = 0;
+  if (res_f32 && !out_f32) return MMSAM_ERR_UNSUPPORTED;            // an fp32 residual goes with an fp32 output
   if (bias && (((uintptr_t)bias) & 15)) return MMSAM_ERR_BAD_ARG;
   if (scale && (((uintptr_t)scale) & 15)) return MMSAM_ERR_BAD_ARG;
   if (max_ctas <= 1 || max_ctas > kNumSMs) max_ctas = kNumSMs;
@@ -723,9 +740,9 @@ static int gemm_impl(const void* A, long long lda, const void* W, long long ldw,
   const int oelt = out_f32 ? 4 : 2;
   const int epc = out_f32 ? 4 : 8;
   int var;
-  if (!vec_ok || (N % epc) != 0 || (out_f32 && (residual || row_mode != 0 || act == 1)) || (row_mode != 0 && act == 1))
+  if (!vec_ok || (N % epc) != 0 || (out_f32 && ((residual && !res_f32) || row_mode != 0 || act == 1)) || (row_mode != 0 && act == 1))
     var = V_GENERIC;
-  else if (out_f32) var = V_F32;
+  else if (out_f32) var = residual ? V_F32_RES : V_F32;
   else if (row_mode != 0) var = V_BF16_MAP;
   else if (act == 1 && !residual) var = V_BF16_GELU;
   else if (act == 1) var = V_GENERIC;
@@ -734,16 +751,18 @@ static int gemm_impl(const void* A, long long lda, const void* W, long long ldw,
   CUtensorMap tmA, tmB;
   int rc = mmsam_host::make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64);
   if (rc) return rc;
-  rc = mmsam_host::make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(bn / 2), 64);
+  rc = mmsam_host::make_tmap_2d_bf16(&tmB, W, (uint64_t)N * groups, (uint64_t)K, (uint64_t)ldw, (uint32_t)(bn / 2), 64);
   if (rc) return rc;
   GemmEpi ep;
-  ep.bias = bias; ep.scale = scale; ep.rowstat = (const float2*)rowstat; ep.residual = (const __nv_bfloat16*)residual; ep.out = out;
+  ep.bias = bias; ep.scale = scale; ep.rowstat = (const float2*)rowstat; ep.residual = residual; ep.out = out;
+  ep.res_f32 = res_f32;
   ep.row_map = row_map_dev; ep.ldo = ldo; ep.ldr = ldr; ep.M = M; ep.N = N; ep.K = K; ep.act = act;
   ep.out_f32 = out_f32; ep.row_mode = row_mode; ep.ps_h = ps_h; ep.ps_w = ps_w; ep.ps_c = ps_c;
-  { const char* d = getenv("MMSAM_GEMM_DBG"); ep.dbg = d ? atoi(d) : 0; }
+  ep.dbg = gemm_dbg_flags();
+  ep.w_group_rows = group_rows;
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tmC = tmA;
-  if (var == V_BF16 || var == V_BF16_GELU || var == V_F32 || var == V_BF16_RES) {
+  if (var == V_BF16 || var == V_BF16_GELU || var == V_F32 || var == V_BF16_RES || var == V_F32_RES) {
     // output tensor map for the per-warp TMA tensor stores: box = one 32-row x 128-byte slab
     mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
     cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
@@ -761,18 +780,19 @@ static int gemm_impl(const void* A, long long lda, const void* W, long long ldw,
     case V_BF16_MAP: return launch_gemm_bn<V_BF16_MAP>(bn, tmA, tmB, tmC, ep, max_ctas, st);
     case V_F32: return launch_gemm_bn<V_F32>(bn, tmA, tmB, tmC, ep, max_ctas, st);
     case V_BF16_RES: return launch_gemm_bn<V_BF16_RES>(bn, tmA, tmB, tmC, ep, max_ctas, st);
+    case V_F32_RES: return launch_gemm_bn<V_F32_RES>(bn, tmA, tmB, tmC, ep, max_ctas, st);
     default: return launch_gemm<128, V_GENERIC>(tmA, tmB, tmC, ep, max_ctas, st);
   }
 }
 
 // See include/mmsam_b200.h for the contract.
 MMSAM_API int mmsam_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
-                              const float* scale, const void* residual, long long ldr, void* out,
+                              const float* scale, const void* residual, int res_f32, long long ldr, void* out,
                               long long ldo, int M, int N, int K, int act, int out_f32, int row_mode,
                               const int* row_map_dev, int ps_h, int ps_w, int ps_c, int block_n,
                               int max_ctas, void* stream) {
   return gemm_impl(A, lda, W, ldw, bias, scale, nullptr, residual, ldr, out, ldo, M, N, K, act, out_f32, row_mode,
-                   row_map_dev, ps_h, ps_w, ps_c, block_n, max_ctas, stream);
+                   row_map_dev, ps_h, ps_w, ps_c, block_n, max_ctas, stream, 0, res_f32);
 }
 
 // LayerNorm folded into the GEMM: out = epilogue(rstd[m] * (A W^T - mean[m] * colsum[n]) + bias[n]); see the header.
@@ -783,4 +803,15 @@ MMSAM_API int mmsam_gemm_ln_bf16(const void* A, long long lda, const void* W, lo
   if (!rowstat || !bias || !colsum) return MMSAM_ERR_BAD_ARG;
   return gemm_impl(A, lda, W, ldw, bias, colsum, rowstat, residual, ldr, out, ldo, M, N, K, act, out_f32, 0, nullptr,
                    0, 0, 0, block_n, max_ctas, stream);
+}
+
+// Grouped GEMM: rows [g * rows_per_group, (g + 1) * rows_per_group) of A are multiplied by their own weight matrix
+// W[g] (W is [G * N, K], G = M / rows_per_group), one launch for all groups; see the header.
+MMSAM_API int mmsam_gemm_grouped_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                                      const float* scale, const void* residual, long long ldr, void* out, long long ldo,
+                                      int M, int N, int K, int rows_per_group, int act, int block_n, int max_ctas,
+                                      void* stream) {
+  if (rows_per_group <= 0) return MMSAM_ERR_BAD_ARG;
+  return gemm_impl(A, lda, W, ldw, bias, scale, nullptr, residual, ldr, out, ldo, M, N, K, act, 0, 0, nullptr, 0, 0, 0,
+                   block_n, max_ctas, stream, rows_per_group);
 }

@@ -12,8 +12,10 @@
 //
 // CTA = (128 x BNJ output tile, pixel chunk, image): warp 4 TMA producer, warp 5 MMA issuer (fp32 accumulators in
 // TMEM: G, and when norms are requested A^T A / B^T B whose diagonals are the squared norms), warps 0-3 epilogue
-// (tcgen05.ld -> fp32 atomics into S / nq / nk; the caller zeroes them). Split over pixel chunks so that every SM
-// has work; HBM-bound: X is read from DRAM once, tiles of the same chunk share it through L2.
+// (tcgen05.ld -> plain stores of this pixel chunk's PARTIAL sums: S_part [chunk][b][n][n], nq/nk_part [chunk][b][n];
+// the consumers (neck.cu: gfe_weff_kernel / gffm_softmax_kernel) add the chunks in a fixed order, so the result does
+// not depend on the CTA schedule — no floating-point atomics anywhere). Split over pixel chunks so that every SM has
+// work; HBM-bound: X is read from DRAM once, tiles of the same chunk share it through L2.
 #include "common.cuh"
 
 namespace mmsam {
@@ -124,7 +126,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const GramParams p) {
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
     const int li = warp * 32 + lane;          // row inside the tile
     const int gi = i0 + li;
-    float* Sb = p.S + (long long)b * p.n * p.n;
+    const long long slot = (long long)blockIdx.y * gridDim.z + b;      // (chunk, image)
+    float* Sb = p.S + slot * p.n * p.n;
     if (nst > 0) {
 #pragma unroll 1
       for (int c = 0; c < BNJ; c += 32) {
@@ -137,7 +140,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const GramParams p) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int gj = j0 + c + j;
-            if (gj < p.n && (p.blk == 0 || gi / p.blk == gj / p.blk)) atomicAdd(Sb + (long long)gi * p.n + gj, __uint_as_float(r[j]));
+            if (gj < p.n && (p.blk == 0 || gi / p.blk == gj / p.blk)) Sb[(long long)gi * p.n + gj] = __uint_as_float(r[j]);
           }
         }
       }
@@ -149,7 +152,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const GramParams p) {
         float v = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v = j == lane ? __uint_as_float(r[j]) : v;
-        if (gi < p.n) atomicAdd(p.nq + (long long)b * p.n + gi, v);
+        if (gi < p.n) p.nq[slot * p.n + gi] = v;
       }
       if (want_nk) {
         uint32_t r[32];
@@ -160,7 +163,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const GramParams p) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v = j == lane ? __uint_as_float(r[j]) : v;
         const int gj = j0 + li;
-        if (gj < p.n) atomicAdd(p.nk + (long long)b * p.n + gj, v);
+        if (gj < p.n) p.nk[slot * p.n + gj] = v;
       }
     }
   }
@@ -175,12 +178,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const GramParams p) {
 template <int BNJ>
 static int launch_gram_tc(const CUtensorMap& tm, const GramParams& p, dim3 grid, cudaStream_t st) {
   constexpr int smem = GR_STAGES * (2 + BNJ / 64) * GR_ATOM + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<BNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  MMSAM_SET_SMEM_ONCE(gram_tc_kernel<BNJ>, smem);
   gram_tc_kernel<BNJ><<<grid, 192, smem, st>>>(tm, p);
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
@@ -188,12 +186,31 @@ static int launch_gram_tc(const CUtensorMap& tm, const GramParams& p, dim3 grid,
 
 }  // namespace mmsam
 
+// Pixel chunking of the tensor-core path: enough CTAs for every SM, at least 4 stages of work each. Returns the number
+// of chunks (= partial sums per element), 0 when the shape does not fit this path.
+int mmsam_gram_tc_plan(int n, int B, int HW, int norms, int* chunk_out) {
+  using namespace mmsam;
+  if (HW % GR_KP != 0 || (long long)B * HW > 0x7fffffffLL) return 0;
+  const int bnj = (norms || n <= 128) ? 128 : 256;
+  const int tiles = ((n + 127) / 128) * ((n + bnj - 1) / bnj) * B;
+  int nchunks = (2 * kNumSMs + tiles - 1) / tiles;
+  const int maxchunks = HW / (4 * GR_KP) > 0 ? HW / (4 * GR_KP) : 1;
+  if (nchunks > maxchunks) nchunks = maxchunks;
+  if (nchunks < 1) nchunks = 1;
+  int chunk = (HW + nchunks - 1) / nchunks;
+  chunk = (chunk + GR_KP - 1) / GR_KP * GR_KP;
+  if (chunk_out) *chunk_out = chunk;
+  return (HW + chunk - 1) / chunk;
+}
+
 // Tensor-core path of mmsam_gram_bf16 (see neck.cu for the entry point and the SIMT fallback).
 // Returns MMSAM_ERR_UNSUPPORTED when the shape does not fit (caller falls back).
 int mmsam_gram_tc(const void* X, long long ld, int qoff, int koff, int n, int B, int HW, int blk, float* S, float* nq,
                   float* nk, cudaStream_t st) {
   using namespace mmsam;
-  if (HW % GR_KP != 0 || (long long)B * HW > 0x7fffffffLL) return MMSAM_ERR_UNSUPPORTED;
+  int chunk = 0;
+  const int nchunks = mmsam_gram_tc_plan(n, B, HW, nq != nullptr, &chunk);
+  if (nchunks == 0) return MMSAM_ERR_UNSUPPORTED;
   mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
   if (!enc) return MMSAM_ERR_DRIVER;
   CUtensorMap tm;
@@ -210,15 +227,6 @@ int mmsam_gram_tc(const void* X, long long ld, int qoff, int koff, int n, int B,
   p.S = S; p.nq = nq; p.nk = nk; p.qoff = qoff; p.koff = koff; p.n = n; p.HW = HW; p.blk = blk;
   p.nti = (n + 127) / 128;
   p.ntj = (n + bnj - 1) / bnj;
-  // pixel chunks: enough CTAs for every SM, at least 4 stages of work each
-  const int tiles = p.nti * p.ntj * B;
-  int nchunks = (2 * kNumSMs + tiles - 1) / tiles;
-  const int maxchunks = HW / (4 * GR_KP) > 0 ? HW / (4 * GR_KP) : 1;
-  if (nchunks > maxchunks) nchunks = maxchunks;
-  if (nchunks < 1) nchunks = 1;
-  int chunk = (HW + nchunks - 1) / nchunks;
-  chunk = (chunk + GR_KP - 1) / GR_KP * GR_KP;
-  nchunks = (HW + chunk - 1) / chunk;
   p.chunk = chunk;
   dim3 grid(p.nti * p.ntj, nchunks, B);
   if (bnj == 128) return launch_gram_tc<128>(tm, p, grid, st);

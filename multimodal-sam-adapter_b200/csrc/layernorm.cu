@@ -21,12 +21,32 @@ namespace mmsam {
 // where a full warp per row would leave 20 of 32 lanes idle: 25 % of HBM peak measured, two rows per warp ~2x), and
 // every lane group keeps R rows in flight (all loads issued before the first reduction): the per-row chain
 // load -> reduce -> reduce -> store is ~2-3 us of latency, and the mid-sized maps only give a warp 1-2 rows.
-template <int NV, int G, int R>
+// XF / YF: the input / output rows are fp32 instead of bf16 (the fp32 residual streams: the ConvNeXt towers' feature
+// map and the ViT token stream are kept in fp32 in HBM, their LayerNorms read them directly).
+__device__ __forceinline__ void ld8(const void* row, int v, bool f32, float* f) {
+  if (f32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(row) + 2 * v), b = __ldg(reinterpret_cast<const float4*>(row) + 2 * v + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(row) + v), f);
+  }
+}
+__device__ __forceinline__ void st8(void* row, int v, bool f32, const float* o) {
+  if (f32) {
+    reinterpret_cast<float4*>(row)[2 * v] = make_float4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<float4*>(row)[2 * v + 1] = make_float4(o[4], o[5], o[6], o[7]);
+  } else {
+    reinterpret_cast<uint4*>(row)[v] = pack8(o);
+  }
+}
+
+template <int NV, int G, int R, bool XF, bool YF>
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y2,
+layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, void* __restrict__ y, void* __restrict__ y2,
                  const int* __restrict__ row_map, long long rows, int C, long long ldx,
                  long long ldy, float eps, int ps_h, int ps_w) {
+  constexpr int XB = XF ? 4 : 2, YB = YF ? 4 : 2;              // bytes per element
   constexpr int RPW = 32 / G;                                   // rows per warp (side by side)
   const int lane = threadIdx.x & (G - 1);                        // lane within the row group
   const int sub = (threadIdx.x & 31) / G;                        // row group within the warp
@@ -85,12 +105,12 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
       }
       s[r] = 0.f;
       if (on[r]) {
-        const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+        const char* xr = reinterpret_cast<const char*>(x) + row * ldx * XB;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const int v = lane + G * i;
           if (v < nvec) {
-            unpack8(__ldg(xr + v), f[r][i]);
+            ld8(xr, v, XF, f[r][i]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) s[r] += f[r][i][j];
           }
@@ -114,8 +134,8 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
         }
       }
       const float rstd = rsqrtf(group_sum(s2) / (float)C + eps);
-      uint4* yr = reinterpret_cast<uint4*>(y + dst[r] * ldy + dcol[r]);
-      uint4* yr2 = y2 ? reinterpret_cast<uint4*>(y2 + dst[r] * ldy + dcol[r]) : nullptr;
+      char* yr = reinterpret_cast<char*>(y) + (dst[r] * ldy + dcol[r]) * YB;
+      char* yr2 = y2 ? reinterpret_cast<char*>(y2) + (dst[r] * ldy + dcol[r]) * YB : nullptr;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int v = lane + G * i;
@@ -131,11 +151,11 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
           o[5] = (f[r][i][5] - mean) * rstd * g1.y + b1.y;
           o[6] = (f[r][i][6] - mean) * rstd * g1.z + b1.z;
           o[7] = (f[r][i][7] - mean) * rstd * g1.w + b1.w;
-          yr[v] = pack8(o);
+          st8(yr, v, YF, o);
           if (yr2) {  // second output: x + LN(x)  (GFE: x + attn(norm1(x)) keeps norm1(x) as a residual)
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] += f[r][i][j];
-            yr2[v] = pack8(o);
+            st8(yr2, v, YF, o);
           }
         }
       }
@@ -200,11 +220,14 @@ rowstats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats,
 
 }  // namespace mmsam
 
-MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* y, void* y2,
-                                   const int* row_map_dev, long long rows, int C, long long ldx,
-                                   long long ldy, float eps, int ps_h, int ps_w, void* stream) {
+MMSAM_API int mmsam_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_dtype, void* y2,
+                              const int* row_map_dev, long long rows, int C, long long ldx,
+                              long long ldy, float eps, int ps_h, int ps_w, void* stream) {
   using namespace mmsam;
   if (rows < 0 || C <= 0 || (C & 7) || C > 2048 || (ldx & 7) || (ldy & 7)) return MMSAM_ERR_BAD_ARG;
+  if ((x_dtype != MMSAM_BF16 && x_dtype != MMSAM_F32) || (y_dtype != MMSAM_BF16 && y_dtype != MMSAM_F32)) return MMSAM_ERR_BAD_DTYPE;
+  if (x_dtype == MMSAM_BF16 && y_dtype == MMSAM_F32) return MMSAM_ERR_UNSUPPORTED;     // bf16 -> fp32 is not instantiated
+  const int mode = x_dtype == MMSAM_BF16 ? 0 : (y_dtype == MMSAM_BF16 ? 1 : 2);
   if (ps_h < 0 || ps_w < 0 || (ps_h > 0 && ((ps_h | ps_w) & 1))) return MMSAM_ERR_BAD_ARG;
   if (rows == 0) return MMSAM_OK;
   if (!x || !gamma || !beta || !y) return MMSAM_ERR_BAD_ARG;
@@ -214,20 +237,24 @@ MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const floa
   const int nvec = C / 8;
   // C = 96 (12 chunks, ConvNeXt stage 0 at 1/4 resolution): 16 lanes per row leave 4 idle; 4 lanes x 3 chunks use them all
   // likewise C = 192 (24 chunks) = 8 lanes x 3 and C = 384 (48 chunks) = 16 lanes x 3 instead of 24 / 48 of 32 / 64 slots
-  const bool narrow = !getenv("MMSAM_LN_NO_G4");
+  static const bool narrow = !getenv("MMSAM_LN_NO_G4");
   const int G = (narrow && nvec == 12) ? 4 : (narrow && nvec == 24) ? 8 : (narrow && nvec == 48) ? 16
                 : (nvec > 16 ? 32 : (nvec > 8 ? 16 : 8));
   const int rpw = 32 / G;
   const int nv = (nvec + 31) / 32;
   const int R = 1;   // rows in flight per lane group: 2 was measured SLOWER everywhere (registers -> occupancy)
   long long blocks = (rows + (long long)wpb * rpw * R - 1) / ((long long)wpb * rpw * R);
-  const long long cap = (long long)kNumSMs * (getenv("MMSAM_LN_CAP") ? atoi(getenv("MMSAM_LN_CAP")) : 16);
+  static const int cap_waves = getenv("MMSAM_LN_CAP") ? atoi(getenv("MMSAM_LN_CAP")) : 16;
+  const long long cap = (long long)kNumSMs * cap_waves;
   if (blocks > cap) blocks = cap;
-  const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
-  __nv_bfloat16* yo = (__nv_bfloat16*)y;
-  __nv_bfloat16* yo2 = (__nv_bfloat16*)y2;
-#define LN_CASE(NV, GG, RR) \
-  layernorm_kernel<NV, GG, RR><<<(unsigned)blocks, wpb * 32, 0, st>>>(xi, gamma, beta, yo, yo2, row_map_dev, rows, C, ldx, ldy, eps, ps_h, ps_w)
+#define LN_LAUNCH(NV, GG, RR, XFF, YFF) \
+  layernorm_kernel<NV, GG, RR, XFF, YFF><<<(unsigned)blocks, wpb * 32, 0, st>>>(x, gamma, beta, y, y2, row_map_dev, rows, C, ldx, ldy, eps, ps_h, ps_w)
+#define LN_CASE(NV, GG, RR)                                    \
+  do {                                                         \
+    if (mode == 0) LN_LAUNCH(NV, GG, RR, false, false);        \
+    else if (mode == 1) LN_LAUNCH(NV, GG, RR, true, false);    \
+    else LN_LAUNCH(NV, GG, RR, true, true);                    \
+  } while (0)
   if (G == 4) LN_CASE(3, 4, 1);
   else if (G == 8 && nvec == 24) LN_CASE(3, 8, 1);
   else if (G == 8) LN_CASE(1, 8, 1);
@@ -242,6 +269,7 @@ MMSAM_API int mmsam_layernorm_bf16(const void* x, const float* gamma, const floa
     default: LN_CASE(8, 32, 1); break;
   }
 #undef LN_CASE
+#undef LN_LAUNCH
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }

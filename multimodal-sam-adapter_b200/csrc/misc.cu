@@ -94,8 +94,20 @@ normalize_u8_kernel(const uint8_t* __restrict__ img, float* __restrict__ out, in
 // output rows — one 32-bit division per thread instead of three 64-bit ones per element, horizontal corners / weights and
 // the BatchNorm scale / shift (registers) computed once per RA_YB outputs (see resize_sum_affine_kernel).
 static constexpr int RA_YB = 8;
+// 8 consecutive channels of a source pixel; SF32: the source map is fp32 (the ViT token stream)
+template <bool SF32>
+__device__ __forceinline__ void ra_load8(const void* base, long long elem_off, float* f) {
+  if constexpr (SF32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off + 4));
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off)), f);
+  }
+}
+template <bool SF32>
 __global__ void __launch_bounds__(256)
-resize_add_affine_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ base,
+resize_add_affine_kernel(const void* __restrict__ src, const __nv_bfloat16* __restrict__ base,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          __nv_bfloat16* __restrict__ out, int B, int Hs, int Ws, int Ho, int Wo, int C,
                          long long src_bstride, long long base_bstride, long long out_bstride, long long ldo,
@@ -122,14 +134,14 @@ resize_add_affine_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloa
   x0 = x0 > Ws - 1 ? Ws - 1 : x0;
   const int x1 = x0 < Ws - 1 ? x0 + 1 : x0;
   const float lx = same ? 0.f : sx - x0;
-  const __nv_bfloat16* sb = src + b * src_bstride + cv * 8;
+  const long long sb = b * src_bstride + cv * 8;            // element offset of this thread's channels in image b
   const long long so0 = (long long)x0 * lds, so1 = (long long)x1 * lds;
   const __nv_bfloat16* bp = base ? base + b * base_bstride + ((long long)y_begin * Wo + x) * ldb + cv * 8 : nullptr;
   __nv_bfloat16* op = out + b * out_bstride + ((long long)y_begin * Wo + x) * ldo + cv * 8;
   for (int y = y_begin; y < y_end; ++y, op += (long long)Wo * ldo) {
     float f[8];
     if (same) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(sb + (long long)y * Ws * lds + so0)), f);
+      ra_load8<SF32>(src, sb + (long long)y * Ws * lds + so0, f);
     } else {
       float sy = (y + 0.5f) * rh - 0.5f;
       sy = sy < 0.f ? 0.f : sy;
@@ -137,13 +149,13 @@ resize_add_affine_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloa
       y0 = y0 > Hs - 1 ? Hs - 1 : y0;
       const int y1 = y0 < Hs - 1 ? y0 + 1 : y0;
       const float ly = sy - y0;
-      const __nv_bfloat16* r0 = sb + (long long)y0 * Ws * lds;
-      const __nv_bfloat16* r1 = sb + (long long)y1 * Ws * lds;
+      const long long r0 = sb + (long long)y0 * Ws * lds;
+      const long long r1 = sb + (long long)y1 * Ws * lds;
       float a[8], c[8], d[8], e[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(r0 + so0)), a);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(r0 + so1)), c);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(r1 + so0)), d);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(r1 + so1)), e);
+      ra_load8<SF32>(src, r0 + so0, a);
+      ra_load8<SF32>(src, r0 + so1, c);
+      ra_load8<SF32>(src, r1 + so0, d);
+      ra_load8<SF32>(src, r1 + so1, e);
       const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaf(w00, a[j], fmaf(w01, c[j], fmaf(w10, d[j], w11 * e[j])));
@@ -455,7 +467,7 @@ MMSAM_API int mmsam_normalize_u8(const void* img_hwc_u8, float* out_nchw, int B,
   return MMSAM_OK;
 }
 
-MMSAM_API int mmsam_resize_add_affine_bf16(const void* src, const void* base, const float* scale,
+MMSAM_API int mmsam_resize_add_affine(const void* src, int src_dtype, const void* base, const float* scale,
                                            const float* shift, void* out, int B, int Hs, int Ws, int Ho, int Wo,
                                            int C, long long src_bstride, long long lds, long long base_bstride,
                                            long long ldb, long long out_bstride, long long ldo, void* stream) {
@@ -463,14 +475,20 @@ MMSAM_API int mmsam_resize_add_affine_bf16(const void* src, const void* base, co
   if (B < 0 || C <= 0 || (C & 7) || Hs <= 0 || Ws <= 0 || Ho <= 0 || Wo <= 0) return MMSAM_ERR_BAD_ARG;
   if ((lds | ldb | ldo | src_bstride | base_bstride | out_bstride) & 7) return MMSAM_ERR_BAD_ARG;
   if ((scale == nullptr) != (shift == nullptr)) return MMSAM_ERR_BAD_ARG;
+  if (src_dtype != MMSAM_BF16 && src_dtype != MMSAM_F32) return MMSAM_ERR_BAD_DTYPE;
   if (B == 0) return MMSAM_OK;
   if (!src || !out) return MMSAM_ERR_BAD_ARG;
   if ((((uintptr_t)src | (uintptr_t)out | (uintptr_t)base | (uintptr_t)scale | (uintptr_t)shift) & 15)) return MMSAM_ERR_BAD_ARG;
   if (B > 65535 || (Ho + RA_YB - 1) / RA_YB > 65535 || (long long)Wo * (C / 8) > (1ll << 31) - 256) return MMSAM_ERR_UNSUPPORTED;
   dim3 grid((unsigned)(((long long)Wo * (C / 8) + 255) / 256), (unsigned)((Ho + RA_YB - 1) / RA_YB), (unsigned)B);
-  resize_add_affine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)src, (const __nv_bfloat16*)base, scale, shift, (__nv_bfloat16*)out, B, Hs, Ws, Ho, Wo, C,
-      src_bstride, base_bstride, out_bstride, ldo, lds, ldb, (float)Hs / (float)Ho, (float)Ws / (float)Wo);
+  if (src_dtype == MMSAM_F32)
+    resize_add_affine_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        src, (const __nv_bfloat16*)base, scale, shift, (__nv_bfloat16*)out, B, Hs, Ws, Ho, Wo, C,
+        src_bstride, base_bstride, out_bstride, ldo, lds, ldb, (float)Hs / (float)Ho, (float)Ws / (float)Wo);
+  else
+    resize_add_affine_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        src, (const __nv_bfloat16*)base, scale, shift, (__nv_bfloat16*)out, B, Hs, Ws, Ho, Wo, C,
+        src_bstride, base_bstride, out_bstride, ldo, lds, ldb, (float)Hs / (float)Ho, (float)Ws / (float)Wo);
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }

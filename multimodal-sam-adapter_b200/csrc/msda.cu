@@ -817,13 +817,8 @@ MMSAM_API int mmsam_msda_fused_staged_bf16(const void* value, const int* level_h
   }
   dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)M, (unsigned)N);
   cudaStream_t st = (cudaStream_t)stream;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(msda_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(msda_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  MMSAM_SET_SMEM_ONCE(msda_staged_kernel<2>, 226 * 1024);
+  MMSAM_SET_SMEM_ONCE(msda_staged_kernel<4>, 226 * 1024);
   // 8 lanes per query: one pass over the region's queries when there are few (injector), 256 threads otherwise
   const unsigned threads = qmax <= 64 ? 512 : 256;
   if (L <= 2) msda_staged_kernel<2><<<grid, threads, smem, st>>>(maps, p);

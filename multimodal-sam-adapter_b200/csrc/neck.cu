@@ -1,8 +1,12 @@
 // Pixel-sized kernels of the RoadFormer2Neck fusion (segmentation/mmseg_custom/models/backbones/
 // adapter_modules_multimodal_mix_mod_new_in_twin_convnext_new.py:75-394) on channels-last bf16 maps.
 // All of them stream the maps once (HBM-bound); the dense contractions of the neck run on gemm.cu /
-// conv3x3.cu. Numerically sensitive reductions (HW-long Gram sums, LayerNorm-over-HW statistics) are
-// accumulated in fp32 per chunk and combined in fp64 / fp32 atomics.
+// conv3x3.cu. Numerically sensitive reductions (HW-long Gram sums, LayerNorm-over-HW statistics) are accumulated in
+// fp32 per pixel chunk and the chunks are combined in a FIXED order by the consumer kernel: there is no floating-point
+// atomic on the path, results are bit-identical from run to run, eager or graph, whatever the batch an image sits in.
+// The O(B*C^2) steps between the pixel passes (softmax of the channel-attention matrices with proj folded in, GFFM's
+// two softmaxes, LayerNorm-over-HW statistics -> FFRM gate, coordinate-attention vectors) are small kernels of this
+// file as well: the neck launches no library kernel.
 #include "common.cuh"
 #include <cstdlib>
 
@@ -73,7 +77,8 @@ gram_kernel(const __nv_bfloat16* __restrict__ X, long long ld, int qoff, int kof
     }
     __syncthreads();
   }
-  float* Sb = S + (long long)b * n * n;
+  const long long slot = (long long)blockIdx.y * gridDim.z + b;   // (chunk, image): this CTA's partial sums
+  float* Sb = S + slot * n * n;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int gi = ti * 64 + ty * 4 + i;
@@ -82,12 +87,141 @@ gram_kernel(const __nv_bfloat16* __restrict__ X, long long ld, int qoff, int kof
     for (int j = 0; j < 4; ++j) {
       const int gj = tj * 64 + tx * 4 + j;
       if (gj >= n || (blk > 0 && gi / blk != gj / blk)) continue;
-      atomicAdd(Sb + (long long)gi * n + gj, acc[i][j]);
+      Sb[(long long)gi * n + gj] = acc[i][j];
     }
   }
   if (do_norm) {
     const int c = ti * 64 + (t & 63);
-    if (c < n) atomicAdd((t < 64 ? nq : nk) + (long long)b * n + c, nacc);
+    if (c < n) (t < 64 ? nq : nk)[slot * n + c] = nacc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// AttentionBase after the Gram pass (:100-107), per (head, image): add the chunk partials in order,
+//   att = softmax_j( S[a, j] / (max(|q_a|, 1e-12) max(|k_j|, 1e-12)) * temperature[h] )
+// and fold `proj` (and scale2) into one [ci, ci] matrix per image so that attn @ v followed by proj is ONE GEMM over
+// the pixels:   Weff[b, i, h*ch + j] = scale2 * sum_a Wproj[i, h*ch + a] * att[b, h, a, j].
+// grid (heads, B, row splits of Weff); every CTA recomputes its head's att (ch x ch, <= 96 x 96) in shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gfe_weff_kernel(const float* __restrict__ S_part, const float* __restrict__ nq_part, const float* __restrict__ nk_part,
+                int nchunks, int B, int ci, int heads, const float* __restrict__ temp, const float* __restrict__ wproj,
+                const float* __restrict__ scale2, __nv_bfloat16* __restrict__ weff) {
+  extern __shared__ float s_gf[];
+  const int ch = ci / heads;
+  float* att = s_gf;                 // [ch][ch + 1]
+  float* rq = att + ch * (ch + 1);   // [ch] 1 / max(|q|, eps)
+  float* rk = rq + ch;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
+  const long long nn = (long long)ci * ci;
+  for (int e = t; e < ch * ch; e += blockDim.x) {
+    const int a = e / ch, j = e - a * ch;
+    const float* src = S_part + (long long)b * nn + (long long)(h * ch + a) * ci + h * ch + j;
+    float acc = 0.f;
+    for (int c = 0; c < nchunks; ++c) acc += src[(long long)c * B * nn];
+    att[a * (ch + 1) + j] = acc;
+  }
+  for (int e = t; e < 2 * ch; e += blockDim.x) {
+    const float* src = (e < ch ? nq_part : nk_part) + (long long)b * ci + h * ch + (e < ch ? e : e - ch);
+    float acc = 0.f;
+    for (int c = 0; c < nchunks; ++c) acc += src[(long long)c * B * ci];
+    (e < ch ? rq : rk)[e < ch ? e : e - ch] = 1.f / fmaxf(sqrtf(acc), 1e-12f);
+  }
+  __syncthreads();
+  const float tp = temp[h];
+  for (int a = warp; a < ch; a += nwarps) {          // warp = one softmax row
+    float* row = att + a * (ch + 1);
+    float mx = -INFINITY;
+    for (int j = lane; j < ch; j += 32) {
+      const float v = row[j] * rq[a] * rk[j] * tp;
+      row[j] = v;
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < ch; j += 32) {
+      const float e = __expf(row[j] - mx);
+      row[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int j = lane; j < ch; j += 32) row[j] *= inv;
+  }
+  __syncthreads();
+  const float s2 = scale2[0];
+  const int rows_per = (ci + gridDim.z - 1) / gridDim.z;
+  const int i0 = blockIdx.z * rows_per, i1 = min(i0 + rows_per, ci);
+  for (int e = t; e < (i1 - i0) * ch; e += blockDim.x) {
+    const int i = i0 + e / ch, j = e % ch;
+    const float* wp = wproj + (long long)i * ci + h * ch;
+    float acc = 0.f;
+    for (int a = 0; a < ch; ++a) acc = fmaf(__ldg(wp + a), att[a * (ch + 1) + j], acc);
+    weff[(long long)b * nn + (long long)i * ci + h * ch + j] = __float2bfloat16_rn(acc * s2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GFFM attention maps (:250-259) from the chunk partials of the cross-modal energy E = fx^T fy  [B, ci, ci]:
+//   ax[b, i, :] = softmax_j E[b, i, j]      ay[b, j, :] = softmax_i E[b, i, j]     (bf16, the GEMM weights)
+// grid (ci, B, 2); block = one row (or column) of E.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gffm_softmax_kernel(const float* __restrict__ E_part, int nchunks, int B, int ci, __nv_bfloat16* __restrict__ ax,
+                    __nv_bfloat16* __restrict__ ay) {
+  __shared__ float s_red[8];
+  __shared__ float s_bc;
+  const int r = blockIdx.x, b = blockIdx.y, tr = blockIdx.z;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const long long nn = (long long)ci * ci;
+  constexpr int PER = 4;                                   // ci <= 1024
+  float v[PER];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int j = t + k * 256;
+    v[k] = -INFINITY;
+    if (j < ci) {
+      const float* src = E_part + (long long)b * nn + (tr == 0 ? (long long)r * ci + j : (long long)j * ci + r);
+      float acc = 0.f;
+      for (int c = 0; c < nchunks; ++c) acc += src[(long long)c * B * nn];
+      v[k] = acc;
+      mx = fmaxf(mx, acc);
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  if (t == 0) {
+    float m = s_red[0];
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w]);
+    s_bc = m;
+  }
+  __syncthreads();
+  mx = s_bc;
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    v[k] = (t + k * 256 < ci) ? __expf(v[k] - mx) : 0.f;
+    sum += v[k];
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  if (t == 0) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += s_red[w];           // fixed order
+    s_bc = 1.f / a;
+  }
+  __syncthreads();
+  const float inv = s_bc;
+  __nv_bfloat16* dst = (tr == 0 ? ax : ay) + (long long)b * nn + (long long)r * ci;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int j = t + k * 256;
+    if (j < ci) dst[j] = __float2bfloat16_rn(v[k] * inv);
   }
 }
 
@@ -101,7 +235,7 @@ colstats_kernel(const __nv_bfloat16* __restrict__ o, const float* __restrict__ w
   const int CV = C >> 3;
   const int b = blockIdx.y, ch = blockIdx.x;
   const int p0 = ch * chunk, p1 = min(p0 + chunk, HW);
-  __shared__ float sred[3][2048];
+  __shared__ float sred[256 * 24];   // [pixel lane][C][3], PL * C <= 2048
   const int PL = blockDim.x / CV;  // pixel lanes (blockDim.x is a multiple of CV)
   const int v = threadIdx.x % CV, pl = threadIdx.x / CV;
   float s[8], q[8], w[8];
@@ -120,23 +254,121 @@ colstats_kernel(const __nv_bfloat16* __restrict__ o, const float* __restrict__ w
       }
     }
   }
-  // reduce the PL pixel lanes through shared memory (C <= 2048)
-  for (int j = threadIdx.x; j < C; j += blockDim.x) { sred[0][j] = 0.f; sred[1][j] = 0.f; sred[2][j] = 0.f; }
-  __syncthreads();
+  // reduce the PL pixel lanes through shared memory in a fixed order (no atomics: bit-reproducible)
   if (pl < PL) {
+    float* mine = sred + ((long long)pl * C + v * 8) * 3;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sred[0][v * 8 + j], s[j]);
-      atomicAdd(&sred[1][v * 8 + j], q[j]);
-      atomicAdd(&sred[2][v * 8 + j], w[j]);
-    }
+    for (int j = 0; j < 8; ++j) { mine[j * 3 + 0] = s[j]; mine[j * 3 + 1] = q[j]; mine[j * 3 + 2] = w[j]; }
   }
   __syncthreads();
   float* dst = part + (((long long)ch * B + b) * C) * 3;
-  for (int j = threadIdx.x; j < C; j += blockDim.x) {
-    dst[j * 3 + 0] = sred[0][j];
-    dst[j * 3 + 1] = sred[1][j];
-    dst[j * 3 + 2] = sred[2][j];
+  for (int j = threadIdx.x; j < C * 3; j += blockDim.x) {
+    float a = 0.f;
+    for (int l = 0; l < PL; ++l) a += sred[(long long)l * C * 3 + j];
+    dst[j] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GFFM's LayerNorm over the spatial axis (:262-264) + FFRM gate (:148-162) from the colstats partials, per image:
+//   mu, rstd per channel (fp64 combination of the chunk partials, in order), GAP of LN_HW(o) analytically
+//   (gap = rstd * (sum o*w - mu * sum w) / HW + mean b), a = Wffrm gap (1x1 conv, no bias), GroupNorm(32), ReLU,
+//   gate = 1 + sigmoid(.)  (the "+1" is FFRM's residual: x * atten + x).
+// grid (B), block 1024.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+ffrm_gate_kernel(const float* __restrict__ part, int nch, int B, int HW, int C, double sum_w, double mean_b, float ln_eps,
+                 const float* __restrict__ wffrm, const float* __restrict__ gn_w, const float* __restrict__ gn_b,
+                 int groups, float gn_eps, float* __restrict__ mu_out, float* __restrict__ rstd_out,
+                 float* __restrict__ gate_out) {
+  extern __shared__ float s_ff[];
+  float* gap = s_ff;        // [C]
+  float* a = gap + C;       // [C]
+  const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
+  for (int c = t; c < C; c += blockDim.x) {
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int k = 0; k < nch; ++k) {
+      const float* p = part + (((long long)k * B + b) * C + c) * 3;
+      s0 += (double)p[0]; s1 += (double)p[1]; s2 += (double)p[2];
+    }
+    const double mu = s0 / HW;
+    double var = s1 / HW - mu * mu;
+    var = var > 0 ? var : 0;
+    const double rstd = 1.0 / sqrt(var + (double)ln_eps);
+    mu_out[(long long)b * C + c] = (float)mu;
+    rstd_out[(long long)b * C + c] = (float)rstd;
+    gap[c] = (float)(rstd * (s2 - mu * sum_w) / HW + mean_b);
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += nwarps) {               // warp = one output channel of the 1x1 conv
+    const float* w = wffrm + (long long)c * C;
+    float acc = 0.f;
+    for (int k = lane; k < C; k += 32) acc = fmaf(__ldg(w + k), gap[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) a[c] = acc;
+  }
+  __syncthreads();
+  const int cg = C / groups;
+  for (int g = warp; g < groups; g += nwarps) {          // warp = one GroupNorm group (biased variance)
+    float s = 0.f;
+    for (int k = lane; k < cg; k += 32) s += a[g * cg + k];
+    const float m = warp_sum(s) / cg;
+    float q = 0.f;
+    for (int k = lane; k < cg; k += 32) { const float d = a[g * cg + k] - m; q = fmaf(d, d, q); }
+    const float rs = rsqrtf(warp_sum(q) / cg + gn_eps);
+    for (int k = lane; k < cg; k += 32) {
+      const int c = g * cg + k;
+      const float y = fmaxf((a[c] - m) * rs * gn_w[c] + gn_b[c], 0.f);
+      gate_out[(long long)b * C + c] = 1.f + 1.f / (1.f + __expf(-y));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CoordinateAttention vectors (:187-215) from the pooled sums of combine_pool_kernel, per (position, image):
+//   y = mean over the other axis [C] -> conv1 (C -> mip, bias) -> eval BN -> h_swish -> conv_h | conv_w (mip -> C) -> sigmoid
+// position < H: a row (ah[b, y, :]), else a column (aw[b, x, :]). grid (H + W, B), block 256.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ca_vectors_kernel(const float* __restrict__ ph, const float* __restrict__ pw_part, int nstrips, int B, int H, int W, int C,
+                  int mip, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ bn_s,
+                  const float* __restrict__ bn_t, const float* __restrict__ wh, const float* __restrict__ bh,
+                  const float* __restrict__ ww, const float* __restrict__ bw, float* __restrict__ ah,
+                  float* __restrict__ aw) {
+  extern __shared__ float s_ca[];
+  float* y = s_ca;          // [C]
+  float* tm = y + C;        // [mip]
+  const int pos = blockIdx.x, b = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
+  const bool is_h = pos < H;
+  for (int c = t; c < C; c += blockDim.x) {
+    float v;
+    if (is_h) v = ph[((long long)b * H + pos) * C + c] / W;
+    else {
+      v = 0.f;
+      for (int s = 0; s < nstrips; ++s) v += pw_part[(((long long)s * B + b) * W + (pos - H)) * C + c];   // strips in order
+      v /= H;
+    }
+    y[c] = v;
+  }
+  __syncthreads();
+  for (int m = warp; m < mip; m += nwarps) {
+    const float* w = w1 + (long long)m * C;
+    float acc = 0.f;
+    for (int k = lane; k < C; k += 32) acc = fmaf(__ldg(w + k), y[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float z = (acc + b1[m]) * bn_s[m] + bn_t[m];
+      tm[m] = z * fminf(fmaxf(z + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    }
+  }
+  __syncthreads();
+  const float* wo = is_h ? wh : ww;
+  const float* bo = is_h ? bh : bw;
+  float* dst = is_h ? ah + ((long long)b * H + pos) * C : aw + ((long long)b * W + (pos - H)) * C;
+  for (int c = t; c < C; c += blockDim.x) {
+    float acc = bo[c];
+    for (int m = 0; m < mip; ++m) acc = fmaf(__ldg(wo + (long long)c * mip + m), tm[m], acc);
+    dst[c] = 1.f / (1.f + __expf(-acc));
   }
 }
 
@@ -170,13 +402,14 @@ combine_pool_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __
                     const float* __restrict__ wpix, const float* __restrict__ bpix, float s1, float s2,
                     __nv_bfloat16* __restrict__ f, float* __restrict__ ph, float* __restrict__ pw_part, int B, int H,
                     int W, int C, int RS) {
-  extern __shared__ float s_ph[];  // [RS][64]
+  extern __shared__ float s_ph[];  // [8 warps][RS][64]: every warp accumulates its own columns, combined in order at the end
   const int strip = blockIdx.x, cb = blockIdx.y, b = blockIdx.z;
+  const int warp_id = threadIdx.x >> 5;
   const int cv = threadIdx.x & 7, xl = threadIdx.x >> 3;
   const int c = cb * 64 + cv * 8;
   const bool cok = c < C;
   const int y0 = strip * RS, y1 = min(y0 + RS, H);
-  for (int i = threadIdx.x; i < RS * 64; i += blockDim.x) s_ph[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * RS * 64; i += blockDim.x) s_ph[i] = 0.f;
   __syncthreads();
   float m[8], r[8], g[8];
 #pragma unroll
@@ -208,13 +441,13 @@ combine_pool_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __
         }
         *reinterpret_cast<uint4*>(f + off) = pack8(v);
       }
-      // row sums: reduce the 4 columns held by this warp, then shared-memory atomics
+      // row sums: reduce the 4 columns held by this warp, accumulate into the warp's private shared-memory row
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float t = v[j];
         t += __shfl_xor_sync(0xffffffffu, t, 8);
         t += __shfl_xor_sync(0xffffffffu, t, 16);
-        if ((threadIdx.x & 31) < 8) atomicAdd(&s_ph[(y - y0) * 64 + cv * 8 + j], t);
+        if ((threadIdx.x & 31) < 8) s_ph[(warp_id * RS + (y - y0)) * 64 + cv * 8 + j] += t;
       }
     }
     if (x < W && cok) {
@@ -226,7 +459,10 @@ combine_pool_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __
   __syncthreads();
   for (int i = threadIdx.x; i < (y1 - y0) * 64; i += blockDim.x) {
     const int yy = i >> 6, cc = cb * 64 + (i & 63);
-    if (cc < C) ph[((long long)b * H + y0 + yy) * C + cc] = s_ph[i];
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += s_ph[w * RS * 64 + i];
+    if (cc < C) ph[((long long)b * H + y0 + yy) * C + cc] = a;
   }
 }
 
@@ -267,27 +503,109 @@ static inline unsigned nk_grid(long long total, int per_block = 256, int waves =
 
 int mmsam_gram_tc(const void* X, long long ld, int qoff, int koff, int n, int B, int HW, int blk, float* S, float* nq,
                   float* nk, cudaStream_t st);   // gram_tc.cu
+int mmsam_gram_tc_plan(int n, int B, int HW, int norms, int* chunk_out);   // gram_tc.cu
 
-MMSAM_API int mmsam_gram_bf16(const void* X, long long ld, int qoff, int koff, int n, int B, int HW, int blk,
-                              float* S, float* nq, float* nk, void* stream) {
-  using namespace mmsam;
-  if (B < 0 || n <= 0 || HW <= 0 || (ld & 7) || (qoff & 7) || (koff & 7) || (n & 7) || blk < 0) return MMSAM_ERR_BAD_ARG;
-  if ((nq == nullptr) != (nk == nullptr)) return MMSAM_ERR_BAD_ARG;
-  if (B == 0) return MMSAM_OK;
-  if (!X || !S || (((uintptr_t)X) & 15)) return MMSAM_ERR_BAD_ARG;
-  if (!getenv("MMSAM_GRAM_SIMT")) {   // tensor-core path; shapes it does not take fall through to the SIMT kernel
-    const int rc = mmsam_gram_tc(X, ld, qoff, koff, n, B, HW, blk, S, nq, nk, (cudaStream_t)stream);
-    if (rc != MMSAM_ERR_UNSUPPORTED) return rc;
-  }
-  const int nt = (n + 63) / 64;
+static int gram_simt_forced() {
+  static const int v = getenv("MMSAM_GRAM_SIMT") != nullptr;
+  return v;
+}
+// pixel chunking of the SIMT fallback (maps whose pixel count is not a multiple of 64)
+static int gram_simt_plan(int HW, int* chunk_out) {
   int nchunks = HW / 2048;
   if (nchunks < 1) nchunks = 1;
   if (nchunks > 16) nchunks = 16;
   int chunk = (HW + nchunks - 1) / nchunks;
   chunk = (chunk + 31) / 32 * 32;
-  nchunks = (HW + chunk - 1) / chunk;
+  if (chunk_out) *chunk_out = chunk;
+  return (HW + chunk - 1) / chunk;
+}
+
+MMSAM_API int mmsam_gram_chunks(int n, int B, int HW, int norms) {
+  if (n <= 0 || B <= 0 || HW <= 0) return 0;
+  if (!gram_simt_forced()) {
+    const int c = mmsam_gram_tc_plan(n, B, HW, norms, nullptr);
+    if (c > 0) return c;
+  }
+  return gram_simt_plan(HW, nullptr);
+}
+
+MMSAM_API int mmsam_gram_bf16(const void* X, long long ld, int qoff, int koff, int n, int B, int HW, int blk,
+                              float* S_part, float* nq_part, float* nk_part, void* stream) {
+  using namespace mmsam;
+  if (B < 0 || n <= 0 || HW <= 0 || (ld & 7) || (qoff & 7) || (koff & 7) || (n & 7) || blk < 0) return MMSAM_ERR_BAD_ARG;
+  if ((nq_part == nullptr) != (nk_part == nullptr)) return MMSAM_ERR_BAD_ARG;
+  if (B == 0) return MMSAM_OK;
+  if (!X || !S_part || (((uintptr_t)X) & 15)) return MMSAM_ERR_BAD_ARG;
+  if (!gram_simt_forced()) {   // tensor-core path; shapes it does not take fall through to the SIMT kernel
+    const int rc = mmsam_gram_tc(X, ld, qoff, koff, n, B, HW, blk, S_part, nq_part, nk_part, (cudaStream_t)stream);
+    if (rc != MMSAM_ERR_UNSUPPORTED) return rc;
+  }
+  const int nt = (n + 63) / 64;
+  int chunk = 0;
+  const int nchunks = gram_simt_plan(HW, &chunk);
   dim3 grid(nt * nt, nchunks, B);
-  gram_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)X, ld, qoff, koff, n, HW, chunk, blk, S, nq, nk);
+  gram_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)X, ld, qoff, koff, n, HW, chunk, blk, S_part,
+                                                      nq_part, nk_part);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+MMSAM_API int mmsam_gfe_weff_bf16(const float* S_part, const float* nq_part, const float* nk_part, int nchunks, int B, int ci,
+                                  int heads, const float* temperature, const float* wproj, const float* scale2, void* weff,
+                                  void* stream) {
+  using namespace mmsam;
+  if (B < 0 || ci <= 0 || heads <= 0 || ci % heads || nchunks <= 0) return MMSAM_ERR_BAD_ARG;
+  if (B == 0) return MMSAM_OK;
+  if (!S_part || !nq_part || !nk_part || !temperature || !wproj || !scale2 || !weff) return MMSAM_ERR_BAD_ARG;
+  const int ch = ci / heads;
+  const int smem = (ch * (ch + 1) + 2 * ch) * (int)sizeof(float);
+  if (smem > 48 * 1024) return MMSAM_ERR_UNSUPPORTED;
+  int zs = (2 * kNumSMs + heads * B - 1) / (heads * B);      // row splits: ~2 CTAs per SM
+  if (zs > (ci + 15) / 16) zs = (ci + 15) / 16;
+  if (zs < 1) zs = 1;
+  dim3 grid(heads, B, zs);
+  gfe_weff_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(S_part, nq_part, nk_part, nchunks, B, ci, heads, temperature,
+                                                             wproj, scale2, (__nv_bfloat16*)weff);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+MMSAM_API int mmsam_gffm_softmax_bf16(const float* E_part, int nchunks, int B, int ci, void* ax, void* ay, void* stream) {
+  using namespace mmsam;
+  if (B < 0 || ci <= 0 || ci > 1024 || nchunks <= 0) return MMSAM_ERR_BAD_ARG;
+  if (B == 0) return MMSAM_OK;
+  if (!E_part || !ax || !ay) return MMSAM_ERR_BAD_ARG;
+  dim3 grid(ci, B, 2);
+  gffm_softmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(E_part, nchunks, B, ci, (__nv_bfloat16*)ax, (__nv_bfloat16*)ay);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+MMSAM_API int mmsam_ffrm_gate_f32(const float* colstats_part, int nchunks, int B, int HW, int C, double sum_w, double mean_b,
+                                  float ln_eps, const float* wffrm, const float* gn_weight, const float* gn_bias, int groups,
+                                  float gn_eps, float* mu, float* rstd, float* gate, void* stream) {
+  using namespace mmsam;
+  if (B < 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups || nchunks <= 0 || C > 4096) return MMSAM_ERR_BAD_ARG;
+  if (B == 0) return MMSAM_OK;
+  if (!colstats_part || !wffrm || !gn_weight || !gn_bias || !mu || !rstd || !gate) return MMSAM_ERR_BAD_ARG;
+  ffrm_gate_kernel<<<B, 1024, 2 * C * sizeof(float), (cudaStream_t)stream>>>(colstats_part, nchunks, B, HW, C, sum_w, mean_b,
+                                                                             ln_eps, wffrm, gn_weight, gn_bias, groups, gn_eps,
+                                                                             mu, rstd, gate);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+MMSAM_API int mmsam_ca_vectors_f32(const float* ph, const float* pw_part, int nstrips, int B, int H, int W, int C, int mip,
+                                   const float* w1, const float* b1, const float* bn_scale, const float* bn_shift,
+                                   const float* wh, const float* bh, const float* ww, const float* bw, float* ah, float* aw,
+                                   void* stream) {
+  using namespace mmsam;
+  if (B < 0 || H <= 0 || W <= 0 || C <= 0 || mip <= 0 || nstrips <= 0 || (C + mip) * 4 > 48 * 1024) return MMSAM_ERR_BAD_ARG;
+  if (B == 0) return MMSAM_OK;
+  if (!ph || !pw_part || !w1 || !b1 || !bn_scale || !bn_shift || !wh || !bh || !ww || !bw || !ah || !aw) return MMSAM_ERR_BAD_ARG;
+  dim3 grid(H + W, B);
+  ca_vectors_kernel<<<grid, 256, (C + mip) * sizeof(float), (cudaStream_t)stream>>>(ph, pw_part, nstrips, B, H, W, C, mip, w1, b1,
+                                                                                    bn_scale, bn_shift, wh, bh, ww, bw, ah, aw);
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }
@@ -335,7 +653,7 @@ MMSAM_API int mmsam_combine_pool_bf16(const void* o, const void* lo, const float
   if ((((uintptr_t)o | (uintptr_t)lo | (uintptr_t)f | (uintptr_t)pw_part) & 15)) return MMSAM_ERR_BAD_ARG;
   const int RS = mmsam_combine_pool_rows(H);
   dim3 grid((H + RS - 1) / RS, (C + 63) / 64, B);
-  combine_pool_kernel<<<grid, 256, RS * 64 * sizeof(float), (cudaStream_t)stream>>>(
+  combine_pool_kernel<<<grid, 256, 8 * RS * 64 * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)o, (const __nv_bfloat16*)lo, mu, rstd, gate, wpix, bpix, s1, s2, (__nv_bfloat16*)f, ph,
       pw_part, B, H, W, C, RS);
   MMSAM_LAUNCH_CHECK();

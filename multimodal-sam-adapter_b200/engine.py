@@ -1,10 +1,14 @@
 """Inference engine: packs the weights of the parameter containers (nn_modules.py) into kernel-ready
 device buffers and runs the MM SAM-Adapter forward as a sequence of this repo's sm_100a kernels.
 
-Data layout in HBM: every activation is channels-last bf16 ([B, H, W, C] == token-major [B*H*W, C]),
-so LayerNorm / LN2d are row ops, 1x1 convs and Linears are the same GEMM, and the token sequence
-c = [c2 | c3 | c4] is one [B, 21*HW/... , C] buffer. fp32 is kept for: LN statistics, GEMM / attention
-accumulation, MSDeformAttn sampling offsets + attention logits, the class logits.
+Data layout in HBM: every activation is channels-last ([B, H, W, C] == token-major [B*H*W, C]), so LayerNorm / LN2d
+are row ops, 1x1 convs and Linears are the same GEMM, and the token sequence c = [c2 | c3 | c4] is one
+[B, 21*HW/... , C] buffer. Storage is bf16 except the two long RESIDUAL STREAMS, which stay fp32 in HBM: the ViT token
+stream x (2 residual adds per block, 24 blocks) and the feature map t of each ConvNeXt tower (36 blocks whose branch is
+scaled by a small layer-scale gamma: rounding t to bf16 after every block was measured to be ~80 % of the towers' error
+against the fp32 reference, 9.7e-3 -> 2.5e-3 rel-L2 at stage 2 with the stream in fp32). Every tensor-core operand is
+bf16 (LayerNorm / depthwise-conv outputs); fp32 is also kept for LN statistics, GEMM / attention accumulation,
+MSDeformAttn sampling offsets + attention logits, and the class logits.
 
 Follows the reference forward (segmentation/mmseg_custom/models/backbones/
 image_encoder_adapter_bimodal_mix_mod_new_in_twin_convnext_new.py:161-349) step by step; the cited
@@ -17,7 +21,18 @@ import torch
 
 from . import kernels as K
 from . import neck as neck_b200
-from . import neck_torch
+
+
+def _on_device(fn):
+    """Run a public engine method with the engine's GPU as the current device: kernels launch on the CURRENT device's
+    stream and opt in to large shared memory per device, so a model living on cuda:1 must not launch from cuda:0."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.dev):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 def _bf(t, dev):
@@ -144,6 +159,27 @@ def pack_interaction(it, dev):
     return d
 
 
+def pack_head(h, dev):
+    """SegformerHead weights (decode_heads/segformer_head.py:24-46): eval BatchNorm folded into the 1x1 convs, the fusion
+    conv's weight sliced per input level (see _Ops._head_logits), conv_seg padded to a multiple of 32 classes."""
+    hd = {"convs": []}
+    for cm in h.convs:
+        s, t = _bn_fold(cm.bn, dev)
+        w = cm.conv.weight.detach().float().reshape(cm.conv.weight.shape[0], -1).to(dev) * s[:, None]
+        hd["convs"].append(_Lin(w, t, dev))
+    s, t = _bn_fold(h.fusion_conv.bn, dev)
+    w = h.fusion_conv.conv.weight.detach().float().reshape(h.fusion_conv.conv.weight.shape[0], -1).to(dev) * s[:, None]
+    chn = w.shape[0]
+    hd["fusion_w"] = [w[:, i * chn:(i + 1) * chn].to(torch.bfloat16).contiguous() for i in range(len(h.convs))]
+    hd["fusion_shift"] = t.float().contiguous()
+    ncls = h.conv_seg.weight.shape[0]
+    npad = (ncls + 31) // 32 * 32
+    hd["cls"] = _Lin(_pad_rows(h.conv_seg.weight.detach().float().reshape(ncls, -1), npad),
+                     _pad_rows(h.conv_seg.bias.detach().float(), npad), dev)
+    hd["ncls"], hd["npad"], hd["channels"] = ncls, npad, h.conv_seg.weight.shape[1]
+    return hd
+
+
 def window_maps(B, H, W, ws, C, dev):
     """Row maps of SAM's window_partition / window_unpartition (base/image_encoder.py:504-551)."""
     nwh, nww = (H + ws - 1) // ws, (W + ws - 1) // ws
@@ -214,21 +250,45 @@ class _Ops:
                 stats_of["c_stats"] = (x.data_ptr(), lnlin.eps, st)
         return K.gemm_ln(x, lnlin.w, lnlin.b, lnlin.colsum, st, **kw)
 
+    def _proj_ln(self, t, ln, lnlin, lin, stats_of=None, out_dtype=torch.bfloat16):
+        """lin(LayerNorm(t)). bf16 rows (the adapter's token buffer c): the LayerNorm is folded into the GEMM (row statistics
+        + GEMM on the raw rows). fp32 rows (the ViT token stream): LayerNorm kernel (fp32 -> bf16), then the plain GEMM."""
+        if LN_FOLD and lnlin is not None and t.dtype == torch.bfloat16:
+            return self._gemm_ln(t, lnlin, stats_of=stats_of, out_dtype=out_dtype)
+        return self._gemm(self._ln(t, ln), lin, out_dtype=out_dtype)
+
     def _msda(self, pk, query, feat, ref, lv, B, geom=None, qn=None, fn=None, c_is=None, sc=None):
         """MSDeformAttn.forward up to (not including) output_proj (ops/modules/ms_deform_attn.py:83-127) on
         query_norm(query) / feat_norm(feat) (adapter_modules_...new.py:494-501, 527-532). c_is: "feat" / "query" tells
         which operand is the adapter's token buffer c (row statistics cached in sc)."""
-        if LN_FOLD and pk.value_ln is not None and pk.qproj_ln is not None:
-            value = self._gemm_ln(feat, pk.value_ln, stats_of=sc if c_is == "feat" else None)                      # [B*S, M*D]
-            qp = self._gemm_ln(query, pk.qproj_ln, stats_of=sc if c_is == "query" else None, out_dtype=torch.float32)  # [B*Lq, M*L*P*3]
-        else:
-            value = self._gemm(self._ln(feat, fn), pk.value)
-            qp = self._gemm(self._ln(query, qn), pk.qproj, out_dtype=torch.float32)
+        value = self._proj_ln(feat, fn, pk.value_ln, pk.value, stats_of=sc if c_is == "feat" else None)           # [B*S, M*D]
+        qp = self._proj_ln(query, qn, pk.qproj_ln, pk.qproj, stats_of=sc if c_is == "query" else None,
+                           out_dtype=torch.float32)                                                                # [B*Lq, M*L*P*3]
         S = feat.shape[0] // B
         return K.msda_fused(value.view(B, S, -1), lv[0], lv[1], qp, ref, pk.n_heads, pk.n_levels, pk.n_points, geom=geom)
 
+    def _head_logits(self, hd, feats):
+        """SegformerHead.forward (decode_heads/segformer_head.py:48-66) on channels-last bf16 maps [B, h, w, C]
+        -> fp32 logits [B*h0*w0, npad], (h0, w0)."""
+        B, h0, w0, _ = feats[0].shape
+        ch = hd["channels"]
+        # fusion(concat_i resize(y_i)) = sum_i resize(W_i y_i): every level's slice of the (BN-scaled) fusion weight is
+        # applied at the level's own resolution; one kernel adds the up-sampled partial sums, the BN shift and the ReLU
+        zs, hws = [], []
+        for i, f in enumerate(feats):
+            _, h, w, Cf = f.shape
+            y = self._gemm(f.reshape(-1, Cf), hd["convs"][i], act="relu")
+            zs.append(K.gemm(y, hd["fusion_w"][i]))
+            hws.append((h, w))
+        if len(zs) > 4:
+            raise NotImplementedError("SegformerHead with more than 4 input levels")
+        o = K.resize_sum_affine(zs[0], zs[1:], hws[1:], (h0, w0), B, ch, shift=hd["fusion_shift"], relu=True)
+        return self._gemm(o, hd["cls"], out_dtype=torch.float32), (h0, w0)
+
     def _block(self, x, blk, sc, tabs, B, out=None):
-        """Block.forward (base/image_encoder.py:382-423). x [B*T, C] is updated in place unless out is given."""
+        """Block.forward (base/image_encoder.py:382-423). x [B*T, C] (the fp32 token stream) is updated in place unless
+        out is given: norm1 / norm2 read it in fp32 and emit the bf16 GEMM operand, the proj / lin2 epilogues add the
+        fp32 residual and store fp32."""
         H, W, T = sc["H"], sc["W"], sc["T"]
         if blk["window"] > 0:
             ws = sc["ws"]
@@ -250,7 +310,7 @@ class _Ops:
         return dst
 
     def _injector(self, x, c, inj, sc, B):
-        """Injector.forward (adapter_modules_...new.py:525-542); returns a NEW [B*T, C] buffer (the input
+        """Injector.forward (adapter_modules_...new.py:525-542); returns a NEW fp32 [B*T, C] buffer (the input
         is one of the saved ViT outputs `outs` and must stay intact)."""
         o = self._msda(inj["attn"], x, c, sc["ref1"], sc["lv3"], B, inj["attn"].geom("inj", sc) if MSDA_STAGED else None,
                        qn=inj["qn"], fn=inj["fn"], c_is="feat", sc=sc)
@@ -278,6 +338,7 @@ class ComponentRunner(_Ops):
     def __init__(self, dim, num_heads, device="cuda"):
         self.C, self.nh, self.dev = dim, num_heads, torch.device(device)
 
+    @_on_device
     @torch.no_grad()
     def block(self, blk_module, x, H, W):
         """x [B, H*W, C] (any float dtype, CUDA) -> same shape, bf16."""
@@ -290,9 +351,20 @@ class ComponentRunner(_Ops):
         tabs = (None, None)
         if pk["rel_h"] is not None:
             tabs = (K.relpos_table(pk["rel_h"], kh), K.relpos_table(pk["rel_w"], kw))
-        xb = x.reshape(B * H * W, self.C).to(torch.bfloat16).contiguous().clone()
+        xb = x.reshape(B * H * W, self.C).float().contiguous().clone()
         return self._block(xb, pk, sc, tabs, B).view(B, H * W, self.C)
 
+    @_on_device
+    @torch.no_grad()
+    def head(self, head_module, feats):
+        """SegformerHead.forward on NCHW feature maps (any float dtype, CUDA) -> fp32 logits [B, num_classes, h0, w0]."""
+        hd = pack_head(head_module, self.dev)
+        nhwc = [f.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous() for f in feats]
+        logits, (h0, w0) = self._head_logits(hd, nhwc)
+        B = feats[0].shape[0]
+        return logits.view(B, h0, w0, -1)[..., : hd["ncls"]].permute(0, 3, 1, 2).contiguous()
+
+    @_on_device
     @torch.no_grad()
     def interaction(self, it_module, x, c, Hi, Wi, blocks=()):
         """InteractionBlock.forward (adapter_modules_...new.py:567-581) for an Hi x Wi image geometry."""
@@ -301,7 +373,7 @@ class ComponentRunner(_Ops):
         H, W = Hi // 16, Wi // 16
         sc = dict(H=H, W=W, T=H * W)
         sc.update(deform_geometry(B, Hi, Wi, self.dev))
-        xb = x.reshape(-1, self.C).to(torch.bfloat16).contiguous().clone()
+        xb = x.reshape(-1, self.C).float().contiguous().clone()
         cb = c.reshape(-1, self.C).to(torch.bfloat16).contiguous().clone()
         xb = self._injector(xb, cb, pk["inj"], sc, B)
         for blk in blocks:
@@ -370,11 +442,7 @@ class EncoderEngine(_Ops):
                 stages.append(e)
             self.cnx[br] = stages
         self.cnx_channels = list(tw.channels)
-        import os
-        if os.environ.get("MMSAM_NECK", "b200") == "torch":   # library cross-check path (tests only)
-            self.neck = neck_torch.NeckTorch(m.spm.smart_fusion, dev)
-        else:
-            self.neck = neck_b200.NeckB200(m.spm.smart_fusion, dev)
+        self.neck = neck_b200.NeckB200(m.spm.smart_fusion, dev)
         le = m.level_embed.detach().float()
         self.fc = []
         for i in range(4):
@@ -392,23 +460,7 @@ class EncoderEngine(_Ops):
         self.final_bn = [_bn_fold(getattr(m, f"norm{i + 1}"), dev) for i in range(4)]
 
     def _pack_head(self, h):
-        dev = self.dev
-        hd = {"convs": []}
-        for cm in h.convs:
-            s, t = _bn_fold(cm.bn, dev)
-            w = cm.conv.weight.detach().float().reshape(cm.conv.weight.shape[0], -1).to(dev) * s[:, None]
-            hd["convs"].append(_Lin(w, t, dev))
-        s, t = _bn_fold(h.fusion_conv.bn, dev)
-        w = h.fusion_conv.conv.weight.detach().float().reshape(h.fusion_conv.conv.weight.shape[0], -1).to(dev) * s[:, None]
-        chn = w.shape[0]
-        hd["fusion_w"] = [w[:, i * chn:(i + 1) * chn].to(torch.bfloat16).contiguous() for i in range(len(h.convs))]
-        hd["fusion_shift"] = t.float().contiguous()
-        ncls = h.conv_seg.weight.shape[0]
-        npad = (ncls + 31) // 32 * 32
-        hd["cls"] = _Lin(_pad_rows(h.conv_seg.weight.detach().float().reshape(ncls, -1), npad),
-                         _pad_rows(h.conv_seg.bias.detach().float(), npad), dev)
-        hd["ncls"], hd["npad"], hd["channels"] = ncls, npad, h.conv_seg.weight.shape[1]
-        self.head = hd
+        self.head = pack_head(h, self.dev)
 
     # ------------------------------------------------------------------ shape-dependent constants
     def _shape(self, B, Hi, Wi):
@@ -423,7 +475,7 @@ class EncoderEngine(_Ops):
         # pos_embed: always bicubic-resized (..._new.py:136-143)
         pe = torch.nn.functional.interpolate(self.pos_embed.permute(0, 3, 1, 2), size=(H, W), mode="bicubic",
                                              align_corners=False)
-        pe = pe.reshape(1, -1, H * W).permute(0, 2, 1).to(torch.bfloat16)
+        pe = pe.reshape(1, -1, H * W).permute(0, 2, 1)                  # fp32: the residual of the patch-embed GEMM
         sc["pos"] = pe.expand(B, -1, -1).reshape(B * H * W, -1).contiguous()
         ws = max((b["window"] for b in self.blocks), default=0)
         if ws > 0:
@@ -444,20 +496,22 @@ class EncoderEngine(_Ops):
 
     # ------------------------------------------------------------------ building blocks
     def _convnext_branch(self, img, c_off, stages, B, Hi, Wi):
-        """twin_convnext.py:445-476 for one modality; returns the 4 normalised stage outputs [B*h*w, C]."""
+        """twin_convnext.py:445-476 for one modality; returns the 4 normalised stage outputs bf16 [B*h*w, C]. The tower's
+        feature map t is an fp32 residual stream (see the module docstring); dwconv / LN read it in fp32 and emit bf16."""
         feats = []
         t = None
         h, w = Hi, Wi
+        f32 = torch.float32
         for i, st in enumerate(stages):
             if i == 0:
                 pch = K.patchify(img, c_off, 3, 4)
                 h, w = Hi // 4, Wi // 4
-                t = self._gemm(pch, st["ds"])
-                t = self._ln(t, st["ds_ln"])
+                t = self._gemm(pch, st["ds"], out_dtype=f32)
+                t = self._ln(t, st["ds_ln"], out=t, out_dtype=f32)
             else:
                 pt = self._ln(t, st["ds_ln"], patchify_hw=(h, w))
                 h, w = h // 2, w // 2
-                t = self._gemm(pt, st["ds"])
+                t = self._gemm(pt, st["ds"], out_dtype=f32)
             C = t.shape[1]
             for b in st["blocks"]:      # ConvNeXtBlock (twin_convnext.py:98-132)
                 y = K.dwconv(t, b["dw_w"], b["dw_b"], 7, [(h, w)], B, C, h * w * C, h * w * C)
@@ -468,15 +522,24 @@ class EncoderEngine(_Ops):
         return feats
 
     # ------------------------------------------------------------------ forward
+    @_on_device
     @torch.no_grad()
     def backbone_nhwc(self, img, debug=None):
         """img fp32 [B, 3+3, Hi, Wi] on the device -> [f1, f2, f3, f4] channels-last bf16 [B, h, w, C]."""
         if not img.is_cuda:
             raise K._lib.MMSamError("input must be a CUDA tensor")
+        if img.device != self.dev:
+            raise K._lib.MMSamError(f"input on {img.device}, engine packed for {self.dev}")
         img = img.contiguous().float()
         B, _, Hi, Wi = img.shape
         if Hi % 32 or Wi % 32:
             raise ValueError("input height/width must be multiples of 32")
+        isz = self.cfg.get("img_size")
+        if isz is not None and (Hi, Wi) != (isz, isz):
+            # the reference's GFFM.norm = nn.LayerNorm(H/4 * W/4) ... is sized from img_size at construction
+            # (adapter_modules_...new.py:236-241, 347-354) and raises on any other input size; so do we
+            raise K._lib.MMSamError(f"the model is resolution-locked to img_size={isz} (fusion-neck LayerNorms over H*W); "
+                                    f"got a {Hi} x {Wi} input")
         sc = self._shape(B, Hi, Wi)
         H, W, T, C, S3 = sc["H"], sc["W"], sc["T"], self.C, sc["S3"]
         # --- SPM (adapter_modules_...new.py:929-964): twin ConvNeXt -> fusion neck -> fc1..4 ---
@@ -505,7 +568,7 @@ class EncoderEngine(_Ops):
             self._gemm(fused[i + 1], self.fc[i + 1], out=c, row_map=sc["c_rowmaps"][i], out_rows=B * S3)
         # --- patch embed + pos embed (image_encoder.py:662-671, ..._new.py:268-278) ---
         pch = K.patchify(img, 0, self.cin, self.patch)
-        x = self._gemm(pch, self.patch_embed, residual=sc["pos"])
+        x = self._gemm(pch, self.patch_embed, residual=sc["pos"], out_dtype=torch.float32)     # fp32 token stream
         if debug is not None:
             debug.update(c1=c1.clone(), c_0=c.clone(), x_0=x.clone())
         # --- interactions (..._new.py:283-292; adapter_modules_...new.py:567-581) ---
@@ -545,26 +608,13 @@ class EncoderEngine(_Ops):
             fs.append(f)
         return fs
 
+    @_on_device
     @torch.no_grad()
     def head_logits(self, feats):
-        """SegformerHead.forward (decode_heads/segformer_head.py:48-66) -> fp32 logits [B*h*w, npad]."""
-        hd = self.head
-        B, h0, w0, _ = feats[0].shape
-        ch = hd["channels"]
-        # fusion(concat_i resize(y_i)) = sum_i resize(W_i y_i): every level's slice of the (BN-scaled) fusion weight is
-        # applied at the level's own resolution; one kernel adds the up-sampled partial sums, the BN shift and the ReLU
-        zs, hws = [], []
-        for i, f in enumerate(feats):
-            _, h, w, Cf = f.shape
-            y = self._gemm(f.view(-1, Cf), hd["convs"][i], act="relu")
-            zs.append(K.gemm(y, hd["fusion_w"][i]))
-            hws.append((h, w))
-        if len(zs) <= 4:
-            o = K.resize_sum_affine(zs[0], zs[1:], hws[1:], (h0, w0), B, ch, shift=hd["fusion_shift"], relu=True)
-        else:
-            raise NotImplementedError("SegformerHead with more than 4 input levels")
-        return self._gemm(o, hd["cls"], out_dtype=torch.float32), (h0, w0)
+        """SegformerHead.forward (decode_heads/segformer_head.py:48-66) -> fp32 logits [B*h*w, npad], (h, w)."""
+        return self._head_logits(self.head, feats)
 
+    @_on_device
     @torch.no_grad()
     def segment(self, img, out_hw=None, crop_hw=None):
         """encode_decode_test + whole_inference_dim(_cut) + softmax/argmax -> uint8 labels [B, H, W]
@@ -575,6 +625,7 @@ class EncoderEngine(_Ops):
         out_hw = (Hi, Wi) if out_hw is None else tuple(out_hw)
         return K.upsample_argmax(logits, B, (h0, w0), self.head["ncls"], out_hw, crop_hw)
 
+    @_on_device
     @torch.no_grad()
     def segment_graphed(self, img, out_hw=None, crop_hw=None):
         """segment() replayed from a CUDA graph (one graph per input shape, captured on first use after an eager

@@ -23,9 +23,19 @@ def _ptr(t):
 
 
 def _need_cuda(*ts):
+    """Every tensor must live on the CURRENT CUDA device: the kernels launch on its current stream and their
+    shared-memory attributes are set per device (run under `with torch.cuda.device(t.device)`; the engine does)."""
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.MMSamError("mmsam_b200 kernels need CUDA tensors (there is no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise _lib.MMSamError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: wrap the call in "
+                                  "`with torch.cuda.device(tensor.device)`")
 
 
 def _count(n=1):
@@ -56,10 +66,11 @@ def msda_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_we
     return out
 
 
-def layernorm(x, gamma, beta, eps, out=None, row_map=None, out_rows=None, patchify_hw=None, out2=None):
-    """x bf16 [..., C] (rows contiguous) -> LN over C. row_map (int32 [rows]) scatters rows into an
-    `out` of out_rows rows (rows never written keep their previous contents). patchify_hw=(H, W):
-    rows are (b,y,x) and the result is the 2x2-patchified [rows/4, 4C] matrix."""
+def layernorm(x, gamma, beta, eps, out=None, row_map=None, out_rows=None, patchify_hw=None, out2=None,
+              out_dtype=torch.bfloat16):
+    """x bf16 or fp32 [..., C] (rows contiguous) -> LN over C (bf16, or fp32 for an fp32 input when out_dtype says so).
+    row_map (int32 [rows]) scatters rows into an `out` of out_rows rows (rows never written keep their previous
+    contents). patchify_hw=(H, W): rows are (b,y,x) and the result is the 2x2-patchified [rows/4, 4C] matrix."""
     _need_cuda(x, gamma, beta)
     C = x.shape[-1]
     x2 = x.reshape(-1, C)
@@ -69,15 +80,15 @@ def layernorm(x, gamma, beta, eps, out=None, row_map=None, out_rows=None, patchi
         ps_h, ps_w = patchify_hw
     if out is None:
         if patchify_hw is not None:
-            out = torch.empty((rows // 4, 4 * C), dtype=x.dtype, device=x.device)
+            out = torch.empty((rows // 4, 4 * C), dtype=out_dtype, device=x.device)
         elif row_map is None:
-            out = torch.empty_like(x2)
+            out = torch.empty(x2.shape, dtype=out_dtype, device=x.device)
         else:
-            out = torch.zeros((out_rows, C), dtype=x.dtype, device=x.device)
-    rc = _lib.load().mmsam_layernorm_bf16(
-        _ptr(x2), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(out2), _ptr(row_map), rows, C, x2.stride(0), out.stride(0),
-        float(eps), ps_h, ps_w, _stream())
-    _lib.check(rc, "mmsam_layernorm_bf16")
+            out = torch.zeros((out_rows, C), dtype=out_dtype, device=x.device)
+    rc = _lib.load().mmsam_layernorm(
+        _ptr(x2), _DT[x2.dtype], _ptr(gamma), _ptr(beta), _ptr(out), _DT[out.dtype], _ptr(out2), _ptr(row_map), rows, C,
+        x2.stride(0), out.stride(0), float(eps), ps_h, ps_w, _stream())
+    _lib.check(rc, "mmsam_layernorm")
     _count()
     if row_map is not None or patchify_hw is not None:
         return out
@@ -106,10 +117,29 @@ def gemm(a, w, bias=None, act=None, scale=None, residual=None, out=None, out_dty
         out = torch.empty((m_out, n_out), dtype=out_dtype, device=a.device)
     rc = _lib.load().mmsam_gemm_bf16(
         _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(scale), _ptr(residual),
+        1 if (residual is not None and residual.dtype == torch.float32) else 0,
         residual.stride(0) if residual is not None else 0, _ptr(out), out.stride(0), M, N, K, ACT[act],
         1 if out.dtype == torch.float32 else 0, row_mode, _ptr(row_map), ps_h, ps_w, ps_c, block_n, max_ctas,
         _stream())
     _lib.check(rc, "mmsam_gemm_bf16")
+    _count()
+    return out
+
+
+def gemm_grouped(a, w, rows_per_group, bias=None, scale=None, residual=None, out=None, act=None, block_n=0, max_ctas=0):
+    """Per-group weights in one launch: rows [g*rows_per_group, (g+1)*rows_per_group) of a [M, K] use w[g] of w [G, N, K]
+    (bf16, contiguous); rows_per_group % 256 == 0. See include/mmsam_b200.h (mmsam_gemm_grouped_bf16)."""
+    _need_cuda(a, w, bias, scale, residual, out)
+    M, K = a.shape
+    G, N, K2 = w.shape
+    assert K2 == K and w.is_contiguous() and a.stride(1) == 1 and G * rows_per_group == M
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    rc = _lib.load().mmsam_gemm_grouped_bf16(
+        _ptr(a), a.stride(0), _ptr(w), K, _ptr(bias), _ptr(scale), _ptr(residual),
+        residual.stride(0) if residual is not None else 0, _ptr(out), out.stride(0), M, N, K, rows_per_group, ACT[act],
+        block_n, max_ctas, _stream())
+    _lib.check(rc, "mmsam_gemm_grouped_bf16")
     _count()
     return out
 
@@ -241,7 +271,7 @@ def dwconv(x, w_tap_major, bias, ksize, grids, B, C, in_bstride, out_bstride, ac
     import ctypes
     _need_cuda(x, w_tap_major, bias)
     if out is None:
-        out = torch.empty_like(x)
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     n = len(grids)
     hw = (ctypes.c_int * (2 * n))(*[v for g in grids for v in g])
     if in_offs is None:
@@ -253,10 +283,10 @@ def dwconv(x, w_tap_major, bias, ksize, grids, B, C, in_bstride, out_bstride, ac
         out_offs = in_offs
     io = (ctypes.c_longlong * n)(*in_offs)
     oo = (ctypes.c_longlong * n)(*out_offs)
-    rc = _lib.load().mmsam_dwconv_bf16(_ptr(x), _ptr(out), _ptr(w_tap_major), _ptr(bias), B, C, ksize, n,
+    rc = _lib.load().mmsam_dwconv(_ptr(x), _DT[x.dtype], _ptr(out), _ptr(w_tap_major), _ptr(bias), B, C, ksize, n,
                                        ctypes.cast(hw, ctypes.c_void_p), ctypes.cast(io, ctypes.c_void_p),
                                        ctypes.cast(oo, ctypes.c_void_p), in_bstride, out_bstride, ACT[act], _stream())
-    _lib.check(rc, "mmsam_dwconv_bf16")
+    _lib.check(rc, "mmsam_dwconv")
     _count()
     return out
 
@@ -292,7 +322,7 @@ def patchify(img, c_off, C, p, out=None):
 
 def resize_add_affine(src, src_hw, out_hw, B, C, base=None, scale=None, shift=None, out=None,
                       src_bstride=None, lds=None, base_bstride=None, ldb=None, out_bstride=None, ldo=None):
-    """Channels-last bf16: out = (base + bilinear(src)) * scale + shift. Strides in elements."""
+    """Channels-last: out = (base + bilinear(src)) * scale + shift (src bf16 or fp32; base / out bf16). Strides in elements."""
     _need_cuda(src, base, scale, shift, out)
     Hs, Ws = src_hw
     Ho, Wo = out_hw
@@ -304,10 +334,10 @@ def resize_add_affine(src, src_hw, out_hw, B, C, base=None, scale=None, shift=No
     out_bstride = Ho * Wo * ldo if out_bstride is None else out_bstride
     if out is None:
         out = torch.empty((B, Ho, Wo, C), dtype=torch.bfloat16, device=src.device)
-    rc = _lib.load().mmsam_resize_add_affine_bf16(
-        _ptr(src), _ptr(base), _ptr(scale), _ptr(shift), _ptr(out), B, Hs, Ws, Ho, Wo, C, src_bstride, lds,
+    rc = _lib.load().mmsam_resize_add_affine(
+        _ptr(src), _DT[src.dtype], _ptr(base), _ptr(scale), _ptr(shift), _ptr(out), B, Hs, Ws, Ho, Wo, C, src_bstride, lds,
         base_bstride, ldb, out_bstride, ldo, _stream())
-    _lib.check(rc, "mmsam_resize_add_affine_bf16")
+    _lib.check(rc, "mmsam_resize_add_affine")
     _count()
     return out
 
@@ -390,29 +420,92 @@ def conv3x3(x, w_packed, B, H, W, Cin, Cout, groups, out=None, max_ctas=0):
 
 
 def gram(x, ld, qoff, koff, n, B, HW, blk=0, norms=False):
-    """-> S fp32 [B,n,n] (and nq, nk fp32 [B,n] when norms)."""
+    """Per-pixel-chunk partial Gram sums: S_part fp32 [nchunks, B, n, n] (and nq_part, nk_part fp32 [nchunks, B, n] when
+    norms). With blk > 0 only the block-diagonal elements are written. The chunks are added in a fixed order by the
+    consumers (gfe_weff / gffm_softmax): no atomics, bit-reproducible."""
     _need_cuda(x)
-    S = torch.zeros((B, n, n), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    nch = lib.mmsam_gram_chunks(n, B, HW, 1 if norms else 0)
+    S = torch.empty((nch, B, n, n), dtype=torch.float32, device=x.device)
     nq = nk = None
     if norms:
-        nq = torch.zeros((B, n), dtype=torch.float32, device=x.device)
-        nk = torch.zeros((B, n), dtype=torch.float32, device=x.device)
-    rc = _lib.load().mmsam_gram_bf16(_ptr(x), ld, qoff, koff, n, B, HW, blk, _ptr(S), _ptr(nq), _ptr(nk), _stream())
+        nq = torch.empty((nch, B, n), dtype=torch.float32, device=x.device)
+        nk = torch.empty((nch, B, n), dtype=torch.float32, device=x.device)
+    rc = lib.mmsam_gram_bf16(_ptr(x), ld, qoff, koff, n, B, HW, blk, _ptr(S), _ptr(nq), _ptr(nk), _stream())
     _lib.check(rc, "mmsam_gram_bf16")
     _count()
     return (S, nq, nk) if norms else S
 
 
-def colstats(o, wpix, B, HW, C):
-    """-> fp64 [B, C, 3] = {sum o, sum o^2, sum o*w[pix]} over the HW pixels of each image."""
+def gfe_weff(S_part, nq_part, nk_part, temperature, wproj, scale2, heads):
+    """AttentionBase softmax + proj fold (see include/mmsam_b200.h) -> weff bf16 [B, ci, ci]."""
+    _need_cuda(S_part, nq_part, nk_part, temperature, wproj, scale2)
+    nch, B, ci, _ = S_part.shape
+    weff = torch.empty((B, ci, ci), dtype=torch.bfloat16, device=S_part.device)
+    rc = _lib.load().mmsam_gfe_weff_bf16(_ptr(S_part), _ptr(nq_part), _ptr(nk_part), nch, B, ci, heads, _ptr(temperature),
+                                         _ptr(wproj), _ptr(scale2), _ptr(weff), _stream())
+    _lib.check(rc, "mmsam_gfe_weff_bf16")
+    _count()
+    return weff
+
+
+def gffm_softmax(E_part):
+    """-> (ax, ay) bf16 [B, ci, ci]: row softmax of E and of E^T."""
+    _need_cuda(E_part)
+    nch, B, ci, _ = E_part.shape
+    ax = torch.empty((B, ci, ci), dtype=torch.bfloat16, device=E_part.device)
+    ay = torch.empty_like(ax)
+    rc = _lib.load().mmsam_gffm_softmax_bf16(_ptr(E_part), nch, B, ci, _ptr(ax), _ptr(ay), _stream())
+    _lib.check(rc, "mmsam_gffm_softmax_bf16")
+    _count()
+    return ax, ay
+
+
+def colstats_part(o, wpix, B, HW, C):
+    """-> fp32 [nchunks, B, C, 3] per-chunk partials {sum o, sum o^2, sum o*w[pix]}."""
     _need_cuda(o, wpix)
     lib = _lib.load()
+    if wpix.numel() != HW:
+        raise _lib.MMSamError(f"colstats: the LayerNorm-over-HW weight has {wpix.numel()} entries, the map {HW} pixels")
     nch = lib.mmsam_colstats_chunks(HW)
     part = torch.empty((nch, B, C, 3), dtype=torch.float32, device=o.device)
     rc = lib.mmsam_colstats_bf16(_ptr(o), _ptr(wpix), _ptr(part), B, HW, C, _stream())
     _lib.check(rc, "mmsam_colstats_bf16")
     _count()
-    return part.double().sum(0)
+    return part
+
+
+def ffrm_gate(part, HW, sum_w, mean_b, ln_eps, wffrm, gn_w, gn_b, groups, gn_eps):
+    """colstats partials -> (mu, rstd, gate) fp32 [B, C] (see include/mmsam_b200.h: mmsam_ffrm_gate_f32)."""
+    _need_cuda(part, wffrm, gn_w, gn_b)
+    nch, B, C, _ = part.shape
+    mu = torch.empty((B, C), dtype=torch.float32, device=part.device)
+    rstd = torch.empty_like(mu)
+    gate_v = torch.empty_like(mu)
+    rc = _lib.load().mmsam_ffrm_gate_f32(_ptr(part), nch, B, HW, C, float(sum_w), float(mean_b), float(ln_eps), _ptr(wffrm),
+                                         _ptr(gn_w), _ptr(gn_b), groups, float(gn_eps), _ptr(mu), _ptr(rstd), _ptr(gate_v),
+                                         _stream())
+    _lib.check(rc, "mmsam_ffrm_gate_f32")
+    _count()
+    return mu, rstd, gate_v
+
+
+def ca_vectors(ph, pw_part, B, H, W, C, w1, b1, bn_s, bn_t, wh, bh, ww, bw):
+    """Pooled sums -> coordinate-attention vectors ah fp32 [B, H, C], aw fp32 [B, W, C]."""
+    _need_cuda(ph, pw_part, w1, b1, bn_s, bn_t, wh, bh, ww, bw)
+    ah = torch.empty((B, H, C), dtype=torch.float32, device=ph.device)
+    aw = torch.empty((B, W, C), dtype=torch.float32, device=ph.device)
+    rc = _lib.load().mmsam_ca_vectors_f32(_ptr(ph), _ptr(pw_part), pw_part.shape[0], B, H, W, C, w1.shape[0], _ptr(w1), _ptr(b1),
+                                          _ptr(bn_s), _ptr(bn_t), _ptr(wh), _ptr(bh), _ptr(ww), _ptr(bw), _ptr(ah), _ptr(aw),
+                                          _stream())
+    _lib.check(rc, "mmsam_ca_vectors_f32")
+    _count()
+    return ah, aw
+
+
+def colstats(o, wpix, B, HW, C):
+    """-> fp64 [B, C, 3] = {sum o, sum o^2, sum o*w[pix]} over the HW pixels of each image (chunks added in order)."""
+    return colstats_part(o, wpix, B, HW, C).double().sum(0)
 
 
 def gate(a, C, out=None):
@@ -427,8 +520,10 @@ def gate(a, C, out=None):
 
 
 def combine_pool(o, lo, mu, rstd, gate_v, wpix, bpix, s1, s2, B, H, W, C):
-    """-> f bf16 [B*H*W, C], ph fp32 [B,H,C] (row sums), pw fp32 [B,W,C] (column sums)."""
+    """-> f bf16 [B*H*W, C], ph fp32 [B,H,C] (row sums), pw_part fp32 [strips, B, W, C] (per-strip column sums)."""
     _need_cuda(o, lo, mu, rstd, gate_v, wpix, bpix)
+    if wpix.numel() != H * W or bpix.numel() != H * W:
+        raise _lib.MMSamError(f"combine_pool: LayerNorm-over-HW affine has {wpix.numel()} entries, the map {H * W} pixels")
     lib = _lib.load()
     RS = lib.mmsam_combine_pool_rows(H)
     ns = (H + RS - 1) // RS
@@ -439,7 +534,7 @@ def combine_pool(o, lo, mu, rstd, gate_v, wpix, bpix, s1, s2, B, H, W, C):
                                      float(s1), float(s2), _ptr(f), _ptr(ph), _ptr(pwp), B, H, W, C, _stream())
     _lib.check(rc, "mmsam_combine_pool_bf16")
     _count()
-    return f, ph, pwp.sum(0)
+    return f, ph, pwp
 
 
 def ca_apply(f, ah, aw, B, H, W, C, out=None):

@@ -12,14 +12,14 @@ sm_100a kernels. Per pyramid level (C = both modalities, ci = C/2, HW pixels, ch
   FFRM / Scale2 / CA   GAP from the statistics, C x C + GroupNorm gate, weighted sum, coordinate-attention
                        pools [combine_pool] -> two tiny 1x1s -> out = f * (1 + a_w a_h) [ca_apply]
 
-Everything that touches a pixel is one of this repo's kernels. The O(B*C^2)-sized glue between them
-(softmax of the [ch, ch] / [ci, ci] matrices, folding proj into Weff, the FFRM / CA vectors: a few kFLOP
-per image) is done with torch tensor ops on the device, in fp32/fp64.
+Everything is one of this repo's kernels, including the O(B*C^2)-sized steps between the pixel passes (softmax of the
+[ch, ch] / [ci, ci] matrices with proj folded into Weff [gfe_weff], the GFFM softmaxes [gffm_softmax], LayerNorm-over-HW
+statistics + FFRM gate [ffrm_gate], coordinate-attention vectors [ca_vectors]). Every reduction adds its partial sums in
+a fixed order: no floating-point atomics, bit-identical results run to run. torch is used for buffers only.
 """
 import os
 
 import torch
-import torch.nn.functional as F
 
 from . import kernels as K
 
@@ -59,8 +59,8 @@ class NeckB200:
                     lnw=_f32(g.norm1.body.weight, dev), lnb=_f32(g.norm1.body.bias, dev),
                     w1=_bf(_blockdiag_1x1(a.qkv1.weight, groups), dev),
                     w2=K.pack_conv3x3_weight(a.qkv2.weight.to(dev), groups), groups=groups, heads=heads,
-                    temp=_f32(a.scale.reshape(-1), dev), scale2=_f32(a.scale2, dev),
-                    wp=_f32(a.proj.weight.reshape(ci, heads, ci // heads), dev))
+                    temp=_f32(a.scale.reshape(-1), dev), scale2=_f32(a.scale2.reshape(1), dev),
+                    wp=_f32(a.proj.weight.reshape(ci, ci), dev))
             for name, key in (("rgb", "local_feature_encoder_rgb"), ("sne", "local_feature_encoder_sne")):
                 l = getattr(m, key)[i]
                 bb = l.bottleneckBlock
@@ -73,7 +73,7 @@ class NeckB200:
             wpix, bpix = _f32(f.norm.weight, dev), _f32(f.norm.bias, dev)
             lv["gffm"] = dict(gx=_f32(f.gammax.scale.detach().reshape(1).expand(ci), dev),
                               gy=_f32(f.gammay.scale.detach().reshape(1).expand(ci), dev), wpix=wpix, bpix=bpix,
-                              sum_w=wpix.double().sum(), mean_b=bpix.double().mean(), eps=f.norm.eps)
+                              sum_w=float(wpix.double().sum()), mean_b=float(bpix.double().mean()), eps=f.norm.eps)
             d = m.detail_feature_extractions[i]
             lv["mlp"] = dict(win=_bf(d.project_in.weight.reshape(2 * C, C), dev),
                              wdw=K.pack_conv3x3_weight(d.dwconv.weight.to(dev), d.dwconv.groups), groups=d.dwconv.groups,
@@ -94,6 +94,19 @@ class NeckB200:
             self.levels.append(lv)
 
     # ------------------------------------------------------------------ pieces
+    @staticmethod
+    def _per_image_gemm(a, w, rows, **kw):
+        """a [B*rows, K] x w[b] (w bf16 [B, N, K]) per image: one grouped launch when a 256-row tile cannot straddle two
+        images, else one launch per image (maps whose pixel count is not a multiple of 256: FMB's 200^2 ... 25^2)."""
+        B = w.shape[0]
+        out, res = kw.pop("out"), kw.pop("residual")
+        if rows % 256 == 0:
+            return K.gemm_grouped(a, w, rows, residual=res, out=out, **kw)
+        for b in range(B):
+            sl = slice(b * rows, (b + 1) * rows)
+            K.gemm(a[sl], w[b], residual=res[sl], out=out[sl], **kw)
+        return out
+
     def _gfe(self, x, p, g_out, col0, B, h, w, ci):
         """GFE.forward (:133-145) + AttentionBase.forward (:90-109); writes g_out[:, col0:col0+ci]."""
         HW = h * w
@@ -102,18 +115,10 @@ class NeckB200:
         qa = K.gemm(n, p["w1"])
         qkv = K.conv3x3(qa, p["w2"], B, h, w, 3 * ci, 3 * ci, p["groups"])
         heads = p["heads"]
-        ch = ci // heads
-        S, nq, nk = K.gram(qkv, 3 * ci, 0, ci, ci, B, HW, blk=ch, norms=True)
-        # [B, heads, ch, ch] diagonal blocks, cosine similarity, temperature, softmax; proj folded in
-        Sb = S.view(B, heads, ch, heads, ch).diagonal(dim1=1, dim2=3).permute(0, 3, 1, 2)
-        qn = nq.sqrt().clamp_min(1e-12).view(B, heads, ch, 1)
-        kn = nk.sqrt().clamp_min(1e-12).view(B, heads, 1, ch)
-        att = torch.softmax(Sb / (qn * kn) * p["temp"].view(1, heads, 1, 1), dim=-1)
-        weff = (torch.einsum("iha,bhaj->bihj", p["wp"], att) * p["scale2"]).reshape(B, ci, ci).to(torch.bfloat16).contiguous()
-        qkv3 = qkv.view(B, HW, 3 * ci)
-        r3, g3 = r.view(B, HW, ci), g_out.view(B, HW, -1)
-        for b in range(B):
-            K.gemm(qkv3[b, :, 2 * ci:], weff[b], residual=r3[b], out=g3[b, :, col0:col0 + ci])
+        S, nq, nk = K.gram(qkv, 3 * ci, 0, ci, ci, B, HW, blk=ci // heads, norms=True)
+        # per-head cosine similarity * temperature -> softmax, with proj (and scale2) folded into one [ci, ci] matrix / image
+        weff = K.gfe_weff(S, nq, nk, p["temp"], p["wp"], p["scale2"], heads)
+        self._per_image_gemm(qkv[:, 2 * ci:], weff, HW, residual=r, out=g_out[:, col0:col0 + ci])
 
     def _mobilenet(self, x, p, l_out, col0, B, h, w, ci):
         """MobileNetV2.forward (:293-295); writes l_out[:, col0:col0+ci]."""
@@ -124,6 +129,10 @@ class NeckB200:
     def _level(self, lv, tx, ty, B, h, w):
         dev = self.dev
         C, ci, HW = lv["C"], lv["ci"], h * w
+        gf = lv["gffm"]
+        if gf["wpix"].numel() != HW:
+            raise K._lib.MMSamError(f"fusion neck built for {gf['wpix'].numel()} pixels at this level, got {h} x {w}: the "
+                                    "model is resolution-locked to img_size (GFFM.norm = LayerNorm(H*W))")
         g = torch.empty((B * HW, C), dtype=torch.bfloat16, device=dev)
         l = torch.empty((B * HW, C), dtype=torch.bfloat16, device=dev)
         self._gfe(tx, lv["gfe_rgb"], g, 0, B, h, w, ci)
@@ -131,39 +140,24 @@ class NeckB200:
         self._mobilenet(tx, lv["mb_rgb"], l, 0, B, h, w, ci)
         self._mobilenet(ty, lv["mb_sne"], l, ci, B, h, w, ci)
         # ---- GFFM (:242-267) ----
-        gf = lv["gffm"]
-        E = K.gram(g, C, 0, ci, ci, B, HW, blk=0)
-        ax = torch.softmax(E, dim=-1).to(torch.bfloat16).contiguous()
-        ay = torch.softmax(E.transpose(1, 2), dim=-1).to(torch.bfloat16).contiguous()
+        ax, ay = K.gffm_softmax(K.gram(g, C, 0, ci, ci, B, HW, blk=0))
         o = torch.empty_like(g)
-        g3, o3 = g.view(B, HW, C), o.view(B, HW, C)
-        for b in range(B):
-            K.gemm(g3[b, :, ci:], ax[b], scale=gf["gx"], residual=g3[b, :, :ci], out=o3[b, :, :ci])
-            K.gemm(g3[b, :, :ci], ay[b], scale=gf["gy"], residual=g3[b, :, ci:], out=o3[b, :, ci:])
-        st = K.colstats(o, gf["wpix"], B, HW, C)                           # fp64 [B, C, 3]
-        mu = st[..., 0] / HW
-        var = (st[..., 1] / HW - mu * mu).clamp_min(0)
-        rstd = 1.0 / torch.sqrt(var + gf["eps"])
-        gap = (rstd * (st[..., 2] - mu * gf["sum_w"]) / HW + gf["mean_b"]).float()      # GAP of LN_HW(o), [B, C]
-        # ---- FFRM gate (:148-162): 1x1 conv (no bias) -> GN(32) -> ReLU -> sigmoid ----
+        self._per_image_gemm(g[:, ci:], ax, HW, scale=gf["gx"], residual=g[:, :ci], out=o[:, :ci])
+        self._per_image_gemm(g[:, :ci], ay, HW, scale=gf["gy"], residual=g[:, ci:], out=o[:, ci:])
+        # ---- LayerNorm over HW (statistics only) + FFRM gate (:148-162): 1x1 conv -> GN(32) -> ReLU -> sigmoid ----
         ff = lv["ffrm"]
-        a = F.group_norm((gap @ ff["w"].t()).unsqueeze(-1), ff["groups"], ff["gw"], ff["gb"], ff["eps"]).squeeze(-1)
-        gate_v = (1.0 + torch.sigmoid(torch.relu(a))).contiguous()
+        mu, rstd, gate_v = K.ffrm_gate(K.colstats_part(o, gf["wpix"], B, HW, C), HW, gf["sum_w"], gf["mean_b"], gf["eps"],
+                                       ff["w"], ff["gw"], ff["gb"], ff["groups"], ff["eps"])
         # ---- gated Mlp on the local branch (:110-132) ----
         mp = lv["mlp"]
         a1 = K.gemm(l, mp["win"])
         a2 = K.conv3x3(a1, mp["wdw"], B, h, w, 2 * C, 2 * C, mp["groups"])
         u = K.gate(a2, C)
         lo = K.gemm(u, mp["wout"])
-        # ---- LN_HW * gate * s1 + local * s2, coordinate-attention pools ----
-        f, ph, pw = K.combine_pool(o, lo, mu.float().contiguous(), rstd.float().contiguous(), gate_v, gf["wpix"],
-                                   gf["bpix"], lv["s1"], lv["s2"], B, h, w, C)
+        # ---- LN_HW * gate * s1 + local * s2, coordinate-attention pools and vectors ----
+        f, ph, pwp = K.combine_pool(o, lo, mu, rstd, gate_v, gf["wpix"], gf["bpix"], lv["s1"], lv["s2"], B, h, w, C)
         ca = lv["ca"]
-        y = torch.cat((ph / w, pw / h), 1)                                  # [B, h + w, C] pooled means
-        y = (y @ ca["w1"].t() + ca["b1"]) * ca["bs"] + ca["bt"]
-        y = y * F.relu6(y + 3) / 6
-        ah = torch.sigmoid(y[:, :h] @ ca["wh"].t() + ca["bh"]).contiguous()
-        aw = torch.sigmoid(y[:, h:] @ ca["ww"].t() + ca["bw"]).contiguous()
+        ah, aw = K.ca_vectors(ph, pwp, B, h, w, C, ca["w1"], ca["b1"], ca["bs"], ca["bt"], ca["wh"], ca["bh"], ca["ww"], ca["bw"])
         return K.ca_apply(f, ah, aw, B, h, w, C)
 
     @torch.no_grad()

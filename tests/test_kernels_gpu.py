@@ -445,17 +445,23 @@ def test_gram(n, blk, HW, norms):
     B, ld = 2, 3 * n
     g = torch.Generator().manual_seed(n + HW)
     x = torch.randn(B, HW, ld, generator=g).to(torch.bfloat16)
-    r = k.gram(x.reshape(-1, ld).cuda(), ld, 0, n, n, B, HW, blk=blk, norms=norms)
-    S = r[0] if norms else r
+    xc = x.reshape(-1, ld).cuda()
+    r = k.gram(xc, ld, 0, n, n, B, HW, blk=blk, norms=norms)
+    Sp = r[0] if norms else r                              # [nchunks, B, n, n] partial sums of the pixel chunks
     q, kk = x[..., :n].double(), x[..., n:2 * n].double()
     ref = q.transpose(1, 2) @ kk
-    if blk:
+    m = torch.ones(n, n, dtype=torch.bool)
+    if blk:                                                # only the block diagonal is written
         m = (torch.arange(n)[:, None] // blk) == (torch.arange(n)[None, :] // blk)
-        ref = ref * m
-    assert (S.cpu().double() - ref).abs().max() < 2e-3 * math.sqrt(HW)
+    S = torch.where(m, Sp.cpu().double(), torch.zeros((), dtype=torch.float64)).sum(0)
+    assert (S - ref * m).abs().max() < 2e-3 * math.sqrt(HW)
     if norms:
-        nq, nk = r[1], r[2]
-        assert torch.allclose(nq.cpu().double(), (q * q).sum(1), rtol=1e-4) and torch.allclose(nk.cpu().double(), (kk * kk).sum(1), rtol=1e-4)
+        nq, nk = r[1].cpu().double().sum(0), r[2].cpu().double().sum(0)
+        assert torch.allclose(nq, (q * q).sum(1), rtol=1e-4) and torch.allclose(nk, (kk * kk).sum(1), rtol=1e-4)
+    # no atomics: a second launch reproduces every partial sum bit for bit
+    r2 = k.gram(xc, ld, 0, n, n, B, HW, blk=blk, norms=norms)
+    Sp2 = r2[0] if norms else r2
+    assert torch.equal(torch.where(m.cuda(), Sp, torch.zeros((), device="cuda")), torch.where(m.cuda(), Sp2, torch.zeros((), device="cuda")))
 
 
 @pytest.mark.parametrize("B,C,hs,ws,ho,wo", [
@@ -649,8 +655,12 @@ def test_combine_pool_and_ca_apply():
     lo = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
     mu, rstd, gt = torch.randn(B, C, generator=g), torch.rand(B, C, generator=g) + 0.5, torch.rand(B, C, generator=g) + 1
     wp, bp = torch.randn(H * W, generator=g), torch.randn(H * W, generator=g)
-    f, ph, pw = k.combine_pool(o.reshape(-1, C).cuda(), lo.reshape(-1, C).cuda(), mu.cuda(), rstd.cuda(), gt.cuda(),
-                               wp.cuda(), bp.cuda(), 0.7, 1.3, B, H, W, C)
+    args = (o.reshape(-1, C).cuda(), lo.reshape(-1, C).cuda(), mu.cuda(), rstd.cuda(), gt.cuda(), wp.cuda(), bp.cuda(), 0.7, 1.3,
+            B, H, W, C)
+    f, ph, pwp = k.combine_pool(*args)
+    f2, ph2, pwp2 = k.combine_pool(*args)
+    assert torch.equal(ph, ph2) and torch.equal(pwp, pwp2) and torch.equal(f, f2)      # reproducible (no atomics)
+    pw = pwp.sum(0)
     ref = 0.7 * (((o.float() - mu[:, None, None]) * rstd[:, None, None]) * wp.view(1, H, W, 1) + bp.view(1, H, W, 1)) \
         * gt[:, None, None] + 1.3 * lo.float()
     fo = f.float().cpu().view(B, H, W, C)
@@ -660,3 +670,177 @@ def test_combine_pool_and_ca_apply():
     out = k.ca_apply(f, ah.cuda(), aw.cuda(), B, H, W, C).float().cpu().view(B, H, W, C)
     ref2 = f.float().cpu().view(B, H, W, C) * (1 + aw[:, None] * ah[:, :, None])
     assert ((out - ref2).abs() <= 0.01 * ref2.abs() + 0.02).all()
+
+
+def test_neck_glue_kernels_vs_torch():
+    """The O(B*C^2) steps of the fusion neck (adapter_modules_...new.py:98-107, 250-259, 148-162, 187-215) against
+    their torch restatement, from the same partial sums."""
+    k = _k()
+    g = torch.Generator().manual_seed(31)
+    B, ci, heads, HW, nch = 2, 96, 8, 4096, 3
+    ch = ci // heads
+    # --- gfe_weff: chunk partials -> cosine attention -> softmax -> proj fold
+    Sp = torch.randn(nch, B, ci, ci, generator=g) * 30
+    nqp, nkp = torch.rand(nch, B, ci, generator=g) * 400 + 50, torch.rand(nch, B, ci, generator=g) * 400 + 50
+    temp = torch.rand(heads, generator=g) + 0.5
+    wp = torch.randn(ci, ci, generator=g) * 0.1
+    s2 = torch.tensor([0.7])
+    weff = k.gfe_weff(Sp.cuda(), nqp.cuda(), nkp.cuda(), temp.cuda(), wp.cuda(), s2.cuda(), heads).float().cpu()
+    S = Sp.sum(0).view(B, heads, ch, heads, ch).diagonal(dim1=1, dim2=3).permute(0, 3, 1, 2)       # [B, heads, ch, ch]
+    qn = nqp.sum(0).sqrt().clamp_min(1e-12).view(B, heads, ch, 1)
+    kn = nkp.sum(0).sqrt().clamp_min(1e-12).view(B, heads, 1, ch)
+    att = torch.softmax(S / (qn * kn) * temp.view(1, heads, 1, 1), -1)
+    ref = (torch.einsum("iha,bhaj->bihj", wp.view(ci, heads, ch), att) * s2).reshape(B, ci, ci)
+    assert (weff - ref).abs().max() < 4e-3 * ref.abs().max() + 1e-4
+    # --- gffm_softmax
+    Ep = torch.randn(nch, B, ci, ci, generator=g) * 3
+    ax, ay = k.gffm_softmax(Ep.cuda())
+    E = Ep.sum(0)
+    assert (ax.float().cpu() - torch.softmax(E, -1)).abs().max() < 4e-3
+    assert (ay.float().cpu() - torch.softmax(E.transpose(1, 2), -1)).abs().max() < 4e-3
+    # --- ffrm_gate: LayerNorm-over-HW statistics, GAP, 1x1 conv, GroupNorm(32), ReLU, sigmoid
+    C = 192
+    o = (torch.randn(B, HW, C, generator=g) * 2 + 0.3).to(torch.bfloat16)
+    wpix, bpix = torch.randn(HW, generator=g), torch.randn(HW, generator=g)
+    wf = torch.randn(C, C, generator=g) * 0.2
+    gw, gb = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    part = k.colstats_part(o.reshape(-1, C).cuda(), wpix.cuda(), B, HW, C)
+    mu, rstd, gate = k.ffrm_gate(part, HW, float(wpix.double().sum()), float(bpix.double().mean()), 1e-5, wf.cuda(), gw.cuda(),
+                                 gb.cuda(), 32, 1e-5)
+    od = o.double()
+    mu_r, var_r = od.mean(1), od.var(1, unbiased=False)
+    ln = (od - mu_r[:, None]) / torch.sqrt(var_r[:, None] + 1e-5) * wpix.double()[None, :, None] + bpix.double()[None, :, None]
+    gap = ln.mean(1).float()
+    a = torch.nn.functional.group_norm((gap @ wf.t()).unsqueeze(-1), 32, gw, gb, 1e-5).squeeze(-1)
+    gate_r = 1 + torch.sigmoid(torch.relu(a))
+    assert torch.allclose(mu.cpu().double(), mu_r, atol=1e-4) and torch.allclose(rstd.cpu().double(), 1 / torch.sqrt(var_r + 1e-5), rtol=1e-4)
+    assert (gate.cpu() - gate_r).abs().max() < 2e-3
+    # --- ca_vectors
+    H, W, mip, ns = 12, 20, 8, 3
+    ph = torch.randn(B, H, C, generator=g) * W
+    pwp = torch.randn(ns, B, W, C, generator=g) * H / ns
+    w1, b1 = torch.randn(mip, C, generator=g) * 0.1, torch.randn(mip, generator=g) * 0.1
+    bs, bt = torch.rand(mip, generator=g) + 0.5, torch.randn(mip, generator=g) * 0.1
+    wh, bh = torch.randn(C, mip, generator=g) * 0.3, torch.randn(C, generator=g) * 0.1
+    ww, bw = torch.randn(C, mip, generator=g) * 0.3, torch.randn(C, generator=g) * 0.1
+    ah, aw = k.ca_vectors(ph.cuda(), pwp.cuda(), B, H, W, C, *(t.cuda() for t in (w1, b1, bs, bt, wh, bh, ww, bw)))
+    y = torch.cat((ph / W, pwp.sum(0) / H), 1)
+    y = (y @ w1.t() + b1) * bs + bt
+    y = y * torch.nn.functional.relu6(y + 3) / 6
+    assert (ah.cpu() - torch.sigmoid(y[:, :H] @ wh.t() + bh)).abs().max() < 1e-4
+    assert (aw.cpu() - torch.sigmoid(y[:, H:] @ ww.t() + bw)).abs().max() < 1e-4
+
+
+def test_gemm_grouped_per_image_weights():
+    """mmsam_gemm_grouped_bf16: rows of image b use weight b (fusion-neck per-image products), one launch."""
+    k = _k()
+    g = torch.Generator().manual_seed(77)
+    G, rows, N, K = 3, 512, 96, 96
+    a = torch.randn(G * rows, 3 * K, generator=g).to(torch.bfloat16)        # strided A: columns [2K, 3K) of a wider matrix
+    w = (torch.randn(G, N, K, generator=g) * 0.1).to(torch.bfloat16)
+    res = torch.randn(G * rows, N, generator=g).to(torch.bfloat16)
+    scale = torch.rand(N, generator=g) + 0.5
+    out = torch.empty(G * rows, 2 * N, dtype=torch.bfloat16, device="cuda")
+    ac = a.cuda()
+    k.gemm_grouped(ac[:, 2 * K:], w.cuda(), rows, scale=scale.cuda(), residual=res.cuda(), out=out[:, N:])
+    ref = torch.cat([(a[i * rows:(i + 1) * rows, 2 * K:].float() @ w[i].float().t()) for i in range(G)]) * scale + res.float()
+    got = out[:, N:].float().cpu()
+    assert ((got - ref).abs() <= 0.01 * ref.abs() + 0.02).all()
+
+
+@pytest.mark.parametrize("C,mode", [(96, "f32"), (384, "f32"), (1024, "f32"), (96, "bf16"), (1024, "bf16"), (192, "patchify")])
+def test_layernorm_fp32_stream(C, mode):
+    """fp32 input (the fp32 residual streams) -> fp32 or bf16 output, incl. the 2x2 patchify scatter."""
+    k = _k()
+    g = torch.Generator().manual_seed(C)
+    H, W = 6, 10
+    x = torch.randn(2 * H * W, C, generator=g) * 3 + 0.5
+    w, b = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    ref = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-6)
+    if mode == "f32":
+        out = k.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-6, out_dtype=torch.float32)
+        assert out.dtype == torch.float32 and (out.cpu() - ref).abs().max() < 1e-4
+        xc = x.cuda()
+        k.layernorm(xc, w.cuda(), b.cuda(), 1e-6, out=xc)                   # in place
+        assert (xc.cpu() - ref).abs().max() < 1e-4
+    elif mode == "bf16":
+        out = k.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-6)
+        assert out.dtype == torch.bfloat16 and ((out.float().cpu() - ref).abs() <= 0.004 * ref.abs() + 1e-3).all()
+    else:
+        out = k.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-6, patchify_hw=(H, W)).float().cpu()
+        exp = ref.view(2, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(2 * (H // 2) * (W // 2), 4 * C)
+        assert ((out - exp).abs() <= 0.004 * exp.abs() + 1e-3).all()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(1000, 384, 1536, 0), (4096, 1024, 1024, 256), (777, 96, 384, 0), (640, 1024, 512, 128)])
+def test_gemm_fp32_residual_stream(M, N, K, bn):
+    """fp32 output + fp32 residual, in place (proj / lin2 / pw2 on the fp32 residual streams), with bias and column scale."""
+    k = _k()
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias, scale = torch.randn(N, generator=g), torch.rand(N, generator=g) + 0.5
+    x = torch.randn(M, N, generator=g) * 4
+    ref = _gemm_ref(a, w, bias=bias, scale=scale, residual=x)
+    xc = x.cuda()
+    out = k.gemm(a.cuda(), w.cuda(), bias=bias.cuda(), scale=scale.cuda(), residual=xc, out=xc, block_n=bn)
+    assert out.dtype == torch.float32 and out.data_ptr() == xc.data_ptr()
+    assert (out.cpu().double() - ref).abs().max() < 2e-3 * math.sqrt(K / 64)
+    out2 = k.gemm(a.cuda(), w.cuda(), residual=x.cuda(), out_dtype=torch.float32)          # fresh output buffer
+    assert (out2.cpu().double() - _gemm_ref(a, w, residual=x)).abs().max() < 2e-3 * math.sqrt(K / 64)
+
+
+def test_dwconv_fp32_input_and_resize_fp32_source():
+    k = _k()
+    g = torch.Generator().manual_seed(5)
+    B, C, h, w = 2, 96, 20, 37
+    x = torch.randn(B, h * w, C, generator=g) * 2
+    wt = torch.randn(C, 1, 7, 7, generator=g) / 7
+    bias = torch.randn(C, generator=g)
+    out = k.dwconv(x.cuda(), wt.reshape(C, 49).t().contiguous().cuda(), bias.cuda(), 7, [(h, w)], B, C, h * w * C, h * w * C)
+    assert out.dtype == torch.bfloat16
+    xi = x.to(torch.bfloat16).float().reshape(B, h, w, C).permute(0, 3, 1, 2)       # the kernel rounds the staged input once
+    ref = torch.nn.functional.conv2d(xi, wt, bias, padding=3, groups=C).permute(0, 2, 3, 1).reshape(B, h * w, C)
+    assert ((out.float().cpu() - ref).abs() <= 0.008 * ref.abs() + 4e-3).all()
+    src = torch.randn(B, 8, 8, 128, generator=g)
+    base = torch.randn(B, 32, 32, 128, generator=g).to(torch.bfloat16)
+    got = k.resize_add_affine(src.cuda(), (8, 8), (32, 32), B, 128, base=base.cuda()).float().cpu()
+    up = torch.nn.functional.interpolate(src.permute(0, 3, 1, 2), size=(32, 32), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    assert ((got - (up + base.float())).abs() <= 0.008 * (up + base.float()).abs() + 4e-3).all()
+
+
+@pytest.mark.parametrize("Lq,shapes", [(4096, [(128, 128), (64, 64), (32, 32)]), (21504, [(64, 64)])])
+def test_msda_baseline_shapes_vs_oracle(Lq, shapes):
+    """Kernel-level parity at the BASELINE shapes: injector (Lq 4096, S 21504, L 3) and extractor
+    (Lq 21504, S 4096, L 1), M 16, D 32, P 4, one image: the generic entry point (mmsam_msda_forward, bf16 value + fp32
+    locations / weights) and the fused front end (mmsam_msda_fused_bf16) against the CPU oracle."""
+    from oracle.msda import ms_deform_attn_core
+    k = _k()
+    g = torch.Generator().manual_seed(Lq)
+    N, M, D, P, L = 1, 16, 32, 4, len(shapes)
+    S = sum(h * w for h, w in shapes)
+    shp = torch.as_tensor(shapes, dtype=torch.long)
+    lsi = torch.cat((shp.new_zeros((1,)), shp.prod(1).cumsum(0)[:-1]))
+    value = torch.randn(N, S, M, D, generator=g).to(torch.bfloat16)
+    # queries on a grid of cell centres (reference points), offsets of a few pixels, joint softmax over L*P
+    side = int(round(math.sqrt(Lq))) if L == 3 else None
+    if L == 3:
+        ys, xs = torch.meshgrid((torch.arange(side) + 0.5) / side, (torch.arange(side) + 0.5) / side, indexing="ij")
+        ref = torch.stack((xs.reshape(-1), ys.reshape(-1)), -1)
+    else:
+        pts = []
+        for hh in (128, 64, 32):
+            ys, xs = torch.meshgrid((torch.arange(hh) + 0.5) / hh, (torch.arange(hh) + 0.5) / hh, indexing="ij")
+            pts.append(torch.stack((xs.reshape(-1), ys.reshape(-1)), -1))
+        ref = torch.cat(pts)
+    off = torch.randn(N, Lq, M, L, P, 2, generator=g) * 2.5
+    logit = torch.randn(N, Lq, M, L * P, generator=g)
+    wh = torch.stack((shp[:, 1], shp[:, 0]), -1).float()
+    loc = ref[None, :, None, None, None, :] + off / wh[None, None, None, :, None, :]
+    aw = torch.softmax(logit, -1).view(N, Lq, M, L, P)
+    want = ms_deform_attn_core(value.float(), shp, loc, aw)
+    got = k.msda_forward(value.cuda(), shp.cuda(), lsi.cuda(), loc.cuda(), aw.cuda()).float().cpu()
+    assert (got - want).abs().max() < 1e-3 + 0.008 * want.abs().max()           # one bf16 rounding of the output
+    qproj = torch.cat((off.reshape(N * Lq, -1), logit.reshape(N * Lq, -1)), 1).contiguous()
+    got2 = k.msda_fused(value.view(N, S, M * D).cuda(), shp.cuda(), lsi.cuda(), qproj.cuda(), ref.contiguous().cuda(), M, L, P).float().cpu()
+    assert (got2 - want).abs().max() < 1e-3 + 0.008 * want.abs().max()

@@ -353,3 +353,138 @@ def test_bucketed_confusion_on_device():
     assert torch.equal(conf[bc.index["motionblur"]], ref([2]))
     assert int(conf[bc.index["night"]].sum()) == 0
     assert abs(bc.metrics()["cloud"]["mIoU"] - em.metrics_from_confusion(ref([0, 2]))["mIoU"]) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Goldens produced by the reference's own head / blocks / full models (tools/make_golden.py), at the sizes BASELINE names
+# ---------------------------------------------------------------------------------------------------------------------
+def _margin_report(name, got_labels, ref_logits):
+    """All-pixel argmax agreement + the oracle top-2 margins of the disagreeing pixels (in units of the logit spread)."""
+    want = ref_logits.argmax(1)
+    ok = got_labels.long() == want
+    top2 = ref_logits.topk(2, dim=1).values
+    rel = (top2[:, 0] - top2[:, 1]) / ref_logits.std(dim=1)
+    bad = rel[~ok]
+    worst = bad.max().item() if bad.numel() else 0.0
+    print(f"{name}: argmax agreement {ok.float().mean().item() * 100:.4f}% of {ok.numel()} pixels; disagreeing pixels: "
+          f"{bad.numel()}, largest oracle margin among them {worst:.4f} of the logit spread "
+          f"(median margin of all pixels {rel.median().item():.3f})")
+    return ok.float().mean().item(), worst
+
+
+def test_head_vitl_vs_reference_golden():
+    """a18: the reference's SegformerHead.forward at the ViT-L head size, random feature maps."""
+    import bench
+    import mmsam_b200  # noqa
+    from mmsam_b200.backbone import SegformerHead
+    from mmsam_b200.engine import ComponentRunner
+    from oracle.perturb import perturb_state_dict
+    rec = torch.load(os.path.join(GOLD, "head_vitl.pt"))
+    torch.manual_seed(31)
+    head = SegformerHead(**bench.VITL_HEAD)
+    sd = perturb_state_dict(head.state_dict(), seed=6)
+    assert sd_digest(sd) == rec["digest"]
+    head.load_state_dict(sd)
+    g = torch.Generator().manual_seed(rec["seed"])
+    feats = [torch.randn(2, 1024, 64 >> i, 64 >> i, generator=g) for i in range(4)]
+    out = ComponentRunner(1024, 16).head(head.eval(), [f.cuda() for f in feats]).cpu()
+    r, c = _report("head (ViT-L size) vs reference", out, rec["out"])
+    assert out.shape == rec["out"].shape and r < 1.5e-2 and c > COS_TOL
+
+
+def test_blocks_68x120_config5b_vs_reference_golden():
+    """BASELINE config 5b: Block (window / global, 8160 tokens) and InteractionBlock on the 1088 x 1920 geometry."""
+    import mmsam_b200  # noqa
+    from mmsam_b200 import nn_modules as M
+    from mmsam_b200.engine import ComponentRunner
+    from mmsam_b200.ops.modules import MSDeformAttn
+    from oracle.perturb import perturb_state_dict
+    rec = torch.load(os.path.join(GOLD, "blocks_68x120.pt"))
+    H, W, dim, nh = rec["H"], rec["W"], rec["dim"], rec["nh"]
+    run = ComponentRunner(dim, nh)
+    x = torch.randn(1, H * W, dim, generator=torch.Generator().manual_seed(rec["x_seed"]))
+    for name, ws in (("window", 14), ("global", 0)):
+        torch.manual_seed(42)
+        blk = M.Block(dim, nh, 4.0, True, True, ws, (64, 64))
+        blk.load_state_dict(perturb_state_dict(blk.state_dict(), seed=7))
+        out = run.block(blk, x.cuda(), H, W).float().cpu()
+        r = rec[name]
+        rl, c = _report(f"68x120 block {name}", out.reshape(-1)[r["idx"]], r["vals"])
+        assert rl < REL_TOL and c > COS_TOL and abs(out.norm().item() - r["norm"]) / r["norm"] < 1e-2
+    r = rec["interaction"]
+    torch.manual_seed(44)
+    it = M.InteractionBlock(dim, nh, 4, True, 0.25, 0.5, 0.5, True, MSDeformAttn)
+    it.load_state_dict(perturb_state_dict(it.state_dict(), seed=8))
+    g = torch.Generator().manual_seed(r["seed"])
+    xq = torch.randn(1, H * W, dim, generator=g)
+    c = torch.randn(1, r["S3"], dim, generator=g)
+    xo, co = run.interaction(it, xq.cuda(), c.cuda(), r["Hi"], r["Wi"])
+    r1, c1 = _report("68x120 interaction x", xo.float().cpu().reshape(-1)[r["idx_x"]], r["vals_x"])
+    r2, c2 = _report("68x120 interaction c", co.float().cpu().reshape(-1)[r["idx_c"]], r["vals_c"])
+    assert r1 < REL_TOL and r2 < REL_TOL and c1 > COS_TOL and c2 > COS_TOL
+
+
+def _full_size_vs_reference(rec, bcfg, hcfg, size, kind, btype, test_cfg, rescale, zero_rows_from=None):
+    from oracle.perturb import synthetic_batch
+    seg, sd = build_segmentor(bcfg, hcfg, test_cfg=test_cfg, btype=btype)
+    assert sd_digest(sd) == rec["digest"]
+    seg = seg.cuda()
+    x = synthetic_batch(1, size, kind=kind)
+    if zero_rows_from is not None:
+        x[:, :, zero_rows_from:] = 0
+    feats, _ = seg.backbone(x.cuda())
+    worst = 0.0
+    for i, (f, idx, vals, nrm) in enumerate(zip(feats, rec["idx"], rec["vals"], rec["norms"])):
+        rl, c = _report(f"f{i + 1} vs reference samples", f.float().cpu().reshape(-1)[idx], vals)
+        assert rl < REL_TOL and c > COS_TOL and abs(f.float().norm().item() - nrm) / nrm < 2e-2
+        worst = max(worst, rl)
+    import numpy as np
+    labels = torch.as_tensor(np.stack(seg.simple_test(x.cuda(), None, rescale)))
+    assert labels.shape == rec["labels"].shape
+    agree = (labels == rec["labels"].long()).float().mean().item()
+    print(f"labels vs the reference's own simple_test: {agree * 100:.4f}% of {labels.numel()} pixels agree")
+    return agree, worst
+
+
+@pytest.mark.timeout(900)
+def test_fmb800_config4_full_size_vs_reference_golden():
+    """BASELINE config 4 at its full size: ...NEWwithcp ViT-L, 800 x 800 padded input, 14 classes, whole_dim_cut (rescale
+    off as in the reference test loop) -> [600, 800] labels, against the reference's own outputs."""
+    from common import FMB, FMB_HEAD, FMB_TEST_CFG
+    rec = torch.load(os.path.join(GOLD, "fmb800_samples.pt"))
+    agree, _ = _full_size_vs_reference(rec, FMB, FMB_HEAD, 800, "thermal", "SAMAdapterbimodalMixModNewInTwinConvNEWwithcp",
+                                       dict(FMB_TEST_CFG), False, zero_rows_from=600)
+    assert agree >= 0.98
+
+
+@pytest.mark.timeout(900)
+def test_vitl1024_config2_vs_reference_golden():
+    """BASELINE config 2, one image, against the reference's own feature samples and label map."""
+    import bench
+    rec = torch.load(os.path.join(GOLD, "vitl1024_samples.pt"))
+    agree, _ = _full_size_vs_reference(rec, bench.VITL, bench.VITL_HEAD, 1024, "lidar", "SAMAdapterbimodalMixModNewInTwinConvNEW",
+                                       dict(bench.TEST_CFG), True)
+    assert agree >= 0.98
+
+
+def test_outputs_are_bit_reproducible(tiny):
+    """No floating-point atomics on the path: two runs, eager vs CUDA-graph replay, and batch-of-1 vs the same image inside
+    a larger batch give IDENTICAL features and labels."""
+    from oracle.perturb import synthetic_batch
+    seg, _ = tiny
+    seg = seg.cuda()
+    x = synthetic_batch(3, 128, seed=91).cuda()
+    f1, _ = seg.backbone(x)
+    f2, _ = seg.backbone(x)
+    for a, b in zip(f1, f2):
+        assert torch.equal(a, b)
+    fa, _ = seg.backbone(x[1:2])
+    for a, b in zip(fa, f1):
+        assert torch.equal(a[0], b[1])                       # an image's result does not depend on its batch
+    seg.use_cuda_graph = False
+    le = seg.encode_decode_labels(x, (128, 128)).clone()
+    seg.use_cuda_graph = True
+    lg1 = seg.encode_decode_labels(x, (128, 128)).clone()
+    lg2 = seg.encode_decode_labels(x, (128, 128)).clone()
+    assert torch.equal(le, lg1) and torch.equal(lg1, lg2)
+    assert torch.equal(seg.encode_decode_labels(x[2:3], (128, 128))[0], le[2])

@@ -147,7 +147,8 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert _lib.load().mmsam_arch() == 100
     # the ctypes stub must agree with every prototype: parameter count and the C type class of each parameter
-    kind = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_longlong: "ll", ctypes.c_float: "float"}
+    kind = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_longlong: "ll", ctypes.c_float: "float",
+            ctypes.c_double: "double"}
     for name, params in re.findall(r"^int\s+(mmsam_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.M | re.S):
         plist = [q.strip() for q in params.replace("\n", " ").split(",")]
         if plist == ["void"]:
@@ -160,6 +161,8 @@ def test_c_abi_exports_every_declared_symbol():
                 want.append("ll")
             elif re.match(r"^(const\s+)?float\b", q):
                 want.append("float")
+            elif re.match(r"^(const\s+)?double\b", q):
+                want.append("double")
             else:
                 assert re.match(r"^(const\s+)?int\b", q), (name, q)
                 want.append("int")
