@@ -186,18 +186,18 @@ static int launch_gram_tc(const CUtensorMap& tm, const GramParams& p, dim3 grid,
 
 }  // namespace mmsam
 
-// Pixel chunking of the tensor-core path: enough CTAs for every SM, at least 4 stages of work each. Returns the number
-// of chunks (= partial sums per element), 0 when the shape does not fit this path.
+// Pixel chunking of the tensor-core path. It depends on the map size ONLY (not on the batch or the tile count): an
+// image's partial sums are then the same whatever batch it sits in, which makes the whole forward batch-invariant bit
+// for bit. HW / 32 pixels per chunk, clamped to [256, 2048] (>= 4 pipeline stages of 64 pixels per CTA; 32 chunks x
+// tiles x images CTAs on the large maps). Returns the number of chunks, 0 when the shape does not fit this path.
 int mmsam_gram_tc_plan(int n, int B, int HW, int norms, int* chunk_out) {
   using namespace mmsam;
+  (void)n; (void)norms;
   if (HW % GR_KP != 0 || (long long)B * HW > 0x7fffffffLL) return 0;
-  const int bnj = (norms || n <= 128) ? 128 : 256;
-  const int tiles = ((n + 127) / 128) * ((n + bnj - 1) / bnj) * B;
-  int nchunks = (2 * kNumSMs + tiles - 1) / tiles;
-  const int maxchunks = HW / (4 * GR_KP) > 0 ? HW / (4 * GR_KP) : 1;
-  if (nchunks > maxchunks) nchunks = maxchunks;
-  if (nchunks < 1) nchunks = 1;
-  int chunk = (HW + nchunks - 1) / nchunks;
+  int chunk = HW / 32;
+  if (chunk < 4 * GR_KP) chunk = 4 * GR_KP;
+  if (chunk > 2048) chunk = 2048;
+  if (chunk > HW) chunk = HW;
   chunk = (chunk + GR_KP - 1) / GR_KP * GR_KP;
   if (chunk_out) *chunk_out = chunk;
   return (HW + chunk - 1) / chunk;

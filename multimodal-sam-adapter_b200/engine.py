@@ -558,7 +558,10 @@ class EncoderEngine(_Ops):
         else:
             fx = self._convnext_branch(img, 0, self.cnx["x"], B, Hi, Wi)
             fy = self._convnext_branch(img, self.cin, self.cnx["y"], B, Hi, Wi)
-        fused = self.neck(fx, fy, B)                                    # 4 x [B*h*w, 2*Ci] bf16
+        nd = [] if debug is not None else None
+        fused = self.neck(fx, fy, B, debug=nd)                          # 4 x [B*h*w, 2*Ci] bf16
+        if debug is not None:
+            debug["neck"] = nd
         if debug is not None:
             debug.update(fx=[(t.clone(), h, w) for t, h, w in fx], fy=[(t.clone(), h, w) for t, h, w in fy], fused=[t.clone() for t in fused])
         c1 = self._gemm(fused[0], self.fc[0])                            # [B*16T, C]

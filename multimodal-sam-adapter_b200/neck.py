@@ -126,7 +126,7 @@ class NeckB200:
         h2 = K.dwconv(h1, p["dw"], None, 3, [(h, w)], B, 2 * ci, h * w * 2 * ci, h * w * 2 * ci, act="relu6")
         K.gemm(h2, p["w4"], scale=p["scale"], residual=x, out=l_out[:, col0:col0 + ci])
 
-    def _level(self, lv, tx, ty, B, h, w):
+    def _level(self, lv, tx, ty, B, h, w, debug=None):
         dev = self.dev
         C, ci, HW = lv["C"], lv["ci"], h * w
         gf = lv["gffm"]
@@ -156,16 +156,19 @@ class NeckB200:
         lo = K.gemm(u, mp["wout"])
         # ---- LN_HW * gate * s1 + local * s2, coordinate-attention pools and vectors ----
         f, ph, pwp = K.combine_pool(o, lo, mu, rstd, gate_v, gf["wpix"], gf["bpix"], lv["s1"], lv["s2"], B, h, w, C)
+        if debug is not None:
+            debug.append(dict(g=g.clone(), l=l.clone(), o=o.clone(), lo=lo.clone(), f=f.clone(), mu=mu.clone(), rstd=rstd.clone(),
+                              gate=gate_v.clone()))
         ca = lv["ca"]
         ah, aw = K.ca_vectors(ph, pwp, B, h, w, C, ca["w1"], ca["b1"], ca["bs"], ca["bt"], ca["wh"], ca["bh"], ca["ww"], ca["bw"])
         return K.ca_apply(f, ah, aw, B, h, w, C)
 
     @torch.no_grad()
-    def __call__(self, fx, fy, B):
+    def __call__(self, fx, fy, B, debug=None):
         """fx / fy: per level (tokens bf16 [B*h*w, ci], h, w) -> list of fused tokens bf16 [B*h*w, C]."""
         items = list(zip(self.levels, fx, fy))
-        if os.environ.get("MMSAM_NECK_STREAMS", "1") == "0" or len(items) < 2:
-            return [self._level(lv, tx, ty, B, h, w) for lv, (tx, h, w), (ty, _, _) in items]
+        if os.environ.get("MMSAM_NECK_STREAMS", "1") == "0" or len(items) < 2 or debug is not None:
+            return [self._level(lv, tx, ty, B, h, w, debug) for lv, (tx, h, w), (ty, _, _) in items]
         # The four pyramid levels are independent until the backbone consumes them, and the kernels of the small levels
         # (32^2 / 64^2 / 128^2 maps: a handful of CTAs each, plus the O(B*C^2) glue) leave most of the GPU idle: they
         # run on side streams next to the 256^2 level (fork / join on the current stream; inside a CUDA graph capture

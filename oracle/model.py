@@ -304,7 +304,7 @@ def coord_att(x, s):
     return x + x * aw * ah
 
 
-def roadformer_neck(feats, s):
+def roadformer_neck(feats, s, stages=None):
     """A:364-394."""
     out = []
     for i, f in enumerate(feats):
@@ -312,11 +312,17 @@ def roadformer_neck(feats, s):
         rgb, aux = f[:, :c], f[:, c:]
         g = torch.cat((gfe(rgb, s.sub(f"global_feature_encoder_rgb.{i}")), gfe(aux, s.sub(f"global_feature_encoder_sne.{i}"))), 1)
         l = torch.cat((mobilenet_v2(rgb, s.sub(f"local_feature_encoder_rgb.{i}")), mobilenet_v2(aux, s.sub(f"local_feature_encoder_sne.{i}"))), 1)
+        if stages is not None:
+            stages.append(dict(g=g.clone(), l=l.clone()))
         g = gffm(g, s.sub(f"fuse_blocks.{i}"))
         l = gated_mlp(l, s.sub(f"detail_feature_extractions.{i}"))
+        if stages is not None:
+            stages[-1].update(o_ln=g.clone(), lo=l.clone())
         g = ffrm(g, s.sub(f"enhance_blocks.{i}"))
         sc = s.sub(f"scale_layers.{i}")
         f2 = g * sc("scale1") + l * sc("scale2")
+        if stages is not None:
+            stages[-1].update(f=f2.clone())
         out.append(coord_att(f2, s.sub(f"ca_blocks.{i}.coord_atten")))
     return out
 
@@ -326,9 +332,11 @@ def spm_bimodal(x, y, s, depths, stages=None):
     tw = twin_convnext(x, y, s.sub("twin_conv"), depths)
     if stages is not None:
         stages["twin"] = [t.clone() for t in tw]
-    feats = roadformer_neck(tw, s.sub("smart_fusion"))
+    nst = [] if stages is not None else None
+    feats = roadformer_neck(tw, s.sub("smart_fusion"), nst)
     if stages is not None:
         stages["fused"] = [t.clone() for t in feats]
+        stages["neck"] = nst
     cs = []
     for i, f in enumerate(feats):
         t = F.conv2d(f, s(f"fc{i + 1}.weight"), s(f"fc{i + 1}.bias"))

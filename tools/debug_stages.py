@@ -12,7 +12,12 @@ from oracle import model as om  # noqa
 from oracle.perturb import synthetic_batch  # noqa
 
 which = sys.argv[1] if len(sys.argv) > 1 else "tiny"
-cfg, hcfg = (TINY, TINY_HEAD) if which == "tiny" else (VITB, VITB_HEAD)
+if which == "vitl":
+    import bench
+    cfg, hcfg = bench.VITL, bench.VITL_HEAD
+    torch.set_num_threads(os.cpu_count() or 1)
+else:
+    cfg, hcfg = (TINY, TINY_HEAD) if which == "tiny" else (VITB, VITB_HEAD)
 seg, sd = build_segmentor(cfg, hcfg)
 x = synthetic_batch(1, cfg["img_size"])
 st = {}
@@ -33,7 +38,10 @@ for i in range(4):
     ci = tw.shape[1] // 2
     print(f"twin level {i}: rgb {rel_l2(dbg['fx'][i][0].float().cpu(), tok(tw[:, :ci])):.3e} aux {rel_l2(dbg['fy'][i][0].float().cpu(), tok(tw[:, ci:])):.3e}")
 for i in range(4):
-    print(f"fused level {i}: {rel_l2(dbg['fused'][i].float().cpu(), tok(st['fused'][i])):.3e}")
+    nd, no = dbg["neck"][i], st["neck"][i]
+    print(f"neck level {i}: g {rel_l2(nd['g'].float().cpu(), tok(no['g'])):.3e} l {rel_l2(nd['l'].float().cpu(), tok(no['l'])):.3e} "
+          f"lo {rel_l2(nd['lo'].float().cpu(), tok(no['lo'])):.3e} f {rel_l2(nd['f'].float().cpu(), tok(no['f'])):.3e} "
+          f"fused {rel_l2(dbg['fused'][i].float().cpu(), tok(st['fused'][i])):.3e}")
 print("c1", rel_l2(dbg["c1"].float().cpu(), st["c1"][0]))
 print("c_0", rel_l2(dbg["c_0"].float().cpu(), st["c_0"][0]))
 print("x_0", rel_l2(dbg["x_0"].float().cpu(), st["x_0"][0]))
