@@ -149,6 +149,16 @@ int mmsam_dwconv(const void* x, int x_dtype, void* y, const float* w_tap_major, 
 int mmsam_normalize_u8(const void* img_hwc_u8, float* out_nchw, int B, int H, int W, int C, int Ctot, int c_off,
                        const float* mean_host, const float* std_host, float prescale, void* stream);
 
+/* One modality's decoded image, HWC uint8 [B, Hs, Ws, C] (C <= 4), straight to the bf16 patch rows
+ * [(b,py,px), (c,ky,kx)] of the p x p / stride p conv that consumes it (p = 4: ConvNeXt stem, 16: ViT patch embed):
+ * zero-extended to H x W with pad_val (Pad_multimodal, pipelines/transform.py:2934, applied before the normalisation),
+ * (v * prescale - mean[c]) / std[c] (Normalize_multimodal, :2717-2815; norm_by_max: prescale = 1/255), swap_rb != 0
+ * reverses the channel order first (to_rgb of mmcv.imnormalize). Replaces normalise + ImageToTensor + patchify: the
+ * fp32 NCHW network input is never materialised. mean / std are HOST pointers. */
+int mmsam_patchify_u8(const void* img_hwc_u8, void* out, int B, int Hs, int Ws, int C, int H, int W, int p,
+                      const float* mean_host, const float* std_host, float prescale, float pad_val, int swap_rb,
+                      void* stream);
+
 /* NCHW fp32 image channels [c_off, c_off+C) -> bf16 rows [(b,py,px), (c,ky,kx)] for p x p / stride p
  * convs as GEMMs (patch embed base/image_encoder.py:662-671; ConvNeXt stem twin_convnext.py:295-312). */
 int mmsam_patchify_f32(const float* img, void* out, int B, int Ctot, int c_off, int C, int H, int W, int p,
@@ -176,6 +186,19 @@ int mmsam_resize_sum_affine_bf16(const void* base, int nsrc, const void* src0, c
  * resize + softmax + argmax (+ crop) of segmentors/encoder_decoder.py:96-117, 329-414, 449, 477. */
 int mmsam_upsample_argmax_f32(const float* logits, void* labels_u8, int B, int hs, int ws, int ldl, int ncls,
                               int Ho, int Wo, int Hc, int Wc, void* stream);
+
+/* Bilinear resize (align_corners=False) of channels-last fp32 logits [B, hs, ws, ld] -> [B, Ho, Wo, ld] (ld % 4 == 0): the
+ * chained resizes of EncoderDecoder when they are not identities (encode_decode -> image size, then whole_inference ->
+ * ori_shape / whole_inference_dim -> test_cfg.dim; encoder_decoder.py:103-107, 317-325, 341-346). */
+int mmsam_resize_logits_f32(const float* src, float* dst, int B, int hs, int ws, int ld, int Ho, int Wo, void* stream);
+
+/* slide_inference after the head (encoder_decoder.py:198-226) in one pass over the frame: crop j of image b is
+ * crop_logits[j * B + b] (fp32 [hs, ws, ld] at the head's resolution); crop_boxes_host [ncrops][4] = (y1, x1, y2, x2) in
+ * frame pixels (HOST pointer, ncrops <= 16). Per frame pixel: sum over the covering crops of the crop logits resized to
+ * the crop size, divided by the overlap count; labels_u8 [B, H, W] = argmax (optional), preds fp32 [B, H, W, ld] (optional:
+ * when a rescale to ori_shape follows, :223-229). ld <= 32. */
+int mmsam_slide_merge_f32(const float* crop_logits, void* labels_u8, float* preds, int B, int hs, int ws, int ld, int ncls,
+                          int H, int W, int ncrops, const int* crop_boxes_host, void* stream);
 
 /* conf_u64[gt*ncls + pred] += 1 for every pixel with gt != ignore_index: device-side
  * intersect_and_union (mmseg_custom/apis/evaluation/metrics_micro.py:26-86). */

@@ -28,6 +28,9 @@ SIGNATURES = {
                                      _vp, _vp, _i, _vp],
     "mmsam_dwconv": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _ll, _i, _vp],
     "mmsam_normalize_u8": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp],
+    "mmsam_patchify_u8": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _f, _i, _vp],
+    "mmsam_resize_logits_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "mmsam_slide_merge_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "mmsam_patchify_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_resize_add_affine": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _vp],
     "mmsam_resize_sum_affine_bf16": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],

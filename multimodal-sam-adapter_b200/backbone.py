@@ -214,14 +214,38 @@ class EncoderDecoder(nn.Module):
             return self._engine().segment_graphed(img, out_hw, crop_hw)
         return self._engine().segment(img, out_hw, crop_hw)
 
+    def set_input_pipeline(self, mean, std, to_rgb=(False, False), norm_by_max=True, pad_size=None, pad_val=0.0):
+        """The test pipeline's Normalize_multimodal + Pad_multimodal arguments (the config's `mod_norm_cfg`, `norm_by_max`,
+        `Pad_multimodal(size=..., pad_val=...)`: pipelines/transform.py:2717-2815, 2934): mean / std are the concatenated
+        per-channel statistics of [rgb | auxiliary]. Enables the uint8 entry points (stream_labels on (rgb_u8, aux_u8) batches,
+        u8_input): normalisation, padding and the HWC -> CHW transpose then run inside the stem / patch-embed kernels."""
+        cin = self.backbone.in_ch_im
+        pre = 1.0 / 255.0 if norm_by_max else 1.0
+        self._pipeline = dict(rgb=(list(mean[:cin]), list(std[:cin]), pre, bool(to_rgb[0])),
+                              aux=(list(mean[cin:]), list(std[cin:]), pre, bool(to_rgb[1])),
+                              pad_size=None if pad_size is None else tuple(pad_size), pad_val=float(pad_val))
+
+    def u8_input(self, rgb_u8, aux_u8):
+        """uint8 HWC device frames [B, H, W, 3] x 2 -> the engine's U8Input (needs set_input_pipeline)."""
+        from . import kernels as K
+        from .engine import U8Input
+        pl = getattr(self, "_pipeline", None)
+        if pl is None:
+            raise RuntimeError("call set_input_pipeline(mean, std, ...) before feeding uint8 frames")
+        hw = pl["pad_size"] or tuple(rgb_u8.shape[1:3])
+        mods = [K.U8Modality(d, *pl[k], pad_val=pl["pad_val"]) for k, d in (("rgb", rgb_u8), ("aux", aux_u8))]
+        return U8Input(mods[0], mods[1], hw)
+
     @torch.no_grad()
     def stream_labels(self, batches, out_hw=None, crop_hw=None):
-        """Whole-image inference over an iterable of HOST batches [B, C, H, W] (the test loop of
-        mmseg_custom/apis/test_bs.py:91-163 feeds one DataLoader batch at a time): yields one uint8 [B, H, W]
-        label tensor in pinned host memory per batch, in order. The host->device copy of batch i+1 runs on a copy
-        stream while batch i is computed, and the labels of batch i are read back asynchronously, so a step costs
-        max(copy, compute) instead of their sum. Pass pinned tensors (tensor.pin_memory()); pageable ones still work
-        but their copies are synchronous. A yielded tensor is valid until the generator has been advanced twice."""
+        """Whole-image inference over an iterable of HOST batches (the test loop of mmseg_custom/apis/test_bs.py:91-163 feeds
+        one DataLoader batch at a time): yields one uint8 [B, H, W] label tensor in pinned host memory per batch, in order.
+        A batch is either the fp32 network input [B, C, H, W] or — after set_input_pipeline — a pair of uint8 HWC frame
+        tensors (rgb [B, H, W, 3], auxiliary [B, H, W, 3]) straight from the decoder: 1 byte per value over PCIe instead
+        of 4. The host->device copy of batch i+1 runs on a copy stream while batch i is computed, and the labels of batch i
+        are read back asynchronously, so a step costs max(copy, compute) instead of their sum. Pass pinned tensors
+        (tensor.pin_memory()); pageable ones still work but their copies are synchronous. A yielded tensor is valid
+        until the generator has been advanced twice."""
         dev = next(self.parameters()).device
         comp = torch.cuda.current_stream(dev)
         if getattr(self, "_copy_stream", None) is None:
@@ -232,17 +256,19 @@ class EncoderDecoder(nn.Module):
         free_ev = [None, None]
 
         def upload(x, slot):
-            buf = self._stage[slot]
-            if buf is None or buf.shape != x.shape or buf.dtype != x.dtype:
-                buf = self._stage[slot] = torch.empty(x.shape, dtype=x.dtype, device=dev)   # allocated on comp
+            xs = list(x) if isinstance(x, (tuple, list)) else [x]
+            bufs = self._stage[slot]
+            if bufs is None or len(bufs) != len(xs) or any(b.shape != t.shape or b.dtype != t.dtype for b, t in zip(bufs, xs)):
+                bufs = self._stage[slot] = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in xs]   # allocated on comp
                 copy.wait_stream(comp)
             with torch.cuda.stream(copy):
                 if free_ev[slot] is not None:
                     copy.wait_event(free_ev[slot])          # the forward that read this slot has consumed it
-                buf.copy_(x, non_blocking=True)
+                for b, t in zip(bufs, xs):
+                    b.copy_(t, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
-            return buf, ev
+            return bufs, ev
 
         it = iter(batches)
         try:
@@ -251,13 +277,13 @@ class EncoderDecoder(nn.Module):
             return
         prev, i = None, 0
         while nxt is not None:
-            (buf, ev), slot = nxt, i % 2
+            (bufs, ev), slot = nxt, i % 2
             try:
                 nxt = upload(next(it), (i + 1) % 2)
             except StopIteration:
                 nxt = None
             comp.wait_event(ev)
-            lab = self.encode_decode_labels(buf, out_hw, crop_hw)
+            lab = self.encode_decode_labels(bufs[0] if len(bufs) == 1 else self.u8_input(bufs[0], bufs[1]), out_hw, crop_hw)
             free_ev[slot] = torch.cuda.Event()
             free_ev[slot].record(comp)
             out = self._out_host[slot]
@@ -273,67 +299,102 @@ class EncoderDecoder(nn.Module):
         prev[1].synchronize()
         yield prev[0]
 
+    # ------------------------------------------------------------------ logits-level API
     @torch.no_grad()
-    def encode_decode(self, img, img_metas=None):
-        """Logits at image size (bilinear, align_corners=False): [B, num_classes, H, W] fp32."""
+    def _head_logits(self, img):
+        """fp32 channels-last head logits [B*h0*w0, npad] + (h0, w0)."""
         eng = self._engine()
-        feats = eng.backbone_nhwc(img)
-        logits, (h0, w0) = eng.head_logits(feats)
-        B = img.shape[0]
-        lg = logits.view(B, h0, w0, -1)[..., : self.num_classes].permute(0, 3, 1, 2)
-        return torch.nn.functional.interpolate(lg, size=img.shape[2:], mode="bilinear", align_corners=False)
+        return eng.head_logits(eng.backbone_nhwc(img))
 
     @torch.no_grad()
-    def slide_labels(self, img, crop_batch=8):
-        """slide_inference (encoder_decoder.py:191-234): overlapping crops, logits averaged by count. The crops of a frame
-        are independent, so they go through the network `crop_batch` at a time (one forward for the 6 crops of a MUSES
-        frame) instead of one by one; the overlap-add / count normalisation is unchanged."""
+    def encode_decode(self, img, img_metas=None):
+        """Logits at image size (bilinear, align_corners=False): [B, num_classes, H, W] fp32 (encoder_decoder.py:85-95)."""
+        from . import kernels as K
+        logits, (h0, w0) = self._head_logits(img)
+        B, (H, W) = img.shape[0], img.shape[2:]
+        with torch.cuda.device(logits.device):
+            lg = K.resize_logits(logits, B, (h0, w0), (H, W))
+        return lg.view(B, H, W, -1)[..., : self.num_classes].permute(0, 3, 1, 2)
+
+    def _slide_boxes(self, h_img, w_img):
+        """Crop grid of slide_inference (encoder_decoder.py:198-212)."""
         h_stride, w_stride = self.test_cfg["stride"]
         h_crop, w_crop = self.test_cfg["crop_size"]
-        B, _, h_img, w_img = img.shape
         h_grids = max(h_img - h_crop + h_stride - 1, 0) // h_stride + 1
         w_grids = max(w_img - w_crop + w_stride - 1, 0) // w_stride + 1
-        preds = img.new_zeros((B, self.num_classes, h_img, w_img))
-        count = img.new_zeros((B, 1, h_img, w_img))
         boxes = []
         for hi in range(h_grids):
             for wi in range(w_grids):
                 y1, x1 = hi * h_stride, wi * w_stride
                 y2, x2 = min(y1 + h_crop, h_img), min(x1 + w_crop, w_img)
                 boxes.append((max(y2 - h_crop, 0), max(x2 - w_crop, 0), y2, x2))
+        return boxes
+
+    @torch.no_grad()
+    def slide_labels(self, img, crop_batch=8, rescale_to=None):
+        """slide_inference (encoder_decoder.py:191-234) -> uint8 labels. The crops of a frame are independent, so they go
+        through the network `crop_batch` at a time (one forward for the 6 crops of a MUSES frame); one kernel
+        (mmsam_slide_merge_f32) then up-samples every crop's head logits, adds the overlaps, divides by the count and
+        takes the argmax in a single pass over the frame. rescale_to=(H, W): the averaged logits are resized first
+        (rescale=True with an ori_shape different from the frame, :223-229)."""
+        from . import kernels as K
+        B, _, h_img, w_img = img.shape
+        boxes = self._slide_boxes(h_img, w_img)
+        if len({(y2 - y1, x2 - x1) for y1, x1, y2, x2 in boxes}) != 1:
+            raise NotImplementedError("frames smaller than the crop size (crops of different sizes)")
         per = max(crop_batch // B, 1)                      # crop positions per forward (each contributes B crops)
+        chunks, hw = [], None
         for i in range(0, len(boxes), per):
-            grp = boxes[i:i + per]
-            same = len({(y2 - y1, x2 - x1) for y1, x1, y2, x2 in grp}) == 1
-            if same and len(grp) > 1:
-                crops = torch.cat([img[:, :, y1:y2, x1:x2] for y1, x1, y2, x2 in grp], 0).contiguous()
-                lg = self.encode_decode(crops)
-                for j, (y1, x1, y2, x2) in enumerate(grp):
-                    preds[:, :, y1:y2, x1:x2] += lg[j * B:(j + 1) * B]
-                    count[:, :, y1:y2, x1:x2] += 1
+            crops = torch.cat([img[:, :, y1:y2, x1:x2] for y1, x1, y2, x2 in boxes[i:i + per]], 0).contiguous()
+            lg, hw = self._head_logits(crops)              # rows ordered (position, image, y, x)
+            chunks.append(lg)
+        logits = chunks[0] if len(chunks) == 1 else torch.cat(chunks, 0)
+        with torch.cuda.device(logits.device):
+            if rescale_to is None or tuple(rescale_to) == (h_img, w_img):
+                return K.slide_merge(logits, B, hw, self.num_classes, (h_img, w_img), boxes)
+            preds = K.slide_merge(logits, B, hw, self.num_classes, (h_img, w_img), boxes, want_preds=True)
+            return K.upsample_argmax(preds, B, (h_img, w_img), self.num_classes, tuple(rescale_to))
+
+    @torch.no_grad()
+    def inference_labels(self, img, img_meta=None, rescale=True):
+        """inference + argmax of simple_test (encoder_decoder.py:417-508) on the device -> uint8 labels [B, H', W'].
+        Every mode of the reference: slide, whole (rescale -> ori_shape), whole_dim (-> test_cfg.dim), whole_dim_cut
+        (-> dim when rescale, then the cut_dim window); flip / flip_direction of img_meta flips the result back."""
+        from . import kernels as K
+        mode = self.test_cfg.get("mode", "whole")
+        meta = img_meta[0] if img_meta else {}
+        in_hw = tuple(img.shape[2:])
+        ori_hw = tuple(meta["ori_shape"][:2]) if "ori_shape" in meta else in_hw
+        if "ori_shape" in meta:
+            assert all(tuple(m["ori_shape"][:2]) == ori_hw for m in img_meta), "one ori_shape per batch (encoder_decoder.py:432-434)"
+        if mode == "slide":
+            lab = self.slide_labels(img, rescale_to=ori_hw if rescale else None)
+        elif mode in ("whole", "whole_dim", "whole_dim_cut"):
+            out_hw, crop = in_hw, None
+            if mode == "whole":
+                out_hw = ori_hw if rescale else in_hw
+            elif mode == "whole_dim":
+                if not rescale:
+                    raise ValueError("whole_inference_dim returns nothing with rescale=False (encoder_decoder.py:329-362)")
+                out_hw = tuple(self.test_cfg["dim"])
             else:
-                for y1, x1, y2, x2 in grp:
-                    preds[:, :, y1:y2, x1:x2] += self.encode_decode(img[:, :, y1:y2, x1:x2].contiguous())
-                    count[:, :, y1:y2, x1:x2] += 1
-        return (preds / count).argmax(1).to(torch.uint8)
+                if rescale:
+                    out_hw = tuple(self.test_cfg["dim"])
+                cw, ch = self.test_cfg["cut_dim"]
+                crop = (min(ch, out_hw[0]), min(cw, out_hw[1]))
+            lab = self.encode_decode_labels(img, out_hw, crop)
+        else:
+            raise ValueError(f"unknown test_cfg.mode {mode!r}")
+        if meta.get("flip", False):
+            direction = meta.get("flip_direction", "horizontal")
+            assert direction in ("horizontal", "vertical")
+            lab = lab.flip(dims=(2,) if direction == "horizontal" else (1,))
+        return lab
 
     @torch.no_grad()
     def simple_test(self, img, img_meta=None, rescale=True):
         """-> list of np.int64 [H, W] label maps, one per image (encoder_decoder.py:471-508)."""
-        mode = self.test_cfg.get("mode", "whole")
-        if mode == "slide":
-            lab = self.slide_labels(img)
-        else:
-            out_hw = crop = None
-            if mode in ("whole_dim", "whole_dim_cut") and rescale:
-                out_hw = tuple(self.test_cfg["dim"])
-                if tuple(out_hw) != tuple(img.shape[2:]):
-                    raise NotImplementedError("test_cfg.dim different from the network input size")
-            if mode == "whole_dim_cut":
-                cw, ch = self.test_cfg["cut_dim"]
-                crop = (ch, cw)
-            lab = self.encode_decode_labels(img, out_hw, crop)
-        return list(lab.cpu().numpy().astype(np.int64))
+        return list(self.inference_labels(img, img_meta, rescale).cpu().numpy().astype(np.int64))
 
     def forward(self, img, img_metas=None, return_loss=False, rescale=True, **kw):
         if return_loss:

@@ -43,6 +43,22 @@ def _f32(t, dev):
     return t.detach().to(device=dev, dtype=torch.float32).contiguous()
 
 
+class U8Input:
+    """The network input as the loader delivers it: the two modalities as uint8 HWC frames (K.U8Modality: data + the
+    normalisation of the test pipeline) and the padded network input size (H, W). Normalise / pad / HWC -> CHW / patchify
+    happen inside the stem and patch-embed operand kernels (mmsam_patchify_u8); the fp32 NCHW tensor never exists."""
+
+    def __init__(self, rgb, aux, hw):
+        self.mods = (rgb, aux)
+        self.H, self.W = int(hw[0]), int(hw[1])
+        self.B = rgb.data.shape[0]
+        assert aux.data.shape[0] == self.B and rgb.data.shape[1:3] == aux.data.shape[1:3]
+
+    @property
+    def shape_key(self):
+        return ("u8", tuple(self.mods[0].data.shape), tuple(self.mods[1].data.shape), self.H, self.W)
+
+
 class _Lin:
     """weight bf16 [N, K] (K contiguous), bias fp32 [N] or None, optional per-channel scale."""
 
@@ -495,6 +511,13 @@ class EncoderEngine(_Ops):
         return sc
 
     # ------------------------------------------------------------------ building blocks
+    def _patches(self, img, which, p):
+        """bf16 patch rows [(b,py,px), (c,ky,kx)] of modality `which` (0 = rgb, 1 = auxiliary) for a p x p / stride p conv."""
+        if isinstance(img, U8Input):
+            return K.patchify_u8(img.mods[which], img.H, img.W, p)
+        c_off = 0 if which == 0 else self.cin
+        return K.patchify(img, c_off, self.cin if which == 0 else img.shape[1] - self.cin, p)
+
     def _convnext_branch(self, img, c_off, stages, B, Hi, Wi):
         """twin_convnext.py:445-476 for one modality; returns the 4 normalised stage outputs bf16 [B*h*w, C]. The tower's
         feature map t is an fp32 residual stream (see the module docstring); dwconv / LN read it in fp32 and emit bf16."""
@@ -504,7 +527,7 @@ class EncoderEngine(_Ops):
         f32 = torch.float32
         for i, st in enumerate(stages):
             if i == 0:
-                pch = K.patchify(img, c_off, 3, 4)
+                pch = self._patches(img, 0 if c_off == 0 else 1, 4)
                 h, w = Hi // 4, Wi // 4
                 t = self._gemm(pch, st["ds"], out_dtype=f32)
                 t = self._ln(t, st["ds_ln"], out=t, out_dtype=f32)
@@ -525,13 +548,19 @@ class EncoderEngine(_Ops):
     @_on_device
     @torch.no_grad()
     def backbone_nhwc(self, img, debug=None):
-        """img fp32 [B, 3+3, Hi, Wi] on the device -> [f1, f2, f3, f4] channels-last bf16 [B, h, w, C]."""
-        if not img.is_cuda:
-            raise K._lib.MMSamError("input must be a CUDA tensor")
-        if img.device != self.dev:
-            raise K._lib.MMSamError(f"input on {img.device}, engine packed for {self.dev}")
-        img = img.contiguous().float()
-        B, _, Hi, Wi = img.shape
+        """img fp32 [B, 3+3, Hi, Wi] on the device, or a U8Input (uint8 HWC frames + normalisation)
+        -> [f1, f2, f3, f4] channels-last bf16 [B, h, w, C]."""
+        if isinstance(img, U8Input):
+            B, Hi, Wi = img.B, img.H, img.W
+            if any(m.data.device != self.dev for m in img.mods):
+                raise K._lib.MMSamError(f"input frames not on {self.dev}")
+        else:
+            if not img.is_cuda:
+                raise K._lib.MMSamError("input must be a CUDA tensor")
+            if img.device != self.dev:
+                raise K._lib.MMSamError(f"input on {img.device}, engine packed for {self.dev}")
+            img = img.contiguous().float()
+            B, _, Hi, Wi = img.shape
         if Hi % 32 or Wi % 32:
             raise ValueError("input height/width must be multiples of 32")
         isz = self.cfg.get("img_size")
@@ -570,7 +599,7 @@ class EncoderEngine(_Ops):
         for i in range(3):
             self._gemm(fused[i + 1], self.fc[i + 1], out=c, row_map=sc["c_rowmaps"][i], out_rows=B * S3)
         # --- patch embed + pos embed (image_encoder.py:662-671, ..._new.py:268-278) ---
-        pch = K.patchify(img, 0, self.cin, self.patch)
+        pch = self._patches(img, 0, self.patch)
         x = self._gemm(pch, self.patch_embed, residual=sc["pos"], out_dtype=torch.float32)     # fp32 token stream
         if debug is not None:
             debug.update(c1=c1.clone(), c_0=c.clone(), x_0=x.clone())
@@ -617,15 +646,24 @@ class EncoderEngine(_Ops):
         """SegformerHead.forward (decode_heads/segformer_head.py:48-66) -> fp32 logits [B*h*w, npad], (h, w)."""
         return self._head_logits(self.head, feats)
 
+    @staticmethod
+    def _in_hw(img):
+        return (img.H, img.W) if isinstance(img, U8Input) else tuple(img.shape[2:])
+
     @_on_device
     @torch.no_grad()
     def segment(self, img, out_hw=None, crop_hw=None):
         """encode_decode_test + whole_inference_dim(_cut) + softmax/argmax -> uint8 labels [B, H, W]
-        (segmentors/encoder_decoder.py:96-117, 329-414, 417-508)."""
-        B, _, Hi, Wi = img.shape
+        (segmentors/encoder_decoder.py:96-117, 329-414, 417-508). The head logits go to the label map in one kernel when
+        out_hw is the input size (the second resize of whole_inference_dim is then the identity); otherwise the logits are
+        first resized to the input size (encode_decode), then to out_hw, as the reference does."""
+        Hi, Wi = self._in_hw(img)
         feats = self.backbone_nhwc(img)
+        B = feats[0].shape[0]
         logits, (h0, w0) = self.head_logits(feats)
         out_hw = (Hi, Wi) if out_hw is None else tuple(out_hw)
+        if out_hw != (Hi, Wi):
+            logits, (h0, w0) = K.resize_logits(logits, B, (h0, w0), (Hi, Wi)), (Hi, Wi)
         return K.upsample_argmax(logits, B, (h0, w0), self.head["ncls"], out_hw, crop_hw)
 
     @_on_device
@@ -635,12 +673,19 @@ class EncoderEngine(_Ops):
         warm-up): the ~4000 kernel launches of a ViT-L forward are submitted with one cudaGraphLaunch, so the
         host is off the critical path. The returned label tensor is the graph's static output buffer (valid
         until the next call with the same shape)."""
-        key = (tuple(img.shape), None if out_hw is None else tuple(out_hw), None if crop_hw is None else tuple(crop_hw))
+        u8 = isinstance(img, U8Input)
+        key = (img.shape_key if u8 else tuple(img.shape), None if out_hw is None else tuple(out_hw),
+               None if crop_hw is None else tuple(crop_hw))
         ent = self._graphs.get(key)
         if ent is None:
             if len(self._graphs) >= 4:
                 self._graphs.pop(next(iter(self._graphs)))
-            static_in = img.detach().clone().float().contiguous()
+            if u8:
+                mods = [K.U8Modality(m.data.detach().clone().contiguous(), m.mean, m.std, m.prescale, m.to_rgb, m.pad_val)
+                        for m in img.mods]
+                static_in = U8Input(mods[0], mods[1], (img.H, img.W))
+            else:
+                static_in = img.detach().clone().float().contiguous()
             self.segment(static_in, out_hw, crop_hw)          # warm-up: shape caches, kernel attributes
             torch.cuda.synchronize()
             n0 = K.LAUNCHES
@@ -650,7 +695,13 @@ class EncoderEngine(_Ops):
             ent = (graph, static_in, out, K.LAUNCHES - n0)
             self._graphs[key] = ent
         graph, static_in, out, nl = ent
-        static_in.copy_(img, non_blocking=True)
+        if u8:
+            for dst, src in zip(static_in.mods, img.mods):
+                if (dst.mean, dst.std, dst.prescale, dst.to_rgb, dst.pad_val) != (src.mean, src.std, src.prescale, src.to_rgb, src.pad_val):
+                    raise K._lib.MMSamError("normalisation changed since this input shape was captured: call invalidate()")
+                dst.data.copy_(src.data, non_blocking=True)
+        else:
+            static_in.copy_(img, non_blocking=True)
         graph.replay()
         self.graph_launches += nl
         return out

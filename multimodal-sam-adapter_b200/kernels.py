@@ -320,6 +320,65 @@ def patchify(img, c_off, C, p, out=None):
     return out
 
 
+class U8Modality:
+    """One modality's decoded frames as they leave the loader: uint8 HWC [B, Hs, Ws, C] on the device, plus the
+    normalisation of Normalize_multimodal (pipelines/transform.py:2717-2815): (v * prescale - mean) / std, prescale =
+    1/255 with norm_by_max; to_rgb reverses the channel order first; pad_val fills the rows / columns Pad_multimodal adds."""
+
+    def __init__(self, data, mean, std, prescale=1.0 / 255.0, to_rgb=False, pad_val=0.0):
+        self.data, self.mean, self.std = data, [float(v) for v in mean], [float(v) for v in std]
+        self.prescale, self.to_rgb, self.pad_val = float(prescale), bool(to_rgb), float(pad_val)
+
+
+def patchify_u8(mod, H, W, p, out=None):
+    """U8Modality -> bf16 [B*(H/p)*(W/p), C*p*p] patch rows of the H x W (padded) normalised image."""
+    import ctypes
+    img = mod.data
+    _need_cuda(img)
+    assert img.dtype == torch.uint8 and img.is_contiguous() and img.dim() == 4
+    B, Hs, Ws, C = img.shape
+    if out is None:
+        out = torch.empty((B * (H // p) * (W // p), C * p * p), dtype=torch.bfloat16, device=img.device)
+    m = (ctypes.c_float * C)(*mod.mean[:C])
+    sd = (ctypes.c_float * C)(*mod.std[:C])
+    rc = _lib.load().mmsam_patchify_u8(_ptr(img), _ptr(out), B, Hs, Ws, C, H, W, p, ctypes.cast(m, ctypes.c_void_p),
+                                       ctypes.cast(sd, ctypes.c_void_p), mod.prescale, mod.pad_val, 1 if mod.to_rgb else 0, _stream())
+    _lib.check(rc, "mmsam_patchify_u8")
+    _count()
+    return out
+
+
+def resize_logits(logits, B, hw, out_hw):
+    """fp32 channels-last logits [B*h*w, ld] -> [B*Ho*Wo, ld], bilinear, align_corners=False."""
+    _need_cuda(logits)
+    ld = logits.shape[-1]
+    out = torch.empty((B * out_hw[0] * out_hw[1], ld), dtype=torch.float32, device=logits.device)
+    rc = _lib.load().mmsam_resize_logits_f32(_ptr(logits), _ptr(out), B, hw[0], hw[1], ld, out_hw[0], out_hw[1], _stream())
+    _lib.check(rc, "mmsam_resize_logits_f32")
+    _count()
+    return out
+
+
+def slide_merge(crop_logits, B, hw, ncls, frame_hw, boxes, want_preds=False):
+    """crop_logits fp32 [ncrops*B*h*w, ld] (crop j of image b at index j*B+b) + boxes [(y1, x1, y2, x2)] -> uint8 labels
+    [B, H, W], or the averaged fp32 logits [B*H*W, ld] when want_preds (a resize to ori_shape follows)."""
+    import ctypes
+    _need_cuda(crop_logits)
+    ld = crop_logits.shape[-1]
+    H, W = frame_hw
+    bx = (ctypes.c_int * (4 * len(boxes)))(*[int(v) for b in boxes for v in b])
+    labels = preds = None
+    if want_preds:
+        preds = torch.empty((B * H * W, ld), dtype=torch.float32, device=crop_logits.device)
+    else:
+        labels = torch.empty((B, H, W), dtype=torch.uint8, device=crop_logits.device)
+    rc = _lib.load().mmsam_slide_merge_f32(_ptr(crop_logits), _ptr(labels), _ptr(preds), B, hw[0], hw[1], ld, ncls, H, W,
+                                           len(boxes), ctypes.cast(bx, ctypes.c_void_p), _stream())
+    _lib.check(rc, "mmsam_slide_merge_f32")
+    _count()
+    return preds if want_preds else labels
+
+
 def resize_add_affine(src, src_hw, out_hw, B, C, base=None, scale=None, shift=None, out=None,
                       src_bstride=None, lds=None, base_bstride=None, ldb=None, out_bstride=None, ldo=None):
     """Channels-last: out = (base + bilinear(src)) * scale + shift (src bf16 or fp32; base / out bf16). Strides in elements."""

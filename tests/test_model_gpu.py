@@ -461,3 +461,67 @@ def test_outputs_are_bit_reproducible(tiny):
     lg2 = seg.encode_decode_labels(x, (128, 128)).clone()
     assert torch.equal(le, lg1) and torch.equal(lg1, lg2)
     assert torch.equal(seg.encode_decode_labels(x[2:3], (128, 128))[0], le[2])
+
+
+def test_inference_modes_vs_reference_segmentor_golden():
+    """a19 / f2: every inference mode of the reference's EncoderDecoder.simple_test (whole_dim with dim == / != input,
+    whole_dim_cut with and without rescale, whole with an ori_shape, flips, slide with the fused overlap-add kernel, slide
+    + rescale), against label maps produced by the reference's own segmentor (tests/golden/segmentor_tiny.pt)."""
+    import numpy as np
+    from oracle.perturb import synthetic_batch
+    rec = torch.load(os.path.join(GOLD, "segmentor_tiny.pt"))
+    seg, sd = build_segmentor(TINY, TINY_HEAD)
+    assert sd_digest(sd) == rec["digest"]
+    seg = seg.cuda()
+    x = synthetic_batch(2, 128, seed=5).cuda()
+    frame = torch.cat([synthetic_batch(1, 128, seed=21), synthetic_batch(1, 128, seed=22)], 3)[:, :, :, :208].contiguous().cuda()
+    # head logits and image-size logits against the reference's
+    lg = seg.encode_decode(x).float().cpu()
+    r = rel_l2(lg.reshape(-1)[rec["logits_img_idx"]], rec["logits_img_vals"])
+    print(f"encode_decode logits vs reference samples: rel-L2 {r:.3e}")
+    assert r < REL_TOL
+    for name, c in rec["cases"].items():
+        seg.test_cfg = dict(c["test_cfg"])
+        img = frame if name.startswith("slide") else x
+        meta = None
+        if c["ori_shape"] is not None or c["flip"]:
+            meta = [dict(ori_shape=tuple(c["ori_shape"] or img.shape[2:]) + (3,), flip=c["flip"], flip_direction=c["direction"])] * img.shape[0]
+        got = torch.as_tensor(np.stack(seg.simple_test(img, meta, c["rescale"])))
+        want = c["labels"].long()
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        agree = (got == want).float().mean().item()
+        print(f"mode {name}: {agree * 100:.3f}% of {want.numel()} pixels agree with the reference segmentor")
+        assert agree >= 0.98, name
+    seg.test_cfg = dict(mode="whole_dim", dim=(128, 128))
+    with pytest.raises(ValueError):
+        seg.simple_test(x, None, False)                      # the reference's whole_inference_dim returns None here
+
+
+def test_uint8_input_pipeline_matches_fp32_path():
+    """f3: uint8 HWC frames + set_input_pipeline (Normalize_multimodal + Pad_multimodal inside the patchify kernels) give the
+    same labels as normalising / padding on the host and feeding the fp32 NCHW tensor; stream_labels on uint8 batches."""
+    seg, _ = build_segmentor(TINY, TINY_HEAD, test_cfg=dict(mode="whole_dim", rescale=True, dim=(128, 128)))
+    seg = seg.cuda()
+    g = torch.Generator().manual_seed(3)
+    mean, std = [0.485, 0.456, 0.406, 0.1, 0.2, 0.3], [0.229, 0.224, 0.225, 1.0, 0.5, 2.0]
+    rgb = torch.randint(0, 256, (2, 96, 128, 3), generator=g, dtype=torch.uint8)         # 96 rows: padded to 128 by the pipeline
+    aux = torch.randint(0, 256, (2, 96, 128, 3), generator=g, dtype=torch.uint8)
+    seg.set_input_pipeline(mean, std, to_rgb=(True, False), norm_by_max=True, pad_size=(128, 128), pad_val=0)
+
+    def host_pipeline(u8, m, s, to_rgb):
+        v = u8.float()
+        v = torch.nn.functional.pad(v, (0, 0, 0, 0, 0, 128 - v.shape[1]))                  # Pad_multimodal: raw zeros, before the normalisation
+        if to_rgb:
+            v = v.flip(-1)
+        v = (v / 255.0 - torch.tensor(m)) / torch.tensor(s)
+        return v.permute(0, 3, 1, 2)
+    x = torch.cat((host_pipeline(rgb, mean[:3], std[:3], True), host_pipeline(aux, mean[3:], std[3:], False)), 1).contiguous()
+    seg.use_cuda_graph = False
+    want = seg.encode_decode_labels(x.cuda(), (128, 128)).cpu()
+    got = seg.encode_decode_labels(seg.u8_input(rgb.cuda(), aux.cuda()), (128, 128)).cpu()
+    agree = (got == want).float().mean().item()
+    print(f"uint8 pipeline vs host-normalised fp32 input: {agree * 100:.4f}% identical labels")
+    assert agree >= 0.9995                                      # (v/255 - m)/s in fp32 on both sides: last-ulp differences only
+    seg.use_cuda_graph = True
+    outs = [o.clone() for o in seg.stream_labels(iter([(rgb.pin_memory(), aux.pin_memory())] * 3), (128, 128))]
+    assert len(outs) == 3 and all(torch.equal(o, outs[0]) for o in outs) and (outs[0] == want).float().mean().item() >= 0.9995
