@@ -248,7 +248,8 @@ def instrumented_pass(eng, x):
         m_n += cnt
     out["msda"] = dict(ms=m_ms, work=m_work, launches=m_n)
     reps, g_ms, g_work, g_n = 8, 0.0, 0.0, 0
-    for ent in calls.values():
+    table = []
+    for key, ent in calls.items():
         cnt, a, w, kw = ent[:4]
         run = (lambda: ogl(a, w, *ent[4], **kw)) if len(ent) > 4 else (lambda: og(a, w, **kw))
         for _ in range(2):
@@ -259,10 +260,17 @@ def instrumented_pass(eng, x):
             run()
         e.record()
         torch.cuda.synchronize()
-        g_ms += cnt * s.elapsed_time(e) / reps
+        t_ms = s.elapsed_time(e) / reps
+        g_ms += cnt * t_ms
         g_work += cnt * 2.0 * a.shape[0] * w.shape[0] * a.shape[1]
         g_n += cnt
+        table.append(dict(M=a.shape[0], N=w.shape[0], K=a.shape[1], count=cnt, us=t_ms * 1e3, total_ms=cnt * t_ms,
+                          tflops=2.0 * a.shape[0] * w.shape[0] * a.shape[1] / (t_ms * 1e-3) / 1e12,
+                          epilogue=dict(act=kw.get("act"), residual=str(kw["residual"].dtype) if kw.get("residual") is not None else None,
+                                        out=str(kw["out"].dtype), ln_fold=len(ent) > 4, row_map=kw.get("row_map") is not None,
+                                        pixel_shuffle=kw.get("pixel_shuffle") is not None)))
     out["gemm"] = dict(ms=g_ms, work=g_work, launches=g_n, configs=len(calls))
+    out["gemm_table"] = sorted(table, key=lambda r: -r["total_ms"])
     return out
 
 
@@ -275,6 +283,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--dump-gemm", default=None, help="write the per-configuration GEMM timing table (JSON) to this path")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -388,6 +397,9 @@ def main():
     pk = peaks()
     inst = instrumented_pass(eng, x)
     gm, md = inst["gemm"], inst["msda"]
+    if args.dump_gemm:
+        with open(args.dump_gemm, "w") as f:
+            json.dump(inst["gemm_table"], f, indent=1)
     tf = gm["work"] / (gm["ms"] / 1e3) / 1e12
     gbs = md["work"] / (md["ms"] / 1e3) / 1e9
     line = {

@@ -505,6 +505,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 
 }  // namespace mmsam
 
+int mmsam_attention_win(const void* qkv, void* out, const int* out_row_map_dev, const void* tab_h, const void* tab_w, int Bp,
+                        int nh, float scale, int max_ctas, cudaStream_t stream);   // attention_win.cu
+
 // See include/mmsam_b200.h for the contract.
 MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const int* out_row_map_dev, const void* tab_h,
                                    const void* tab_w, int Bp, int T, int nh, int Kh, int Kw, float scale,
@@ -517,6 +520,12 @@ MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const int* out_ro
   const bool has_bias = tab_h != nullptr && tab_w != nullptr;
   if ((tab_h != nullptr) != (tab_w != nullptr)) return MMSAM_ERR_BAD_ARG;
   if (has_bias && (Kh <= 0 || Kw <= 0 || Kh * Kw != T)) return MMSAM_ERR_BAD_ARG;
+  // SAM's 14 x 14 windows: the single-pass kernel (attention_win.cu)
+  static const int use_win = [] { const char* e = getenv("MMSAM_ATT_WIN"); return e ? atoi(e) : 1; }();
+  if (use_win && T == 196 && (!has_bias || (Kh == 14 && Kw == 14))) {
+    if (has_bias && (((uintptr_t)tab_h | (uintptr_t)tab_w) & 15)) return MMSAM_ERR_BAD_ARG;
+    return mmsam_attention_win(qkv, out, out_row_map_dev, tab_h, tab_w, Bp, nh, scale, max_ctas, (cudaStream_t)stream);
+  }
   if (!has_bias) { Kh = 1; Kw = T; }
   AttnParams p;
   p.out = (__nv_bfloat16*)out;
@@ -559,7 +568,8 @@ MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const int* out_ro
   int smem_bytes = fixed + p.kv_stages * 2 * TILE_BYTES;
   if (smem_bytes > budget) return MMSAM_ERR_UNSUPPORTED;
   p.q_bufs = 1;
-  { const char* e = getenv("MMSAM_ATT_DBG"); p.dbg = e ? atoi(e) : 0; }
+  static const int dbg_flags = [] { const char* e = getenv("MMSAM_ATT_DBG"); return e ? atoi(e) : 0; }();
+  p.dbg = dbg_flags;
   if (smem_bytes + TILE_BYTES <= budget) { p.q_bufs = 2; smem_bytes += TILE_BYTES; }
   if (!has_bias) { p.Kh = 1; p.Kw = 1 << 30; }
 

@@ -13,6 +13,7 @@
 // so the inner loop is pure fp32 FMA (K*K per output, the CUDA-core floor) with conflict-free 4-byte
 // shared-memory reads.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace mmsam {
 
@@ -32,17 +33,22 @@ struct DwParams {
   int tiles_x[3], tiles_y[3], tile_start[4];
 };
 
-template <int K, int TH, int TW, bool XF32>
+// SF32: the halo is staged as fp32 (converted once while staging) so that the inner loop reads its packed fp32x2 operand
+// with one LDS.64 and no bf16 -> fp32 unpacking (2 ALU instructions per loaded value, ~10 % of the kernel's issue slots;
+// the kernel is issue-bound: 67 % issue-active with the FMA pipe at 38 %). Used for the 7x7 (97 KB + weights, 2 CTAs / SM).
+template <int K, int TH, int TW, bool XF32, bool SF32>
 __global__ void __launch_bounds__(256, 2)
 dwconv_kernel(const DwParams p) {
   constexpr int R = K / 2;
   constexpr int IH = TH + K - 1, IW = TW + K - 1;
   constexpr int CB = 64;  // channels per CTA
   constexpr int XO = 4;   // adjacent output columns per thread
+  constexpr int SB = SF32 ? 4 : 2;   // bytes per staged element
   static_assert(TW == 32, "thread map assumes 8 column groups of 4");
   extern __shared__ __align__(16) uint8_t dw_smem[];
-  __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(dw_smem);                 // [IH*IW][CB]
-  float* s_w = reinterpret_cast<float*>(dw_smem + IH * IW * CB * 2);               // [K*K][CB]
+  __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(dw_smem);                 // [IH*IW][CB] (bf16 or fp32)
+  float* s_inf = reinterpret_cast<float*>(dw_smem);
+  float* s_w = reinterpret_cast<float*>(dw_smem + IH * IW * CB * SB);              // [K*K][CB]
 
   // which grid / tile
   int t = blockIdx.x, gi = 0;
@@ -70,14 +76,20 @@ dwconv_kernel(const DwParams p) {
     if (iy >= 0 && iy < H && ix >= 0 && ix < W && cv * 8 < cvalid) {
       const long long e = xoff + ((long long)iy * W + ix) * p.C + c0 + cv * 8;
       if constexpr (XF32) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + e));
-        const float4 c4 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + e + 4));
-        v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c4.x, c4.y), pack_bf16(c4.z, c4.w));
+        const float4 fa = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + e));
+        const float4 fb = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + e + 4));
+        // the operands of the path are bf16: round the fp32 stream once here (SF32 and bf16 staging then agree bit for bit)
+        v = make_uint4(pack_bf16(fa.x, fa.y), pack_bf16(fa.z, fa.w), pack_bf16(fb.x, fb.y), pack_bf16(fb.z, fb.w));
       } else {
         v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + e));
       }
     }
-    *reinterpret_cast<uint4*>(&s_in[(pix * CB) + cv * 8]) = v;
+    if constexpr (SF32) {
+      *reinterpret_cast<float4*>(&s_inf[pix * CB + cv * 8]) = make_float4(bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y));
+      *reinterpret_cast<float4*>(&s_inf[pix * CB + cv * 8 + 4]) = make_float4(bf16lo(v.z), bf16hi(v.z), bf16lo(v.w), bf16hi(v.w));
+    } else {
+      *reinterpret_cast<uint4*>(&s_in[(pix * CB) + cv * 8]) = v;
+    }
   }
   __syncthreads();
 
@@ -107,8 +119,12 @@ dwconv_kernel(const DwParams p) {
       u64 in[XO + K - 1];
 #pragma unroll
       for (int i = 0; i < XO + K - 1; ++i) {
-        const uint32_t v = s_in32[((r + ky) * IW + xg * XO + i) * (CB / 2) + cp];
-        in[i] = pack2(bf16lo(v), bf16hi(v));
+        if constexpr (SF32) {
+          in[i] = *reinterpret_cast<const u64*>(&s_inf[((r + ky) * IW + xg * XO + i) * CB + cp * 2]);
+        } else {
+          const uint32_t v = s_in32[((r + ky) * IW + xg * XO + i) * (CB / 2) + cp];
+          in[i] = pack2(bf16lo(v), bf16hi(v));
+        }
       }
 #pragma unroll
       for (int xo = 0; xo < XO; ++xo)
@@ -134,11 +150,11 @@ dwconv_kernel(const DwParams p) {
   }
 }
 
-template <int K, int TH, int TW, bool XF32>
+template <int K, int TH, int TW, bool XF32, bool SF32>
 static int launch_dw(const DwParams& p, dim3 grid, cudaStream_t st) {
-  constexpr int smem = (TH + K - 1) * (TW + K - 1) * 64 * 2 + K * K * 64 * 4;
-  MMSAM_SET_SMEM_ONCE((dwconv_kernel<K, TH, TW, XF32>), smem);
-  dwconv_kernel<K, TH, TW, XF32><<<grid, 256, smem, st>>>(p);
+  constexpr int smem = (TH + K - 1) * (TW + K - 1) * 64 * (SF32 ? 4 : 2) + K * K * 64 * 4;
+  MMSAM_SET_SMEM_ONCE((dwconv_kernel<K, TH, TW, XF32, SF32>), smem);
+  dwconv_kernel<K, TH, TW, XF32, SF32><<<grid, 256, smem, st>>>(p);
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }
@@ -181,6 +197,10 @@ MMSAM_API int mmsam_dwconv(const void* x, int x_dtype, void* y, const float* w_t
   p.tile_start[3] = total;
   dim3 grid(total, (C + 63) / 64, B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (ksize == 7) return x_dtype == MMSAM_F32 ? launch_dw<7, 4, 32, true>(p, grid, st) : launch_dw<7, 4, 32, false>(p, grid, st);
-  return launch_dw<3, 8, 32, false>(p, grid, st);
+  static const int variant = [] { const char* e = getenv("MMSAM_DW_VARIANT"); return e ? atoi(e) : 1; }();   // 0: bf16 staging
+  if (ksize == 7) {
+    if (variant == 0) return x_dtype == MMSAM_F32 ? launch_dw<7, 4, 32, true, false>(p, grid, st) : launch_dw<7, 4, 32, false, false>(p, grid, st);
+    return x_dtype == MMSAM_F32 ? launch_dw<7, 4, 32, true, true>(p, grid, st) : launch_dw<7, 4, 32, false, true>(p, grid, st);
+  }
+  return launch_dw<3, 8, 32, false, false>(p, grid, st);
 }

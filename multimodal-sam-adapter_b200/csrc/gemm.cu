@@ -60,7 +60,7 @@ struct GemmEpi {
 // V_F32_RES: fp32 output + fp32 residual (in place on the fp32 residual streams: ViT tokens, ConvNeXt feature maps)
 enum { V_BF16 = 0, V_BF16_GELU = 1, V_BF16_MAP = 2, V_F32 = 3, V_GENERIC = 4, V_BF16_RES = 5, V_F32_RES = 6 };
 // Variants whose residual block is streamed into a third slab with cp.async (see epilogue_fast).
-__host__ __device__ constexpr bool var_async_res(int var) { return var == V_BF16_MAP || var == V_BF16_RES; }
+__host__ __device__ constexpr bool var_async_res(int var) { return var == V_BF16_MAP || var == V_BF16_RES || var == V_F32_RES; }
 
 template <int BN, int VAR = V_BF16> struct GemmCfg {
   static constexpr int BM = 128;            // rows per CTA (the pair computes 256)

@@ -370,6 +370,8 @@ def test_gemm_row_map_big():
     (1, 1, 8, 16, False),     # single block, no bias
     (1, 2, 32, 32, True),     # ViT-B/512 global (1024 tokens)
     (2, 3, 19, 25, True),     # non-square grid (475 tokens, ragged)
+    (3, 4, 14, 14, False),    # SAM window without bias (single-pass window kernel)
+    (150, 16, 14, 14, True),  # more (window, head) items than CTAs x 2 stages: the window kernel's ring wraps several times
     (50, 16, 14, 14, True),   # many windows: exercises the persistent tile loop (2 images x 25 windows)
     (1, 16, 64, 64, True),    # ViT-L/1024 global: 4096 tokens, 127-row tables, two G chunks
     (1, 2, 68, 120, True),    # MUSES whole frame 1088x1920 (BASELINE config 5b): 8160 tokens, half-precision bias rows

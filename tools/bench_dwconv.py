@@ -10,9 +10,11 @@ for (name, ks, C, grids, act) in (("cnx0 7x7", 7, 96, [(256, 256)], None), ("cnx
                                   ("convffn 3x3", 3, 256, [(128, 128), (64, 64), (32, 32)], "gelu")):
     S = sum(h * w for h, w in grids)
     x = torch.randn(B, S, C, device="cuda").to(torch.bfloat16)
+    if ks == 7 and os.environ.get("DW_F32", "1") == "1":
+        x = x.float()                       # the ConvNeXt towers' fp32 residual stream
     w = torch.randn(ks * ks, C, device="cuda")
     b = torch.randn(C, device="cuda")
-    out = torch.empty_like(x)
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device="cuda")
     for _ in range(3):
         K.dwconv(x, w, b, ks, grids, B, C, S * C, S * C, act=act, out=out)
     torch.cuda.synchronize()
