@@ -9,8 +9,11 @@ Workload (BASELINE.json configs[1]): SAM ViT-L MM-adapter + Segformer head, DeLi
 -> uint8 labels) over one batch. Multi-GPU: images sharded by rank (weak scaling), no collective on the
 data path; one all-gather of the per-rank 25x25 confusion matrix after the loop.
 
+Inputs are the decoder's output: uint8 HWC frames (RGB + LiDAR projected to 3 channels, 1 byte per value); the test
+pipeline's Normalize_multimodal (configs/DELIVER/...RGBLIDAR.py:70-72, norm_by_max) runs inside the patchify kernels.
+
 The JSON line carries: value (img/s, inputs resident in HBM), e2e (same metric through the public
-EncoderDecoder API with pinned-host inputs, H2D + D2H inside the timed region), roofline (dominant kernel:
+EncoderDecoder API with pinned-host uint8 frames, H2D + D2H inside the timed region), roofline (dominant kernel:
 the tcgen05 GEMM, achieved TFLOP/s measured live with CUDA events in an instrumented pass), roofline_msda
 (MSDeformAttn GB/s vs measured HBM peak), cpu_baseline (the oracle port on the host cores, 1 image),
 clocks, gpu_launches.
@@ -45,6 +48,27 @@ BATCH = 8
 METRIC = "img/s @1024^2 RGB+LiDAR ViT-L adapter fwd"
 
 
+# Normalize_multimodal arguments of the DeLiVER RGB+LiDAR config (configs/DELIVER/...RGBLIDAR.py:70-72, 94)
+PIPELINE = dict(mean=[0.485, 0.456, 0.406, 0, 0, 0], std=[0.229, 0.224, 0.225, 1, 1, 1], to_rgb=(True, True), norm_by_max=True)
+
+
+def synthetic_frames(batch, hw, seed):
+    """uint8 HWC frames as the image decoder hands them over: dense RGB + a 10 %-dense LiDAR projection (3 channels)."""
+    H, W = (hw, hw) if isinstance(hw, int) else hw
+    g = torch.Generator().manual_seed(seed)
+    rgb = torch.randint(0, 256, (batch, H, W, 3), generator=g, dtype=torch.uint8)
+    aux = torch.randint(1, 256, (batch, H, W, 3), generator=g, dtype=torch.uint8)
+    aux[torch.rand(batch, H, W, 3, generator=g) >= 0.1] = 0
+    return rgb, aux
+
+
+def host_normalise(rgb, aux):
+    """The same Normalize_multimodal on the host -> the fp32 NCHW network input (the reference arm's input)."""
+    m, sd_ = torch.tensor(PIPELINE["mean"]), torch.tensor(PIPELINE["std"])
+    v = torch.cat((rgb.flip(-1) if PIPELINE["to_rgb"][0] else rgb, aux.flip(-1) if PIPELINE["to_rgb"][1] else aux), -1).float()
+    return ((v / 255.0 - m) / sd_).permute(0, 3, 1, 2).contiguous()
+
+
 def peaks():
     p = dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
     try:
@@ -58,7 +82,9 @@ def peaks():
 
 def bench_config(world, B, graph):
     """`config` of the JSON line: identical for both arms."""
-    return {"workload": WORKLOAD, "global_batch": world * B, "l2": "inputs per step exceed the 126 MB L2",
+    return {"workload": WORKLOAD, "global_batch": world * B,
+            "input": "uint8 HWC frames (rgb + lidar, 6.3 MB per image); Normalize_multimodal fused into the patchify kernels",
+            "l2": "a 256 MB buffer is overwritten between timed steps (L2 flush, inside the timed region)",
             "parallelism": f"image-sharded x{world}, no data-path collective",
             "launch": "cuda-graph replay" if graph else "eager"}
 
@@ -101,7 +127,7 @@ def cpu_reference_img_per_s(sd, threads, steps, warmup, median=False):
     from oracle.perturb import synthetic_batch
     torch.set_num_threads(threads)
     fn, kind = cpu_reference_runner(sd)
-    x = synthetic_batch(1, 1024)
+    x = host_normalise(*synthetic_frames(1, 1024, 1234))
     ts = []
     with torch.no_grad():
         for i in range(warmup + steps):
@@ -234,6 +260,7 @@ def instrumented_pass(eng, x):
                 os.environ[k] = v
     out = {}
     reps, m_ms, m_work, m_n = 8, 0.0, 0.0, 0
+    shapes = {}
     for cnt, by, margs, geom in mcalls.values():
         for _ in range(2):
             om_(*margs, geom=geom)
@@ -246,7 +273,9 @@ def instrumented_pass(eng, x):
         m_ms += cnt * s.elapsed_time(e) / reps
         m_work += cnt * by
         m_n += cnt
+        shapes["injector" if margs[6] > 1 else "extractor"] = dict(bytes=by, us=s.elapsed_time(e) / reps * 1e3, count=cnt)
     out["msda"] = dict(ms=m_ms, work=m_work, launches=m_n)
+    out["msda_shapes"] = shapes
     reps, g_ms, g_work, g_n = 8, 0.0, 0.0, 0
     table = []
     for key, ent in calls.items():
@@ -274,6 +303,92 @@ def instrumented_pass(eng, x):
     return out
 
 
+def reference_kernel_times(B):
+    """The reference's own CUDA forward kernel (ms_deformable_im2col_gpu_kernel, ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299)
+    compiled unmodified for sm_100a into oracle/_ref/libref_msda.so (oracle/Makefile), timed on this GPU at the two shapes of
+    the step, fp32 and fp16. It needs sampling locations and softmaxed weights as tensors (the reference computes them with
+    ATen kernels that are NOT timed here), so this is a lower bound of the reference op's cost. -> None when the library
+    is absent."""
+    import ctypes
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_msda.so")
+    if not os.path.exists(path):
+        return None
+    lib = ctypes.CDLL(path)
+    fn = lib.ref_msda_im2col
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int] * 8 + [ctypes.c_void_p]
+    M, D, P = 16, 32, 4
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for name, qn, vshapes in (("injector", 4096, [(128, 128), (64, 64), (32, 32)]), ("extractor", 21504, [(64, 64)])):
+        L = len(vshapes)
+        sh = torch.as_tensor(vshapes, dtype=torch.long)
+        S = int(sh.prod(1).sum())
+        lsi = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1])).cuda()
+        shc = sh.cuda()
+        g = torch.Generator(device="cuda").manual_seed(5)
+        for half in (0, 1):
+            dt = torch.float16 if half else torch.float32
+            value = torch.randn(B, S, M, D, device="cuda", generator=g).to(dt)
+            loc = torch.rand(B, qn, M, L, P, 2, device="cuda", generator=g).to(dt)
+            attn = torch.softmax(torch.randn(B, qn, M, L * P, device="cuda", generator=g), -1).view(B, qn, M, L, P).to(dt)
+            o = torch.empty(B, qn, M * D, device="cuda", dtype=dt)
+            st = torch.cuda.current_stream().cuda_stream
+            args = (value.data_ptr(), shc.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(), o.data_ptr(), B, S, M, D, qn, L, P, half, st)
+            for _ in range(2):
+                assert fn(*args) == 0
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                assert fn(*args) == 0
+                e.record()
+                torch.cuda.synchronize()
+                ts.append(s.elapsed_time(e))
+            out[f"{name}_{'fp16' if half else 'fp32'}_us"] = statistics.median(ts) * 1e3
+    return out
+
+
+def other_configs():
+    """BASELINE configs 4 (FMB 800x800 ...NEWwithcp, whole_dim_cut, 14 classes) and 5a (MUSES 1080x1920 slide, 6 crops of
+    1024^2 batched into one forward, 19 classes) at full size: device-timed throughput, 1 warm-up + 3 runs (extra keys of the
+    bench line; parity for both is in tests/test_model_gpu.py)."""
+    from common import build_segmentor
+    from oracle.perturb import synthetic_batch
+
+    def timed(fn, n=3):
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / n
+
+    out = {}
+    cfg4 = dict(VITL, img_size=800, modalities_name=["rgb", "thermal"], conv_drop_path_rate=0.3)
+    seg, _ = build_segmentor(cfg4, dict(VITL_HEAD, num_classes=14), btype="SAMAdapterbimodalMixModNewInTwinConvNEWwithcp",
+                             test_cfg=dict(mode="whole_dim_cut", rescale=False, dim=(600, 800), cut_dim=(800, 600)))
+    seg = seg.cuda()
+    x = synthetic_batch(8, 800, kind="thermal").cuda()
+    x[:, :, 600:] = 0
+    ms = timed(lambda: seg.encode_decode_labels(x, (800, 800), (600, 800)))
+    out["config4_fmb_800x800_whole_dim_cut"] = {"img_per_s": 8e3 / ms, "ms_per_batch_of_8": ms}
+    del seg
+    torch.cuda.empty_cache()
+    seg, _ = build_segmentor(VITL, dict(VITL_HEAD, num_classes=19), test_cfg=dict(mode="slide", crop_size=(1024, 1024), stride=(640, 640)))
+    seg = seg.cuda()
+    fr = synthetic_batch(1, (1080, 1920)).cuda()
+    ms = timed(lambda: seg.slide_labels(fr))
+    out["config5a_muses_1080x1920_slide"] = {"frames_per_s": 1e3 / ms, "crops_per_s": 6e3 / ms, "ms_per_frame": ms}
+    del seg
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -283,6 +398,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-extras", action="store_true", help="skip the reference-kernel timing and the config-4 / 5a legs")
     ap.add_argument("--dump-gemm", default=None, help="write the per-configuration GEMM timing table (JSON) to this path")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -321,31 +437,40 @@ def main():
     B = args.batch
     seg, sd = build_model()
     seg = seg.cuda()
+    seg.set_input_pipeline(PIPELINE["mean"], PIPELINE["std"], to_rgb=PIPELINE["to_rgb"], norm_by_max=PIPELINE["norm_by_max"])
     eng = seg.backbone.engine(seg.decode_head)
-    x_host = synthetic_batch(B, 1024, seed=1234 + rank * B).pin_memory()
-    x = x_host.cuda()
-    g = torch.Generator().manual_seed(99 + rank)
-    gt = torch.randint(0, 25, (B, 1024, 1024), generator=g, dtype=torch.uint8)
-    gt[torch.rand(gt.shape, generator=g) < 0.01] = 255
+
+    def rank_data(r):
+        rgb, aux = synthetic_frames(B, 1024, 1234 + r * B)
+        g = torch.Generator().manual_seed(99 + r)
+        gt = torch.randint(0, 25, (B, 1024, 1024), generator=g, dtype=torch.uint8)
+        gt[torch.rand(gt.shape, generator=g) < 0.01] = 255
+        return rgb, aux, gt
+
+    rgb_host, aux_host, gt = rank_data(rank)
+    rgb_host, aux_host = rgb_host.pin_memory(), aux_host.pin_memory()
+    frames = seg.u8_input(rgb_host.cuda(), aux_host.cuda())
     gt = gt.cuda()
     conf = torch.zeros((25, 25), dtype=torch.int64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- value: inputs resident in HBM (201 MB fp32 per step > 126 MB L2) ----------------
+    # ---------------- value: uint8 frames resident in HBM; L2 flushed between steps ----------------
     run = eng.segment if args.no_graph else eng.segment_graphed   # CUDA-graph replay of the same kernels
     for _ in range(max(W, 1)):
-        run(x)
+        run(frames)
     barrier()
     clocks = ClockSampler(local)
     l0 = K.LAUNCHES + eng.graph_launches
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(args.steps):
-        labels = run(x)
+        flush.zero_()
+        labels = run(frames)
         K.confusion(labels, gt, 25, out=conf)
     e.record()
     barrier()
@@ -363,16 +488,16 @@ def main():
         conf_all = conf
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---------------- e2e: public API, pinned host input -> H2D -> forward -> D2H labels ----------------
+    # ---------------- e2e: public API, pinned host uint8 frames -> H2D -> forward -> D2H labels ----------------
     # EncoderDecoder.stream_labels is the test-loop call: one host batch in, one host label map out, per step; the
     # copy of step i+1 overlaps the forward of step i (copy stream), every step's H2D and D2H is inside the timed region
     seg.use_cuda_graph = not args.no_graph
 
     def host_batches(n):
         for _ in range(n):
-            yield x_host
+            yield (rgb_host, aux_host)
 
-    for lab in seg.stream_labels(host_batches(max(min(W, 2), 1)), (1024, 1024)):
+    for lab in seg.stream_labels(host_batches(max(min(W, 3), 1)), (1024, 1024)):
         pass
     barrier()
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -388,14 +513,24 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms2 = t.item()
     e2e = world * B * args.steps / (ms2 / 1e3)
+    h2d = rgb_host.numel() + aux_host.numel()
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
+    # BASELINE config 3: the sharded run must reproduce the single-process result bit for bit. Rank 0 re-runs every
+    # rank's images alone (eager launches, not the graph) and compares the confusion matrix with the all-gathered one.
+    single = torch.zeros_like(conf)
+    for r in range(world):
+        rgb_r, aux_r, gt_r = (rgb_host, aux_host, gt) if r == rank else rank_data(r)
+        lab_r = eng.segment(seg.u8_input(rgb_r.cuda(), aux_r.cuda()))
+        K.confusion(lab_r, gt_r.cuda(), 25, out=single)
+    equal_single = bool(torch.equal(single * args.steps, conf_all))
+
     pk = peaks()
-    inst = instrumented_pass(eng, x)
+    inst = instrumented_pass(eng, frames)
     gm, md = inst["gemm"], inst["msda"]
     if args.dump_gemm:
         with open(args.dump_gemm, "w") as f:
@@ -407,7 +542,7 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": bench_config(world, B, not args.no_graph),
-        "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": world * x_host.numel() * 4, "d2h_bytes_per_step": world * d2h,
+        "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * d2h,
                 "api": "EncoderDecoder.stream_labels (H2D of step i+1 overlaps the forward of step i)"},
         "gpu_launches": launches,
         "clocks": clk,
@@ -415,7 +550,8 @@ def main():
                      "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops_sustained"],
                      # ncu --set full, lin1 (32768x4096x1024, GELU) launch: dram__bytes_read + dram__bytes_write
                      # (profiles/r01_gemm_ncu_summary.txt); algorithmic bytes of that launch: 343 MB
-                     "traffic": 291.6e6, "traffic_of": "lin1 GEMM launch (M=32768 N=4096 K=1024)",
+                     "traffic": 291.6e6, "traffic_of": "lin1 GEMM launch (M=32768 N=4096 K=1024), dram read + write of one ncu --set full "
+                                                        "capture (profiles/r01_gemm_ncu_summary.txt), not re-measured by this run",
                      "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
                      "launches_per_step": gm["launches"], "distinct_configs": gm["configs"], "ms_per_step": gm["ms"],
                      "timing": "every distinct GEMM configuration of the step replayed 8x back to back (CUDA events), weighted by its launch count",
@@ -429,8 +565,27 @@ def main():
                                      "peak at 11.5 TB/s chip-wide (tools/micro/gather_bench.cu) -> 22 % of HBM peak",
                           "launches_per_step": md["launches"],
                           "ms_per_step": md["ms"], "peak_source": pk["source"]},
-        "miou_check": {"pixels": int(conf_all.sum().item())},
+        "miou_check": {"pixels": int(conf_all.sum().item()), "equal_single": equal_single,
+                       "equal_single_of": f"all-gathered confusion matrix of {world} rank(s) x {args.steps} steps == {args.steps} x one single-process "
+                                          f"eager pass over the same {world * B} images"},
     }
+    if not args.no_extras:
+        rk = reference_kernel_times(B)
+        if rk is not None:
+            # same algorithmic bytes (bf16 value / output convention of SURVEY 8(d)) over the reference kernel's time
+            mc = inst["msda_shapes"]
+            rk["reference_kernel_gbs_fp32"] = (4 * mc["injector"]["bytes"] + 6 * mc["extractor"]["bytes"]) / \
+                ((4 * rk["injector_fp32_us"] + 6 * rk["extractor_fp32_us"]) * 1e-6) / 1e9
+            rk["reference_kernel_gbs_fp16"] = (4 * mc["injector"]["bytes"] + 6 * mc["extractor"]["bytes"]) / \
+                ((4 * rk["injector_fp16_us"] + 6 * rk["extractor_fp16_us"]) * 1e-6) / 1e9
+            rk["ours_us"] = {k: v["us"] for k, v in mc.items()}
+            rk["note"] = ("the reference's kernel needs sampling locations + softmaxed weights materialised by separate ATen kernels "
+                          "(not timed); ours computes them in-kernel from the raw projection")
+            line["roofline_msda"]["reference_kernel"] = rk
+        del eng
+        seg.backbone.invalidate()
+        torch.cuda.empty_cache()
+        line["other_configs"] = other_configs()
     if not args.no_cpu_baseline:
         v, spi, kind = cpu_reference_img_per_s(sd, threads, 3, 1, median=True)
         line["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": threads, "kind": kind,

@@ -23,6 +23,7 @@ SIGNATURES = {
     "mmsam_gemm_grouped_bf16": [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_rowstats_bf16": [_vp, _vp, _ll, _i, _ll, _f, _vp],
     "mmsam_gemm_ln_bf16": [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mmsam_convnext_mlp_bf16": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _vp],
     "mmsam_msda_fused_bf16": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_msda_fused_staged_bf16": [_vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i,
                                      _vp, _vp, _i, _vp],

@@ -35,7 +35,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
-                and os.path.getmtime(obj) > os.path.getmtime(os.path.join(CSRC, "common.cuh"))
+                and all(os.path.getmtime(obj) > os.path.getmtime(os.path.join(CSRC, h)) for h in os.listdir(CSRC) if h.endswith(".cuh"))
                 and os.path.getmtime(obj) > os.path.getmtime(HEADER)):
             continue
         cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]

@@ -95,6 +95,8 @@ class _LinLN:
 # LayerNorm folded into the consumer GEMM (row statistics + column sums) for the adapter's LN -> Linear pairs; set
 # MMSAM_LN_FOLD=0 to run the separate LayerNorm kernel + plain GEMM instead.
 LN_FOLD = os.environ.get("MMSAM_LN_FOLD", "1") != "0"
+# ConvNeXt block tail (LN + pwconv1 + GELU + pwconv2 + gamma + residual) as one kernel; MMSAM_MLP_FUSED=0: LN + two GEMMs
+MLP_FUSED = os.environ.get("MMSAM_MLP_FUSED", "1") != "0"
 
 
 def _bn_fold(bn, dev):
@@ -452,7 +454,9 @@ class EncoderEngine(_Ops):
                         dw_b=_f32(b.depthwise_conv.bias, dev), ln=_LN(b.norm, dev),
                         pw1=_Lin(b.pointwise_conv1.weight, b.pointwise_conv1.bias, dev),
                         pw2=_Lin(b.pointwise_conv2.weight, b.pointwise_conv2.bias, dev,
-                                 scale=b.gamma if b.gamma is not None else None)))
+                                 scale=b.gamma if b.gamma is not None else None),
+                        # LN folded into pwconv1 for the one-launch block tail (mmsam_convnext_mlp_bf16)
+                        pw1_ln=_LinLN(b.pointwise_conv1.weight, b.pointwise_conv1.bias, b.norm, dev) if c in (96, 192, 384) else None))
                 e["blocks"] = blocks
                 e["out_ln"] = _LN(getattr(tw, f"norm_{br}{i}"), dev)
                 stages.append(e)
@@ -538,6 +542,11 @@ class EncoderEngine(_Ops):
             C = t.shape[1]
             for b in st["blocks"]:      # ConvNeXtBlock (twin_convnext.py:98-132)
                 y = K.dwconv(t, b["dw_w"], b["dw_b"], 7, [(h, w)], B, C, h * w * C, h * w * C)
+                f = b["pw1_ln"]
+                if f is not None and MLP_FUSED:
+                    # norm -> pwconv1 -> GELU -> pwconv2 -> gamma -> += t in one launch (the 4C intermediate stays on chip)
+                    K.convnext_mlp(y, f.w, f.colsum, f.b, b["pw2"].w, b["pw2"].b, b["pw2"].scale, t, f.eps)
+                    continue
                 y = self._ln(y, b["ln"])
                 y = self._gemm(y, b["pw1"], act="gelu")
                 self._gemm(y, b["pw2"], residual=t, out=t)

@@ -175,6 +175,20 @@ def gemm_ln(a, w, bias, colsum, rowstat, act=None, residual=None, out=None, out_
     return out
 
 
+def convnext_mlp(y, w1, colsum1, bias1, w2, bias2, gamma, t, eps, max_ctas=0):
+    """ConvNeXt block tail in one launch: t += gamma * (GELU(LN(y) @ w1^T + b1) @ w2^T + b2), in place on the fp32 stream t;
+    the LayerNorm affine is folded into w1 / colsum1 / bias1 (see include/mmsam_b200.h)."""
+    _need_cuda(y, w1, colsum1, bias1, w2, bias2, gamma, t)
+    M, C = y.shape
+    assert t.shape == (M, C) and t.dtype == torch.float32 and y.dtype == torch.bfloat16 and y.stride(1) == 1 and t.stride(1) == 1
+    assert w1.shape == (4 * C, C) and w2.shape == (C, 4 * C) and w1.is_contiguous() and w2.is_contiguous()
+    rc = _lib.load().mmsam_convnext_mlp_bf16(_ptr(y), y.stride(0), _ptr(w1), _ptr(colsum1), _ptr(bias1), _ptr(w2), _ptr(bias2),
+                                             _ptr(gamma), _ptr(t), t.stride(0), M, C, float(eps), max_ctas, _stream())
+    _lib.check(rc, "mmsam_convnext_mlp_bf16")
+    _count()
+    return t
+
+
 def relpos_table(rel_pos, size):
     """SAM get_rel_pos for q_size == k_size == size (base/image_encoder.py:554-584): linear
     interpolation of the [L, 64] table to 2*size-1 rows when L differs; row r = q - k + size - 1.

@@ -518,6 +518,41 @@ def test_gemm_with_folded_layernorm(M, N, K, f32, act):
     assert rel_l2(out, ref) < 8e-3
 
 
+@pytest.mark.parametrize("M,C,gamma_on", [(256, 96, True), (1000, 96, True), (37, 192, True), (2048 + 128, 192, False),
+                                          (900, 384, True), (256 * 80 + 8, 384, True), (256 * 150, 96, True)])
+def test_convnext_mlp_fused(M, C, gamma_on):
+    """ConvNeXt block tail in one launch (LN -> pwconv1 -> GELU -> pwconv2 -> gamma -> += into the fp32 stream,
+    twin_convnext.py:98-132) against F.layer_norm / F.linear / F.gelu in fp32; ragged M (partial 256-row tiles, a peer CTA
+    with no rows), more tiles than CTA pairs (the persistent loop and both weight rings wrap), rows with a large offset."""
+    k = _k()
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(M + C)
+    y = (torch.randn(M, C, generator=g) * (0.5 + torch.rand(M, 1, generator=g) * 2) + torch.randn(M, 1, generator=g) * 2).to(torch.bfloat16)
+    lw, lb = 1 + 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    W1, b1 = torch.randn(4 * C, C, generator=g) / C ** 0.5, 0.5 * torch.randn(4 * C, generator=g)
+    W2, b2 = torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5, 0.5 * torch.randn(C, generator=g)
+    gamma = (0.3 + 0.1 * torch.randn(C, generator=g)) if gamma_on else None
+    t0 = torch.randn(M, C, generator=g) * 3
+    eps = 1e-6
+    h = F.gelu(F.linear(F.layer_norm(y.float(), (C,), lw, lb, eps), W1, b1))
+    delta = F.linear(h, W2, b2)
+    if gamma is not None:
+        delta = delta * gamma
+    w1f = (W1 * lw[None, :]).to(torch.bfloat16)
+    t = t0.clone().cuda()
+    k.convnext_mlp(y.cuda(), w1f.cuda(), w1f.float().sum(1).cuda(), (W1 @ lb + b1).cuda(), W2.to(torch.bfloat16).cuda(), b2.cuda(),
+                   None if gamma is None else gamma.cuda(), t, eps)
+    got = t.cpu() - t0
+    err = (got - delta).abs()
+    assert (err <= 2e-2 * delta.abs() + 2e-2).all(), (err.max(), err.argmax())
+    assert rel_l2(got, delta) < 8e-3
+    # the residual add itself is exact fp32: t - delta_kernel reproduces t0 to rounding
+    t2 = t0.clone().cuda()
+    k.convnext_mlp(y.cuda(), w1f.cuda(), w1f.float().sum(1).cuda(), (W1 @ lb + b1).cuda(), W2.to(torch.bfloat16).cuda(), b2.cuda(),
+                   None if gamma is None else gamma.cuda(), t2, eps)
+    assert torch.equal(t, t2)                       # deterministic
+
+
 @pytest.mark.parametrize("B,C,ho,wo,srcs,relu", [
     (2, 64, 32, 32, [(16, 16), (8, 8), (4, 4)], True),      # Segformer head: 3 coarser levels added to the 1/4 level
     (1, 16, 27, 40, [(12, 20), (7, 9), (27, 40)], False),   # ragged row blocks, non-integer ratios, same-size source
