@@ -159,6 +159,128 @@ static int launch_dw(const DwParams& p, dim3 grid, cudaStream_t st) {
   return MMSAM_OK;
 }
 
+// ---- 7x7 on the fp32 residual stream of the ConvNeXt towers (72 launches per step) ---------------------------------------
+// The generic kernel above is bound by shared-memory bandwidth, not by the FMA pipe: with 4 output columns per thread it
+// reads 10 staged fp32 pairs (LDS.64 = 2 wavefronts each) per 28 packed FMAs, 23.5 wavefronts against 21 FMA-pipe cycles per
+// SM, and its 64-channel CTAs waste a third of the second channel block at C = 96. This kernel:
+//   * thread = one channel pair x 8 adjacent output columns x 4 rows: 14 loads per 56 FFMA2 (31.5 wavefronts against 42
+//     FMA-pipe cycles) -> bound by the FMA pipe, the floor of a depthwise conv on CUDA cores;
+//   * CTA = 32 channels (divides 96 / 192 / 384 / 768) x 32 columns x 4 RG rows, 64 RG threads;
+//   * the (4 RG + 6) x 38 x 32-channel fp32 halo arrives by ONE 4-D TMA box whose out-of-bounds elements are zero-filled
+//     by the copy engine ("same" padding, ragged right / bottom tiles); fp32 operands are used as they are (no bf16
+//     rounding of the stream);
+//   * the bf16 output tile is staged over the consumed halo and leaves by ONE TMA store (clipped at the map's edges).
+template <int RG>
+__global__ void __launch_bounds__(64 * RG, RG == 4 ? 2 : 3)
+dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const float* __restrict__ wt,
+                   const float* __restrict__ bias, int C, int tiles_x) {
+  constexpr int K = 7, CB = 32, XO = 8, TH = 4, TW = 32;
+  constexpr int ROWS = TH * RG, IH = ROWS + K - 1, IW = TW + K - 1;
+  extern __shared__ __align__(128) uint8_t dw_smem[];
+  uint8_t* base = dw_smem + ((128u - (smem_u32(dw_smem) & 127u)) & 127u);
+  float* s_in = reinterpret_cast<float*>(base);                                  // [IH][IW][CB] fp32
+  float* s_w = reinterpret_cast<float*>(base + IH * IW * CB * 4);                // [K*K][CB]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + IH * IW * CB * 4 + K * K * CB * 4);
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int c0 = blockIdx.y * CB, b = blockIdx.z;
+  const int y0 = ty * ROWS, x0 = tx * TW;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(bar, IH * IW * CB * 4);
+    tma_load_4d(s_in, &tmX, bar, c0, x0 - K / 2, y0 - K / 2, b);
+  }
+  for (int i = threadIdx.x; i < K * K * CB; i += blockDim.x) s_w[i] = wt[(i / CB) * C + c0 + (i % CB)];
+  const int cp = threadIdx.x & 15, xg = (threadIdx.x >> 4) & 3, rg = threadIdx.x >> 6;
+  u64 acc[TH][XO];
+  {
+    const float b0 = bias ? bias[c0 + cp * 2] : 0.f, b1 = bias ? bias[c0 + cp * 2 + 1] : 0.f;
+#pragma unroll
+    for (int r = 0; r < TH; ++r)
+#pragma unroll
+      for (int xo = 0; xo < XO; ++xo) acc[r][xo] = pack2(b0, b1);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+  const float* in0 = s_in + ((rg * TH) * IW + xg * XO) * CB + cp * 2;
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    u64 w[K];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) w[kx] = *reinterpret_cast<const u64*>(&s_w[(ky * K + kx) * CB + cp * 2]);
+#pragma unroll
+    for (int r = 0; r < TH; ++r) {
+      u64 in[XO + K - 1];
+#pragma unroll
+      for (int i = 0; i < XO + K - 1; ++i) in[i] = *reinterpret_cast<const u64*>(in0 + ((r + ky) * IW + i) * CB);
+#pragma unroll
+      for (int xo = 0; xo < XO; ++xo)
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) acc[r][xo] = fma2(in[xo + kx], w[kx], acc[r][xo]);
+    }
+  }
+  __syncthreads();                      // every warp is done with the halo: reuse it as the [ROWS][TW][CB] bf16 output tile
+  uint32_t* s_out = reinterpret_cast<uint32_t*>(base);
+#pragma unroll
+  for (int r = 0; r < TH; ++r)
+#pragma unroll
+    for (int xo = 0; xo < XO; ++xo) {
+      float a0, a1;
+      unpack2(acc[r][xo], a0, a1);
+      s_out[((rg * TH + r) * TW + xg * XO + xo) * (CB / 2) + cp] = pack_bf16(a0, a1);
+    }
+  fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(&tmY)),
+                 "r"(smem_u32(s_out)), "r"(c0), "r"(x0), "r"(y0), "r"(b)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
+template <int RG>
+static int launch_dw7_tma(const CUtensorMap& tmX, const CUtensorMap& tmY, const float* w, const float* bias, int C, int H, int W,
+                          int B, cudaStream_t st) {
+  constexpr int smem = (4 * RG + 6) * 38 * 32 * 4 + 49 * 32 * 4 + 16 + 128;
+  MMSAM_SET_SMEM_ONCE((dwconv7_tma_kernel<RG>), smem);
+  const int tiles_x = (W + 31) / 32, tiles_y = (H + 4 * RG - 1) / (4 * RG);
+  dwconv7_tma_kernel<RG><<<dim3(tiles_x * tiles_y, C / 32, B), 64 * RG, smem, st>>>(tmX, tmY, w, bias, C, tiles_x);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
+// fp32 [B][H][W][C] -> bf16 [B][H][W][C] through the TMA kernel; batch strides in elements
+static int dwconv7_tma(const float* x, __nv_bfloat16* y, const float* w, const float* bias, int B, int C, int H, int W,
+                       long long in_bstride, long long out_bstride, cudaStream_t st) {
+  mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
+  if (!enc) return MMSAM_ERR_DRIVER;
+  static const int rg_env = [] { const char* e = getenv("MMSAM_DW_RG"); return e ? atoi(e) : 0; }();
+  // rows per CTA: 8 (128 threads, 3 CTAs / SM) measured 3-10 % faster than 16 (256 threads, 2 CTAs / SM) at every stage of
+  // the step (110 / 60 / 33 / 21 us vs 114 / 64 / 37 / 22): 22.4 TFMA/s at stage 0 = the FFMA2 issue rate of the chip
+  const int rg = rg_env == 4 ? 4 : 2;
+  CUtensorMap tmX, tmY;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  {
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)in_bstride * 4};
+    cuuint32_t box[4] = {32, 38, (cuuint32_t)(4 * rg + 6), 1};
+    if (enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MMSAM_ERR_DRIVER;
+  }
+  {
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)out_bstride * 2};
+    cuuint32_t box[4] = {32, 32, (cuuint32_t)(4 * rg), 1};
+    if (enc(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MMSAM_ERR_DRIVER;
+  }
+  return rg == 2 ? launch_dw7_tma<2>(tmX, tmY, w, bias, C, H, W, B, st) : launch_dw7_tma<4>(tmX, tmY, w, bias, C, H, W, B, st);
+}
+
 }  // namespace mmsam
 
 // See include/mmsam_b200.h for the contract.
@@ -198,6 +320,10 @@ MMSAM_API int mmsam_dwconv(const void* x, int x_dtype, void* y, const float* w_t
   dim3 grid(total, (C + 63) / 64, B);
   cudaStream_t st = (cudaStream_t)stream;
   static const int variant = [] { const char* e = getenv("MMSAM_DW_VARIANT"); return e ? atoi(e) : 1; }();   // 0: bf16 staging
+  if (ksize == 7 && x_dtype == MMSAM_F32 && ngrids == 1 && C % 32 == 0 && act == 0 && variant != 0 && variant != 2 &&
+      (long long)p.g[0].W * C % 4 == 0 && (in_bstride & 3) == 0)
+    return dwconv7_tma(reinterpret_cast<const float*>(x) + p.g[0].in_off, p.y + p.g[0].out_off, w_tap_major, bias, B, C, p.g[0].H,
+                       p.g[0].W, in_bstride, out_bstride, st);
   if (ksize == 7) {
     if (variant == 0) return x_dtype == MMSAM_F32 ? launch_dw<7, 4, 32, true, false>(p, grid, st) : launch_dw<7, 4, 32, false, false>(p, grid, st);
     return x_dtype == MMSAM_F32 ? launch_dw<7, 4, 32, true, true>(p, grid, st) : launch_dw<7, 4, 32, false, true>(p, grid, st);

@@ -836,7 +836,7 @@ def test_dwconv_fp32_input_and_resize_fp32_source():
     bias = torch.randn(C, generator=g)
     out = k.dwconv(x.cuda(), wt.reshape(C, 49).t().contiguous().cuda(), bias.cuda(), 7, [(h, w)], B, C, h * w * C, h * w * C)
     assert out.dtype == torch.bfloat16
-    xi = x.to(torch.bfloat16).float().reshape(B, h, w, C).permute(0, 3, 1, 2)       # the kernel rounds the staged input once
+    xi = x.reshape(B, h, w, C).permute(0, 3, 1, 2)       # fp32 operands, as the reference's conv sees them
     ref = torch.nn.functional.conv2d(xi, wt, bias, padding=3, groups=C).permute(0, 2, 3, 1).reshape(B, h * w, C)
     assert ((out.float().cpu() - ref).abs() <= 0.008 * ref.abs() + 4e-3).all()
     src = torch.randn(B, 8, 8, 128, generator=g)
@@ -844,6 +844,23 @@ def test_dwconv_fp32_input_and_resize_fp32_source():
     got = k.resize_add_affine(src.cuda(), (8, 8), (32, 32), B, 128, base=base.cuda()).float().cpu()
     up = torch.nn.functional.interpolate(src.permute(0, 3, 1, 2), size=(32, 32), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
     assert ((got - (up + base.float())).abs() <= 0.008 * (up + base.float()).abs() + 4e-3).all()
+
+
+@pytest.mark.parametrize("B,C,h,w", [(1, 32, 7, 5), (2, 96, 33, 70), (3, 384, 64, 64), (8, 768, 32, 32), (1, 192, 128, 128),
+                                     (2, 96, 16, 32), (1, 64, 17, 33)])
+def test_dwconv7_fp32_stream(B, C, h, w):
+    """ConvNeXt 7x7 depthwise conv on the fp32 residual stream (twin_convnext.py:98-101): the TMA-staged kernel (halo
+    zero-filled by the copy engine, output clipped by the TMA store) against F.conv2d in fp32: maps smaller than one tile,
+    ragged right / bottom tiles, both row-group variants (the small-map heuristic picks 8-row tiles), batch strides."""
+    k = _k()
+    g = torch.Generator().manual_seed(B * 1000 + C + h)
+    x = torch.randn(B, h * w, C, generator=g) * 2
+    wt = torch.randn(C, 1, 7, 7, generator=g) / 7
+    bias = torch.randn(C, generator=g)
+    out = k.dwconv(x.cuda(), wt.reshape(C, 49).t().contiguous().cuda(), bias.cuda(), 7, [(h, w)], B, C, h * w * C, h * w * C)
+    ref = torch.nn.functional.conv2d(x.reshape(B, h, w, C).permute(0, 3, 1, 2), wt, bias, padding=3, groups=C).permute(0, 2, 3, 1).reshape(B, h * w, C)
+    err = (out.float().cpu() - ref).abs()
+    assert (err <= 0.004 * ref.abs() + 1e-3).all(), err.max().item()      # bf16 rounding of the output only
 
 
 @pytest.mark.parametrize("Lq,shapes", [(4096, [(128, 128), (64, 64), (32, 32)]), (21504, [(64, 64)])])
