@@ -15,10 +15,10 @@ t = torch.randn(M, C, device="cuda")
 for _ in range(3):
     K.convnext_mlp(y, w1, cs, b1, w2, b2, gm, t, 1e-6)
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * (3 * 64 * 8))()
+buf = (ctypes.c_longlong * (3 * 64 * 12))()
 lib = ctypes.CDLL(_lib.LIB_PATH)
 assert lib.mmsam_dbg_mlp_trace(buf) == 1
-T = [[[buf[(r * 64 + g) * 8 + e] for e in range(8)] for g in range(64)] for r in range(3)]
+T = [[[buf[(r * 64 + g) * 12 + e] for e in range(12)] for g in range(64)] for r in range(3)]
 t0 = T[0][0][0]
 print("MMA thread (leader): per chunk g: G1 wait-start, w1 ready, G1 issued+committed | G2(g): wait start, h_ready, w2/o ready, issued")
 for g in range(4, 30):
@@ -30,6 +30,14 @@ for r in (1, 2):
     for g in range(4, 30):
         e = T[r][g]
         print(f" g={g:2d} {e[0]-e0:7d} +{e[1]-e[0]:5d} +{e[2]-e[1]:4d} +{e[3]-e[2]:4d} +{e[4]-e[3]:4d} +{e[5]-e[4]:4d} | period {T[r][g][0]-T[r][g-1][0]:5d}")
+NCH = 4 * C // 128
+print("tile boundaries (leader CTA, warp 0): last chunk arrive -> next A wait start -> A normalised / a_ready arrive -> o_full wait start -> o_full -> drain done | MMA: a_ready wait start -> seen")
+for tb in range(1, 4):
+    g = tb * NCH
+    if g >= 64 or T[1][g][6] == 0:
+        break
+    e, l, m = T[1][g], T[1][g - 1], T[0][g]
+    print(f" tile {tb}: {l[5]-t0} -> {e[6]-t0} -> {e[8]-t0} -> {l[9]-t0} -> {l[10]-t0} -> {l[11]-t0} | MMA {m[7]-t0} -> {m[8]-t0}; first G1 issued {m[2]-t0}")
 # same-SM correlation (leader CTA): G1 commit of chunk g -> epilogue wake
 print("leader: G1(g) committed -> epilogue warp 0 sees hacc_full; epilogue arrive -> MMA thread sees h_ready")
 for g in range(4, 16):
