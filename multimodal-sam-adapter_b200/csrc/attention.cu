@@ -505,6 +505,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 
 }  // namespace mmsam
 
+int mmsam_attention_glb(const void* qkv, void* out, const int* out_row_map_dev, const void* tab_h, const void* tab_w, int Bp, int T,
+                        int nh, int Kh, float scale, int max_ctas, cudaStream_t stream);   // attention_glb.cu
 int mmsam_attention_win(const void* qkv, void* out, const int* out_row_map_dev, const void* tab_h, const void* tab_w, int Bp,
                         int nh, float scale, int max_ctas, cudaStream_t stream);   // attention_win.cu
 
@@ -525,6 +527,12 @@ MMSAM_API int mmsam_attention_bf16(const void* qkv, void* out, const int* out_ro
   if (use_win && T == 196 && (!has_bias || (Kh == 14 && Kw == 14))) {
     if (has_bias && (((uintptr_t)tab_h | (uintptr_t)tab_w) & 15)) return MMSAM_ERR_BAD_ARG;
     return mmsam_attention_win(qkv, out, out_row_map_dev, tab_h, tab_w, Bp, nh, scale, max_ctas, (cudaStream_t)stream);
+  }
+  // 64-wide token grids (ViT-L global blocks at 1024^2): the two-tile ping-pong kernel (attention_glb.cu)
+  static const int use_glb = [] { const char* e = getenv("MMSAM_ATT_GLB"); return e ? atoi(e) : 1; }();
+  if (use_glb && has_bias && Kw == 64 && Kh >= 2 && Kh <= 64 && (Kh & 1) == 0) {
+    if ((((uintptr_t)tab_h | (uintptr_t)tab_w) & 15)) return MMSAM_ERR_BAD_ARG;
+    return mmsam_attention_glb(qkv, out, out_row_map_dev, tab_h, tab_w, Bp, T, nh, Kh, scale, max_ctas, (cudaStream_t)stream);
   }
   if (!has_bias) { Kh = 1; Kw = T; }
   AttnParams p;

@@ -399,6 +399,44 @@ def test_attention_vs_oracle(Bp, nh, Kh, Kw, bias):
     assert rel < 1e-2 and err < 0.05, (rel, err)
 
 
+@pytest.mark.parametrize("Bp,nh,Kh,ramp", [
+    (1, 2, 2, 0.0),      # 128 tokens: one key block, tile B of the only item has no rows
+    (2, 3, 6, 0.0),      # 384 tokens: the second item of a (batch, head) has only tile A
+    (1, 2, 34, 0.0),     # 2176 tokens = 17 tiles, 65-row key-row table (zero-filled to 128 by the copy engine)
+    (5, 16, 8, 0.0),     # more items than CTAs x ...: 160 items over 148 CTAs, the persistent loop wraps
+    (1, 2, 16, 24.0),    # logits ramp by ~24 log2 units per key block: every block takes the power-of-two rescale path
+])
+def test_attention_global_two_tile_kernel(Bp, nh, Kh, ramp):
+    """64-wide token grids run the two-tile ping-pong kernel (attention_glb.cu): single-pass softmax with a stale reference
+    maximum, P in tensor memory, key-column bias in registers. Against the fp64 oracle (base/image_encoder.py:483-501,
+    587-623), including key rows whose logits keep growing (the exact power-of-two rescale of P, sum and accumulator)."""
+    from oracle.model import attention_core
+    k = _k()
+    Kw, T = 64, Kh * 64
+    g = torch.Generator().manual_seed(Bp * 1000 + T)
+    qkv = (torch.randn(Bp, T, 3, nh, 64, generator=g) * 1.5)
+    if ramp:
+        # k = c(key row) * q_dir: the score of every query with the later key rows grows without bound along the row
+        qdir = torch.randn(64, generator=g)
+        qdir = qdir / qdir.norm()
+        qkv[:, :, 0] = qkv[:, :, 0] * 0.2 + 3.0 * qdir
+        rows = torch.arange(T) // 128
+        qkv[:, :, 1] = qkv[:, :, 1] * 0.2 + (ramp * 8 * 0.6931 / 3.0) * rows[None, :, None, None].float() * qdir
+    qkv = qkv.to(torch.bfloat16)
+    rph = (torch.randn(2 * Kh - 1, 64, generator=g) * 0.2).to(torch.bfloat16)
+    rpw = (torch.randn(2 * Kw - 1, 64, generator=g) * 0.2).to(torch.bfloat16)
+    th, tw = k.relpos_table(rph.cuda(), Kh), k.relpos_table(rpw.cuda(), Kw)
+    out = k.attention(qkv.view(Bp, T, -1).cuda(), nh, (Kh, Kw), th, tw).cpu().float()
+    q, kk, v = qkv.float().permute(2, 0, 3, 1, 4).reshape(3, Bp * nh, T, 64).unbind(0)
+    nchk = min(Bp * nh, 48)
+    ref = attention_core(q[:nchk].double(), kk[:nchk].double(), v[:nchk].double(), Kh, Kw, rph.double(), rpw.double()).float()
+    got = out.view(Bp, T, nh, 64).permute(0, 2, 1, 3).reshape(Bp * nh, T, 64)[:nchk]
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel < 1e-2 and err < 0.05, (rel, err)
+
+
 def test_attention_relpos_interpolated_table():
     """FMB-shaped case: a 127-row table interpolated to 2*50-1 = 99 rows (get_rel_pos :566-575)."""
     from oracle.model import attention_core
