@@ -239,8 +239,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       }
     }
   } else if (warp == 9) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer: the whole warp runs the loop, one elected lane issues (see elect_one) ===========================
+    {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, ATT_BN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, ATT_D, 0, 1);  // V is MN-major
       if (has_bias) { mbar_wait(tab_full, 0); }
@@ -257,15 +257,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         pph ^= 1;
         tc_fence_after();
         const uint32_t v_addr = smem_u32(sKV + stage * 2 * TILE_BYTES + TILE_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < ATT_BN / 16; ++kk) {
-          const uint32_t a = p_addr + (kk >> 2) * TILE_BYTES + (kk & 3) * 32;
-          const uint32_t b = v_addr + kk * 16 * 128;
-          umma_f16_ss(tmem + TM_O + (kk >> 2) * ATT_D, umma_desc_sw128(a), umma_desc_sw128(b), idesc_pv,
-                      (first && (kk & 3) == 0) ? 0u : 1u);
+          for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+            const uint32_t a = p_addr + (kk >> 2) * TILE_BYTES + (kk & 3) * 32;
+            const uint32_t b = v_addr + kk * 16 * 128;
+            umma_f16_ss(tmem + TM_O + (kk >> 2) * ATT_D, umma_desc_sw128(a), umma_desc_sw128(b), idesc_pv,
+                        (first && (kk & 3) == 0) ? 0u : 1u);
+          }
+          umma_commit(pv_done);
+          umma_commit(&kv_empty[stage]);
         }
-        umma_commit(pv_done);
-        umma_commit(&kv_empty[stage]);
+        __syncwarp();
       };
       // S_j = Q . K_j^T into the double-buffered score tile
       auto issue_qk = [&]() {
@@ -273,11 +276,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         mbar_wait(&s_empty[g & 1], ((g >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sKV + st * 2 * TILE_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem + TM_S + (g & 1) * ATT_BN, umma_desc_sw128(q_addr + k * 32),
-                      umma_desc_sw128(k_addr + k * 32), idesc_qk, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[g & 1]);
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem + TM_S + (g & 1) * ATT_BN, umma_desc_sw128(q_addr + k * 32),
+                        umma_desc_sw128(k_addr + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[g & 1]);
+        }
+        __syncwarp();
         if (++st == p.kv_stages) { st = 0; kph ^= 1; }
         ++g;
       };
@@ -300,14 +306,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           tc_fence_after();
           const uint32_t t_addr = smem_u32(sTab) + ((is_w ? p.nh_pad : 0) + c0) * 128;
           const uint32_t idesc_g = umma_idesc_bf16(128, n, 0, 0);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ss(tmem + TM_G, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(t_addr + k * 32), idesc_g,
-                        k != 0 ? 1u : 0u);
-          umma_commit(g_full);
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(tmem + TM_G, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(t_addr + k * 32), idesc_g,
+                          k != 0 ? 1u : 0u);
+            umma_commit(g_full);
+          }
+          __syncwarp();
           gph ^= 1;
         }
-        if (nkb == 1) umma_commit(q_empty + qi * 17);   // every MMA that reads this Q has been issued
+        if (nkb == 1) {                                 // every MMA that reads this Q has been issued
+          if (elect_one()) umma_commit(q_empty + qi * 17);
+          __syncwarp();
+        }
       };
       uint32_t it = 0;
       if ((int)blockIdx.x < p.num_tiles) prologue(0);
@@ -315,7 +327,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         // ---- main loop: QK_j issued ahead of PV_{j-1} ----
         for (int j = 1; j < nkb; ++j) {
           issue_qk();
-          if (j == nkb - 1) umma_commit(q_empty + (p.q_bufs == 2 ? (it & 1) : 0) * 17);
+          if (j == nkb - 1) {
+            if (elect_one()) umma_commit(q_empty + (p.q_bufs == 2 ? (it & 1) : 0) * 17);
+            __syncwarp();
+          }
           issue_pv(st_pv, j == 1);
           if (++st_pv == p.kv_stages) st_pv = 0;
         }

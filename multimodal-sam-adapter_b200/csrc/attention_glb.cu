@@ -49,7 +49,12 @@ struct GlbParams {
   int nqp;             // 256-row query pairs per (batch, head)
   int num_items;
   float scale_log2;
+  long long* trace;    // perf debug (MMSAM_ATT_TRACE): clock64 stamps of CTA 0, first item: [role 0..2][block < 64][event < 8]
 };
+#define GLB_TRACE(role, blk, ev)                                                                              \
+  do {                                                                                                       \
+    if (p.trace && blockIdx.x == 0 && it == 0 && (blk) < 64) p.trace[((role) * 64 + (blk)) * 8 + (ev)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ float glb_ex2(float x) {
   float y;
@@ -59,24 +64,32 @@ __device__ __forceinline__ float glb_ex2(float x) {
 
 // One 32-column chunk of the score row. MAXONLY: running maximum of u = s * scale + bw (the key-row bias is added by the
 // caller); else: p = exp2(u + nb), row sum, bf16 P written to the P columns of the chunk, maximum of u tracked on the side.
+// The exponentials are issued as ONE block of 32 MUFU.EX2 (volatile, in place) between the arithmetic that feeds them and
+// the sums / packs that consume them: with the consumers right behind each pair (what the compiler schedules by itself)
+// every FADD2 / F2FP waits out the MUFU latency, and a softmax warp has only one other warp on its scheduler to hide it.
 template <bool MAXONLY>
-__device__ __forceinline__ void glb_chunk(const uint32_t (&r)[32], const u64* bw2, u64 sc2, u64 nb2, float& mx, u64& sum2,
+__device__ __forceinline__ void glb_chunk(const uint32_t (&r)[32], const u64* bw2, u64 sc2, u64 nb2, float& mx, u64 (&sum2)[2],
                                           uint32_t p_addr) {
-  uint32_t pk[16];
+  float e[32];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    u64 u = fma2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, bw2[i]);
+    const u64 u = fma2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, bw2[i]);
     float a, b;
     unpack2(u, a, b);
     mx = max3(mx, a, b);
-    if constexpr (!MAXONLY) {
-      unpack2(add2(u, nb2), a, b);
-      const float p0 = glb_ex2(a), p1 = glb_ex2(b);
-      sum2 = add2(sum2, pack2(p0, p1));
-      pk[i] = pack_bf16(p0, p1);
-    }
+    if constexpr (!MAXONLY) unpack2(add2(u, nb2), e[2 * i], e[2 * i + 1]);
   }
-  if constexpr (!MAXONLY) tmem_st_32x32b_x16(p_addr, pk);
+  if constexpr (!MAXONLY) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(e[i]));
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(sum2[i & 1]) : "l"(pack2(e[2 * i], e[2 * i + 1])));
+      asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(e[2 * i + 1]), "f"(e[2 * i]));
+    }
+    tmem_st_32x32b_x16(p_addr, pk);
+  }
 }
 
 __global__ void __launch_bounds__(320, 1)
@@ -101,7 +114,8 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint64_t* pv_done = bars + 10;    // [2]
   uint64_t* kv_full = bars + 12;    // [NST]
   uint64_t* kv_empty = bars + 15;   // [NST]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* b_go = bars + 18;       // 4 warps: group A is half-way through its first key block of the item
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.T / BN;
@@ -110,7 +124,7 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(tab_full, 1);
-    mbar_init(g_full, 1); mbar_init(g_done, 8); mbar_init(o_free, 8);
+    mbar_init(g_full, 1); mbar_init(g_done, 8); mbar_init(o_free, 8); mbar_init(b_go, 4);
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
     for (int i = 0; i < NST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     fence_barrier_init();
@@ -147,8 +161,8 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       }
     }
   } else if (warp == 9) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer: the whole warp runs the loop, one elected lane issues ===========================
+    {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, BN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, D, 0, 1);      // A = P in tensor memory, B = V MN-major
       mbar_wait(tab_full, 0);
@@ -157,22 +171,30 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       int st = 0; uint32_t kph = 0;
       int st_pv = 0;
       uint32_t pph[2] = {0, 0};
+      int trace_it = 0, trace_j = 0;
       auto issue_qk = [&](int g, uint32_t k_addr) {
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem + TM_S + g * BN, umma_desc_sw128(q_addr[g] + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_qk,
-                      k != 0 ? 1u : 0u);
-        umma_commit(&s_full[g]);
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem + TM_S + g * BN, umma_desc_sw128(q_addr[g] + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_qk,
+                        k != 0 ? 1u : 0u);
+          umma_commit(&s_full[g]);
+        }
+        __syncwarp();
       };
       auto issue_pv = [&](int g, uint32_t v_addr, bool first) {
         mbar_wait(&p_full[g], pph[g]);
         pph[g] ^= 1;
         tc_fence_after();
+        if (lane == 0 && p.trace && blockIdx.x == 0 && trace_it == 0 && trace_j < 64) p.trace[(2 * 64 + trace_j) * 8 + g * 2] = clock64();
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk)
-          umma_f16_ts(tmem + TM_O + g * D, tmem + TM_S + g * BN + kk * 8, umma_desc_sw128(v_addr + kk * 16 * 128), idesc_pv,
-                      (first && kk == 0) ? 0u : 1u);
-        umma_commit(&pv_done[g]);
+          for (int kk = 0; kk < BN / 16; ++kk)
+            umma_f16_ts(tmem + TM_O + g * D, tmem + TM_S + g * BN + kk * 8, umma_desc_sw128(v_addr + kk * 16 * 128), idesc_pv,
+                        (first && kk == 0) ? 0u : 1u);
+          umma_commit(&pv_done[g]);
+        }
+        __syncwarp();
       };
       for (int it = 0; it < n_my; ++it) {
         // ---- bias pre-products of both tiles and both axes: Gw(A) -> S_A, Gh(A) -> scratch, Gw(B) -> S_B, Gh(B) -> O ----
@@ -180,37 +202,55 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         mbar_wait(o_free, (it & 1) ^ 1);
         tc_fence_after();
         const uint32_t gdst[4] = {tmem + TM_S, tmem + TM_X, tmem + TM_S + BN, tmem + TM_O};
+        if (elect_one()) {
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {
-          const uint32_t tab = t_addr + ((gi & 1) ? 0 : 128 * 128);        // even: key-column table (Rw), odd: key-row table (Rh)
+          for (int gi = 0; gi < 4; ++gi) {
+            const uint32_t tab = t_addr + ((gi & 1) ? 0 : 128 * 128);        // even: key-column table (Rw), odd: key-row table (Rh)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ss(gdst[gi], umma_desc_sw128(q_addr[gi >> 1] + k * 32), umma_desc_sw128(tab + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(gdst[gi], umma_desc_sw128(q_addr[gi >> 1] + k * 32), umma_desc_sw128(tab + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+          }
+          umma_commit(g_full);
         }
-        umma_commit(g_full);
+        __syncwarp();
         mbar_wait(g_done, it & 1);
         tc_fence_after();
         // ---- key blocks ----
+        trace_it = it;
         for (int j = 0; j < nkb; ++j) {
+          trace_j = j;
+          if (lane == 0) GLB_TRACE(2, j, 4);
           mbar_wait(&kv_full[st], kph);
+          if (lane == 0) GLB_TRACE(2, j, 5);
           const uint32_t k_addr = smem_u32(sKV + st * 2 * TILE);
           const uint32_t v_prev = smem_u32(sKV + st_pv * 2 * TILE + TILE);
           if (j > 0) issue_pv(0, v_prev, j == 1);
           issue_qk(0, k_addr);
+          if (lane == 0) GLB_TRACE(2, j, 1);
           if (j > 0) {
             issue_pv(1, v_prev, j == 1);
-            umma_commit(&kv_empty[st_pv]);
+            if (elect_one()) umma_commit(&kv_empty[st_pv]);
+            __syncwarp();
             if (++st_pv == NST) st_pv = 0;
+          } else {
+            // The two groups share the MUFU units: in phase they would both sit in their exponentials and then both wait for
+            // the tensor core. Group B starts half a key block behind group A and keeps that distance for the whole item.
+            mbar_wait(b_go, it & 1);
           }
           issue_qk(1, k_addr);
-          if (j == nkb - 1) umma_commit(q_empty);       // every MMA that reads this item's Q has been issued
+          if (lane == 0) GLB_TRACE(2, j, 3);
+          if (j == nkb - 1) {                           // every MMA that reads this item's Q has been issued
+            if (elect_one()) umma_commit(q_empty);
+            __syncwarp();
+          }
           if (++st == NST) { st = 0; kph ^= 1; }
         }
         {
           const uint32_t v_prev = smem_u32(sKV + st_pv * 2 * TILE + TILE);
           issue_pv(0, v_prev, nkb == 1);
           issue_pv(1, v_prev, nkb == 1);
-          umma_commit(&kv_empty[st_pv]);
+          if (elect_one()) umma_commit(&kv_empty[st_pv]);
+          __syncwarp();
           if (++st_pv == NST) st_pv = 0;
         }
       }
@@ -274,12 +314,14 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       }
       float m_ref = 0.f, l_run = 0.f;
       for (int j = 0; j < nkb; ++j) {
+        if (wq == 0 && lane == 0) GLB_TRACE(g, j, 0);
         mbar_wait(&s_full[g], sph);
         sph ^= 1;
         tc_fence_after();
+        if (wq == 0 && lane == 0) GLB_TRACE(g, j, 1);
         const float bh0 = slice[(2 * j) * 32], bh1 = slice[(2 * j + 1) * 32];
         uint32_t ra[32], rb[32];
-        u64 sum2 = pack2(0.f, 0.f);
+        u64 sum2[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
         float mx0 = -INFINITY, mx1 = -INFINITY;
         if (j == 0) {
           // exact row maximum of the first block (no reference yet)
@@ -307,14 +349,19 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tmem_ld_wait();
         tmem_ld_32x32b_x32(s_addr + 64, ra);
         glb_chunk<false>(rb, bw2 + 16, sc2, nb0, mx0, sum2, s_addr + 16);
+        if (j == 0 && g == 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_go);
+        }
         tmem_ld_wait();
         tmem_ld_32x32b_x32(s_addr + 96, rb);
         glb_chunk<false>(ra, bw2, sc2, nb1, mx1, sum2, s_addr + 32);
         tmem_ld_wait();
         glb_chunk<false>(rb, bw2 + 16, sc2, nb1, mx1, sum2, s_addr + 48);
-        float ls0, ls1;
-        unpack2(sum2, ls0, ls1);
-        float lsum = ls0 + ls1;
+        float ls0, ls1, ls2, ls3;
+        unpack2(sum2[0], ls0, ls1);
+        unpack2(sum2[1], ls2, ls3);
+        float lsum = (ls0 + ls1) + (ls2 + ls3);
         const float m_blk = fmaxf(mx0 + bh0, mx1 + bh1);
         if (__any_sync(0xffffffffu, m_blk > m_ref + kThresh)) {
           // rare: this block's logits exceed the reference by more than 2^16. Rescale by an exact power of two: P of this block,
@@ -349,10 +396,12 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           }
         }
         l_run += lsum;
+        if (wq == 0 && lane == 0) GLB_TRACE(g, j, 2);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
+        if (wq == 0 && lane == 0) GLB_TRACE(g, j, 3);
         ++npv;
       }
       // ---- item epilogue: O / l -> bf16 -> global ----
@@ -398,6 +447,15 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
 }  // namespace mmsam
 
+static long long* g_glb_trace_buf = nullptr;
+// perf debug: copy the clock64 trace of the last traced launch to the host (3 x 64 x 8 values); returns 0 when tracing is off
+extern "C" __attribute__((visibility("default"))) int mmsam_dbg_attn_glb_trace(long long* host_out) {
+  if (!g_glb_trace_buf) return 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(host_out, g_glb_trace_buf, 3 * 64 * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+  return 1;
+}
+
 // qkv bf16 [Bp, T, 3, nh, 64] -> out; T = Kh * 64 tokens, Kh even and <= 64, both tables zero-padded to 128 rows.
 int mmsam_attention_glb(const void* qkv, void* out, const int* out_row_map_dev, const void* tab_h, const void* tab_w, int Bp, int T,
                         int nh, int Kh, float scale, int max_ctas, cudaStream_t stream) {
@@ -409,6 +467,12 @@ int mmsam_attention_glb(const void* qkv, void* out, const int* out_row_map_dev, 
   p.nqp = (T + 255) / 256;
   p.num_items = Bp * nh * p.nqp;
   p.scale_log2 = scale * glb::kLog2e;
+  static const int want_trace = getenv("MMSAM_ATT_TRACE") != nullptr;
+  if (want_trace && !g_glb_trace_buf) {
+    cudaMalloc(&g_glb_trace_buf, 3 * 64 * 8 * sizeof(long long));
+    cudaMemset(g_glb_trace_buf, 0, 3 * 64 * 8 * sizeof(long long));
+  }
+  p.trace = want_trace ? g_glb_trace_buf : nullptr;
   mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
   if (!enc) return MMSAM_ERR_DRIVER;
   CUtensorMap tmQKV, tmH, tmW;

@@ -202,8 +202,8 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
       }
     }
   } else if (warp == 9) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer: the whole warp runs the loop, one elected lane issues (see elect_one) ===========================
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, NK, 0, 0);
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, D, 0, 1);      // A = P in TMEM (K-major), B = V MN-major
@@ -217,31 +217,40 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
         ++gn;
         tc_fence_after();
         WIN_TRACE(2, it, g * 4 + 1);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem + g * TM_SLOT, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
-        if (p.has_bias) {
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16_ss(tmem + TM_G, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(t_addr + k * 32), idesc_g, k != 0 ? 1u : 0u);
+            umma_f16_ss(tmem + g * TM_SLOT, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
+          if (p.has_bias) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(tmem + TM_G, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(t_addr + k * 32), idesc_g, k != 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[g]);
         }
-        umma_commit(&s_full[g]);
+        __syncwarp();
       };
       auto issue_pv = [&](int g, uint32_t v_addr, int it) {
         WIN_TRACE(2, it, g * 4 + 2);
         mbar_wait(&p_half[g], it & 1);          // keys 0..159 (P columns 0..83 are written)
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 10; ++kk)
-          umma_f16_ts(tmem + g * TM_SLOT + TM_O, tmem + g * TM_SLOT + kk * 8, umma_desc_sw128(v_addr + kk * 16 * 128), idesc_pv,
-                      kk != 0 ? 1u : 0u);
+          for (int kk = 0; kk < 10; ++kk)
+            umma_f16_ts(tmem + g * TM_SLOT + TM_O, tmem + g * TM_SLOT + kk * 8, umma_desc_sw128(v_addr + kk * 16 * 128), idesc_pv,
+                        kk != 0 ? 1u : 0u);
+        }
+        __syncwarp();
         mbar_wait(&p_full[g], it & 1);          // keys 160..207
         tc_fence_after();
         WIN_TRACE(2, it, g * 4 + 3);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 10; kk < NK / 16; ++kk)
-          umma_f16_ts(tmem + g * TM_SLOT + TM_O, tmem + g * TM_SLOT + kk * 8, umma_desc_sw128(v_addr + kk * 16 * 128), idesc_pv, 1u);
-        umma_commit(&o_full[g]);
+          for (int kk = 10; kk < NK / 16; ++kk)
+            umma_f16_ts(tmem + g * TM_SLOT + TM_O, tmem + g * TM_SLOT + kk * 8, umma_desc_sw128(v_addr + kk * 16 * 128), idesc_pv, 1u);
+          umma_commit(&o_full[g]);
+        }
+        __syncwarp();
       };
       // Issue order: the two groups run HALF A PERIOD apart. While group 0's exponentials of tile A(it) run, the tensor core
       // finishes tile B(it - 1) (P.V) and starts tile B(it) (S, G); while group 1's exponentials of B(it) run, it finishes
@@ -258,7 +267,8 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
         const uint32_t k_addr = base + QA_BYTES + QB_BYTES, v_addr = k_addr + KV_BYTES;
         if (it > 0) {
           issue_pv(1, stage_of(it - 1) + QA_BYTES + QB_BYTES + KV_BYTES, it - 1);
-          umma_commit(&item_empty[(it - 1) & 1]);   // every MMA reading that stage has been issued
+          if (elect_one()) umma_commit(&item_empty[(it - 1) & 1]);   // every MMA reading that stage has been issued
+          __syncwarp();
         }
         issue_s(1, base + QA_BYTES, k_addr, it);
         issue_pv(0, v_addr, it);
@@ -270,7 +280,8 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
       }
       if (n_my > 0) {
         issue_pv(1, stage_of(n_my - 1) + QA_BYTES + QB_BYTES + KV_BYTES, n_my - 1);
-        umma_commit(&item_empty[(n_my - 1) & 1]);
+        if (elect_one()) umma_commit(&item_empty[(n_my - 1) & 1]);
+        __syncwarp();
       }
     }
   } else {

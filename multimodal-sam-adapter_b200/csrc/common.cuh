@@ -226,6 +226,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
                : "memory");
 }
+// One lane of a CONVERGED warp. tcgen05.mma / tcgen05.commit read their operands from uniform registers: issued under
+// `if (lane == 0)` (divergent code) ptxas wraps every instruction in an ELECT / BRA.U.ANY loop with four R2UR moves in
+// front - ~85 cycles of the issuing thread per MMA (measured: 4 MMAs into an idle pipe took 346 cycles). With the whole
+// warp running the issue loop and only the instruction itself under elect.sync, descriptors stay in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread.
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                             uint32_t idesc, uint32_t accumulate) {

@@ -101,7 +101,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    {   // the whole warp runs the loop, one elected lane issues (see elect_one)
       constexpr uint32_t idesc = umma_idesc_bf16(128, CV_BN, 0, 0);
       int s = 0; uint32_t ph = 0; int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -115,14 +115,18 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * CV_STAGE_BYTES);
           const uint32_t b_addr = a_addr + CV_A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[s]);
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty[s]);
+          }
+          __syncwarp();
           if (++s == CV_STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        if (elect_one()) umma_commit(&tfull[acc]);
+        __syncwarp();
       }
     }
   } else {

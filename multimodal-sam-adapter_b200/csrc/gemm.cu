@@ -505,8 +505,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     __syncwarp();
   } else if (warp == 9) {
-    // ---------------- MMA issuer (leader CTA only) ----------------
-    if (lane == 0 && rank == 0) {
+    // ---------------- MMA issuer (leader CTA only): the whole warp runs the loop, one elected lane issues (see elect_one) ----------------
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * Cfg::BM, BN, 0, 0);
       int s = 0; uint32_t ph = 0; int it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
@@ -520,16 +520,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < Cfg::BK / 16; ++k) {
-            if (ep.dbg & 8) break;
-            umma_f16_ss_cg2(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                            (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < Cfg::BK / 16; ++k) {
+              if (ep.dbg & 8) break;
+              umma_f16_ss_cg2(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_cg2(&empty[s]);
+            if (kb == num_k - 1) umma_commit_cg2(&tfull[acc]);
           }
-          umma_commit_cg2(&empty[s]);
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit_cg2(&tfull[acc]);
+        if (num_k == 0) {
+          if (elect_one()) umma_commit_cg2(&tfull[acc]);
+          __syncwarp();
+        }
       }
       // the peer's last remote arrivals must have landed before this CTA's barriers can go away
       if (it > 0) {

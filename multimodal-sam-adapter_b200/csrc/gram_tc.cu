@@ -96,7 +96,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const GramParams p) {
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    {   // the whole warp runs the loop, one elected lane issues (see elect_one)
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, BNJ, 1, 1);
       constexpr uint32_t idesc_n = umma_idesc_bf16(128, 128, 1, 1);
       int s = 0; uint32_t ph = 0;
@@ -105,19 +105,23 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const GramParams p) {
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t b_addr = a_addr + NA * GR_ATOM;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < GR_KP / 16; ++ks) {
-          const uint64_t da = umma_desc_sw128_mn(a_addr + ks * 16 * 128, GR_ATOM);
-          const uint64_t db = umma_desc_sw128_mn(b_addr + ks * 16 * 128, GR_ATOM);
-          const uint32_t acc = (it | ks) != 0 ? 1u : 0u;
-          umma_f16_ss(tmem + TM_G, da, db, idesc_g, acc);
-          if (want_nq) umma_f16_ss(tmem + TM_NQ, da, da, idesc_n, acc);
-          if (want_nk) umma_f16_ss(tmem + TM_NK, db, db, idesc_n, acc);
+          for (int ks = 0; ks < GR_KP / 16; ++ks) {
+            const uint64_t da = umma_desc_sw128_mn(a_addr + ks * 16 * 128, GR_ATOM);
+            const uint64_t db = umma_desc_sw128_mn(b_addr + ks * 16 * 128, GR_ATOM);
+            const uint32_t acc = (it | ks) != 0 ? 1u : 0u;
+            umma_f16_ss(tmem + TM_G, da, db, idesc_g, acc);
+            if (want_nq) umma_f16_ss(tmem + TM_NQ, da, da, idesc_n, acc);
+            if (want_nk) umma_f16_ss(tmem + TM_NK, db, db, idesc_n, acc);
+          }
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        __syncwarp();
         if (++s == GR_STAGES) { s = 0; ph ^= 1; }
       }
-      umma_commit(done);
+      if (elect_one()) umma_commit(done);
+      __syncwarp();
     }
   } else {
     // ---------------- epilogue: thread = output row i ----------------

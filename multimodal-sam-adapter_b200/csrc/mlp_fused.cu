@@ -177,68 +177,80 @@ convnext_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     __syncwarp();
   } else if (warp == 9) {
-    // ---------------- MMA issuer (leader CTA only) ----------------
-    if (lane == 0 && rank == 0) {
+    // ---------------- MMA issuer (leader CTA only): the whole warp runs the loop, one elected lane issues (see elect_one) ----------------
+    if (rank == 0) {
       constexpr uint32_t idesc1 = umma_idesc_bf16(256, Cfg::HN, 0, 0);
       constexpr uint32_t idesc2 = umma_idesc_bf16(256, Cfg::N2, 0, 0);
       int s1 = 0, s2 = 0; uint32_t ph1 = 0, ph2 = 0;
       const uint32_t a_addr = smem_u32(sA);
       auto issue_g2 = [&](int gp) {
         const int jp = gp % NCH, tp = gp / NCH, hb = gp % NACC;
-        MLP_TRACE(0, gp, 3);
+        if (lane == 0) MLP_TRACE(0, gp, 3);
         mbar_wait(&g2_rdy[hb], (gp / NACC) & 1);
         if (jp == 0) mbar_wait(o_empty, (tp & 1) ^ 1);
         tc_fence_after();
-        MLP_TRACE(0, gp, 4);
+        if (lane == 0) MLP_TRACE(0, gp, 4);
         const uint32_t h_addr = smem_u32(sH + hb * Cfg::H_BYTES);
+        if (lane == 0) MLP_TRACE(0, gp, 5);
+        const bool leader = elect_one();
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
-          if (kb == 0) MLP_TRACE(0, gp, 5);
           const uint32_t w_addr = smem_u32(sW2 + s2 * Cfg::W2_UNIT);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4 && !(p.dbg & 8); ++k) {
+            for (int k = 0; k < 4 && !(p.dbg & 8); ++k) {
 #pragma unroll
-            for (int h = 0; h < Cfg::NSPLIT; ++h)
-              umma_f16_ss_cg2(tmem_base + h * Cfg::N2, umma_desc_sw128(h_addr + kb * 16384 + k * 32),
-                              umma_desc_sw128(w_addr + h * (Cfg::N2 / 2) * 128 + k * 32), idesc2, (jp | kb | k) != 0 ? 1u : 0u);
+              for (int h = 0; h < Cfg::NSPLIT; ++h)
+                umma_f16_ss_cg2(tmem_base + h * Cfg::N2, umma_desc_sw128(h_addr + kb * 16384 + k * 32),
+                                umma_desc_sw128(w_addr + h * (Cfg::N2 / 2) * 128 + k * 32), idesc2, (jp | kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_cg2(&w2_empty[s2]);
           }
-          umma_commit_cg2(&w2_empty[s2]);
           if (++s2 == NU2) { s2 = 0; ph2 ^= 1; }
         }
-        umma_commit_cg2(&h_free[hb]);
-        MLP_TRACE(0, gp, 6);
-        if (jp == NCH - 1) umma_commit_cg2(o_full);
+        if (leader) {
+          umma_commit_cg2(&h_free[hb]);
+          if (jp == NCH - 1) umma_commit_cg2(o_full);
+        }
+        __syncwarp();
+        if (lane == 0) MLP_TRACE(0, gp, 6);
       };
       int g = 0, ti = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++ti) {
         // the previous tile's last G2 first: its o_full lets the epilogue warps drain and move on to this tile's A
         // (they announce a_ready), so it must not wait behind this tile's first G1
         if (g > 0) issue_g2(g - 1);
-        MLP_TRACE(0, g, 7);
+        if (lane == 0) MLP_TRACE(0, g, 7);
         mbar_wait(a_ready, ti & 1);
-        MLP_TRACE(0, g, 8);
+        if (lane == 0) MLP_TRACE(0, g, 8);
         for (int j = 0; j < NCH; ++j, ++g) {
           const int ab = g % NACC;
-          MLP_TRACE(0, g, 0);
+          if (lane == 0) MLP_TRACE(0, g, 0);
           mbar_wait(&g1_rdy[ab], (g / NACC) & 1);
           tc_fence_after();
-          MLP_TRACE(0, g, 1);
+          if (lane == 0) MLP_TRACE(0, g, 1);
           const uint32_t d_tmem = tmem_base + TM_H + ab * Cfg::HN;
+          const bool leader = elect_one();
 #pragma unroll
           for (int kb = 0; kb < KB1; ++kb) {
             const uint32_t w_addr = smem_u32(sW1 + s1 * Cfg::W1_UNIT);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (kb * 4 + k < Cfg::KS1 && !(p.dbg & 4))
-                umma_f16_ss_cg2(d_tmem, umma_desc_sw128(a_addr + kb * 16384 + k * 32), umma_desc_sw128(w_addr + k * 32), idesc1,
-                                (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                if (kb * 4 + k < Cfg::KS1 && !(p.dbg & 4))
+                  umma_f16_ss_cg2(d_tmem, umma_desc_sw128(a_addr + kb * 16384 + k * 32), umma_desc_sw128(w_addr + k * 32), idesc1,
+                                  (kb | k) != 0 ? 1u : 0u);
+              }
+              umma_commit_cg2(&w1_empty[s1]);
             }
-            umma_commit_cg2(&w1_empty[s1]);
             if (++s1 == NU1) { s1 = 0; ph1 ^= 1; }
           }
-          umma_commit_cg2(&hacc_full[ab]);
-          MLP_TRACE(0, g, 2);
-          if (j == NCH - 1) umma_commit_cg2(a_empty);
+          if (leader) {
+            umma_commit_cg2(&hacc_full[ab]);
+            if (j == NCH - 1) umma_commit_cg2(a_empty);
+          }
+          __syncwarp();
+          if (lane == 0) MLP_TRACE(0, g, 2);
           if (j > 0) issue_g2(g - 1);
         }
       }
