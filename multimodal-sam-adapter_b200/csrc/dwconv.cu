@@ -281,6 +281,130 @@ static int dwconv7_tma(const float* x, __nv_bfloat16* y, const float* w, const f
   return rg == 2 ? launch_dw7_tma<2>(tmX, tmY, w, bias, C, H, W, B, st) : launch_dw7_tma<4>(tmX, tmY, w, bias, C, H, W, B, st);
 }
 
+// ---- 3x3 on bf16 maps (ConvFFN's DWConv over the three token grids + GELU, MobileNetV2's depthwise + ReLU6) -----------------
+// Same structure as the 7x7 above: one 4-D TMA box per tile (zero-filled halo), thread = channel pair x 8 columns x 4 rows,
+// 32-channel CTAs, TMA store of the bf16 tile. The halo is staged as bf16 (the copy engine cannot convert), unpacked on
+// load; the fused activation runs on the packed pair. Up to three grids per launch (one tensor-map pair each).
+struct Dw3Maps { CUtensorMap x[3], y[3]; };
+struct Dw3Params {
+  const float* w;      // [9][C] tap-major
+  const float* bias;   // [C] or null
+  int C, act, ngrids;
+  int tiles_x[3], tile_start[4];
+};
+
+__global__ void __launch_bounds__(256, 2)
+dwconv3_tma_kernel(const __grid_constant__ Dw3Maps maps, const Dw3Params p) {
+  constexpr int K = 3, CB = 32, XO = 8, TH = 4, TW = 32, RG = 4;
+  constexpr int ROWS = TH * RG, IH = ROWS + K - 1, IW = TW + K - 1;
+  extern __shared__ __align__(128) uint8_t dw_smem[];
+  uint8_t* base = dw_smem + ((128u - (smem_u32(dw_smem) & 127u)) & 127u);
+  const uint32_t* s_in = reinterpret_cast<const uint32_t*>(base);                 // [IH][IW][CB / 2] bf16 pairs
+  float* s_w = reinterpret_cast<float*>(base + IH * IW * CB * 2);                 // [9][CB]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + IH * IW * CB * 2 + K * K * CB * 4);
+  int t = blockIdx.x, gi = 0;
+  while (gi + 1 < p.ngrids && t >= p.tile_start[gi + 1]) ++gi;
+  t -= p.tile_start[gi];
+  const int tx = t % p.tiles_x[gi], ty = t / p.tiles_x[gi];
+  const int c0 = blockIdx.y * CB, b = blockIdx.z;
+  const int y0 = ty * ROWS, x0 = tx * TW;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(bar, IH * IW * CB * 2);
+    tma_load_4d(base, &maps.x[gi], bar, c0, x0 - 1, y0 - 1, b);
+  }
+  for (int i = threadIdx.x; i < K * K * CB; i += blockDim.x) s_w[i] = p.w[(i / CB) * p.C + c0 + (i % CB)];
+  const int cp = threadIdx.x & 15, xg = (threadIdx.x >> 4) & 3, rg = threadIdx.x >> 6;
+  u64 acc[TH][XO];
+  {
+    const float b0 = p.bias ? p.bias[c0 + cp * 2] : 0.f, b1 = p.bias ? p.bias[c0 + cp * 2 + 1] : 0.f;
+#pragma unroll
+    for (int r = 0; r < TH; ++r)
+#pragma unroll
+      for (int xo = 0; xo < XO; ++xo) acc[r][xo] = pack2(b0, b1);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+  const uint32_t* in0 = s_in + ((rg * TH) * IW + xg * XO) * (CB / 2) + cp;
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    u64 w[K];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) w[kx] = *reinterpret_cast<const u64*>(&s_w[(ky * K + kx) * CB + cp * 2]);
+#pragma unroll
+    for (int r = 0; r < TH; ++r) {
+      u64 in[XO + K - 1];
+#pragma unroll
+      for (int i = 0; i < XO + K - 1; ++i) {
+        const uint32_t v = in0[((r + ky) * IW + i) * (CB / 2)];
+        in[i] = pack2(bf16lo(v), bf16hi(v));
+      }
+#pragma unroll
+      for (int xo = 0; xo < XO; ++xo)
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) acc[r][xo] = fma2(in[xo + kx], w[kx], acc[r][xo]);
+    }
+  }
+  __syncthreads();                      // every warp is done with the halo: reuse it as the [ROWS][TW][CB] bf16 output tile
+  uint32_t* s_out = reinterpret_cast<uint32_t*>(base);
+#pragma unroll
+  for (int r = 0; r < TH; ++r)
+#pragma unroll
+    for (int xo = 0; xo < XO; ++xo) {
+      float a0, a1;
+      unpack2(acc[r][xo], a0, a1);
+      if (p.act == 1) gelu_erf2(a0, a1);
+      else if (p.act == 3) { a0 = fminf(fmaxf(a0, 0.f), 6.f); a1 = fminf(fmaxf(a1, 0.f), 6.f); }
+      s_out[((rg * TH + r) * TW + xg * XO + xo) * (CB / 2) + cp] = pack_bf16(a0, a1);
+    }
+  fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(&maps.y[gi])),
+                 "r"(smem_u32(s_out)), "r"(c0), "r"(x0), "r"(y0), "r"(b)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
+static int dwconv3_tma(const __nv_bfloat16* x, __nv_bfloat16* y, const float* w, const float* bias, int B, int C, int ngrids,
+                       const DwGrid* g, long long in_bstride, long long out_bstride, int act, cudaStream_t st) {
+  mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
+  if (!enc) return MMSAM_ERR_DRIVER;
+  Dw3Maps maps;
+  Dw3Params p;
+  p.w = w; p.bias = bias; p.C = C; p.act = act; p.ngrids = ngrids;
+  int total = 0;
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 3; ++i) {
+    const int gi = i < ngrids ? i : 0;          // unused slots repeat grid 0 (a valid descriptor, never dereferenced)
+    const int H = g[gi].H, W = g[gi].W;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t sx[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)in_bstride * 2};
+    cuuint64_t sy[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)out_bstride * 2};
+    cuuint32_t bx[4] = {32, 34, 18, 1}, by[4] = {32, 32, 16, 1};
+    if (enc(&maps.x[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x) + g[gi].in_off, dims, sx, bx, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MMSAM_ERR_DRIVER;
+    if (enc(&maps.y[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y + g[gi].out_off, dims, sy, by, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MMSAM_ERR_DRIVER;
+    p.tiles_x[i] = i < ngrids ? (W + 31) / 32 : 0;
+    p.tile_start[i] = total;
+    if (i < ngrids) total += p.tiles_x[i] * ((H + 15) / 16);
+  }
+  p.tile_start[3] = total;
+  constexpr int smem = 18 * 34 * 32 * 2 + 9 * 32 * 4 + 16 + 128;
+  MMSAM_SET_SMEM_ONCE(dwconv3_tma_kernel, smem);
+  dwconv3_tma_kernel<<<dim3(total, C / 32, B), 256, smem, st>>>(maps, p);
+  MMSAM_LAUNCH_CHECK();
+  return MMSAM_OK;
+}
+
 }  // namespace mmsam
 
 // See include/mmsam_b200.h for the contract.
@@ -327,6 +451,11 @@ MMSAM_API int mmsam_dwconv(const void* x, int x_dtype, void* y, const float* w_t
   if (ksize == 7) {
     if (variant == 0) return x_dtype == MMSAM_F32 ? launch_dw<7, 4, 32, true, false>(p, grid, st) : launch_dw<7, 4, 32, false, false>(p, grid, st);
     return x_dtype == MMSAM_F32 ? launch_dw<7, 4, 32, true, true>(p, grid, st) : launch_dw<7, 4, 32, false, true>(p, grid, st);
+  }
+  if (variant != 0 && variant != 2 && C % 32 == 0) {
+    bool ok = true;      // TMA needs 16-byte global strides
+    for (int i = 0; i < ngrids; ++i) ok = ok && ((long long)p.g[i].W * C % 8 == 0);
+    if (ok) return dwconv3_tma(reinterpret_cast<const __nv_bfloat16*>(x), p.y, w_tap_major, bias, B, C, ngrids, p.g, in_bstride, out_bstride, act, st);
   }
   return launch_dw<3, 8, 32, false, false>(p, grid, st);
 }

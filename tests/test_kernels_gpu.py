@@ -675,6 +675,9 @@ def test_patchify_vs_unfold(p, C, c_off, H, W):
     (7, 3, 384, [(16, 16)], None),                      # many (channel group, image, tile) items per persistent CTA
     (3, 2, 256, [(32, 32), (16, 16), (8, 8)], "gelu"),  # ConvFFN DWConv: three token grids, shared weights, fused GELU
     (3, 1, 192, [(19, 25)], "relu6"),                   # MobileNetV2 block of the fusion neck
+    (3, 2, 256, [(40, 72), (20, 36), (10, 18)], "gelu"),  # 3x3 TMA kernel: several tiles per grid, ragged right / bottom tiles
+    (3, 1, 64, [(5, 7)], None),                         # map smaller than one tile
+    (3, 2, 40, [(12, 12)], "gelu"),                     # C % 32 != 0: the generic kernel
 ])
 def test_dwconv_vs_torch(K, B, C, grids, act):
     """Depthwise KxK (twin_convnext.py:98-101, adapter_modules_...new.py:456-471, :281-295) against F.conv2d(groups=C)."""

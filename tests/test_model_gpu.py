@@ -525,3 +525,72 @@ def test_uint8_input_pipeline_matches_fp32_path():
     seg.use_cuda_graph = True
     outs = [o.clone() for o in seg.stream_labels(iter([(rgb.pin_memory(), aux.pin_memory())] * 3), (128, 128))]
     assert len(outs) == 3 and all(torch.equal(o, outs[0]) for o in outs) and (outs[0] == want).float().mean().item() >= 0.9995
+
+
+def test_converted_checkpoints_run_on_the_gpu(tiny, tmp_path):
+    """SURVEY §8(f)-4 on the GPU: a released-format SAM checkpoint (`image_encoder.*` + neck / prompt-encoder tensors,
+    tools/SAM_checkpoint_convert.py:15-33), a single-tower ConvNeXt checkpoint (`backbone.`-prefixed, wrapped in
+    `state_dict`; base/twin_convnext.py:399-443) and a DataParallel-wrapped segmentor checkpoint (mmcv_custom/checkpoint.py
+    :319-515) are written to disk, ingested by checkpoint.py into FRESH modules, and the engine packed from them must
+    label a batch exactly like the module the tensors came from (kernels are deterministic -> torch.equal)."""
+    from mmsam_b200 import checkpoint as ck
+    from oracle.perturb import synthetic_batch
+    seg, sd = tiny
+    seg = seg.cuda()
+    cfg = dict(mode="whole_dim", rescale=True, dim=(128, 128))
+    x = synthetic_batch(2, 128, seed=5).cuda()
+    want = seg.encode_decode_labels(x, (128, 128), (128, 128)).cpu()
+
+    TW = "backbone.spm.twin_conv."
+
+    def is_vit(k):
+        return k.startswith("backbone.") and k[len("backbone."):].startswith(("pos_embed", "patch_embed.", "blocks."))
+
+    def tower(k):           # 'x' / 'y' for the keys a single-tower checkpoint provides (downsample_layers_*, stages_*), else None
+        if not k.startswith(TW):
+            return None
+        head = k[len(TW):].split(".")[0]
+        return head[-1] if head in ("downsample_layers_x", "downsample_layers_y", "stages_x", "stages_y") else None
+
+    sam = {"image_encoder." + k[len("backbone."):]: v.clone() for k, v in sd.items() if is_vit(k)}
+    assert sam
+    sam["image_encoder.neck.0.weight"] = torch.ones(4)
+    sam["prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"] = torch.ones(2, 3)
+    torch.save(sam, tmp_path / "sam_vit_release.pth")
+    single = {"backbone." + k[len(TW):].replace("_x", "", 1): v.clone() for k, v in sd.items() if tower(k) == "x"}
+    assert single
+    torch.save({"state_dict": single, "meta": {}}, tmp_path / "convnext_single_tower.pth")
+    torch.save({"state_dict": {"module." + k: v for k, v in sd.items()}, "meta": {"epoch": 1}}, tmp_path / "segmentor_dp.pth")
+
+    # (a) the whole segmentor from the DataParallel-wrapped file
+    fresh, _ = build_segmentor(TINY, TINY_HEAD, seed=123, perturb_seed=9, test_cfg=cfg)
+    missing, unexpected = ck.load_checkpoint(fresh, str(tmp_path / "segmentor_dp.pth"))
+    assert missing == [] and unexpected == []
+    got = fresh.cuda().encode_decode_labels(x, (128, 128), (128, 128)).cpu()
+    assert torch.equal(got, want)
+
+    # (b) ViT weights through the SAM conversion, both ConvNeXt towers from the single-tower file (the y tower then holds
+    #     the x tower's weights: that is what the reference does), everything else copied over
+    fresh2, _ = build_segmentor(TINY, TINY_HEAD, seed=321, perturb_seed=11, test_cfg=cfg)
+    rest = {k: v for k, v in sd.items() if not is_vit(k) and tower(k) is None}
+    fresh2.load_state_dict(rest, strict=False)
+    enc = ck.convert_sam_image_encoder(torch.load(tmp_path / "sam_vit_release.pth"))
+    assert enc and not any("neck" in k or "prompt" in k for k in enc)
+    res = fresh2.backbone.load_state_dict(enc, strict=False)
+    assert res.unexpected_keys == []
+    left = ck.load_twin_convnext(fresh2.backbone.spm.twin_conv, str(tmp_path / "convnext_single_tower.pth"))
+    assert left == []
+    expect = dict(sd)
+    for k in sd:
+        if tower(k) == "y":
+            expect[k] = sd[k.replace("_y", "_x", 1)]
+    sd2 = fresh2.state_dict()
+    for k, v in expect.items():
+        if not k.endswith("num_batches_tracked"):
+            assert torch.equal(sd2[k], v), k
+    ref_mod, _ = build_segmentor(TINY, TINY_HEAD, test_cfg=cfg)
+    ref_mod.load_state_dict(expect)
+    want2 = ref_mod.cuda().encode_decode_labels(x, (128, 128), (128, 128)).cpu()
+    got2 = fresh2.cuda().encode_decode_labels(x, (128, 128), (128, 128)).cpu()
+    assert torch.equal(got2, want2)
+    assert not torch.equal(want2, want)          # the y tower really changed
