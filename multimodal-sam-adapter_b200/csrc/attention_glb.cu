@@ -14,16 +14,19 @@
 //            block are two scalar shared-memory reads. One pass: p = exp2(s * scale + bw + bh - m_ref) with a STALE
 //            reference maximum (exact maximum of the first block; later blocks only track their maximum and, should it
 //            exceed m_ref by more than 2^16, rescale P, the running sum and O by an exact power of two - a path real
-//            attention rows do not take). P (bf16) overwrites the score columns it came from: O += P V reads it from
-//            TENSOR MEMORY (tcgen05.mma TS form) - no shared-memory panel, no proxy fence, one barrier each way.
-//   warp 9   MMA issuer: PV_A(j-1), QK_A(j), PV_B(j-1), QK_B(j): group A's exponentials run while the tensor core
-//            serves group B and vice versa (the groups share the four MUFU units, which are the floor: 2048 cycles per
-//            key block for both tiles).
+//            attention rows do not take). P (bf16) goes to 64 scratch columns of TENSOR MEMORY and O += P V reads it
+//            from there (tcgen05.mma TS form) - no shared-memory panel, no proxy fence. Because P does not overwrite S,
+//            the group releases S as soon as the block is in registers (s_free) and the tensor core computes the NEXT
+//            block's scores while this block's exponentials run: the softmax warps wait ~250 cycles per block
+//            (clock64 trace, tools/attn_glb_trace.py) instead of 1300 when P aliased S.
+//   warp 9   MMA issuer (whole warp, one elected lane): per block and group  s_free -> Q.K^T(j+1),  p_full -> P.V(j).
 //   warp 8   TMA producer.
 // Bias set-up per item: G = Q . table^T for both axes and both tiles (4 MMAs of N = 128 into the idle S / O / scratch
 // columns), scattered per row through the warp's 8 KB slice of shared memory: first the key-column values (Toeplitz
 // gather, then into registers), then the key-row values, which stay there as bh[key row][lane].
-// TMEM: S_A / P_A [0,128), S_B / P_B [128,256), O_A [256,320), O_B [320,384), scratch [384,512).
+// Measured (8 x 16 heads x 4096^2): 0.79 ms per launch = 693 TFLOP/s; the two groups' exponentials keep the MUFU units
+// ~70 % busy (2048 of ~2900 cycles per key block), which is what bounds it now.
+// TMEM: S_A [0,128), S_B [128,256), O_A [256,320), O_B [320,384), P_A [384,448), P_B [448,512) (= the bias scratch).
 #include "common.cuh"
 #include <cstdlib>
 
@@ -69,7 +72,7 @@ __device__ __forceinline__ float glb_ex2(float x) {
 // every FADD2 / F2FP waits out the MUFU latency, and a softmax warp has only one other warp on its scheduler to hide it.
 template <bool MAXONLY>
 __device__ __forceinline__ void glb_chunk(const uint32_t (&r)[32], const u64* bw2, u64 sc2, u64 nb2, float& mx, u64 (&sum2)[2],
-                                          uint32_t p_addr) {
+                                          uint32_t (&pk)[16]) {
   float e[32];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -82,13 +85,11 @@ __device__ __forceinline__ void glb_chunk(const uint32_t (&r)[32], const u64* bw
   if constexpr (!MAXONLY) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(e[i]));
-    uint32_t pk[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(sum2[i & 1]) : "l"(pack2(e[2 * i], e[2 * i + 1])));
       asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(e[2 * i + 1]), "f"(e[2 * i]));
     }
-    tmem_st_32x32b_x16(p_addr, pk);
   }
 }
 
@@ -114,8 +115,8 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint64_t* pv_done = bars + 10;    // [2]
   uint64_t* kv_full = bars + 12;    // [NST]
   uint64_t* kv_empty = bars + 15;   // [NST]
-  uint64_t* b_go = bars + 18;       // 4 warps: group A is half-way through its first key block of the item
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* s_free = bars + 18;     // [2] 4 warps each: the group holds its whole score row block in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.T / BN;
@@ -124,8 +125,8 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(tab_full, 1);
-    mbar_init(g_full, 1); mbar_init(g_done, 8); mbar_init(o_free, 8); mbar_init(b_go, 4);
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
+    mbar_init(g_full, 1); mbar_init(g_done, 8); mbar_init(o_free, 8);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); mbar_init(&s_free[i], 4); }
     for (int i = 0; i < NST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     fence_barrier_init();
   }
@@ -169,8 +170,8 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       const uint32_t q_addr[2] = {smem_u32(sQ), smem_u32(sQ + TILE)};
       const uint32_t t_addr = smem_u32(sTab);
       int st = 0; uint32_t kph = 0;
-      int st_pv = 0;
       uint32_t pph[2] = {0, 0};
+      uint32_t sfree_ph[2] = {0, 0};
       int trace_it = 0, trace_j = 0;
       auto issue_qk = [&](int g, uint32_t k_addr) {
         if (elect_one()) {
@@ -190,7 +191,7 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BN / 16; ++kk)
-            umma_f16_ts(tmem + TM_O + g * D, tmem + TM_S + g * BN + kk * 8, umma_desc_sw128(v_addr + kk * 16 * 128), idesc_pv,
+            umma_f16_ts(tmem + TM_O + g * D, tmem + TM_X + g * 64 + kk * 8, umma_desc_sw128(v_addr + kk * 16 * 128), idesc_pv,
                         (first && kk == 0) ? 0u : 1u);
           umma_commit(&pv_done[g]);
         }
@@ -215,44 +216,50 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         __syncwarp();
         mbar_wait(g_done, it & 1);
         tc_fence_after();
-        // ---- key blocks ----
+        // ---- key blocks. P lives in the scratch columns, not over S: Q.K^T of block j + 1 is issued as soon as the group
+        //      holds block j in registers (s_free), long before its exponentials are done - the softmax warps never wait for the
+        //      tensor core in steady state; P.V of block j follows when P is written. ----
         trace_it = it;
-        for (int j = 0; j < nkb; ++j) {
-          trace_j = j;
-          if (lane == 0) GLB_TRACE(2, j, 4);
+        uint32_t sfph[2] = {sfree_ph[0], sfree_ph[1]};
+        {
           mbar_wait(&kv_full[st], kph);
-          if (lane == 0) GLB_TRACE(2, j, 5);
           const uint32_t k_addr = smem_u32(sKV + st * 2 * TILE);
-          const uint32_t v_prev = smem_u32(sKV + st_pv * 2 * TILE + TILE);
-          if (j > 0) issue_pv(0, v_prev, j == 1);
           issue_qk(0, k_addr);
-          if (lane == 0) GLB_TRACE(2, j, 1);
-          if (j > 0) {
-            issue_pv(1, v_prev, j == 1);
-            if (elect_one()) umma_commit(&kv_empty[st_pv]);
-            __syncwarp();
-            if (++st_pv == NST) st_pv = 0;
-          } else {
-            // The two groups share the MUFU units: in phase they would both sit in their exponentials and then both wait for
-            // the tensor core. Group B starts half a key block behind group A and keeps that distance for the whole item.
-            mbar_wait(b_go, it & 1);
-          }
           issue_qk(1, k_addr);
-          if (lane == 0) GLB_TRACE(2, j, 3);
-          if (j == nkb - 1) {                           // every MMA that reads this item's Q has been issued
+          if (nkb == 1) {
             if (elect_one()) umma_commit(q_empty);
             __syncwarp();
           }
-          if (++st == NST) { st = 0; kph ^= 1; }
         }
-        {
-          const uint32_t v_prev = smem_u32(sKV + st_pv * 2 * TILE + TILE);
-          issue_pv(0, v_prev, nkb == 1);
-          issue_pv(1, v_prev, nkb == 1);
-          if (elect_one()) umma_commit(&kv_empty[st_pv]);
+        for (int j = 0; j < nkb; ++j) {
+          trace_j = j;
+          const int st_next = st + 1 == NST ? 0 : st + 1;
+          const uint32_t kph_next = st + 1 == NST ? kph ^ 1 : kph;
+          const bool more = j + 1 < nkb;
+          if (lane == 0) GLB_TRACE(2, j, 4);
+          if (more) mbar_wait(&kv_full[st_next], kph_next);
+          if (lane == 0) GLB_TRACE(2, j, 5);
+          const uint32_t k_next = smem_u32(sKV + st_next * 2 * TILE);
+          const uint32_t v_addr = smem_u32(sKV + st * 2 * TILE + TILE);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(&s_free[g], sfph[g]);
+            sfph[g] ^= 1;
+            if (more) {
+              tc_fence_after();
+              issue_qk(g, k_next);
+            }
+            if (lane == 0) GLB_TRACE(2, j, 1 + 2 * g);
+            issue_pv(g, v_addr, j == 0);
+          }
+          if (elect_one()) {
+            umma_commit(&kv_empty[st]);
+            if (j + 2 == nkb) umma_commit(q_empty);       // every MMA that reads this item's Q has been issued
+          }
           __syncwarp();
-          if (++st_pv == NST) st_pv = 0;
+          st = st_next; kph = kph_next;
         }
+        sfree_ph[0] = sfph[0]; sfree_ph[1] = sfph[1];
       }
     }
   } else {
@@ -262,6 +269,7 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
     const uint32_t s_addr = lane_addr + TM_S + g * BN;
     const uint32_t o_addr = lane_addr + TM_O + g * D;
+    const uint32_t p_addr = lane_addr + TM_X + g * 64;      // P (bf16 pairs): 64 scratch columns per group
     float* slice = sBh + warp * (64 * 32) + lane;        // this warp's [64][lane] area, this lane's column
     const u64 sc2 = pack2(p.scale_log2, p.scale_log2);
     const int qw = (wq & 1) * 32 + lane;                 // token column of this row (tile rows = 2 token rows x 64)
@@ -320,7 +328,7 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tc_fence_after();
         if (wq == 0 && lane == 0) GLB_TRACE(g, j, 1);
         const float bh0 = slice[(2 * j) * 32], bh1 = slice[(2 * j + 1) * 32];
-        uint32_t ra[32], rb[32];
+        uint32_t ra[32], rb[32], pka[16], pkb[16];
         u64 sum2[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
         float mx0 = -INFINITY, mx1 = -INFINITY;
         if (j == 0) {
@@ -328,15 +336,15 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           tmem_ld_32x32b_x32(s_addr, ra);
           tmem_ld_wait();
           tmem_ld_32x32b_x32(s_addr + 32, rb);
-          glb_chunk<true>(ra, bw2, sc2, 0ull, mx0, sum2, 0u);
+          glb_chunk<true>(ra, bw2, sc2, 0ull, mx0, sum2, pka);
           tmem_ld_wait();
           tmem_ld_32x32b_x32(s_addr + 64, ra);
-          glb_chunk<true>(rb, bw2 + 16, sc2, 0ull, mx0, sum2, 0u);
+          glb_chunk<true>(rb, bw2 + 16, sc2, 0ull, mx0, sum2, pka);
           tmem_ld_wait();
           tmem_ld_32x32b_x32(s_addr + 96, rb);
-          glb_chunk<true>(ra, bw2, sc2, 0ull, mx1, sum2, 0u);
+          glb_chunk<true>(ra, bw2, sc2, 0ull, mx1, sum2, pka);
           tmem_ld_wait();
-          glb_chunk<true>(rb, bw2 + 16, sc2, 0ull, mx1, sum2, 0u);
+          glb_chunk<true>(rb, bw2 + 16, sc2, 0ull, mx1, sum2, pka);
           m_ref = fmaxf(mx0 + bh0, mx1 + bh1);
           mx0 = mx1 = -INFINITY;
         }
@@ -345,19 +353,31 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tmem_ld_32x32b_x32(s_addr, ra);
         tmem_ld_wait();
         tmem_ld_32x32b_x32(s_addr + 32, rb);
-        glb_chunk<false>(ra, bw2, sc2, nb0, mx0, sum2, s_addr);
+        glb_chunk<false>(ra, bw2, sc2, nb0, mx0, sum2, pka);
         tmem_ld_wait();
         tmem_ld_32x32b_x32(s_addr + 64, ra);
-        glb_chunk<false>(rb, bw2 + 16, sc2, nb0, mx0, sum2, s_addr + 16);
-        if (j == 0 && g == 0) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(b_go);
+        glb_chunk<false>(rb, bw2 + 16, sc2, nb0, mx0, sum2, pkb);
+        if (j > 0) {
+          // P of the previous block must have been consumed before it is overwritten; two chunks into this block its P.V
+          // (issued when that P was handed over) has normally completed
+          if (wq == 0 && lane == 0) GLB_TRACE(g, j, 4);
+          mbar_wait(&pv_done[g], (npv - 1) & 1);
+          tc_fence_after();
+          if (wq == 0 && lane == 0) GLB_TRACE(g, j, 5);
         }
+        tmem_st_32x32b_x16(p_addr, pka);
+        tmem_st_32x32b_x16(p_addr + 16, pkb);
         tmem_ld_wait();
         tmem_ld_32x32b_x32(s_addr + 96, rb);
-        glb_chunk<false>(ra, bw2, sc2, nb1, mx1, sum2, s_addr + 32);
+        glb_chunk<false>(ra, bw2, sc2, nb1, mx1, sum2, pka);
+        tmem_st_32x32b_x16(p_addr + 32, pka);
         tmem_ld_wait();
-        glb_chunk<false>(rb, bw2 + 16, sc2, nb1, mx1, sum2, s_addr + 48);
+        // the whole block is in registers: the tensor core may overwrite S with the next block's scores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[g]);
+        glb_chunk<false>(rb, bw2 + 16, sc2, nb1, mx1, sum2, pkb);
+        tmem_st_32x32b_x16(p_addr + 48, pkb);
         float ls0, ls1, ls2, ls3;
         unpack2(sum2[0], ls0, ls1);
         unpack2(sum2[1], ls2, ls3);
@@ -372,11 +392,11 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 #pragma unroll 1
           for (int c0 = 0; c0 < 64; c0 += 32) {
             uint32_t pr[32];
-            tmem_ld_32x32b_x32(s_addr + c0, pr);
+            tmem_ld_32x32b_x32(p_addr + c0, pr);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) pr[i] = pack_bf16(bf16lo(pr[i]) * f, bf16hi(pr[i]) * f);
-            tmem_st_32x32b_x32(s_addr + c0, pr);
+            tmem_st_32x32b_x32(p_addr + c0, pr);
           }
           lsum *= f;
           l_run *= f;

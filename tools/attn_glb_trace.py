@@ -18,7 +18,7 @@ lib = ctypes.CDLL(_lib.LIB_PATH)
 assert lib.mmsam_dbg_attn_glb_trace(buf) == 1
 E = [[[buf[(r * 64 + j) * 8 + e] for e in range(8)] for j in range(64)] for r in range(3)]
 t0 = E[0][0][0]
-print("block j | group A: wait start, +wait, +softmax, +arrive | group B: same | MMA: kv wait start, +kv, p_full A seen, QK_A issued, p_full B seen, QK_B issued")
+print("block j | group A: s_full wait start, +wait, +softmax (of which pv_done wait), +arrive | group B: same | MMA: kv wait start, +kv, p_full A seen, s_free A seen / QK_A(j+1) issued, p_full B seen, QK_B(j+1) issued")
 for j in range(0, 32):
     a, b, m = E[0][j], E[1][j], E[2][j]
-    print(f" j={j:2d} | A {a[0]-t0:7d} +{a[1]-a[0]:5d} +{a[2]-a[1]:5d} +{a[3]-a[2]:4d} | B {b[0]-t0:7d} +{b[1]-b[0]:5d} +{b[2]-b[1]:5d} +{b[3]-b[2]:4d} | MMA {m[4]-t0:7d} +{m[5]-m[4]:4d}  pA {m[0]-t0:7d} qkA {m[1]-t0:7d} pB {m[2]-t0:7d} qkB {m[3]-t0:7d}")
+    print(f" j={j:2d} | A {a[0]-t0:7d} +{a[1]-a[0]:5d} +{a[2]-a[1]:5d} ({a[5]-a[4]:4d}) +{a[3]-a[2]:4d} | B {b[0]-t0:7d} +{b[1]-b[0]:5d} +{b[2]-b[1]:5d} ({b[5]-b[4]:4d}) +{b[3]-b[2]:4d} | MMA {m[4]-t0:7d} +{m[5]-m[4]:4d}  pA {m[0]-t0:7d} qkA {m[1]-t0:7d} pB {m[2]-t0:7d} qkB {m[3]-t0:7d}")
