@@ -137,26 +137,35 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 8) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(tab_full, TAB_BYTES);
-      tma_load_2d(sTab, &tmTabH, tab_full, 0, 0);
-      tma_load_2d(sTab + 128 * 128, &tmTabW, tab_full, 0, 0);
+    // =========================== TMA producer: the whole warp runs the loop, one elected lane issues ===========================
+    {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(tab_full, TAB_BYTES);
+        tma_load_2d(sTab, &tmTabH, tab_full, 0, 0);
+        tma_load_2d(sTab + 128 * 128, &tmTabW, tab_full, 0, 0);
+      }
+      __syncwarp();
       int st = 0; uint32_t kph = 0;
       for (int it = 0; it < n_my; ++it) {
         const int item = blockIdx.x + it * gridDim.x;
         const int qp = item % p.nqp, bh = item / p.nqp;
         const int head = bh % p.nh, bp = bh / p.nh;
         mbar_wait(q_empty, (it & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full, 2 * TILE);
-        tma_load_4d(sQ, &tmQKV, q_full, 0, head, qp * 256, bp);
-        tma_load_4d(sQ + TILE, &tmQKV, q_full, 0, head, qp * 256 + 128, bp);        // rows >= T: zero-filled
+        if (elect_one()) {
+          mbar_arrive_expect_tx(q_full, 2 * TILE);
+          tma_load_4d(sQ, &tmQKV, q_full, 0, head, qp * 256, bp);
+          tma_load_4d(sQ + TILE, &tmQKV, q_full, 0, head, qp * 256 + 128, bp);        // rows >= T: zero-filled
+        }
+        __syncwarp();
         for (int j = 0; j < nkb; ++j) {
           mbar_wait(&kv_empty[st], kph ^ 1);
-          mbar_arrive_expect_tx(&kv_full[st], 2 * TILE);
-          uint8_t* sk = sKV + st * 2 * TILE;
-          tma_load_4d(sk, &tmQKV, &kv_full[st], 0, p.nh + head, j * BN, bp);
-          tma_load_4d(sk + TILE, &tmQKV, &kv_full[st], 0, 2 * p.nh + head, j * BN, bp);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&kv_full[st], 2 * TILE);
+            uint8_t* sk = sKV + st * 2 * TILE;
+            tma_load_4d(sk, &tmQKV, &kv_full[st], 0, p.nh + head, j * BN, bp);
+            tma_load_4d(sk + TILE, &tmQKV, &kv_full[st], 0, 2 * p.nh + head, j * BN, bp);
+          }
+          __syncwarp();
           if (++st == NST) { st = 0; kph ^= 1; }
         }
       }

@@ -181,24 +181,30 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 8) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
+    // =========================== TMA producer: the whole warp runs the loop, one elected lane issues ===========================
+    {
       if (p.has_bias) {
-        mbar_arrive_expect_tx(tab_full, TAB_BYTES);
-        tma_load_2d(sTab, &tmTabH, tab_full, 0, 0);
-        tma_load_2d(sTab + 32 * 128, &tmTabW, tab_full, 0, 0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(tab_full, TAB_BYTES);
+          tma_load_2d(sTab, &tmTabH, tab_full, 0, 0);
+          tma_load_2d(sTab + 32 * 128, &tmTabW, tab_full, 0, 0);
+        }
+        __syncwarp();
       }
       for (int it = 0; it < n_my; ++it) {
         const int item = blockIdx.x + it * gridDim.x;
         const int head = item % p.nh, bp = item / p.nh;
         const int st = it & 1;
         mbar_wait(&item_empty[st], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&item_full[st], STAGE_BYTES);
-        uint8_t* s = sStage + st * STAGE_BYTES;
-        tma_load_4d(s, &tmQA, &item_full[st], 0, head, 0, bp);
-        tma_load_4d(s + QA_BYTES, &tmQB, &item_full[st], 0, head, 128, bp);
-        tma_load_4d(s + QA_BYTES + QB_BYTES, &tmKV, &item_full[st], 0, p.nh + head, 0, bp);
-        tma_load_4d(s + QA_BYTES + QB_BYTES + KV_BYTES, &tmKV, &item_full[st], 0, 2 * p.nh + head, 0, bp);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&item_full[st], STAGE_BYTES);
+          uint8_t* s = sStage + st * STAGE_BYTES;
+          tma_load_4d(s, &tmQA, &item_full[st], 0, head, 0, bp);
+          tma_load_4d(s + QA_BYTES, &tmQB, &item_full[st], 0, head, 128, bp);
+          tma_load_4d(s + QA_BYTES + QB_BYTES, &tmKV, &item_full[st], 0, p.nh + head, 0, bp);
+          tma_load_4d(s + QA_BYTES + QB_BYTES + KV_BYTES, &tmKV, &item_full[st], 0, 2 * p.nh + head, 0, bp);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 9) {

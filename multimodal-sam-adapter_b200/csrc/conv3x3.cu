@@ -76,7 +76,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   };
 
   if (warp == 8) {
-    if (lane == 0) {
+    {   // TMA producer: the whole warp runs the loop, one elected lane issues (see elect_one: a TMA issued from divergent code
+        // costs a ~90-cycle ELECT / BRA.U.ANY round trip, and this kernel's k-blocks are only ~256 tensor-core cycles long)
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int nt, x0, y0, b;
@@ -84,19 +85,24 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         // first input channel of the first group touched, aligned down to 8 channels: a TMA box must start on
         // a 16-byte boundary of the innermost dimension
         const int kwin = (((nt * p.NS) / p.cg_out) * p.cg_in) & ~7;
-        for (int kb = 0; kb < num_k; ++kb) {
-          const int tap = kb / p.KC, kc = kb - tap * p.KC;
+        int kb = 0;
+        for (int tap = 0; tap < 9; ++tap) {
           const int dy = tap / 3, dx = tap - dy * 3;
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], CV_STAGE_BYTES);
-          uint8_t* sa = smem + s * CV_STAGE_BYTES;
-          asm volatile(
-              "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-              ::"r"(smem_u32(sa)), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(&full[s])),
-              "r"(kwin + kc * 64), "r"(x0 + dx - 1), "r"(y0 + dy - 1), "r"(b)
-              : "memory");
-          tma_load_2d(sa + CV_A_BYTES, &tmW, &full[s], 0, ((nt * 9 + tap) * p.KC + kc) * 64);
-          if (++s == CV_STAGES) { s = 0; ph ^= 1; }
+          for (int kc = 0; kc < p.KC; ++kc, ++kb) {
+            mbar_wait(&empty[s], ph ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full[s], CV_STAGE_BYTES);
+              uint8_t* sa = smem + s * CV_STAGE_BYTES;
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                  ::"r"(smem_u32(sa)), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(&full[s])),
+                  "r"(kwin + kc * 64), "r"(x0 + dx - 1), "r"(y0 + dy - 1), "r"(b)
+                  : "memory");
+              tma_load_2d(sa + CV_A_BYTES, &tmW, &full[s], 0, ((nt * 9 + tap) * p.KC + kc) * 64);
+            }
+            __syncwarp();
+            if (++s == CV_STAGES) { s = 0; ph ^= 1; }
+          }
         }
       }
     }

@@ -127,25 +127,31 @@ convnext_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr uint32_t TM_H = C;               // Hacc[a] at TM_H + 128 a
 
   if (warp == 8) {
-    // ---------------- A tile + W1 ring producer (both CTAs) ----------------
-    if (lane == 0) {
+    // ---------------- A tile + W1 ring producer (both CTAs): the whole warp runs the loop, one elected lane issues ----------------
+    {
       int s1 = 0; uint32_t ph1 = 0; int ti = 0, g = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++ti) {
         const int m0 = tile * 256 + (int)rank * 128;
         mbar_wait(a_empty, (ti & 1) ^ 1);
-        mbar_arrive_expect_tx(a_full, Cfg::A_BYTES);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(a_full, Cfg::A_BYTES);
 #pragma unroll
-        for (int kb = 0; kb < KB1; ++kb) tma_load_2d(sA + kb * 16384, &tmA, a_full, kb * 64, m0);
+          for (int kb = 0; kb < KB1; ++kb) tma_load_2d(sA + kb * 16384, &tmA, a_full, kb * 64, m0);
+        }
+        __syncwarp();
         for (int j = 0; j < NCH; ++j, ++g) {
           const uint32_t lead = mapa_shared(smem_u32(&g1_rdy[g % NACC]), 0);
 #pragma unroll 1
           for (int kb = 0; kb < KB1; ++kb) {
             mbar_wait(&w1_empty[s1], ph1 ^ 1);
-            if (kb == 0) {        // after the wait: the G1 that used this stage last has been issued, i.e. its phase is over
-              if (rank == 0) mbar_arrive_expect_tx(&g1_rdy[g % NACC], 2 * KB1 * Cfg::W1_UNIT);
-              else mbar_arrive_cluster(lead);
+            if (elect_one()) {
+              if (kb == 0) {      // after the wait: the G1 that used this stage last has been issued, i.e. its phase is over
+                if (rank == 0) mbar_arrive_expect_tx(&g1_rdy[g % NACC], 2 * KB1 * Cfg::W1_UNIT);
+                else mbar_arrive_cluster(lead);
+              }
+              tma_load_2d_cg2(smem_u32(sW1 + s1 * Cfg::W1_UNIT), &tmW1, lead, kb * 64, j * Cfg::HN + (int)rank * (Cfg::HN / 2));
             }
-            tma_load_2d_cg2(smem_u32(sW1 + s1 * Cfg::W1_UNIT), &tmW1, lead, kb * 64, j * Cfg::HN + (int)rank * (Cfg::HN / 2));
+            __syncwarp();
             if (++s1 == NU1) { s1 = 0; ph1 ^= 1; }
           }
         }
@@ -153,8 +159,8 @@ convnext_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     __syncwarp();
   } else if (warp == 10) {
-    // ---------------- W2 ring producer (both CTAs) ----------------
-    if (lane == 0) {
+    // ---------------- W2 ring producer (both CTAs): the whole warp runs the loop, one elected lane issues ----------------
+    {
       int s2 = 0, g = 0; uint32_t ph2 = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         for (int j = 0; j < NCH; ++j, ++g) {
@@ -162,14 +168,17 @@ convnext_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
           for (int kb = 0; kb < 2; ++kb) {
             mbar_wait(&w2_empty[s2], ph2 ^ 1);
-            if (kb == 0) {
-              if (rank == 0) mbar_arrive_expect_tx(&g2_rdy[g % NACC], 2 * 2 * Cfg::W2_UNIT);
-              else mbar_arrive_cluster(lead);
-            }
             const uint32_t dst = smem_u32(sW2 + s2 * Cfg::W2_UNIT);
+            if (elect_one()) {
+              if (kb == 0) {
+                if (rank == 0) mbar_arrive_expect_tx(&g2_rdy[g % NACC], 2 * 2 * Cfg::W2_UNIT);
+                else mbar_arrive_cluster(lead);
+              }
 #pragma unroll
-            for (int h = 0; h < Cfg::NSPLIT; ++h)
-              tma_load_2d_cg2(dst + h * (Cfg::N2 / 2) * 128, &tmW2, lead, j * Cfg::HN + kb * 64, h * Cfg::N2 + (int)rank * (Cfg::N2 / 2));
+              for (int h = 0; h < Cfg::NSPLIT; ++h)
+                tma_load_2d_cg2(dst + h * (Cfg::N2 / 2) * 128, &tmW2, lead, j * Cfg::HN + kb * 64, h * Cfg::N2 + (int)rank * (Cfg::N2 / 2));
+            }
+            __syncwarp();
             if (++s2 == NU2) { s2 = 0; ph2 ^= 1; }
           }
         }
