@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(320, 1)
 attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTabH,
                      const __grid_constant__ CUtensorMap tmTabW, const GlbParams p) {
   using namespace glb;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                               // tiles A, B
@@ -135,6 +136,7 @@ attention_glb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
 
   if (warp == 8) {
     // =========================== TMA producer: the whole warp runs the loop, one elected lane issues ===========================
@@ -523,7 +525,8 @@ int mmsam_attention_glb(const void* qkv, void* out, const int* out_row_map_dev, 
   if (max_ctas <= 0 || max_ctas > kNumSMs) max_ctas = kNumSMs;
   const int grid = p.num_items < max_ctas ? p.num_items : max_ctas;
   MMSAM_SET_SMEM_ONCE((attention_glb_kernel), glb::SMEM_BYTES);
-  attention_glb_kernel<<<grid, 320, glb::SMEM_BYTES, stream>>>(tmQKV, tmH, tmW, p);
+  cudaError_t le = mmsam_host::launch_pdl(attention_glb_kernel, dim3(grid), dim3(320), glb::SMEM_BYTES, stream, tmQKV, tmH, tmW, p);
+  if (le != cudaSuccess) return (int)le;
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }

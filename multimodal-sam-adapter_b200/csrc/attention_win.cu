@@ -143,6 +143,7 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
                      const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmTabH,
                      const __grid_constant__ CUtensorMap tmTabW, const WinParams p) {
   using namespace win;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sStage = smem;
@@ -179,6 +180,7 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
 
   if (warp == 8) {
     // =========================== TMA producer: the whole warp runs the loop, one elected lane issues ===========================
@@ -470,7 +472,8 @@ int mmsam_attention_win(const void* qkv, void* out, const int* out_row_map_dev, 
   MMSAM_SET_SMEM_ONCE(attention_win_kernel, SMEM_BYTES);
   if (max_ctas <= 0 || max_ctas > kNumSMs) max_ctas = kNumSMs;
   const int grid = p.num_items < max_ctas ? p.num_items : max_ctas;
-  attention_win_kernel<<<grid, 320, SMEM_BYTES, stream>>>(tmQA, tmQB, tmKV, tmH, tmW, p);
+  cudaError_t le = mmsam_host::launch_pdl(attention_win_kernel, dim3(grid), dim3(320), SMEM_BYTES, stream, tmQA, tmQB, tmKV, tmH, tmW, p);
+  if (le != cudaSuccess) return (int)le;
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }

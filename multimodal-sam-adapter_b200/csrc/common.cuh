@@ -47,6 +47,30 @@
     }                                                                                                   \
   } while (0)
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------------------
+// A forward is ~580 dependent launches; a graph node costs 2.6 us (LayerNorm) to 5.3 us (a tcgen05 kernel: cluster launch,
+// barrier init, TMEM allocation) of fixed time (tools/launch_gap.py). Kernels launched through launch_pdl() may start while
+// the previous kernel of the stream is still draining: they run their prologue, then block in pdl_wait() until that kernel
+// has COMPLETED and its writes are visible - so every global-memory access of such a kernel must come after pdl_wait().
+// pdl_launch_dependents() at the top of a kernel lets the next one do the same with it. OFF by default (MMSAM_PDL=1 turns it
+// on): it did not pay on the whole step, see pdl_enabled() in gemm.cu for the measurement.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+namespace mmsam_host {
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+}  // namespace mmsam_host
+
 namespace mmsam {
 
 static constexpr int kNumSMs = 148;

@@ -187,6 +187,9 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
+  }
+  pdl_wait();
+  if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar, IH * IW * CB * 4);
     tma_load_4d(s_in, &tmX, bar, c0, x0 - K / 2, y0 - K / 2, b);
   }
@@ -247,7 +250,8 @@ static int launch_dw7_tma(const CUtensorMap& tmX, const CUtensorMap& tmY, const 
   constexpr int smem = (4 * RG + 6) * 38 * 32 * 4 + 49 * 32 * 4 + 16 + 128;
   MMSAM_SET_SMEM_ONCE((dwconv7_tma_kernel<RG>), smem);
   const int tiles_x = (W + 31) / 32, tiles_y = (H + 4 * RG - 1) / (4 * RG);
-  dwconv7_tma_kernel<RG><<<dim3(tiles_x * tiles_y, C / 32, B), 64 * RG, smem, st>>>(tmX, tmY, w, bias, C, tiles_x);
+  cudaError_t le = mmsam_host::launch_pdl(dwconv7_tma_kernel<RG>, dim3(tiles_x * tiles_y, C / 32, B), dim3(64 * RG), smem, st, tmX, tmY, w, bias, C, tiles_x);
+  if (le != cudaSuccess) return (int)le;
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }
@@ -311,6 +315,9 @@ dwconv3_tma_kernel(const __grid_constant__ Dw3Maps maps, const Dw3Params p) {
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
+  }
+  pdl_wait();
+  if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar, IH * IW * CB * 2);
     tma_load_4d(base, &maps.x[gi], bar, c0, x0 - 1, y0 - 1, b);
   }
@@ -400,7 +407,8 @@ static int dwconv3_tma(const __nv_bfloat16* x, __nv_bfloat16* y, const float* w,
   p.tile_start[3] = total;
   constexpr int smem = 18 * 34 * 32 * 2 + 9 * 32 * 4 + 16 + 128;
   MMSAM_SET_SMEM_ONCE(dwconv3_tma_kernel, smem);
-  dwconv3_tma_kernel<<<dim3(total, C / 32, B), 256, smem, st>>>(maps, p);
+  cudaError_t le = mmsam_host::launch_pdl(dwconv3_tma_kernel, dim3(total, C / 32, B), dim3(256), smem, st, maps, p);
+  if (le != cudaSuccess) return (int)le;
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }

@@ -445,6 +445,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmC, const GemmEpi ep) {
   using Cfg = GemmCfg<BN, VAR>;
   constexpr int STAGES = Cfg::STAGES;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from the __shared__ array (so loads compile to LDS, not generic LD)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -478,6 +479,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();                         // barrier inits + TMEM address visible cluster-wide
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
   // The two single-lane roles take the HIGHEST warp ids: the SMSP arbiter prefers high warp ids, so the TMA and
   // MMA issue slots are never starved by epilogue math running on the same scheduler.
@@ -573,7 +575,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int num_tiles = ((ep.M + 255) / 256) * ((ep.N + BN - 1) / BN);
   int pairs = max_ctas / 2;
   if (num_tiles < pairs) pairs = num_tiles;
-  gemm_bf16_kernel<BN, VAR><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, ep);
+  cudaError_t le = mmsam_host::launch_pdl(gemm_bf16_kernel<BN, VAR>, dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, tmC, ep);
+  if (le != cudaSuccess) return (int)le;
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }
@@ -589,6 +592,14 @@ static int launch_gemm_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB
 }  // namespace mmsam
 
 namespace mmsam_host {
+bool pdl_enabled() {
+  // opt-in (MMSAM_PDL=1). Measured on the bench step (tools/launch_gap.py, bench.py A/B in one gpurun call): chains of tcgen05
+  // kernels gain 1.4 us per node (5.3 -> 3.9 us), but a full-chip LayerNorm followed by a full-chip GEMM loses ~7 us per pair
+  // (the early-launched 227 KB CTAs take SMs the LayerNorm's last wave still wants), and the step as a whole is 0.3 - 0.6 ms
+  // SLOWER (59.2 - 59.5 vs 58.9 ms) - so the default stays plain stream order.
+  static const bool on = [] { const char* e = getenv("MMSAM_PDL"); return e && e[0] == '1'; }();
+  return on;
+}
 EncodeTiledFn get_encode_tiled() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {

@@ -46,6 +46,7 @@ layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, void* __restrict__ y, void* __restrict__ y2,
                  const int* __restrict__ row_map, long long rows, int C, long long ldx,
                  long long ldy, float eps, int ps_h, int ps_w) {
+  pdl_wait();
   constexpr int XB = XF ? 4 : 2, YB = YF ? 4 : 2;              // bytes per element
   constexpr int RPW = 32 / G;                                   // rows per warp (side by side)
   const int lane = threadIdx.x & (G - 1);                        // lane within the row group
@@ -176,6 +177,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 rowstats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats, long long rows, int C, long long ldx,
                 float eps) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -248,7 +250,7 @@ MMSAM_API int mmsam_layernorm(const void* x, int x_dtype, const float* gamma, co
   const long long cap = (long long)kNumSMs * cap_waves;
   if (blocks > cap) blocks = cap;
 #define LN_LAUNCH(NV, GG, RR, XFF, YFF) \
-  layernorm_kernel<NV, GG, RR, XFF, YFF><<<(unsigned)blocks, wpb * 32, 0, st>>>(x, gamma, beta, y, y2, row_map_dev, rows, C, ldx, ldy, eps, ps_h, ps_w)
+  mmsam_host::launch_pdl(layernorm_kernel<NV, GG, RR, XFF, YFF>, dim3((unsigned)blocks), dim3(wpb * 32), 0, st, x, gamma, beta, y, y2, row_map_dev, rows, C, ldx, ldy, eps, ps_h, ps_w)
 #define LN_CASE(NV, GG, RR)                                    \
   do {                                                         \
     if (mode == 0) LN_LAUNCH(NV, GG, RR, false, false);        \
@@ -283,7 +285,7 @@ MMSAM_API int mmsam_rowstats_bf16(const void* x, float* stats, long long rows, i
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
   const int nv = (C / 8 + 31) / 32;
   cudaStream_t st = (cudaStream_t)stream;
-#define ROWSTATS(NVV) rowstats_kernel<NVV><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (float2*)stats, rows, C, ldx, eps)
+#define ROWSTATS(NVV) mmsam_host::launch_pdl(rowstats_kernel<NVV>, dim3((unsigned)blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, (float2*)stats, rows, C, ldx, eps)
   if (nv <= 1) ROWSTATS(1);
   else if (nv <= 2) ROWSTATS(2);
   else if (nv <= 4) ROWSTATS(4);

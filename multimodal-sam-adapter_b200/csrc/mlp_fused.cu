@@ -77,6 +77,7 @@ convnext_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmT, const MlpParams p) {
   using Cfg = MlpCfg<C>;
   constexpr int NU1 = Cfg::NU1, NU2 = Cfg::NU2, NCH = Cfg::NCH, NACC = Cfg::NACC, KB1 = Cfg::KB1;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
@@ -125,6 +126,7 @@ convnext_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t TM_H = C;               // Hacc[a] at TM_H + 128 a
+  pdl_wait();          // the prologue above overlapped the previous kernel's tail; global memory is touched only from here on
 
   if (warp == 8) {
     // ---------------- A tile + W1 ring producer (both CTAs): the whole warp runs the loop, one elected lane issues ----------------
@@ -497,7 +499,8 @@ static int launch_mlp(const CUtensorMap& tmA, const CUtensorMap& tmW1, const CUt
   const int num_tiles = (p.M + 255) / 256;
   int pairs = max_ctas / 2;
   if (num_tiles < pairs) pairs = num_tiles;
-  convnext_mlp_kernel<C><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW1, tmW2, tmT, p);
+  cudaError_t le = mmsam_host::launch_pdl(convnext_mlp_kernel<C>, dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmA, tmW1, tmW2, tmT, p);
+  if (le != cudaSuccess) return (int)le;
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;
 }
