@@ -90,6 +90,15 @@ int mmsam_attention_bf16(const void* qkv, void* out, const int* out_row_map_dev,
                          const void* tab_w, int Bp, int T, int nh, int Kh, int Kw, float scale, int max_ctas,
                          void* stream);
 
+/* SAM window attention with the window un-partition fused into the store (base/image_encoder.py:399-416, 529-551):
+ * qkv = bf16 [B * nwh * nww, 196, 3, nh, 64] in window order (window (b, wy, wx) = (b * nwh + wy) * nww + wx, 14 x 14 tokens
+ * each, zero-padded windows at the right / bottom edge included: nwh = ceil(H / 14), nww = ceil(W / 14)), out = bf16
+ * [B, H, W, nh * 64], the token map proj consumes. Same arithmetic as mmsam_attention_bf16 with Kh = Kw = 14 (padded tokens
+ * are ordinary keys); each 126- / 70-row tile leaves through one 4-D TMA store that the copy engine clips at the image
+ * edge. tab_h / tab_w as in mmsam_attention_bf16 (both or neither). */
+int mmsam_attention_window_bf16(const void* qkv, void* out, const void* tab_h, const void* tab_w, int B, int H, int W, int nh,
+                                float scale, int max_ctas, void* stream);
+
 /* stats[row] = (mean, 1 / sqrt(var + eps)) fp32 pairs of the rows of a bf16 [rows, C] matrix (row stride ldx), the
  * statistics nn.LayerNorm would use (biased variance). C % 8 == 0, C <= 2048. */
 int mmsam_rowstats_bf16(const void* x, float* stats, long long rows, int C, long long ldx, float eps, void* stream);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "mmsam_combine_pool_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "mmsam_ca_apply_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "mmsam_attention_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp],
+    "mmsam_attention_window_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp],
 }
 
 _lib = None

@@ -21,6 +21,7 @@
 //           over O. No online rescaling, no key blocks, no P panel in shared memory.
 // TMEM: slot 0 [0, 208), slot 1 [208, 416), G [416, 480).
 #include "common.cuh"
+#include "cg2.cuh"
 #include <cstdlib>
 
 namespace mmsam {
@@ -42,6 +43,11 @@ struct WinParams {
   __nv_bfloat16* out;
   const int* out_map;
   int Bp, nh, num_items, has_bias;
+  // Row tiles: A = rows [0, qa_rows), B = rows [qb_row0, 196). Plain / row-mapped output: 128 | 68 rows. Un-partitioned output
+  // (H > 0: out is the [B, H, W, nh * 64] token map, windows of 14 x 14 tokens, nwh x nww per image): 126 | 70 rows = 9 | 5
+  // whole window rows, so that each tile leaves through ONE 4-D TMA store, clipped at the image edge by the copy engine.
+  int qa_rows, qb_row0;
+  int H, W, nwh, nww;
   float scale_log2;
   long long* trace;     // perf debug (MMSAM_ATT_TRACE): clock64 stamps of CTA 0, [role 0..2][item < 16][event < 8]
 };
@@ -141,7 +147,8 @@ __device__ __forceinline__ void win_row_pass(uint32_t s_addr, const float* gh, b
 __global__ void __launch_bounds__(320, 1)
 attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant__ CUtensorMap tmQB,
                      const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmTabH,
-                     const __grid_constant__ CUtensorMap tmTabW, const WinParams p) {
+                     const __grid_constant__ CUtensorMap tmTabW, const __grid_constant__ CUtensorMap tmOA,
+                     const __grid_constant__ CUtensorMap tmOB, const WinParams p) {
   using namespace win;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -202,7 +209,7 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
           mbar_arrive_expect_tx(&item_full[st], STAGE_BYTES);
           uint8_t* s = sStage + st * STAGE_BYTES;
           tma_load_4d(s, &tmQA, &item_full[st], 0, head, 0, bp);
-          tma_load_4d(s + QA_BYTES, &tmQB, &item_full[st], 0, head, 128, bp);
+          tma_load_4d(s + QA_BYTES, &tmQB, &item_full[st], 0, head, p.qb_row0, bp);
           tma_load_4d(s + QA_BYTES + QB_BYTES, &tmKV, &item_full[st], 0, p.nh + head, 0, bp);
           tma_load_4d(s + QA_BYTES + QB_BYTES + KV_BYTES, &tmKV, &item_full[st], 0, 2 * p.nh + head, 0, bp);
         }
@@ -296,9 +303,10 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
     // =========================== softmax groups (warps 0-3: row tile A, warps 4-7: row tile B) ===========================
     const int g = warp >> 2, wq = warp & 3;
     const int row = wq * 32 + lane;                       // TMEM lane == query row inside the tile
-    const int q = g * 128 + row;
-    const bool warp_valid = g * 128 + wq * 32 < T;        // tile B: warps 2 (4 rows) .. 3 (none)
-    const bool row_valid = q < T;
+    const int q = g ? p.qb_row0 + row : row;
+    const bool warp_valid = g == 0 || p.qb_row0 + wq * 32 < T;   // tile B: warp 2 has 4 (6) rows, warp 3 none
+    const bool row_valid = q < T && (g == 1 || row < p.qa_rows);
+    const uint32_t grp_stg = smem_u32(sG + g * 4 * G_WARP_FLOATS);   // un-partitioned output: the group's rows, 128 B each
     const int qc = row_valid ? q : T - 1;
     const int qh = qc / KS, qw = qc - qh * KS;
     const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
@@ -318,6 +326,7 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         store_pending = false;
       }
+      if (p.H > 0) asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");   // ... for every warp of the group
       if (p.has_bias) {
         if (warp_valid) {
           uint32_t r[64];
@@ -367,26 +376,63 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
       mbar_wait(&o_full[g], it & 1);
       tc_fence_after();
       WIN_TRACE(g, it, 5);
+      uint32_t o[64];
       if (warp_valid) {
-        uint32_t o[64];
         tmem_ld_32x32b_x32(s_addr + TM_O, o);
         tmem_ld_32x32b_x32(s_addr + TM_O + 32, o + 32);
         tmem_ld_wait();
         WIN_TRACE(g, it, 7);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&slot_free[g]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_free[g]);
+      const float inv = 1.f / l;
+      if (p.H > 0) {
+        // ---- un-partitioned output: the group's 126 / 70 rows are whole window rows -> staged densely in token order and
+        //      written by ONE 4-D TMA store (box 64 ch x 14 x 9 | 5 tokens), out-of-image tokens clipped by the copy engine.
+        //      (32 per-row bulk copies per warp, each issued by its own lane, cost ~2600 cycles per tile.) ----
+        WIN_TRACE(3 + g, it, 0);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");      // every warp of the group is done with its gather area
+        WIN_TRACE(3 + g, it, 1);
+        if (warp_valid && row_valid) {
+          const uint32_t stg = grp_stg + row * 128;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(o[8 * i + j]) * inv;
+            sts128(stg + i * 16, pack8(f));
+          }
+        }
+        WIN_TRACE(3 + g, it, 2);
+        fence_proxy_async();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        WIN_TRACE(3 + g, it, 3);
+        if (wq == 0) {
+          if (elect_one()) {
+            const int wx = bp % p.nww, wy = (bp / p.nww) % p.nwh, b = bp / (p.nww * p.nwh);
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(g ? &tmOB : &tmOA)),
+                         "r"(grp_stg), "r"(head * D), "r"(wx * KS), "r"(wy * KS + (g ? 9 : 0)), "r"(b)
+                         : "memory");
+          }
+          __syncwarp();
+        }
+        WIN_TRACE(3 + g, it, 4);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        store_pending = true;
+        WIN_TRACE(3 + g, it, 5);
+        WIN_TRACE(g, it, 6);
+      } else if (warp_valid) {
         // Output rows are nh * 128 B apart in global memory. Plain stores (a thread's own row as 8 x 16 B, or transposed so
         // that 8 lanes cover a row) took ~3000 cycles per tile: with 227 of the SM's 228 KB carved out as shared memory the
         // LSU path tracks only a few outstanding lines and every store instruction waits for a slot. Each lane instead
         // stages its row (128 contiguous bytes; the warp's bias-gather area is free once bh / bw are in registers) and
         // hands it to the bulk-copy engine: one cp.async.bulk per row, asynchronous, no LSU slot held.
         WIN_TRACE(3 + g, it, 0);
-        const float inv = 1.f / l;
         long long orow = (long long)bp * T + q;
         if (row_valid && p.out_map) orow = p.out_map[orow];
         if (!row_valid) orow = -1;
-        if (inv == 123.456f) orow = -1;
         WIN_TRACE(3 + g, it, 1);
         uint8_t* stg = reinterpret_cast<uint8_t*>(sG + (g * 4 + wq) * G_WARP_FLOATS) + lane * 128;   // 32 x 128 B of the warp's 7 KB
 #pragma unroll
@@ -409,10 +455,6 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
         store_pending = true;
         WIN_TRACE(3 + g, it, 5);
         WIN_TRACE(g, it, 6);
-      } else {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&slot_free[g]);
       }
     }
   }
@@ -430,8 +472,27 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
 extern long long* g_win_trace_buf;
 
 // SAM-window specialisation of mmsam_attention_bf16 (same contract; T == 196, Kh == Kw == 14). Called by attention.cu.
+static int attention_win_launch(const void* qkv, void* out, const int* out_row_map_dev, const void* tab_h, const void* tab_w, int Bp,
+                                int nh, float scale, int max_ctas, cudaStream_t stream, int B, int H, int W);
+
 int mmsam_attention_win(const void* qkv, void* out, const int* out_row_map_dev, const void* tab_h, const void* tab_w, int Bp,
                         int nh, float scale, int max_ctas, cudaStream_t stream) {
+  return attention_win_launch(qkv, out, out_row_map_dev, tab_h, tab_w, Bp, nh, scale, max_ctas, stream, 0, 0, 0);
+}
+
+// See include/mmsam_b200.h for the contract.
+MMSAM_API int mmsam_attention_window_bf16(const void* qkv, void* out, const void* tab_h, const void* tab_w, int B, int H, int W, int nh,
+                                          float scale, int max_ctas, void* stream) {
+  if (B < 0 || H <= 0 || W <= 0 || nh <= 0) return MMSAM_ERR_BAD_ARG;
+  if (B == 0) return MMSAM_OK;
+  if (!qkv || !out || (tab_h != nullptr) != (tab_w != nullptr)) return MMSAM_ERR_BAD_ARG;
+  if ((((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)tab_h | (uintptr_t)tab_w) & 15)) return MMSAM_ERR_BAD_ARG;
+  const int nwh = (H + 13) / 14, nww = (W + 13) / 14;
+  return attention_win_launch(qkv, out, nullptr, tab_h, tab_w, B * nwh * nww, nh, scale, max_ctas, (cudaStream_t)stream, B, H, W);
+}
+
+static int attention_win_launch(const void* qkv, void* out, const int* out_row_map_dev, const void* tab_h, const void* tab_w, int Bp,
+                                int nh, float scale, int max_ctas, cudaStream_t stream, int B, int H, int W) {
   using namespace mmsam;
   using namespace mmsam::win;
   mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
@@ -442,6 +503,7 @@ int mmsam_attention_win(const void* qkv, void* out, const int* out_row_map_dev, 
   cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)(3 * nh), (cuuint64_t)T, (cuuint64_t)Bp};
   cuuint64_t strides[3] = {(cuuint64_t)D * 2, C3 * 2, (cuuint64_t)T * C3 * 2};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  const bool unpart = H > 0;
   const cuuint32_t rows[3] = {128, QB_ROWS, NK};
   CUtensorMap* maps[3] = {&tmQA, &tmQB, &tmKV};
   for (int i = 0; i < 3; ++i) {
@@ -458,8 +520,22 @@ int mmsam_attention_win(const void* qkv, void* out, const int* out_row_map_dev, 
   } else {
     tmH = tmQA; tmW = tmQA;
   }
+  CUtensorMap tmOA = tmQA, tmOB = tmQA;
+  if (unpart) {
+    const uint64_t C = (uint64_t)nh * D;
+    cuuint64_t odims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t ostr[3] = {C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t boxa[4] = {D, KS, 9, 1}, boxb[4] = {D, KS, 5, 1};
+    if (enc(&tmOA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, odims, ostr, boxa, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+        enc(&tmOB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, odims, ostr, boxb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MMSAM_ERR_DRIVER;
+  }
   WinParams p;
   p.out = (__nv_bfloat16*)out; p.out_map = out_row_map_dev; p.Bp = Bp; p.nh = nh; p.num_items = Bp * nh; p.has_bias = has_bias ? 1 : 0;
+  p.qa_rows = unpart ? 9 * KS : 128; p.qb_row0 = unpart ? 9 * KS : 128;
+  p.H = H; p.W = W; p.nwh = unpart ? (H + KS - 1) / KS : 0; p.nww = unpart ? (W + KS - 1) / KS : 0;
   p.scale_log2 = scale * kLog2e;
   static long long* trace_buf = nullptr;
   static const int want_trace = getenv("MMSAM_ATT_TRACE") != nullptr;
@@ -472,7 +548,7 @@ int mmsam_attention_win(const void* qkv, void* out, const int* out_row_map_dev, 
   MMSAM_SET_SMEM_ONCE(attention_win_kernel, SMEM_BYTES);
   if (max_ctas <= 0 || max_ctas > kNumSMs) max_ctas = kNumSMs;
   const int grid = p.num_items < max_ctas ? p.num_items : max_ctas;
-  cudaError_t le = mmsam_host::launch_pdl(attention_win_kernel, dim3(grid), dim3(320), SMEM_BYTES, stream, tmQA, tmQB, tmKV, tmH, tmW, p);
+  cudaError_t le = mmsam_host::launch_pdl(attention_win_kernel, dim3(grid), dim3(320), SMEM_BYTES, stream, tmQA, tmQB, tmKV, tmH, tmW, tmOA, tmOB, p);
   if (le != cudaSuccess) return (int)le;
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;

@@ -313,8 +313,11 @@ class _Ops:
             y = self._ln(x, blk["norm1"], out=sc["win_buf"], row_map=sc["win_fwd"])
             qkv = self._gemm(y, blk["qkv"])
             # window_unpartition is fused into the attention store: pad rows are dropped, proj runs on B*T rows
-            a = K.attention(qkv.view(sc["win_bp"], ws * ws, -1), self.nh, (ws, ws), tabs[0], tabs[1],
-                            out_map=sc["win_inv"], out_rows=B * T)
+            if ws == 14:       # SAM's window size: un-partition by one TMA store per row tile
+                a = K.attention_window(qkv.view(sc["win_bp"], ws * ws, -1), self.nh, B, H, W, tabs[0], tabs[1])
+            else:
+                a = K.attention(qkv.view(sc["win_bp"], ws * ws, -1), self.nh, (ws, ws), tabs[0], tabs[1],
+                                out_map=sc["win_inv"], out_rows=B * T)
             self._gemm(a, blk["proj"], residual=x, out=x)
         else:
             y = self._ln(x, blk["norm1"])

@@ -223,6 +223,24 @@ def attention(qkv, num_heads, hw, tab_h=None, tab_w=None, out=None, max_ctas=0, 
     return out
 
 
+def attention_window(qkv, num_heads, B, H, W, tab_h=None, tab_w=None, out=None, max_ctas=0):
+    """SAM window attention (14 x 14 windows) with window_unpartition fused into the store: qkv bf16
+    [B * nwh * nww, 196, 3 * nh * 64] in window order -> the token map [B * H * W, nh * 64] (base/image_encoder.py:399-416,
+    529-551)."""
+    _need_cuda(qkv, tab_h, tab_w)
+    nwh, nww = (H + 13) // 14, (W + 13) // 14
+    Bp, T, C3 = qkv.shape
+    if T != 196 or Bp != B * nwh * nww or C3 != 3 * num_heads * 64 or not qkv.is_contiguous():
+        raise _lib.MMSamError("attention_window: qkv must be contiguous [B * ceil(H/14) * ceil(W/14), 196, 3 * heads * 64]")
+    if out is None:
+        out = torch.empty((B * H * W, num_heads * 64), dtype=torch.bfloat16, device=qkv.device)
+    rc = _lib.load().mmsam_attention_window_bf16(_ptr(qkv), _ptr(out), _ptr(tab_h), _ptr(tab_w), B, H, W, num_heads, 64.0 ** -0.5,
+                                                 max_ctas, _stream())
+    _lib.check(rc, "mmsam_attention_window_bf16")
+    _count()
+    return out
+
+
 class MsdaGeometry:
     """Host-side geometry for the shared-memory staged MSDeformAttn kernel (mmsam_msda_fused_staged_bf16): level
     shapes, query grids (row-major, reference points = cell centres, adapter_modules_...new.py:397-431), the anchor

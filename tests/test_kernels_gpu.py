@@ -437,6 +437,30 @@ def test_attention_global_two_tile_kernel(Bp, nh, Kh, ramp):
     assert rel < 1e-2 and err < 0.05, (rel, err)
 
 
+@pytest.mark.parametrize("B,nh,H,W,bias", [(2, 16, 64, 64, True), (1, 2, 19, 25, True), (3, 3, 28, 28, True), (1, 2, 14, 70, False),
+                                           (8, 16, 64, 64, True)])
+def test_attention_window_unpartitioned_store(B, nh, H, W, bias):
+    """SAM window attention with window_unpartition fused into the store (mmsam_attention_window_bf16: 126 | 70-row tiles,
+    one 4-D TMA store per tile, clipped at the image edge) against the row-mapped path of mmsam_attention_bf16, which the
+    oracle tests pin: same per-row arithmetic -> identical bits; padded window tokens must not reach the output."""
+    from mmsam_b200.engine import window_maps
+    k = _k()
+    g = torch.Generator().manual_seed(B * 100 + H + W)
+    sc = window_maps(B, H, W, 14, 8, "cuda")
+    Bp = sc["win_bp"]
+    qkv = (torch.randn(Bp, 196, 3 * nh * 64, generator=g) * 1.5).to(torch.bfloat16).cuda()
+    th = tw = None
+    if bias:
+        th = k.relpos_table((torch.randn(27, 64, generator=g) * 0.2).cuda(), 14)
+        tw = k.relpos_table((torch.randn(27, 64, generator=g) * 0.2).cuda(), 14)
+    want = k.attention(qkv, nh, (14, 14), th, tw, out_map=sc["win_inv"], out_rows=B * H * W)
+    out = torch.full((B * H * W + 64, nh * 64), 7.0, dtype=torch.bfloat16, device="cuda")      # guard rows behind the map
+    k.attention_window(qkv, nh, B, H, W, th, tw, out=out[:B * H * W])
+    torch.cuda.synchronize()
+    assert torch.equal(out[:B * H * W], want)
+    assert (out[B * H * W:] == 7.0).all()
+
+
 def test_attention_relpos_interpolated_table():
     """FMB-shaped case: a 127-row table interpolated to 2*50-1 = 99 rows (get_rel_pos :566-575)."""
     from oracle.model import attention_core
