@@ -549,9 +549,10 @@ def main():
         "roofline": {"kernel": "gemm_bf16_kernel (tcgen05)", "bound": "tensor", "achieved": tf,
                      "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops_sustained"],
                      # ncu --set full, lin1 (32768x4096x1024, GELU) launch: dram__bytes_read + dram__bytes_write
-                     # (profiles/r01_gemm_ncu_summary.txt); algorithmic bytes of that launch: 343 MB
-                     "traffic": 291.6e6, "traffic_of": "lin1 GEMM launch (M=32768 N=4096 K=1024), dram read + write of one ncu --set full "
-                                                        "capture (profiles/r01_gemm_ncu_summary.txt), not re-measured by this run",
+                     # (profiles/r02_gemm_ncu_summary.txt); algorithmic bytes of that launch: 343 MB
+                     "traffic": 289.3e6, "traffic_of": "lin1 GEMM launch (M=32768 N=4096 K=1024): dram__bytes_read 75.6 MB + dram__bytes_write "
+                                                        "213.7 MB of one ncu --set full capture of this kernel (profiles/r02_gemm_ncu_summary.txt, "
+                                                        "launch 0); algorithmic 343 MB (A 67 + W 8 + out 268); not re-measured by this run",
                      "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
                      "launches_per_step": gm["launches"], "distinct_configs": gm["configs"], "ms_per_step": gm["ms"],
                      "timing": "every distinct GEMM configuration of the step replayed 8x back to back (CUDA events), weighted by its launch count",

@@ -116,10 +116,12 @@ int mmsam_gemm_ln_bf16(const void* A, long long lda, const void* W, long long ld
 /* ConvNeXt block tail (twin_convnext.py:98-132: norm -> pwconv1 -> GELU -> pwconv2 -> gamma -> residual) in one launch:
  *   t[m, :] += gamma (.) ( GELU( LN(y[m, :]) W1^T + b1 ) W2^T + b2 ),   LN over the C channels (biased variance, eps)
  * y = bf16 [M, C] (row stride ldy: the depthwise conv output), t = fp32 [M, C] (row stride ldt), updated IN PLACE (each
- * element receives exactly one fp32 add, by a TMA reduction). The LayerNorm affine is pre-folded by the caller:
- * W1 = bf16(ln_weight (.) W_pwconv1) [4C, C] contiguous, colsum1[n] = sum_k W1[n,k] (of the rounded weight),
- * bias1 = W_pwconv1 ln_bias + b_pwconv1; W2 = bf16 [C, 4C] contiguous; gamma may be null (= 1). C in {96, 192, 384}
- * (the 4C-wide intermediate stays in tensor memory; C = 768 does not fit -> MMSAM_ERR_UNSUPPORTED, use the GEMMs).
+ * element receives exactly one fp32 add, by a TMA reduction: deterministic). The LayerNorm AFFINE is pre-folded by the
+ * caller: W1 = bf16(ln_weight (.) W_pwconv1) [4C, C] contiguous, bias1 = W_pwconv1 ln_bias + b_pwconv1; the normalisation
+ * itself ((y - mean) * rstd, rounded to bf16) is applied by the kernel to the tile it holds in shared memory. colsum1 is
+ * unused (kept from the first version of this entry point, which folded the statistics into the epilogue) and may be
+ * null. W2 = bf16 [C, 4C] contiguous; gamma may be null (= 1). C in {96, 192, 384} (the output tile [128 x C] fp32 stays
+ * in tensor memory; C = 768 does not fit -> MMSAM_ERR_UNSUPPORTED, use LayerNorm + two GEMMs).
  * Pointers 16-byte aligned, ldy % 8 == 0, ldt % 4 == 0. */
 int mmsam_convnext_mlp_bf16(const void* y, long long ldy, const void* W1, const float* colsum1, const float* bias1,
                             const void* W2, const float* bias2, const float* gamma, float* t, long long ldt, int M, int C,

@@ -56,7 +56,7 @@ template <int C> struct MlpCfg {
 };
 
 struct MlpParams {
-  const float* colsum1;   // [4C]  sum_k W1'[n, k]  (W1' = W1 * ln_weight, as stored in the bf16 weight)
+  const float* colsum1;   // unused: the LayerNorm is applied to the resident A tile, not folded into the epilogue
   const float* bias1;     // [4C]  b1 + W1 . ln_bias
   const float* bias2;     // [C]
   const float* gamma;     // [C] or null
@@ -523,7 +523,7 @@ MMSAM_API int mmsam_convnext_mlp_bf16(const void* y, long long ldy, const void* 
   using namespace mmsam;
   if (M < 0) return MMSAM_ERR_BAD_ARG;
   if (M == 0) return MMSAM_OK;
-  if (!y || !W1 || !colsum1 || !bias1 || !W2 || !bias2 || !t) return MMSAM_ERR_BAD_ARG;
+  if (!y || !W1 || !bias1 || !W2 || !bias2 || !t) return MMSAM_ERR_BAD_ARG;      // colsum1: unused (see the header), may be null
   if (C != 96 && C != 192 && C != 384) return MMSAM_ERR_UNSUPPORTED;
   if ((ldy & 7) || ldy < C || (ldt & 3) || ldt < C) return MMSAM_ERR_BAD_ARG;
   if ((((uintptr_t)y | (uintptr_t)W1 | (uintptr_t)W2 | (uintptr_t)t | (uintptr_t)colsum1 | (uintptr_t)bias1 | (uintptr_t)bias2 |
