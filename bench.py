@@ -233,7 +233,8 @@ def instrumented_pass(eng, x):
         key = (N, S, MD, Lq, n_levels)
         ent = mcalls.get(key)
         if ent is None:
-            mcalls[key] = [1, by, (value, shapes, lsi, qproj, ref, n_heads, n_levels, n_points, r), geom]
+            # clones: the engine's buffers are reused by later layers, and the staged kernel's speed depends on the offsets
+            mcalls[key] = [1, by, (value.clone(), shapes, lsi, qproj.clone(), ref, n_heads, n_levels, n_points, torch.empty_like(r)), geom]
         else:
             ent[0] += 1
         return r
@@ -557,7 +558,7 @@ def main():
                      "launches_per_step": gm["launches"], "distinct_configs": gm["configs"], "ms_per_step": gm["ms"],
                      "timing": "every distinct GEMM configuration of the step replayed 8x back to back (CUDA events), weighted by its launch count",
                      "share_of_step": gm["ms"] / (ms / args.steps)},
-        "roofline_msda": {"kernel": "msda_fused_coop_kernel", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
+        "roofline_msda": {"kernel": "msda_fused_coop_kernel (injector, L1 gathers) + msda_staged2_kernel (extractor, shared-memory gathers)", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
                           "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                           # ncu --set full inside a forward (profiles/r01_msda_ncu_summary.txt): dram read + write per
                           # launch, injector 280.1 MB / extractor 302.2 MB, averaged over the step's 4 + 6 launches

@@ -81,17 +81,20 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const GramParams p) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
+    {   // TMA producer: the whole warp runs the loop, one elected lane issues (see elect_one)
       int s = 0; uint32_t ph = 0;
       for (int it = 0; it < nst; ++it) {
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-        uint8_t* st = smem + s * STAGE_BYTES;
-        const int prow = b * p.HW + p0 + it * GR_KP;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          const int prow = b * p.HW + p0 + it * GR_KP;
 #pragma unroll
-        for (int a = 0; a < NA; ++a) tma_load_2d(st + a * GR_ATOM, &tmX, &full[s], p.qoff + i0 + a * 64, prow);
+          for (int a = 0; a < NA; ++a) tma_load_2d(st + a * GR_ATOM, &tmX, &full[s], p.qoff + i0 + a * 64, prow);
 #pragma unroll
-        for (int a = 0; a < NB; ++a) tma_load_2d(st + (NA + a) * GR_ATOM, &tmX, &full[s], p.koff + j0 + a * 64, prow);
+          for (int a = 0; a < NB; ++a) tma_load_2d(st + (NA + a) * GR_ATOM, &tmX, &full[s], p.koff + j0 + a * 64, prow);
+        }
+        __syncwarp();
         if (++s == GR_STAGES) { s = 0; ph ^= 1; }
       }
     }

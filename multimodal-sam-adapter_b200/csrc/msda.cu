@@ -17,6 +17,7 @@
 //  * msda_generic_kernel - any D / dtype (incl. fp64), one thread per output element; used for the
 //    reference's own known-answer shapes (D = 2) and as the catch-all.
 #include "common.cuh"
+#include "cg2.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
@@ -431,9 +432,12 @@ struct MsdaStagedParams {
   int gh[3], gw[3], gstart[3];
   unsigned tx_bytes, bar_off;
   unsigned qoff_off, qlg_off, qref_off, qidx_off;   // per-query staging areas: offsets, logits, ref point, query index
+  unsigned rec_off, xy_off, in_off, seg_off, sref_off;   // msda_staged2_kernel: per-warp point records / fall-back
+                                                         // coordinates / input ring; per-CTA pass list / reference points
   int dbg;                               // perf-debug switches (MMSAM_MSDA_DBG): 1 = no TMA staging, 2 = no gather
 };
 struct MsdaMaps { CUtensorMap m[4]; };
+struct MsdaMaps2 { CUtensorMap m[4]; CUtensorMap qoff, qlg; };   // + the projection matrix: offsets / logits boxes of 8 rows
 
 __device__ __forceinline__ int cdiv_pos(int num, int den) { return (num + den - 1) / den; }   // num >= 1 - den
 __device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* src) {
@@ -625,6 +629,295 @@ msda_staged_kernel(const __grid_constant__ MsdaMaps maps, const MsdaStagedParams
   }
 }
 
+// Second structure for the same staging (default of mmsam_msda_fused_staged_bf16; MMSAM_MSDA_STAGED_V=1 selects the
+// kernel above). msda_staged_kernel is issue-bound on its skeleton (8 lanes per query at 50 % lane efficiency for
+// L = 1, 5 shuffles per point, scalar FMA); here
+//   * the region's queries are cut into PASSES of up to 8 consecutive queries of one grid row; the pass list
+//     {first query, count} and the reference points are built once per CTA in shared memory, so the loop has no
+//     integer division and no per-lane search;
+//   * a warp owns a pass at a time and nothing is shared between warps after the box has landed (no CTA barrier in
+//     the loop); the projection slices of the next DEPTH passes (a {2 L P, 8 rows} box of offsets and a {L P, 8 rows}
+//     box of logits of the fp32 projection matrix) are in flight in a per-warp TMA ring with one mbarrier per slot:
+//     no per-lane address arithmetic, no LSU wavefronts for the copies;
+//   * phase A: lane = (query, point of a level): location, softmax weight (two width-4 shuffles), bilinear factors
+//     and the byte offset of the top-left corner in the staged box -> one 16-byte record {offset, lw, a_top, a_bot}
+//     per point in the warp's shared-memory slab. The box is zero-filled outside the map, so a staged sample needs no
+//     bounds logic at all (coordinates are clamped to [-2, size + 1]: everything beyond has four invalid corners);
+//   * phase B: lane = (query, 16-byte channel chunk): per point ONE broadcast LDS.128 of the record (no shuffles),
+//     four LDS.128 corner reads and packed FFMA2 accumulation. The two queries of a quarter warp read the two x
+//     neighbours in opposite order when needed, so that their 64-byte units always sit in opposite halves of the
+//     128-byte bank line: every corner read is conflict-free (tools/micro/gather_bench.cu mode 9: 0.54 cycles per
+//     unit against 0.78 for unordered units and 1.6 through L1). A pass in which some sample left its box (warp
+//     vote) runs the same loop with the global-memory fall-back compiled in; the others run branch-free.
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <int MAXL, int DEPTH>
+__global__ void __launch_bounds__(256, 2)
+msda_staged2_kernel(const __grid_constant__ MsdaMaps2 maps, const MsdaStagedParams p) {
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  uint64_t& bar = *reinterpret_cast<uint64_t*>(st_smem + p.bar_off);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int ql = lane >> 2, pl = lane & 3;   // query slot of the pass; point (phase A) / channel chunk (phase B)
+  const int m = blockIdx.y, n = blockIdx.z;
+  const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
+  const int X0 = tx * p.TAW, X1 = min(X0 + p.TAW, p.AW), Y0 = ty * p.TAH, Y1 = min(Y0 + p.TAH, p.AH);
+  const float fx0 = (float)X0 / (float)p.AW, fy0 = (float)Y0 / (float)p.AH;
+  const uint32_t sbase = smem_u32(st_smem);
+  const uint32_t seg_s = sbase + p.seg_off;          // [pass] {first query, count}
+  const uint32_t ref_s = sbase + p.sref_off;         // [pass][8] reference point (x, y)
+  const uint32_t hdr_s = sbase + p.bar_off + 16;     // [3 grids] {x0, y0, width in passes, rows} + pass count
+  uint64_t* ring_bar = reinterpret_cast<uint64_t*>(st_smem + p.bar_off + 64) + (threadIdx.x >> 5) * DEPTH;   // [warp][slot]
+
+  int ox[MAXL], oy[MAXL];
+  float rW[MAXL], rH[MAXL];
+#pragma unroll
+  for (int l = 0; l < MAXL; ++l) {
+    const int ll = l < p.L ? l : 0;
+    rW[l] = 1.f / (float)p.W[ll]; rH[l] = 1.f / (float)p.H[ll];
+    ox[l] = (int)floorf(fx0 * p.W[ll] - 0.5f + p.pmin[ll][m][0]) - p.margin;
+    oy[l] = (int)floorf(fy0 * p.H[ll] - 0.5f + p.pmin[ll][m][1]) - p.margin;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    for (int i = 0; i < 8 * DEPTH; ++i) mbar_init(reinterpret_cast<uint64_t*>(st_smem + p.bar_off + 64) + i, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(&bar, p.tx_bytes);
+#pragma unroll
+    for (int l = 0; l < MAXL; ++l)
+      if (l < p.L) tma_load_4d(st_smem + p.box_off[l], &maps.m[l], &bar, m * 32, ox[l], oy[l], n);
+  }
+  // the region's rectangle of every query grid: queries whose cell centre (i + 0.5) / g lies in [X0, X1) / AW.
+  // One thread per grid does the divisions; the pass list is then built by one thread per pass.
+  if (threadIdx.x < 3) {
+    const int g = threadIdx.x;
+    int ix0 = 0, iy0 = 0, w = 0, h = 0;
+    if (g < p.NG) {
+      ix0 = cdiv_pos(2 * X0 * p.gw[g] - p.AW, 2 * p.AW);
+      iy0 = cdiv_pos(2 * Y0 * p.gh[g] - p.AH, 2 * p.AH);
+      w = cdiv_pos(2 * X1 * p.gw[g] - p.AW, 2 * p.AW) - ix0;
+      h = cdiv_pos(2 * Y1 * p.gh[g] - p.AH, 2 * p.AH) - iy0;
+    }
+    sts128(hdr_s + g * 16, make_uint4((uint32_t)ix0, (uint32_t)iy0, (uint32_t)w, (uint32_t)h));
+  }
+  __syncthreads();
+  int npass = 0;
+  {
+    int pbase[4];
+    uint4 hd[3];
+    pbase[0] = 0;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      hd[g] = lds128(hdr_s + g * 16);
+      pbase[g + 1] = pbase[g] + (int)hd[g].w * (((int)hd[g].z + 7) >> 3);
+    }
+    npass = pbase[3];
+    for (int k = threadIdx.x; k < npass; k += blockDim.x) {
+      const int g = k >= pbase[2] ? 2 : (k >= pbase[1] ? 1 : 0);
+      const uint4 h4 = g == 2 ? hd[2] : (g == 1 ? hd[1] : hd[0]);
+      const int r = k - (g == 2 ? pbase[2] : (g == 1 ? pbase[1] : 0));
+      const int spr = ((int)h4.z + 7) >> 3;                     // passes per row
+      const int iy = r / spr, sx = (r - iy * spr) * 8;
+      const int gw = g == 2 ? p.gw[2] : (g == 1 ? p.gw[1] : p.gw[0]);
+      const int gs = g == 2 ? p.gstart[2] : (g == 1 ? p.gstart[1] : p.gstart[0]);
+      const int q0 = gs + ((int)h4.y + iy) * gw + (int)h4.x + sx;
+      const int c = min(8, (int)h4.z - sx);
+      sts64(seg_s + k * 8, (uint32_t)q0, (uint32_t)c);
+      for (int s8 = 0; s8 < 8; ++s8) {
+        const float2 rf = __ldg(reinterpret_cast<const float2*>(p.ref + 2 * (q0 + min(s8, c - 1))));
+        sts64(ref_s + (k * 8 + s8) * 8, __float_as_uint(rf.x), __float_as_uint(rf.y));
+      }
+    }
+  }
+  __syncthreads();        // pass list, reference points, mbarrier init visible to every thread
+
+  const uint32_t rec_w = sbase + p.rec_off + (uint32_t)warp * (MAXL * 4 * 8 * 16);   // [point][query slot ^ 2 point] 16 B
+  const uint32_t xy_w = sbase + p.xy_off + (uint32_t)warp * (MAXL * 4 * 8 * 4);
+  const int LP = p.L * 4;
+  const long long vrow = (long long)p.M * 32;
+  const __nv_bfloat16* vimg = p.value + (long long)n * p.S * vrow + (long long)m * 32 + pl * 8;
+  const uint32_t orow32 = (uint32_t)p.M * 32u;    // in-image offsets fit 32 bits (host check)
+  __nv_bfloat16* olane = p.out + (long long)n * p.Lq * vrow + m * 32 + pl * 8;
+
+  // input ring: slot = [8 queries][L P float2 offsets] | [8 queries][L P logits], one TMA box each
+  const int STAGE = LP * 96;
+  const uint32_t in_w = sbase + p.in_off + (uint32_t)(warp * DEPTH * STAGE);
+  auto issue_pass = [&](int k, int slot) {
+    if (k < npass) {                        // warp-uniform
+      if (elect_one()) {
+        const int row = n * p.Lq + (int)lds32(seg_s + k * 8);
+        uint8_t* st = st_smem + p.in_off + (warp * DEPTH + slot) * STAGE;
+        mbar_arrive_expect_tx(&ring_bar[slot], (uint32_t)STAGE);
+        tma_load_2d(st, &maps.qoff, &ring_bar[slot], m * LP * 2, row);
+        tma_load_2d(st + LP * 64, &maps.qlg, &ring_bar[slot], p.M * LP * 2 + m * LP, row);
+      }
+      __syncwarp();
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < DEPTH; ++d) issue_pass(warp + d * nwarp, d);
+  mbar_wait(&bar, 0);
+
+  int slot = 0;
+  uint32_t ring_ph = 0;
+  for (int k = warp; k < npass; k += nwarp) {     // warp-uniform
+    const uint2 sg = lds64(seg_s + k * 8);
+    const bool valid = ql < (int)sg.y;
+    const int q = (int)sg.x + min(ql, (int)sg.y - 1);
+    const uint2 rfu = lds64(ref_s + (k * 8 + ql) * 8);
+    const float rx = __uint_as_float(rfu.x), ry = __uint_as_float(rfu.y);
+    mbar_wait(&ring_bar[slot], ring_ph);
+    float2 of_c[MAXL];
+    float lg_c[MAXL];
+    {
+      const uint32_t st = in_w + (uint32_t)(slot * STAGE);
+#pragma unroll
+      for (int l = 0; l < MAXL; ++l) {
+        lg_c[l] = -INFINITY;
+        of_c[l] = make_float2(0.f, 0.f);
+        if (l < p.L) {
+          const uint2 o = lds64(st + (uint32_t)(ql * (LP * 8) + l * 32 + pl * 8));
+          of_c[l] = make_float2(__uint_as_float(o.x), __uint_as_float(o.y));
+          lg_c[l] = __uint_as_float(lds32(st + (uint32_t)(LP * 64 + ql * (LP * 4) + l * 16 + pl * 4)));
+        }
+      }
+    }
+    const int slot_read = slot;
+    if (++slot == DEPTH) { slot = 0; ring_ph ^= 1u; }
+
+    // ---- phase A: lane = (query ql, point pl of every level) ----
+    float e[MAXL];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int l = 0; l < MAXL; ++l) mx = fmaxf(mx, lg_c[l]);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float den = 0.f;
+#pragma unroll
+    for (int l = 0; l < MAXL; ++l) {
+      e[l] = l < p.L ? ex2_ftz((lg_c[l] - mx) * 1.4426950408889634f) : 0.f;
+      den += e[l];
+    }
+    den += __shfl_xor_sync(0xffffffffu, den, 1);
+    den += __shfl_xor_sync(0xffffffffu, den, 2);
+    const float inv = rcp_ftz(den);              // den in [1, 4 L]
+    bool spill = false;                          // some sample of this lane is not in its box
+#pragma unroll
+    for (int l = 0; l < MAXL; ++l) {
+      if (l < p.L) {
+        const float Hf = (float)p.H[l], Wf = (float)p.W[l];
+        // the reference's loc = ref + off / (W, H); im = loc * size - 0.5, with the division as a multiplication by
+        // the reciprocal (exact for power-of-two maps, else an ulp of the location: the interpolation is continuous).
+        // Clamped to [-2, size + 1]: beyond, all four corners are outside the map (the reference skips the sample),
+        // and a NaN location becomes -2 (skipped by the reference's comparisons as well).
+        const float h_im = fminf(fmaxf((ry + of_c[l].y * rH[l]) * Hf - 0.5f, -2.f), Hf + 1.f);
+        const float w_im = fminf(fmaxf((rx + of_c[l].x * rW[l]) * Wf - 0.5f, -2.f), Wf + 1.f);
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        const int y0 = (int)hf, x0 = (int)wf;
+        const float lh = h_im - hf;
+        const float aw = e[l] * inv;
+        const int bx = x0 - ox[l], by = y0 - oy[l];
+        const bool inbox = (unsigned)bx <= (unsigned)(p.BW[l] - 2) && (unsigned)by <= (unsigned)(p.BH[l] - 2) && !(p.dbg & 4);
+        uint4 rec;
+        // staged: byte offset of the top-left corner; not staged: -1 - level, the corners come from global memory
+        rec.x = (uint32_t)(inbox ? p.box_off[l] + (by * p.BW[l] + bx) * 64 : -1 - l);
+        rec.y = __float_as_uint(w_im - wf);
+        rec.z = __float_as_uint(aw * (1.f - lh));
+        rec.w = __float_as_uint(aw * lh);
+        sts128(rec_w + (uint32_t)(((l * 4 + pl) * 8 + (ql ^ (2 * pl))) * 16), rec);
+        if (!inbox) {
+          sts32(xy_w + (uint32_t)(((l * 4 + pl) * 8 + ql) * 4), (uint32_t)((y0 * 65536) | (x0 & 0xffff)));
+          spill = true;
+        }
+      }
+    }
+    const bool any_spill = __any_sync(0xffffffffu, spill);
+    __syncwarp();          // the records are visible to the whole warp; every lane has consumed its ring slot
+    issue_pass(k + DEPTH * nwarp, slot_read);      // refill the slot just read
+
+    // ---- phase B: lane = (query ql, channel chunk pl) ----
+    u64 acc2[4] = {0ull, 0ull, 0ull, 0ull};
+    auto gather = [&](auto with_fallback) {
+#pragma unroll
+      for (int l = 0; l < MAXL; ++l) {
+        if (l < p.L && !(p.dbg & 2)) {
+          const uint32_t rowb = (uint32_t)p.BW[l] * 64u;
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            const uint4 rec = lds128(rec_w + (uint32_t)(((l * 4 + pp) * 8 + (ql ^ (2 * pp))) * 16));
+            const int so = (int)rec.x;
+            const float lw = __uint_as_float(rec.y), at = __uint_as_float(rec.z), ab = __uint_as_float(rec.w);
+            uint4 u0, u1, u2, u3;
+            float w0;        // x weight of (u0, u2); (u1, u3) carry 1 - w0
+            if (!decltype(with_fallback)::value || so >= 0) {
+              // d = 1: this lane reads the right neighbour first, so that the pair (ql even, ql odd) of a quarter
+              // warp always hits opposite halves of the 128-byte bank line
+              const uint32_t d = (((uint32_t)so >> 6) ^ (uint32_t)ql) & 1u;
+              const uint32_t a0 = sbase + (uint32_t)so + (uint32_t)pl * 16u;
+              const uint32_t af = a0 + d * 64u, as = a0 + 64u - d * 64u;
+              u0 = lds128(af); u1 = lds128(as); u2 = lds128(af + rowb); u3 = lds128(as + rowb);
+              w0 = d ? lw : 1.f - lw;
+            } else {
+              const int lv = -1 - so;
+              const int pxy = (int)lds32(xy_w + (uint32_t)(((l * 4 + pp) * 8 + ql) * 4));
+              const int H = p.H[lv], W = p.W[lv];
+              const int x = (int)(short)(pxy & 0xffff), y = pxy >> 16;
+              const __nv_bfloat16* vl = vimg + (long long)p.lsi[lv] * vrow;
+              u0 = u1 = u2 = u3 = make_uint4(0, 0, 0, 0);
+              const bool yt = y >= 0 && y < H, yb = y + 1 >= 0 && y + 1 < H;
+              if (x >= 0 && x < W) {
+                if (yt) u0 = __ldg(reinterpret_cast<const uint4*>(vl + ((long long)y * W + x) * vrow));
+                if (yb) u2 = __ldg(reinterpret_cast<const uint4*>(vl + ((long long)(y + 1) * W + x) * vrow));
+              }
+              if (x + 1 >= 0 && x + 1 < W) {
+                if (yt) u1 = __ldg(reinterpret_cast<const uint4*>(vl + ((long long)y * W + x + 1) * vrow));
+                if (yb) u3 = __ldg(reinterpret_cast<const uint4*>(vl + ((long long)(y + 1) * W + x + 1) * vrow));
+              }
+              w0 = 1.f - lw;
+            }
+            const float w1 = 1.f - w0;
+            const float k0 = at * w0, k1 = at * w1, k2 = ab * w0, k3 = ab * w1;
+            const u64 kk0 = pack2(k0, k0), kk1 = pack2(k1, k1), kk2 = pack2(k2, k2), kk3 = pack2(k3, k3);
+            const uint32_t* c0 = reinterpret_cast<const uint32_t*>(&u0);
+            const uint32_t* c1 = reinterpret_cast<const uint32_t*>(&u1);
+            const uint32_t* c2 = reinterpret_cast<const uint32_t*>(&u2);
+            const uint32_t* c3 = reinterpret_cast<const uint32_t*>(&u3);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              acc2[i] = fma2(pack2(bf16lo(c0[i]), bf16hi(c0[i])), kk0, acc2[i]);
+              acc2[i] = fma2(pack2(bf16lo(c1[i]), bf16hi(c1[i])), kk1, acc2[i]);
+              acc2[i] = fma2(pack2(bf16lo(c2[i]), bf16hi(c2[i])), kk2, acc2[i]);
+              acc2[i] = fma2(pack2(bf16lo(c3[i]), bf16hi(c3[i])), kk3, acc2[i]);
+            }
+          }
+        }
+      }
+    };
+    if (any_spill) gather(std::true_type{});
+    else gather(std::false_type{});
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) unpack2(acc2[i], acc[2 * i], acc[2 * i + 1]);
+    if (valid) *reinterpret_cast<uint4*>(olane + (uint32_t)q * orow32) = pack8(acc);
+    __syncwarp();          // the records are rewritten by the next pass
+  }
+}
+
 template <typename VT, typename AT>
 static int launch_msda(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
                        const void* attw, void* out, int N, int S, int M, int D, int Lq, int L, int P,
@@ -794,9 +1087,25 @@ MMSAM_API int mmsam_msda_fused_staged_bf16(const void* value, const int* level_h
   p.qref_off = off; off += qmax * 8;
   p.qidx_off = off; off += qmax * 4;
   off = (off + 15u) & ~15u;
+  static const int version = [] { const char* e = getenv("MMSAM_MSDA_STAGED_V"); return e ? atoi(e) : 2; }();
+  if (version != 1 && ((long long)N * Lq >= (1ll << 31) || (long long)Lq * M * 32 >= (1ll << 32) || ldq < (long long)M * LP * 3)) return MMSAM_ERR_UNSUPPORTED;
+  if (version != 1) {      // msda_staged2_kernel keeps the query inputs in registers: the areas above are not used
+    off = p.qoff_off;
+    const unsigned maxl = L <= 1 ? 1u : 4u;
+    p.rec_off = off; off += 8u * maxl * 4u * 8u * 16u;      // 8 warps x points x 8 query slots x 16 B
+    p.xy_off = off; off += 8u * maxl * 4u * 8u * 4u;
+    off = (off + 127u) & ~127u;
+    p.in_off = off; off += 8u * (L <= 1 ? 4u : 2u) * (LP * 96u);   // 8 warps x DEPTH x STAGE (TMA destinations: 128-byte multiples)
+    unsigned pmax = 0;     // passes (<= 8 consecutive queries of a grid row) of the largest region
+    for (int g = 0; g < n_qgrids; ++g)
+      pmax += (unsigned)(((max_cells(anchor_w, tile_w, p.gw[g]) + 7) / 8) * max_cells(anchor_h, tile_h, p.gh[g]));
+    p.seg_off = off; off += pmax * 8u;
+    p.sref_off = off; off += pmax * 64u;
+    off = (off + 15u) & ~15u;
+  }
   p.bar_off = off;
   { const char* e = getenv("MMSAM_MSDA_DBG"); p.dbg = e ? atoi(e) : 0; }
-  const unsigned smem = off + 16;
+  const unsigned smem = off + 64 + 8 * 4 * 8;      // mbarrier + the rectangle header + the ring barriers of msda_staged2_kernel
   if (smem > 226u * 1024u) return MMSAM_ERR_UNSUPPORTED;
   p.tiles_x = (anchor_w + tile_w - 1) / tile_w;
   const int tiles_y = (anchor_h + tile_h - 1) / tile_h;
@@ -819,6 +1128,27 @@ MMSAM_API int mmsam_msda_fused_staged_bf16(const void* value, const int* level_h
   cudaStream_t st = (cudaStream_t)stream;
   MMSAM_SET_SMEM_ONCE(msda_staged_kernel<2>, 226 * 1024);
   MMSAM_SET_SMEM_ONCE(msda_staged_kernel<4>, 226 * 1024);
+  if (version != 1) {
+    MsdaMaps2 maps2;
+    for (int l = 0; l < 4; ++l) maps2.m[l] = maps.m[l];
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)ldq, (cuuint64_t)N * Lq};
+      cuuint64_t strides[1] = {(cuuint64_t)ldq * 4};
+      cuuint32_t estr[2] = {1, 1};
+      cuuint32_t box_o[2] = {LP * 2, 8}, box_l[2] = {LP, 8};
+      if (enc(&maps2.qoff, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)qproj, dims, strides, box_o, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+          enc(&maps2.qlg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)qproj, dims, strides, box_l, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return MMSAM_ERR_DRIVER;
+    }
+    MMSAM_SET_SMEM_ONCE((msda_staged2_kernel<1, 4>), 226 * 1024);
+    MMSAM_SET_SMEM_ONCE((msda_staged2_kernel<4, 2>), 226 * 1024);
+    if (L <= 1) msda_staged2_kernel<1, 4><<<grid, 256, smem, st>>>(maps2, p);
+    else msda_staged2_kernel<4, 2><<<grid, 256, smem, st>>>(maps2, p);
+    MMSAM_LAUNCH_CHECK();
+    return MMSAM_OK;
+  }
   // 8 lanes per query: one pass over the region's queries when there are few (injector), 256 threads otherwise
   const unsigned threads = qmax <= 64 ? 512 : 256;
   if (L <= 2) msda_staged_kernel<2><<<grid, threads, smem, st>>>(maps, p);

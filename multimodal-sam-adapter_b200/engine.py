@@ -113,9 +113,10 @@ def _pad_rows(w, n):
     return out
 
 
-# The shared-memory staged MSDeformAttn kernel is correct (tests/test_kernels_gpu.py::test_msda_staged_vs_oracle) but
-# issue-bound and slower than the L1-gather kernel at the bench shapes (profiles/r01_msda_notes.md): opt-in only.
-MSDA_STAGED = os.environ.get("MMSAM_MSDA_STAGED", "0") == "1"
+# Shared-memory staged MSDeformAttn kernel (msda_staged2_kernel, profiles/r02_msda_notes.md): 1.27x faster than the
+# L1-gather kernel on the extractor (one 64 x 64 value level, 21504 queries), slower on the injector (three levels per
+# region leave one CTA per SM): default = extractor only.
+MSDA_STAGED = os.environ.get("MMSAM_MSDA_STAGED", "ext")         # "0" | "1" (injector + extractor) | "ext" (extractor only)
 
 
 class _MSDA:
@@ -333,14 +334,14 @@ class _Ops:
     def _injector(self, x, c, inj, sc, B):
         """Injector.forward (adapter_modules_...new.py:525-542); returns a NEW fp32 [B*T, C] buffer (the input
         is one of the saved ViT outputs `outs` and must stay intact)."""
-        o = self._msda(inj["attn"], x, c, sc["ref1"], sc["lv3"], B, inj["attn"].geom("inj", sc) if MSDA_STAGED else None,
+        o = self._msda(inj["attn"], x, c, sc["ref1"], sc["lv3"], B, inj["attn"].geom("inj", sc) if MSDA_STAGED == "1" else None,
                        qn=inj["qn"], fn=inj["fn"], c_is="feat", sc=sc)
         return K.gemm(o.view(-1, o.shape[-1]), inj["attn"].out.w, bias=inj["attn"].out.b, scale=inj["gamma"],
                       residual=x, out=torch.empty_like(x))
 
     def _extractor(self, c, x, e, sc, B):
         """Extractor.forward (adapter_modules_...new.py:490-511); c [B*S3, C] updated in place."""
-        o = self._msda(e["attn"], c, x, sc["ref2"], sc["lv1"], B, e["attn"].geom("ext", sc) if MSDA_STAGED else None,
+        o = self._msda(e["attn"], c, x, sc["ref2"], sc["lv1"], B, e["attn"].geom("ext", sc) if MSDA_STAGED in ("1", "ext") else None,
                        qn=e["qn"], fn=e["fn"], c_is="query", sc=sc)
         sc["c_stats"] = None                                   # c is about to change
         self._gemm(o.view(-1, o.shape[-1]), e["attn"].out, residual=c, out=c)
