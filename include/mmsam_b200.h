@@ -139,7 +139,8 @@ int mmsam_msda_fused_bf16(const void* value, const int64_t* spatial_shapes_dev,
 
 /* Same contract as mmsam_msda_fused_bf16, for callers that know the geometry on the host (the backbone does:
  * deform_inputs, adapter_modules_...new.py:397-431): the value windows are staged in shared memory by TMA and
- * gathered from there (~3x the L1 gather rate). level_hw_host [L][2] = (H_l, W_l), levels packed back to back in
+ * gathered from there (~3x the L1 gather rate; off / (W, H) is computed as off * (1 / W, 1 / H): exact for power-of-two
+ * maps, else an ulp of the location). level_hw_host [L][2] = (H_l, W_l), levels packed back to back in
  * value (sum = S); qgrid_hw_host [n_qgrids][2]: the queries are n_qgrids <= 3 row-major grids back to back
  * (sum = Lq) whose reference points are the cell centres; a CTA owns one head of a tile_h x tile_w tile of the
  * anchor_h x anchor_w anchor grid (a partition of the normalised plane) and serves every query whose cell centre
