@@ -17,6 +17,7 @@
 // not depend on the CTA schedule — no floating-point atomics anywhere). Split over pixel chunks so that every SM has
 // work; HBM-bound: X is read from DRAM once, tiles of the same chunk share it through L2.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace mmsam {
 
@@ -136,6 +137,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const GramParams p) {
     const long long slot = (long long)blockIdx.y * gridDim.z + b;      // (chunk, image)
     float* Sb = p.S + slot * p.n * p.n;
     if (nst > 0) {
+      // A thread holds one ROW of the tile: stored as is, every store instruction would touch 32 different lines
+      // (17 us of sector writes for a 128 x 256 tile). The 32 x 32 block of a warp goes through shared memory (the
+      // pipeline stages are free once `done` has fired; row pitch 36 floats: conflict-free both ways) and leaves as
+      // 16-byte pieces, 8 lanes per row = full 128-byte lines.
+      const bool vec4 = (p.blk & 3) == 0;
+      const uint32_t tb = smem_u32(smem) + (uint32_t)warp * (32 * 36 * 4);
 #pragma unroll 1
       for (int c = 0; c < BNJ; c += 32) {
         if (j0 + c >= p.n) break;
@@ -143,7 +150,24 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const GramParams p) {
         __syncwarp();
         tmem_ld_32x32b_x32(lane_addr + TM_G + c, r);
         tmem_ld_wait();
-        if (gi < p.n) {
+        if (vec4) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tb + (uint32_t)(lane * 36 + k * 4) * 4u), "r"(r[4 * k]),
+                         "r"(r[4 * k + 1]), "r"(r[4 * k + 2]), "r"(r[4 * k + 3]) : "memory");
+          __syncwarp();
+          const int cg = j0 + c + (lane & 7) * 4;
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int row = rr * 4 + (lane >> 3);
+            const int gr = i0 + warp * 32 + row;
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(tb + (uint32_t)(row * 36 + (lane & 7) * 4) * 4u));
+            if (gr < p.n && cg < p.n && (p.blk == 0 || gr / p.blk == cg / p.blk))
+              *reinterpret_cast<uint4*>(Sb + (long long)gr * p.n + cg) = v;
+          }
+        } else if (gi < p.n) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int gj = j0 + c + j;
@@ -193,17 +217,26 @@ static int launch_gram_tc(const CUtensorMap& tm, const GramParams& p, dim3 grid,
 
 }  // namespace mmsam
 
-// Pixel chunking of the tensor-core path. It depends on the map size ONLY (not on the batch or the tile count): an
+// Pixel chunking of the tensor-core path. It depends on the map size and the matrix size ONLY (not on the batch): an
 // image's partial sums are then the same whatever batch it sits in, which makes the whole forward batch-invariant bit
-// for bit. HW / 32 pixels per chunk, clamped to [256, 2048] (>= 4 pipeline stages of 64 pixels per CTA; 32 chunks x
-// tiles x images CTAs on the large maps). Returns the number of chunks, 0 when the shape does not fit this path.
+// for bit. The chunk count is chosen so that (output tiles that run) x (chunks) ~ 18 CTAs per image (one wave of the
+// 148 SMs at the bench batch of 8; measured against 36 and 72: tools/bench_gram.py): few chunks for the large matrices of the deep levels — every chunk costs a full
+// [n, n] fp32 partial that the consumer has to read back — many for the 96-channel level whose single tile would
+// otherwise leave the machine empty. At least 4 pipeline stages of 64 pixels per CTA. Returns the number of chunks,
+// 0 when the shape does not fit this path.
 int mmsam_gram_tc_plan(int n, int B, int HW, int norms, int* chunk_out) {
   using namespace mmsam;
-  (void)n; (void)norms;
+  (void)B;
   if (HW % GR_KP != 0 || (long long)B * HW > 0x7fffffffLL) return 0;
-  int chunk = HW / 32;
+  static const int target = [] { const char* e = getenv("MMSAM_GRAM_TARGET"); return e ? atoi(e) : 18; }();
+  const int bnj = (norms || n <= 128) ? 128 : 256;
+  const int nti = (n + 127) / 128, ntj = (n + bnj - 1) / bnj;
+  int tiles = nti * ntj;
+  if (norms && 3 * nti - 2 < tiles) tiles = 3 * nti - 2;      // per-head blocks: only tiles on the block diagonal run
+  int nch = target / tiles;          // rounded down: tiles x chunks x 8 images stay within one wave of 148 CTAs
+  if (nch < 1) nch = 1;
+  int chunk = (HW + nch - 1) / nch;
   if (chunk < 4 * GR_KP) chunk = 4 * GR_KP;
-  if (chunk > 2048) chunk = 2048;
   if (chunk > HW) chunk = HW;
   chunk = (chunk + GR_KP - 1) / GR_KP * GR_KP;
   if (chunk_out) *chunk_out = chunk;

@@ -109,8 +109,10 @@ gfe_weff_kernel(const float* __restrict__ S_part, const float* __restrict__ nq_p
                 const float* __restrict__ scale2, __nv_bfloat16* __restrict__ weff) {
   extern __shared__ float s_gf[];
   const int ch = ci / heads;
-  float* att = s_gf;                 // [ch][ch + 1]
-  float* rq = att + ch * (ch + 1);   // [ch] 1 / max(|q|, eps)
+  const bool vec = (ch & 3) == 0;      // 4 x 4 register tiles with 16-byte loads in the proj fold
+  const int cs = vec ? ch + 4 : ch + 1;
+  float* att = s_gf;                 // [ch][cs]
+  float* rq = att + ch * cs;         // [ch] 1 / max(|q|, eps)
   float* rk = rq + ch;
   const int h = blockIdx.x, b = blockIdx.y;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
@@ -120,7 +122,7 @@ gfe_weff_kernel(const float* __restrict__ S_part, const float* __restrict__ nq_p
     const float* src = S_part + (long long)b * nn + (long long)(h * ch + a) * ci + h * ch + j;
     float acc = 0.f;
     for (int c = 0; c < nchunks; ++c) acc += src[(long long)c * B * nn];
-    att[a * (ch + 1) + j] = acc;
+    att[a * cs + j] = acc;
   }
   for (int e = t; e < 2 * ch; e += blockDim.x) {
     const float* src = (e < ch ? nq_part : nk_part) + (long long)b * ci + h * ch + (e < ch ? e : e - ch);
@@ -131,7 +133,7 @@ gfe_weff_kernel(const float* __restrict__ S_part, const float* __restrict__ nq_p
   __syncthreads();
   const float tp = temp[h];
   for (int a = warp; a < ch; a += nwarps) {          // warp = one softmax row
-    float* row = att + a * (ch + 1);
+    float* row = att + a * cs;
     float mx = -INFINITY;
     for (int j = lane; j < ch; j += 32) {
       const float v = row[j] * rq[a] * rk[j] * tp;
@@ -150,15 +152,63 @@ gfe_weff_kernel(const float* __restrict__ S_part, const float* __restrict__ nq_p
     for (int j = lane; j < ch; j += 32) row[j] *= inv;
   }
   __syncthreads();
+  // proj fold: Weff[i, h ch + j] = scale2 * sum_a wproj[i, h ch + a] * att[a, j]  for this CTA's rows [i0, i1).
+  // ci x ch x ch FMAs per (head, image): with one load pair per FMA the kernel sat on the LSU (238 us at ci = 768);
+  // a thread now owns a 4 x 4 tile and reads wproj / att 16 bytes at a time (8 loads per 64 FMAs).
   const float s2 = scale2[0];
   const int rows_per = (ci + gridDim.z - 1) / gridDim.z;
   const int i0 = blockIdx.z * rows_per, i1 = min(i0 + rows_per, ci);
-  for (int e = t; e < (i1 - i0) * ch; e += blockDim.x) {
-    const int i = i0 + e / ch, j = e % ch;
-    const float* wp = wproj + (long long)i * ci + h * ch;
-    float acc = 0.f;
-    for (int a = 0; a < ch; ++a) acc = fmaf(__ldg(wp + a), att[a * (ch + 1) + j], acc);
-    weff[(long long)b * nn + (long long)i * ci + h * ch + j] = __float2bfloat16_rn(acc * s2);
+  if (vec) {
+    const int jq_n = ch >> 2, iq_n = (i1 - i0 + 3) >> 2;
+    for (int tile = t; tile < iq_n * jq_n; tile += blockDim.x) {
+      const int iq = tile / jq_n, jq = tile - iq * jq_n;
+      const int ib = i0 + iq * 4;
+      const float* wp[4];
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) wp[ii] = wproj + (long long)min(ib + ii, i1 - 1) * ci + h * ch;
+      float acc[4][4];
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[ii][jj] = 0.f;
+      for (int a4 = 0; a4 < ch; a4 += 4) {
+        float4 w[4], at[4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) w[ii] = __ldg(reinterpret_cast<const float4*>(wp[ii] + a4));
+#pragma unroll
+        for (int aa = 0; aa < 4; ++aa) at[aa] = *reinterpret_cast<const float4*>(att + (a4 + aa) * cs + jq * 4);
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const float wv[4] = {w[ii].x, w[ii].y, w[ii].z, w[ii].w};
+#pragma unroll
+          for (int aa = 0; aa < 4; ++aa) {      // a ascending: the summation order of the scalar path
+            acc[ii][0] = fmaf(wv[aa], at[aa].x, acc[ii][0]);
+            acc[ii][1] = fmaf(wv[aa], at[aa].y, acc[ii][1]);
+            acc[ii][2] = fmaf(wv[aa], at[aa].z, acc[ii][2]);
+            acc[ii][3] = fmaf(wv[aa], at[aa].w, acc[ii][3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        if (ib + ii < i1) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(acc[ii][0] * s2, acc[ii][1] * s2);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(acc[ii][2] * s2, acc[ii][3] * s2);
+          uint2 v;
+          v.x = *reinterpret_cast<uint32_t*>(&lo);
+          v.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(weff + (long long)b * nn + (long long)(ib + ii) * ci + h * ch + jq * 4) = v;
+        }
+      }
+    }
+  } else {
+    for (int e = t; e < (i1 - i0) * ch; e += blockDim.x) {
+      const int i = i0 + e / ch, j = e % ch;
+      const float* wp = wproj + (long long)i * ci + h * ch;
+      float acc = 0.f;
+      for (int a = 0; a < ch; ++a) acc = fmaf(__ldg(wp + a), att[a * cs + j], acc);
+      weff[(long long)b * nn + (long long)i * ci + h * ch + j] = __float2bfloat16_rn(acc * s2);
+    }
   }
 }
 
@@ -558,9 +608,9 @@ MMSAM_API int mmsam_gfe_weff_bf16(const float* S_part, const float* nq_part, con
   if (B == 0) return MMSAM_OK;
   if (!S_part || !nq_part || !nk_part || !temperature || !wproj || !scale2 || !weff) return MMSAM_ERR_BAD_ARG;
   const int ch = ci / heads;
-  const int smem = (ch * (ch + 1) + 2 * ch) * (int)sizeof(float);
+  const int smem = (ch * (ch + 4) + 2 * ch) * (int)sizeof(float);
   if (smem > 48 * 1024) return MMSAM_ERR_UNSUPPORTED;
-  int zs = (2 * kNumSMs + heads * B - 1) / (heads * B);      // row splits: ~2 CTAs per SM
+  int zs = (2 * kNumSMs + heads * B - 1) / (heads * B);      // row splits: ~2 CTAs per SM (more splits repeat the partial sums and the softmax: 4 per SM measured slower)
   if (zs > (ci + 15) / 16) zs = (ci + 15) / 16;
   if (zs < 1) zs = 1;
   dim3 grid(heads, B, zs);
