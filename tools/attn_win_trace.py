@@ -7,11 +7,16 @@ import mmsam_b200  # noqa
 from mmsam_b200 import kernels as K, _lib
 nh, Bp, T = 16, 200, 196
 bias = len(sys.argv) < 2 or sys.argv[1] != "nobias"
-qkv = torch.randn(Bp, T, 3 * nh * 64, device="cuda").to(torch.bfloat16)
 th = K.relpos_table(torch.randn(27, 64, device="cuda") * 0.2, 14) if bias else None
 tw = K.relpos_table(torch.randn(27, 64, device="cuda") * 0.2, 14) if bias else None
-for _ in range(3):
-    out = K.attention(qkv, nh, (14, 14), th, tw)
+if os.environ.get("WIN_LEGACY"):        # partitioned input / output (the row-mapped path)
+    qkv = torch.randn(Bp, T, 3 * nh * 64, device="cuda").to(torch.bfloat16)
+    for _ in range(3):
+        out = K.attention(qkv, nh, (14, 14), th, tw)
+else:                                   # what the model runs: 64 x 64 token images, window_unpartition fused into the store
+    qkv = torch.randn(Bp, T, 3 * nh * 64, device="cuda").to(torch.bfloat16)      # 8 images x 25 windows (64 -> 70 tokens padded)
+    for _ in range(3):
+        out = K.attention_window(qkv, nh, 8, 64, 64, th, tw)
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * (5 * 16 * 8))()
 lib = ctypes.CDLL(_lib.LIB_PATH)
