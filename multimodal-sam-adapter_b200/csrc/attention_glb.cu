@@ -70,6 +70,33 @@ __device__ __forceinline__ float glb_ex2(float x) {
 // The exponentials are issued as ONE block of 32 MUFU.EX2 (volatile, in place) between the arithmetic that feeds them and
 // the sums / packs that consume them: with the consumers right behind each pair (what the compiler schedules by itself)
 // every FADD2 / F2FP waits out the MUFU latency, and a softmax warp has only one other warp on its scheduler to hide it.
+// exp2 on the FMA pipe for a pair of values <= ~16: Cody-Waite split x = n + f (n = round(x) through the 1.5 * 2^23 magic
+// add, f in [-0.5, 0.5]), degree-3 minimax polynomial for 2^f (relative error 7.5e-5: P is rounded to bf16, 4e-3, right
+// after), 2^n added into the exponent field. ~6 instructions per element on the FMA / ALU pipes against one MUFU.EX2 that
+// occupies the 4-lane special-function unit for 8 cycles per warp. GLB_POLY_MASK (one bit per pair of a 32-column chunk)
+// moves a fraction of every chunk's exponentials off that unit (the split FlashAttention-4 uses on this chip).
+// MEASURED: 25 % of the exponentials through the polynomial (mask 0x8888) = 0.807 ms per launch against 0.78 - 0.79 with
+// all of them on the MUFU (and 24 bytes of spills): with two softmax warps per scheduler the loop is bound by the
+// latency of its dependent chains, not by the throughput of either pipe, and the polynomial adds a 9-deep chain.
+// Default 0 = off; kept for a structure with more resident softmax warps.
+#ifndef GLB_POLY_MASK
+#define GLB_POLY_MASK 0x0000u
+#endif
+__device__ __forceinline__ void glb_ex2_poly2(float& x0, float& x1) {
+  const u64 x2 = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const u64 t = add2(x2, pack2(12582912.f, 12582912.f));
+  const u64 n = add2(t, pack2(-12582912.f, -12582912.f));
+  const u64 f = fma2(n, pack2(-1.f, -1.f), x2);
+  u64 q = fma2(f, pack2(0.05517164617776871f, 0.05517164617776871f), pack2(0.2426111251115799f, 0.2426111251115799f));
+  q = fma2(q, f, pack2(0.6932609677314758f, 0.6932609677314758f));
+  q = fma2(q, f, pack2(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, t0, t1;
+  unpack2(q, q0, q1);
+  unpack2(t, t0, t1);
+  x0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  x1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
 template <bool MAXONLY>
 __device__ __forceinline__ void glb_chunk(const uint32_t (&r)[32], const u64* bw2, u64 sc2, u64 nb2, float& mx, u64 (&sum2)[2],
                                           uint32_t (&pk)[16]) {
@@ -84,7 +111,11 @@ __device__ __forceinline__ void glb_chunk(const uint32_t (&r)[32], const u64* bw
   }
   if constexpr (!MAXONLY) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(e[i]));
+    for (int i = 0; i < 32; ++i)
+      if (!((GLB_POLY_MASK >> (i >> 1)) & 1u)) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(e[i]));
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if ((GLB_POLY_MASK >> i) & 1u) glb_ex2_poly2(e[2 * i], e[2 * i + 1]);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(sum2[i & 1]) : "l"(pack2(e[2 * i], e[2 * i + 1])));
