@@ -6,19 +6,23 @@
 // (Conv2d(3c, 3c, 3, padding=1, groups=32), :84) and Mlp.dwconv (Conv2d(2c, 2c, 3, padding=1,
 // groups=c), :118-119). Any groups count works, including 1 (dense 3x3).
 //
-// Tile = 128 output pixels (an 8 x 16 spatial patch of one image) x 64 output channels. For every filter
-// tap (dy, dx) the A operand is the same patch shifted by (dy-1, dx-1): ONE 4-D TMA box
-// {64 ch, 16 w, 8 h, 1 b} out of the NHWC input, with the hardware's out-of-bounds zero fill doing the
-// spatial zero padding and the channel tail. Because the conv is grouped, the 64 output channels of a
-// tile only read a short window of input channels (the groups they belong to): the K loop is
-// 9 taps x KC 64-channel blocks of that window, against weight blocks pre-packed per
-// (n-tile, tap, k-block) with zeros outside each group. Same warp specialisation as gemm.cu
-// (TMA producer warp, one MMA-issuer lane, 8 epilogue warps, 2 TMEM accumulators).
+// Tile = 128 output pixels (a 16-row x 8-column spatial patch of one image) x 64 output channels. The A operand of
+// filter tap (dy, dx) is the same patch shifted by (dy-1, dx-1). ONE 4-D TMA box {64 ch, 8 w, 18 h, 1 b} per column
+// shift dx serves the three taps of that column: the box is 18 image rows of 8 pixels = 18 SWIZZLE_128B atoms of 8
+// rows x 128 B, so the row shift dy is a start address dy * 1024 B further into the box — still on an atom boundary,
+// the descriptor needs nothing else. The hardware's out-of-bounds zero fill does the spatial zero padding and the
+// channel tail. Because the conv is grouped, the 64 output channels of a tile only read a short window of input
+// channels (the groups they belong to): the K loop is KC 64-channel blocks of that window x 3 column shifts (one
+// pipeline unit each: the 18 KB box + the three 8 KB weight blocks of its taps, 12 MMAs of 128 x 64 x 16), against
+// weight blocks pre-packed per (n-tile, tap, k-block) with zeros outside each group. Same warp specialisation as
+// gemm.cu (TMA producer warp, one MMA-issuer lane, 8 epilogue warps, 2 TMEM accumulators).
 //
-// Measured (tools/bench_conv3x3.py, batch 8): ~0.33 us per k-block (one 16 KB shifted input box + one 8 KB weight block
-// + four 128x64x16 MMAs) whatever the grouping, i.e. ~600 cycles per 128-row box: the per-row request rate of the 4-D
-// box loads, not bytes or FLOPs, bounds the kernel. Halving the k-blocks per tile (n-tile stride below) pays in full;
-// keeping the weights resident in shared memory (tried: n-tile-major ranges, 72 KB of tap blocks) does not.
+// History (tools/bench_conv3x3.py, batch 8): with one shifted 16 KB box per TAP (8 x 16 patches, 9 boxes per k-block)
+// the kernel took ~0.33 us per (tap, k-block) = ~600 cycles per 128-row box whatever the grouping: the per-row request
+// rate of the box loads — not bytes or FLOPs — bounded it, and the same input rows were fetched nine times. Sharing a box
+// between the three row shifts loads 3 x 144 instead of 9 x 128 rows per k-block. Halving the k-blocks per tile (n-tile
+// stride below) pays in full; keeping the weights resident in shared memory (tried: n-tile-major ranges, 72 KB of tap
+// blocks) does not.
 #include "common.cuh"
 #include <cstdlib>
 
@@ -33,9 +37,11 @@ struct ConvParams {
   int tiles_x, tiles_y, num_n, num_tiles;
 };
 
-static constexpr int CV_BN = 64, CV_STAGES = 8;
-static constexpr int CV_A_BYTES = 128 * 64 * 2, CV_B_BYTES = CV_BN * 64 * 2;
-static constexpr int CV_STAGE_BYTES = CV_A_BYTES + CV_B_BYTES;
+static constexpr int CV_BN = 64, CV_STAGES = 4;
+static constexpr int CV_TH = 16, CV_TW = 8;                                  // patch: rows x columns
+static constexpr int CV_A_BYTES = (CV_TH + 2) * CV_TW * 64 * 2;              // 18 atoms of 8 pixels x 64 channels
+static constexpr int CV_B_BYTES = CV_BN * 64 * 2;                            // one tap's weight block
+static constexpr int CV_STAGE_BYTES = CV_A_BYTES + 3 * CV_B_BYTES;           // unit = one column shift of one k-block
 static constexpr int CV_EPI_PITCH = 80;   // bytes per staged row (64 B of data): 16-byte stores of a quarter warp hit distinct banks
 static constexpr int CV_SMEM = CV_STAGES * CV_STAGE_BYTES + 1024 + 256 + 8 * 32 * CV_EPI_PITCH;
 
@@ -50,7 +56,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint64_t* tempty = bars + 2 * CV_STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CV_STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_k = 9 * p.KC;
+  const int num_k = 3 * p.KC;          // pipeline units per tile
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -69,9 +75,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   auto decode = [&](int tile, int& nt, int& x0, int& y0, int& b) {
     nt = tile % p.num_n;
     int t = tile / p.num_n;
-    x0 = (t % p.tiles_x) * 16;
+    x0 = (t % p.tiles_x) * CV_TW;
     t /= p.tiles_x;
-    y0 = (t % p.tiles_y) * 8;
+    y0 = (t % p.tiles_y) * CV_TH;
     b = t / p.tiles_y;
   };
 
@@ -85,10 +91,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         // first input channel of the first group touched, aligned down to 8 channels: a TMA box must start on
         // a 16-byte boundary of the innermost dimension
         const int kwin = (((nt * p.NS) / p.cg_out) * p.cg_in) & ~7;
-        int kb = 0;
-        for (int tap = 0; tap < 9; ++tap) {
-          const int dy = tap / 3, dx = tap - dy * 3;
-          for (int kc = 0; kc < p.KC; ++kc, ++kb) {
+        for (int kc = 0; kc < p.KC; ++kc) {
+          for (int dx = 0; dx < 3; ++dx) {
             mbar_wait(&empty[s], ph ^ 1);
             if (elect_one()) {
               mbar_arrive_expect_tx(&full[s], CV_STAGE_BYTES);
@@ -96,9 +100,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
               asm volatile(
                   "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                   ::"r"(smem_u32(sa)), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(&full[s])),
-                  "r"(kwin + kc * 64), "r"(x0 + dx - 1), "r"(y0 + dy - 1), "r"(b)
+                  "r"(kwin + kc * 64), "r"(x0 + dx - 1), "r"(y0 - 1), "r"(b)
                   : "memory");
-              tma_load_2d(sa + CV_A_BYTES, &tmW, &full[s], 0, ((nt * 9 + tap) * p.KC + kc) * 64);
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy)
+                tma_load_2d(sa + CV_A_BYTES + dy * CV_B_BYTES, &tmW, &full[s], 0, ((nt * 9 + dy * 3 + dx) * p.KC + kc) * 64);
             }
             __syncwarp();
             if (++s == CV_STAGES) { s = 0; ph ^= 1; }
@@ -123,9 +129,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           const uint32_t b_addr = a_addr + CV_A_BYTES;
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                          (kb | k) != 0 ? 1u : 0u);
+            for (int dy = 0; dy < 3; ++dy)        // row shift: dy atoms (8 pixels x 128 B) into the box
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + dy * (CV_TW * 128) + k * 32),
+                            umma_desc_sw128(b_addr + dy * CV_B_BYTES + k * 32), idesc, (kb | dy | k) != 0 ? 1u : 0u);
             umma_commit(&empty[s]);
           }
           __syncwarp();
@@ -162,7 +170,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       if (nval == 32 && (col & 7) == 0) {
         // aligned full tile (NS = 64): four 16-byte stores per thread are cheaper than the slab round trip
         const int rr = quad * 32 + lane;
-        const int y = y0 + (rr >> 4), x = x0 + (rr & 15);
+        const int y = y0 + (rr >> 3), x = x0 + (rr & 7);
         if (y < p.H && x < p.W) {
           float v[32];
 #pragma unroll
@@ -187,7 +195,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       for (int i = 0; i < 16; ++i) {
         const int rl = 2 * i + rsel;                 // row of this warp's 32
         const int rr = quad * 32 + rl;
-        const int y = y0 + (rr >> 4), x = x0 + (rr & 15);
+        const int y = y0 + (rr >> 3), x = x0 + (rr & 7);
         if (y < p.H && x < p.W && 2 * sub < nval) {
           const uint32_t w2 = *reinterpret_cast<const uint32_t*>(slab + rl * CV_EPI_PITCH + sub * 4);
           __nv_bfloat16* op = p.out + (((long long)b * p.H + y) * p.W + x) * p.Cout + col + 2 * sub;
@@ -268,7 +276,7 @@ MMSAM_API int mmsam_conv3x3_bf16(const void* x, const void* w_packed, void* out,
   p.out = (__nv_bfloat16*)out;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.cg_in = Cin / groups; p.cg_out = Cout / groups; p.KC = KC;
   p.NS = mmsam_conv3x3_nstride(Cin, Cout, groups);
-  p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 7) / 8; p.num_n = (Cout + p.NS - 1) / p.NS;
+  p.tiles_x = (W + CV_TW - 1) / CV_TW; p.tiles_y = (H + CV_TH - 1) / CV_TH; p.num_n = (Cout + p.NS - 1) / p.NS;
   p.num_tiles = p.num_n * p.tiles_x * p.tiles_y * B;
   mmsam_host::EncodeTiledFn enc = mmsam_host::get_encode_tiled();
   if (!enc) return MMSAM_ERR_DRIVER;
@@ -276,7 +284,7 @@ MMSAM_API int mmsam_conv3x3_bf16(const void* x, const void* w_packed, void* out,
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-    cuuint32_t box[4] = {64, 16, 8, 1};
+    cuuint32_t box[4] = {64, CV_TW, CV_TH + 2, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
