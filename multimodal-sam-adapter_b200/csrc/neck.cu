@@ -324,7 +324,9 @@ colstats_kernel(const __nv_bfloat16* __restrict__ o, const float* __restrict__ w
 //   mu, rstd per channel (fp64 combination of the chunk partials, in order), GAP of LN_HW(o) analytically
 //   (gap = rstd * (sum o*w - mu * sum w) / HW + mean b), a = Wffrm gap (1x1 conv, no bias), GroupNorm(32), ReLU,
 //   gate = 1 + sigmoid(.)  (the "+1" is FFRM's residual: x * atten + x).
-// grid (B), block 1024.
+// grid (B, splits), block 1024: a CTA owns whole GroupNorm groups (their rows of the 1x1 conv), so the splits are
+// independent; every CTA rebuilds the pooled vector (cheap) and CTA (b, 0) writes mu / rstd. With one CTA per image
+// (round 1) eight SMs streamed the C x C fp32 weight alone: 172 us at C = 1536.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 ffrm_gate_kernel(const float* __restrict__ part, int nch, int B, int HW, int C, double sum_w, double mean_b, float ln_eps,
@@ -345,12 +347,17 @@ ffrm_gate_kernel(const float* __restrict__ part, int nch, int B, int HW, int C, 
     double var = s1 / HW - mu * mu;
     var = var > 0 ? var : 0;
     const double rstd = 1.0 / sqrt(var + (double)ln_eps);
-    mu_out[(long long)b * C + c] = (float)mu;
-    rstd_out[(long long)b * C + c] = (float)rstd;
+    if (blockIdx.y == 0) {
+      mu_out[(long long)b * C + c] = (float)mu;
+      rstd_out[(long long)b * C + c] = (float)rstd;
+    }
     gap[c] = (float)(rstd * (s2 - mu * sum_w) / HW + mean_b);
   }
   __syncthreads();
-  for (int c = warp; c < C; c += nwarps) {               // warp = one output channel of the 1x1 conv
+  const int cg = C / groups;
+  const int gper = (groups + gridDim.y - 1) / gridDim.y;
+  const int g_lo = blockIdx.y * gper, g_hi = min(g_lo + gper, groups);
+  for (int c = g_lo * cg + warp; c < g_hi * cg; c += nwarps) {   // warp = one output channel of the 1x1 conv
     const float* w = wffrm + (long long)c * C;
     float acc = 0.f;
     for (int k = lane; k < C; k += 32) acc = fmaf(__ldg(w + k), gap[k], acc);
@@ -358,8 +365,7 @@ ffrm_gate_kernel(const float* __restrict__ part, int nch, int B, int HW, int C, 
     if (lane == 0) a[c] = acc;
   }
   __syncthreads();
-  const int cg = C / groups;
-  for (int g = warp; g < groups; g += nwarps) {          // warp = one GroupNorm group (biased variance)
+  for (int g = g_lo + warp; g < g_hi; g += nwarps) {     // warp = one GroupNorm group (biased variance)
     float s = 0.f;
     for (int k = lane; k < cg; k += 32) s += a[g * cg + k];
     const float m = warp_sum(s) / cg;
@@ -638,7 +644,8 @@ MMSAM_API int mmsam_ffrm_gate_f32(const float* colstats_part, int nchunks, int B
   if (B < 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups || nchunks <= 0 || C > 4096) return MMSAM_ERR_BAD_ARG;
   if (B == 0) return MMSAM_OK;
   if (!colstats_part || !wffrm || !gn_weight || !gn_bias || !mu || !rstd || !gate) return MMSAM_ERR_BAD_ARG;
-  ffrm_gate_kernel<<<B, 1024, 2 * C * sizeof(float), (cudaStream_t)stream>>>(colstats_part, nchunks, B, HW, C, sum_w, mean_b,
+  int splits = groups < 16 ? groups : 16;          // whole groups per CTA; every split re-reads the colstats partials
+  ffrm_gate_kernel<<<dim3(B, splits), 1024, 2 * C * sizeof(float), (cudaStream_t)stream>>>(colstats_part, nchunks, B, HW, C, sum_w, mean_b,
                                                                              ln_eps, wffrm, gn_weight, gn_bias, groups, gn_eps,
                                                                              mu, rstd, gate);
   MMSAM_LAUNCH_CHECK();
