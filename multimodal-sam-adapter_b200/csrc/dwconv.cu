@@ -293,88 +293,116 @@ struct Dw3Maps { CUtensorMap x[3], y[3]; };
 struct Dw3Params {
   const float* w;      // [9][C] tap-major
   const float* bias;   // [C] or null
-  int C, act, ngrids;
+  int C, act, ngrids, B;
   int tiles_x[3], tile_start[4];
 };
 
+// Persistent: a CTA walks items (tile, 32-channel block, image; channel block fastest, so the CTAs that run together
+// read neighbouring 64-byte pieces of the same pixels) with the halo double-buffered — the TMA load of the next item is in
+// flight while the current one is computed (a one-shot CTA per tile exposed the load latency with two CTAs per SM:
+// 2.6 - 3.1 TB/s). The output tile is staged over the halo it came from; the next load into that buffer waits for
+// the bulk store to have read it.
 __global__ void __launch_bounds__(256, 2)
 dwconv3_tma_kernel(const __grid_constant__ Dw3Maps maps, const Dw3Params p) {
   constexpr int K = 3, CB = 32, XO = 8, TH = 4, TW = 32, RG = 4;
   constexpr int ROWS = TH * RG, IH = ROWS + K - 1, IW = TW + K - 1;
+  constexpr int HALO = (IH * IW * CB * 2 + 127) / 128 * 128;
   extern __shared__ __align__(128) uint8_t dw_smem[];
   uint8_t* base = dw_smem + ((128u - (smem_u32(dw_smem) & 127u)) & 127u);
-  const uint32_t* s_in = reinterpret_cast<const uint32_t*>(base);                 // [IH][IW][CB / 2] bf16 pairs
-  float* s_w = reinterpret_cast<float*>(base + IH * IW * CB * 2);                 // [9][CB]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(base + IH * IW * CB * 2 + K * K * CB * 4);
-  int t = blockIdx.x, gi = 0;
-  while (gi + 1 < p.ngrids && t >= p.tile_start[gi + 1]) ++gi;
-  t -= p.tile_start[gi];
-  const int tx = t % p.tiles_x[gi], ty = t / p.tiles_x[gi];
-  const int c0 = blockIdx.y * CB, b = blockIdx.z;
-  const int y0 = ty * ROWS, x0 = tx * TW;
+  float* s_w = reinterpret_cast<float*>(base + 2 * HALO);                          // [9][CB]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + 2 * HALO + K * K * CB * 4);   // [2]
+  const int ncb = p.C / CB, ntile = p.tile_start[3];
+  const int items = ntile * ncb * p.B;
+  auto decode = [&](int item, int& gi, int& x0, int& y0, int& c0, int& b) {
+    const int r = item / ncb;
+    c0 = (item - r * ncb) * CB;
+    b = r / ntile;
+    int t = r - b * ntile;
+    gi = 0;
+    while (gi + 1 < p.ngrids && t >= p.tile_start[gi + 1]) ++gi;
+    t -= p.tile_start[gi];
+    const int ty = t / p.tiles_x[gi];
+    x0 = (t - ty * p.tiles_x[gi]) * TW;
+    y0 = ty * ROWS;
+  };
+  auto issue = [&](int item, int buf) {       // one thread
+    int gi, x0, y0, c0, b;
+    decode(item, gi, x0, y0, c0, b);
+    mbar_arrive_expect_tx(&bar[buf], IH * IW * CB * 2);
+    tma_load_4d(base + buf * HALO, &maps.x[gi], &bar[buf], c0, x0 - 1, y0 - 1, b);
+  };
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
+    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
     fence_barrier_init();
   }
   pdl_wait();
-  if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar, IH * IW * CB * 2);
-    tma_load_4d(base, &maps.x[gi], bar, c0, x0 - 1, y0 - 1, b);
-  }
-  for (int i = threadIdx.x; i < K * K * CB; i += blockDim.x) s_w[i] = p.w[(i / CB) * p.C + c0 + (i % CB)];
+  if (threadIdx.x == 0 && (int)blockIdx.x < items) issue(blockIdx.x, 0);
   const int cp = threadIdx.x & 15, xg = (threadIdx.x >> 4) & 3, rg = threadIdx.x >> 6;
-  u64 acc[TH][XO];
-  {
-    const float b0 = p.bias ? p.bias[c0 + cp * 2] : 0.f, b1 = p.bias ? p.bias[c0 + cp * 2 + 1] : 0.f;
+  int it = 0;
+  for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+    const int buf = it & 1;
+    int gi, x0, y0, c0, b;
+    decode(item, gi, x0, y0, c0, b);
+    __syncthreads();                    // every thread is done with s_w and with the other buffer (item - 1)
+    if (threadIdx.x == 0 && item + (int)gridDim.x < items) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the store of item - 1 has read that buffer
+      issue(item + gridDim.x, buf ^ 1);
+    }
+    for (int i = threadIdx.x; i < K * K * CB; i += blockDim.x) s_w[i] = p.w[(i / CB) * p.C + c0 + (i % CB)];
+    u64 acc[TH][XO];
+    {
+      const float b0 = p.bias ? p.bias[c0 + cp * 2] : 0.f, b1 = p.bias ? p.bias[c0 + cp * 2 + 1] : 0.f;
+#pragma unroll
+      for (int r = 0; r < TH; ++r)
+#pragma unroll
+        for (int xo = 0; xo < XO; ++xo) acc[r][xo] = pack2(b0, b1);
+    }
+    __syncthreads();
+    mbar_wait(&bar[buf], (it >> 1) & 1);
+    const uint32_t* s_in = reinterpret_cast<const uint32_t*>(base + buf * HALO);      // [IH][IW][CB / 2] bf16 pairs
+    const uint32_t* in0 = s_in + ((rg * TH) * IW + xg * XO) * (CB / 2) + cp;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      u64 w[K];
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) w[kx] = *reinterpret_cast<const u64*>(&s_w[(ky * K + kx) * CB + cp * 2]);
+#pragma unroll
+      for (int r = 0; r < TH; ++r) {
+        u64 in[XO + K - 1];
+#pragma unroll
+        for (int i = 0; i < XO + K - 1; ++i) {
+          const uint32_t v = in0[((r + ky) * IW + i) * (CB / 2)];
+          in[i] = pack2(bf16lo(v), bf16hi(v));
+        }
+#pragma unroll
+        for (int xo = 0; xo < XO; ++xo)
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) acc[r][xo] = fma2(in[xo + kx], w[kx], acc[r][xo]);
+      }
+    }
+    __syncthreads();                      // every warp is done with the halo: reuse it as the [ROWS][TW][CB] bf16 output tile
+    uint32_t* s_out = reinterpret_cast<uint32_t*>(base + buf * HALO);
 #pragma unroll
     for (int r = 0; r < TH; ++r)
 #pragma unroll
-      for (int xo = 0; xo < XO; ++xo) acc[r][xo] = pack2(b0, b1);
-  }
-  __syncthreads();
-  mbar_wait(bar, 0);
-  const uint32_t* in0 = s_in + ((rg * TH) * IW + xg * XO) * (CB / 2) + cp;
-#pragma unroll
-  for (int ky = 0; ky < K; ++ky) {
-    u64 w[K];
-#pragma unroll
-    for (int kx = 0; kx < K; ++kx) w[kx] = *reinterpret_cast<const u64*>(&s_w[(ky * K + kx) * CB + cp * 2]);
-#pragma unroll
-    for (int r = 0; r < TH; ++r) {
-      u64 in[XO + K - 1];
-#pragma unroll
-      for (int i = 0; i < XO + K - 1; ++i) {
-        const uint32_t v = in0[((r + ky) * IW + i) * (CB / 2)];
-        in[i] = pack2(bf16lo(v), bf16hi(v));
+      for (int xo = 0; xo < XO; ++xo) {
+        float a0, a1;
+        unpack2(acc[r][xo], a0, a1);
+        if (p.act == 1) gelu_erf2(a0, a1);
+        else if (p.act == 3) { a0 = fminf(fmaxf(a0, 0.f), 6.f); a1 = fminf(fmaxf(a1, 0.f), 6.f); }
+        s_out[((rg * TH + r) * TW + xg * XO + xo) * (CB / 2) + cp] = pack_bf16(a0, a1);
       }
-#pragma unroll
-      for (int xo = 0; xo < XO; ++xo)
-#pragma unroll
-        for (int kx = 0; kx < K; ++kx) acc[r][xo] = fma2(in[xo + kx], w[kx], acc[r][xo]);
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                       reinterpret_cast<uint64_t>(&maps.y[gi])),
+                   "r"(smem_u32(s_out)), "r"(c0), "r"(x0), "r"(y0), "r"(b)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   }
-  __syncthreads();                      // every warp is done with the halo: reuse it as the [ROWS][TW][CB] bf16 output tile
-  uint32_t* s_out = reinterpret_cast<uint32_t*>(base);
-#pragma unroll
-  for (int r = 0; r < TH; ++r)
-#pragma unroll
-    for (int xo = 0; xo < XO; ++xo) {
-      float a0, a1;
-      unpack2(acc[r][xo], a0, a1);
-      if (p.act == 1) gelu_erf2(a0, a1);
-      else if (p.act == 3) { a0 = fminf(fmaxf(a0, 0.f), 6.f); a1 = fminf(fmaxf(a1, 0.f), 6.f); }
-      s_out[((rg * TH + r) * TW + xg * XO + xo) * (CB / 2) + cp] = pack_bf16(a0, a1);
-    }
-  fence_proxy_async();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                     reinterpret_cast<uint64_t>(&maps.y[gi])),
-                 "r"(smem_u32(s_out)), "r"(c0), "r"(x0), "r"(y0), "r"(b)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 static int dwconv3_tma(const __nv_bfloat16* x, __nv_bfloat16* y, const float* w, const float* bias, int B, int C, int ngrids,
@@ -405,9 +433,13 @@ static int dwconv3_tma(const __nv_bfloat16* x, __nv_bfloat16* y, const float* w,
     if (i < ngrids) total += p.tiles_x[i] * ((H + 15) / 16);
   }
   p.tile_start[3] = total;
-  constexpr int smem = 18 * 34 * 32 * 2 + 9 * 32 * 4 + 16 + 128;
+  constexpr int smem = 2 * ((18 * 34 * 32 * 2 + 127) / 128 * 128) + 9 * 32 * 4 + 16 + 128;
   MMSAM_SET_SMEM_ONCE(dwconv3_tma_kernel, smem);
-  cudaError_t le = mmsam_host::launch_pdl(dwconv3_tma_kernel, dim3(total, C / 32, B), dim3(256), smem, st, maps, p);
+  p.B = B;
+  const long long items = (long long)total * (C / 32) * B;
+  if (items > 0x7fffffffLL) return MMSAM_ERR_UNSUPPORTED;
+  const int grid = items < 2 * kNumSMs ? (int)items : 2 * kNumSMs;
+  cudaError_t le = mmsam_host::launch_pdl(dwconv3_tma_kernel, dim3(grid), dim3(256), smem, st, maps, p);
   if (le != cudaSuccess) return (int)le;
   MMSAM_LAUNCH_CHECK();
   return MMSAM_OK;

@@ -26,3 +26,19 @@ for (name, ks, C, grids, act) in (("cnx0 7x7", 7, 96, [(256, 256)], None), ("cnx
     ms = s.elapsed_time(e) / 10
     fma = B * S * C * ks * ks
     print(f"dwconv {name}: {ms * 1e3:.0f} us, {B * S * C * 4 / ms / 1e6:.0f} GB/s (in+out), {fma / ms / 1e9:.2f} TFMA/s")
+# MobileNetV2 depthwise 3x3 + ReLU6 of the neck's four levels (2 ci channels)
+for (hw, C) in ((256, 192), (128, 384), (64, 768), (32, 1536)):
+    S = hw * hw
+    x = torch.randn(B, S, C, device="cuda").to(torch.bfloat16)
+    w = torch.randn(9, C, device="cuda")
+    out = torch.empty_like(x)
+    for _ in range(3):
+        K.dwconv(x, w, None, 3, [(hw, hw)], B, C, S * C, S * C, act="relu6", out=out)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(10):
+        K.dwconv(x, w, None, 3, [(hw, hw)], B, C, S * C, S * C, act="relu6", out=out)
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    print(f"dwconv neck 3x3 {hw}^2 x {C}: {ms * 1e3:.0f} us, {B * S * C * 4 / ms / 1e6:.0f} GB/s (in+out)")
