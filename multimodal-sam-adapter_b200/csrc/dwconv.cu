@@ -263,7 +263,9 @@ static int dwconv7_tma(const float* x, __nv_bfloat16* y, const float* w, const f
   if (!enc) return MMSAM_ERR_DRIVER;
   static const int rg_env = [] { const char* e = getenv("MMSAM_DW_RG"); return e ? atoi(e) : 0; }();
   // rows per CTA: 8 (128 threads, 3 CTAs / SM) measured 3-10 % faster than 16 (256 threads, 2 CTAs / SM) at every stage of
-  // the step (110 / 60 / 33 / 21 us vs 114 / 64 / 37 / 22): 22.4 TFMA/s at stage 0 = the FFMA2 issue rate of the chip
+  // the step (110 / 60 / 33 / 21 us vs 114 / 64 / 37 / 22): 22.4 TFMA/s at stage 0 = the FFMA2 issue rate of the chip.
+  // A persistent 256-thread CTA per SM with the halo and the tap block double-buffered (what made the 3x3 kernel below
+  // 20 % faster) measured 115 / 63 / 37 / 21 us: this kernel waits for its FMA pipe, not for its loads.
   const int rg = rg_env == 4 ? 4 : 2;
   CUtensorMap tmX, tmY;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
