@@ -560,11 +560,14 @@ def main():
                      "share_of_step": gm["ms"] / (ms / args.steps)},
         "roofline_msda": {"kernel": "msda_fused_coop_kernel (injector, L1 gathers) + msda_staged2_kernel (extractor, shared-memory gathers)", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
                           "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                          # ncu --set full inside a forward (profiles/r01_msda_ncu_summary.txt): dram read + write per
-                          # launch, injector 280.1 MB / extractor 302.2 MB, averaged over the step's 4 + 6 launches
-                          "traffic": (4 * 280.1e6 + 6 * 302.2e6) / 10, "traffic_of": "average msda launch of the step",
-                          "ceiling": "SM load path, not HBM: gathered bytes are 8.2x the algorithmic bytes and L1 gathers "
-                                     "peak at 11.5 TB/s chip-wide (tools/micro/gather_bench.cu) -> 22 % of HBM peak",
+                          # ncu --set full: dram read + write per launch, injector (L1-gather kernel,
+                          # profiles/r01_msda_ncu_summary.txt) 280.1 MB / extractor (staged kernel,
+                          # profiles/r02_msda_staged2_ncu_summary.txt) 305.6 MB, averaged over the step's 4 + 6 launches
+                          "traffic": (4 * 280.1e6 + 6 * 305.6e6) / 10, "traffic_of": "average msda launch of the step (not re-measured by this run)",
+                          "ceiling": "SM side, not HBM: the gathered bytes are 8.2x the algorithmic bytes. Injector: L1 gathers peak at "
+                                     "11.5 TB/s chip-wide (tools/micro/gather_bench.cu) -> 22 % of HBM peak on algorithmic bytes; extractor: "
+                                     "shared-memory gathers, bound by instruction issue (474 warp instructions per 8 items, half of them "
+                                     "bf16 -> fp32 unpacks; profiles/r02_msda_notes.md)",
                           "launches_per_step": md["launches"],
                           "ms_per_step": md["ms"], "peak_source": pk["source"]},
         "miou_check": {"pixels": int(conf_all.sum().item()), "equal_single": equal_single,
