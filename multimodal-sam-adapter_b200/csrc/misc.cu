@@ -322,6 +322,142 @@ resize_sum_affine_kernel(const ResizeSumParams p) {
   }
 }
 
+// Staged variant for the Segformer head: three sources exactly 2x / 4x / 8x smaller than the output, C % 64 == 0.
+// The kernel above reads 12 corner vectors per 16-byte output through L1 (13x its output: 586 us at the head's shape, the
+// L1 gather ceiling). Caching x-interpolated source rows in registers with run-time row bookkeeping made every row
+// change a dependent global load (629 us), and with the windows staged in shared memory the bookkeeping itself cost 325
+// instructions per output (593 us, issue-bound under ncu). With integer factors and row tiles aligned to 8 the pattern
+// is static: output row i of a tile samples source rows floor((i + 0.5) / F - 0.5) and the next one, relative to the
+// tile. So: a CTA owns a tile of 8 rows x 32 columns x 64 channels, stages the source windows it samples in shared
+// memory (coordinates clamped to the map: the clamped duplicates reproduce F.interpolate's edge handling), and a
+// thread = (column, 8 channels) walks each source's window rows ONCE — two x-interpolated rows in registers, the
+// contributions of the output rows between them accumulated with compile-time weights. 3 + 4 + 6 shared-memory row
+// fetches per 8 outputs instead of 96 corner loads; the base rows are requested up front.
+static constexpr int RT_Y = 8, RT_X = 32, RT_C = 64;
+struct ResizeStagedParams {
+  ResizeSumParams q;
+  int nc[3], off[3];      // window columns / byte offset in shared memory (window rows: RT_Y / F + 2)
+};
+template <int F>
+__device__ __forceinline__ void rs_source(const uint8_t* win, int nc, int xa, int xb, float lx, int cvl, u64 (&acc)[RT_Y][4]) {
+  constexpr int NR = RT_Y / F + 2;
+  const u64 l1 = pack2(lx, lx), l0 = pack2(1.f - lx, 1.f - lx);
+  u64 prev[4], cur[4];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const uint8_t* rp = win + (r * nc) * 128 + cvl * 16;
+    const uint4 q0 = *reinterpret_cast<const uint4*>(rp + xa * 128);
+    const uint4 q1 = *reinterpret_cast<const uint4*>(rp + xb * 128);
+    const uint32_t* e0 = reinterpret_cast<const uint32_t*>(&q0);
+    const uint32_t* e1 = reinterpret_cast<const uint32_t*>(&q1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      prev[j] = cur[j];
+      cur[j] = fma2(pack2(bf16lo(e1[j]), bf16hi(e1[j])), l1, mul2(pack2(bf16lo(e0[j]), bf16hi(e0[j])), l0));
+    }
+    if (r > 0) {
+      // output rows i with floor((i + 0.5) / F - 0.5) + 1 == r - 1 lie between window rows r - 1 (prev) and r (cur)
+#pragma unroll
+      for (int i = 0; i < RT_Y; ++i) {
+        const int num = 2 * i + 1 + F;                      // (i + 0.5) / F - 0.5 + 1 = num / (2 F)
+        if (num / (2 * F) == r - 1) {
+          const float ly = (float)(num % (2 * F)) / (float)(2 * F);
+          const u64 w1 = pack2(ly, ly), w0 = pack2(1.f - ly, 1.f - ly);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma2(cur[j], w1, fma2(prev[j], w0, acc[i][j]));
+        }
+      }
+    }
+  }
+}
+template <int F0, int F1, int F2>
+__global__ void __launch_bounds__(256, 2)
+resize_sum_staged_kernel(const ResizeStagedParams ps) {
+  extern __shared__ __align__(16) uint8_t rs_smem[];
+  const ResizeSumParams& p = ps.q;
+  const int ncb = p.C / RT_C;
+  const int tx = blockIdx.x / ncb, cb = blockIdx.x - tx * ncb;
+  const int x_t = tx * RT_X, y_t = blockIdx.y * RT_Y, b = blockIdx.z;
+  const int cvl = threadIdx.x & 7, xl = threadIdx.x >> 3;          // 8 channel vectors (128 B) x 32 columns
+  const int c0 = cb * RT_C + cvl * 8;
+  const int x = x_t + xl;
+  constexpr int FS[3] = {F0, F1, F2};
+  // ---- stage the windows: rows y_t / F - 1 ... y_t / F + RT_Y / F, columns from the first one the tile samples ----
+  int wx0[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float sx = (x_t + 0.5f) * p.rw[k] - 0.5f;
+    sx = sx < 0.f ? 0.f : sx;
+    wx0[k] = min((int)sx, p.Ws[k] - 1);
+    const int wy0 = y_t / FS[k] - 1;
+    const int n = (RT_Y / FS[k] + 2) * ps.nc[k] * 8;
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const int v = i & 7, px = i >> 3;
+      const int ry = px / ps.nc[k], rx = px - ry * ps.nc[k];
+      const int sy = min(max(wy0 + ry, 0), p.Hs[k] - 1), sxx = min(wx0[k] + rx, p.Ws[k] - 1);
+      const uint4 val = __ldg(reinterpret_cast<const uint4*>(p.src[k] + (((long long)b * p.Hs[k] + sy) * p.Ws[k] + sxx) * p.C + cb * RT_C + v * 8));
+      *reinterpret_cast<uint4*>(rs_smem + ps.off[k] + (px * 8 + v) * 16) = val;
+    }
+  }
+  const bool active = x < p.Wo;
+  const int xc = active ? x : p.Wo - 1;
+  const long long pix_row = (long long)p.Wo * p.C;
+  const long long off0 = ((long long)b * p.Ho + y_t) * pix_row + (long long)xc * p.C + c0;
+  uint4 gb[RT_Y];
+#pragma unroll
+  for (int i = 0; i < RT_Y; ++i)
+    gb[i] = (p.base && y_t + i < p.Ho) ? __ldg(reinterpret_cast<const uint4*>(p.base + off0 + i * pix_row)) : make_uint4(0, 0, 0, 0);
+  // horizontal corners (window-relative) and weights of every source
+  int xa[3], xb[3];
+  float lxs[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float sx = (xc + 0.5f) * p.rw[k] - 0.5f;
+    sx = sx < 0.f ? 0.f : sx;
+    int x0 = (int)sx;
+    x0 = x0 > p.Ws[k] - 1 ? p.Ws[k] - 1 : x0;
+    const int x1 = x0 < p.Ws[k] - 1 ? x0 + 1 : x0;
+    lxs[k] = sx - x0;
+    xa[k] = x0 - wx0[k]; xb[k] = x1 - wx0[k];
+  }
+  __syncthreads();
+  u64 acc[RT_Y][4];
+#pragma unroll
+  for (int i = 0; i < RT_Y; ++i) {
+    const uint4 bv = gb[i];
+    acc[i][0] = pack2(bf16lo(bv.x), bf16hi(bv.x)); acc[i][1] = pack2(bf16lo(bv.y), bf16hi(bv.y));
+    acc[i][2] = pack2(bf16lo(bv.z), bf16hi(bv.z)); acc[i][3] = pack2(bf16lo(bv.w), bf16hi(bv.w));
+  }
+  rs_source<F0>(rs_smem + ps.off[0], ps.nc[0], xa[0], xb[0], lxs[0], cvl, acc);
+  rs_source<F1>(rs_smem + ps.off[1], ps.nc[1], xa[1], xb[1], lxs[1], cvl, acc);
+  rs_source<F2>(rs_smem + ps.off[2], ps.nc[2], xa[2], xb[2], lxs[2], cvl, acc);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
+  if (p.scale) {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0)), a1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
+    sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+  }
+  if (p.shift) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0)), b1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+    sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+  }
+  __nv_bfloat16* op = p.out + off0;
+#pragma unroll
+  for (int i = 0; i < RT_Y; ++i, op += pix_row) {
+    if (y_t + i >= p.Ho) break;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) unpack2(acc[i][j], f[2 * j], f[2 * j + 1]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (p.relu) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (active) *reinterpret_cast<uint4*>(op) = pack8(f);
+  }
+}
+
 // labels[b,y,x] = argmax_c bilinear(logits[b])[y,x,c]  (first maximum wins, like torch.argmax).
 // Replaces resize(logits -> image size) + softmax + argmax of EncoderDecoder.encode_decode_test /
 // whole_inference_dim(_cut) / simple_test (encoder_decoder.py:96-117, 329-414, 449, 477); softmax is
@@ -555,6 +691,23 @@ MMSAM_API int mmsam_resize_sum_affine_bf16(const void* base, int nsrc, const voi
   if (B > 65535 || (Ho + RS_YB - 1) / RS_YB > 65535 || (long long)Wo * (C / 8) > (1ll << 31) - 256 ||
       (long long)Wo * C >= (1ll << 31))
     return MMSAM_ERR_UNSUPPORTED;
+  if (nsrc == 3 && base && (C % RT_C) == 0 && Ho == 2 * p.Hs[0] && Wo == 2 * p.Ws[0] && Ho == 4 * p.Hs[1] && Wo == 4 * p.Ws[1] &&
+      Ho == 8 * p.Hs[2] && Wo == 8 * p.Ws[2] && getenv("MMSAM_RESIZE_SUM_LEGACY") == nullptr) {
+    // the Segformer head: sources exactly 2x / 4x / 8x smaller than the output (staged kernel with static row patterns)
+    ResizeStagedParams ps;
+    ps.q = p;
+    int off = 0;
+    const int fs[3] = {2, 4, 8};
+    for (int k = 0; k < 3; ++k) {
+      ps.nc[k] = (RT_X - 1) / fs[k] + 3;        // columns a 32-wide tile can touch
+      ps.off[k] = off;
+      off += (RT_Y / fs[k] + 2) * ps.nc[k] * 128;
+    }
+    dim3 grid((unsigned)(((Wo + RT_X - 1) / RT_X) * (C / RT_C)), (unsigned)((Ho + RT_Y - 1) / RT_Y), (unsigned)B);
+    resize_sum_staged_kernel<2, 4, 8><<<grid, 256, off, (cudaStream_t)stream>>>(ps);
+    MMSAM_LAUNCH_CHECK();
+    return MMSAM_OK;
+  }
   dim3 grid((unsigned)(((long long)Wo * (C / 8) + 255) / 256), (unsigned)((Ho + RS_YB - 1) / RS_YB), (unsigned)B);
   resize_sum_affine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   MMSAM_LAUNCH_CHECK();

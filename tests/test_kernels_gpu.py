@@ -621,6 +621,9 @@ def test_convnext_mlp_fused(M, C, gamma_on):
     (1, 8, 6, 6, [(1, 1), (2, 3)], True),                   # degenerate sources (all corners clamp to one pixel)
     (1, 24, 25, 19, [(13, 10), (25, 19)], False),           # ragged, one source already at the output size
     (2, 8, 12, 12, [], True),                               # base only
+    (1, 128, 27, 40, [(12, 20), (7, 9), (14, 40)], False),  # 64-channel blocks but non-integer ratios: the general kernel
+    (2, 64, 40, 72, [(20, 36), (10, 18), (5, 9)], True),    # staged kernel (exact 2x / 4x / 8x): several tiles per axis, ragged last column tile
+    (1, 128, 8, 16, [(4, 8), (2, 4), (1, 2)], False),       # staged, one tile: every window row / column clamps at a map edge
 ])
 def test_resize_sum_affine(B, C, ho, wo, srcs, relu):
     """act((base + sum_k bilinear(src_k)) * scale + shift) against F.interpolate(align_corners=False); with the fusion
