@@ -479,7 +479,26 @@ combine_pool_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __
     float col[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) col[j] = 0.f;
-    for (int y = y0; y < y1; ++y) {
+    // four rows of loads are requested before the first is consumed: with one (o, lo) pair in flight per thread and
+    // ~2.6 CTAs per SM the kernel ran at 45 % of its HBM floor (208 us for 604 MB at the 256^2 level)
+    for (int yb = y0; yb < y1; yb += 4) {
+    uint4 ua[4], ul[4];
+    float wp4[4], bp4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ua[q] = ul[q] = make_uint4(0, 0, 0, 0); wp4[q] = bp4[q] = 0.f;
+      if (yb + q < y1 && x < W && cok) {
+        const long long pix = (long long)(yb + q) * W + x;
+        const long long off = ((long long)b * H * W + pix) * C + c;
+        ua[q] = __ldg(reinterpret_cast<const uint4*>(o + off));
+        ul[q] = __ldg(reinterpret_cast<const uint4*>(lo + off));
+        wp4[q] = __ldg(wpix + pix); bp4[q] = __ldg(bpix + pix);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int y = yb + q;
+      if (y >= y1) break;                 // uniform over the CTA
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -487,9 +506,9 @@ combine_pool_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __
         const long long pix = (long long)y * W + x;
         const long long off = ((long long)b * H * W + pix) * C + c;
         float a[8], l[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(o + off)), a);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(lo + off)), l);
-        const float wp = __ldg(wpix + pix), bp = __ldg(bpix + pix);
+        unpack8(ua[q], a);
+        unpack8(ul[q], l);
+        const float wp = wp4[q], bp = bp4[q];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           v[j] = fmaf(fmaf((a[j] - m[j]) * r[j], wp, bp), g[j], s2 * l[j]);
@@ -505,6 +524,7 @@ combine_pool_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __
         t += __shfl_xor_sync(0xffffffffu, t, 16);
         if ((threadIdx.x & 31) < 8) s_ph[(warp_id * RS + (y - y0)) * 64 + cv * 8 + j] += t;
       }
+    }
     }
     if (x < W && cok) {
       float* dst = pw_part + (((long long)strip * B + b) * W + x) * C + c;
