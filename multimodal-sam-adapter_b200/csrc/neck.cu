@@ -117,12 +117,27 @@ gfe_weff_kernel(const float* __restrict__ S_part, const float* __restrict__ nq_p
   const int h = blockIdx.x, b = blockIdx.y;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
   const long long nn = (long long)ci * ci;
-  for (int e = t; e < ch * ch; e += blockDim.x) {
-    const int a = e / ch, j = e - a * ch;
-    const float* src = S_part + (long long)b * nn + (long long)(h * ch + a) * ci + h * ch + j;
-    float acc = 0.f;
-    for (int c = 0; c < nchunks; ++c) acc += src[(long long)c * B * nn];
-    att[a * cs + j] = acc;
+  // four elements per trip: their chunk-0 loads are requested together (one load in flight per thread made this phase a
+  // chain of ~36 L2 latencies per CTA at ch = 96)
+  for (int e0 = t; e0 < ch * ch; e0 += 4 * blockDim.x) {
+    float acc[4];
+    const float* src[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = min(e0 + u * (int)blockDim.x, ch * ch - 1);
+      const int a = e / ch, j = e - a * ch;
+      src[u] = S_part + (long long)b * nn + (long long)(h * ch + a) * ci + h * ch + j;
+      acc[u] = src[u][0];
+    }
+    for (int c = 1; c < nchunks; ++c) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += src[u][(long long)c * B * nn];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * (int)blockDim.x;
+      if (e < ch * ch) { const int a = e / ch, j = e - a * ch; att[a * cs + j] = acc[u]; }
+    }
   }
   for (int e = t; e < 2 * ch; e += blockDim.x) {
     const float* src = (e < ch ? nq_part : nk_part) + (long long)b * ci + h * ch + (e < ch ? e : e - ch);
@@ -171,6 +186,7 @@ gfe_weff_kernel(const float* __restrict__ S_part, const float* __restrict__ nq_p
       for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) acc[ii][jj] = 0.f;
+#pragma unroll 2
       for (int a4 = 0; a4 < ch; a4 += 4) {
         float4 w[4], at[4];
 #pragma unroll
@@ -401,7 +417,17 @@ ca_vectors_kernel(const float* __restrict__ ph, const float* __restrict__ pw_par
     if (is_h) v = ph[((long long)b * H + pos) * C + c] / W;
     else {
       v = 0.f;
-      for (int s = 0; s < nstrips; ++s) v += pw_part[(((long long)s * B + b) * W + (pos - H)) * C + c];   // strips in order
+      // strips in order; the loads of four strips are requested together (the kernel is a chain of short latency-bound
+      // phases: 126 us at the 256^2 level with one load in flight per thread)
+      int s = 0;
+      for (; s + 4 <= nstrips; s += 4) {
+        const float p0 = pw_part[(((long long)s * B + b) * W + (pos - H)) * C + c];
+        const float p1 = pw_part[(((long long)(s + 1) * B + b) * W + (pos - H)) * C + c];
+        const float p2 = pw_part[(((long long)(s + 2) * B + b) * W + (pos - H)) * C + c];
+        const float p3 = pw_part[(((long long)(s + 3) * B + b) * W + (pos - H)) * C + c];
+        v += p0; v += p1; v += p2; v += p3;
+      }
+      for (; s < nstrips; ++s) v += pw_part[(((long long)s * B + b) * W + (pos - H)) * C + c];
       v /= H;
     }
     y[c] = v;
@@ -410,6 +436,7 @@ ca_vectors_kernel(const float* __restrict__ ph, const float* __restrict__ pw_par
   for (int m = warp; m < mip; m += nwarps) {
     const float* w = w1 + (long long)m * C;
     float acc = 0.f;
+#pragma unroll 8
     for (int k = lane; k < C; k += 32) acc = fmaf(__ldg(w + k), y[k], acc);
     acc = warp_sum(acc);
     if (lane == 0) {
@@ -423,6 +450,7 @@ ca_vectors_kernel(const float* __restrict__ ph, const float* __restrict__ pw_par
   float* dst = is_h ? ah + ((long long)b * H + pos) * C : aw + ((long long)b * W + (pos - H)) * C;
   for (int c = t; c < C; c += blockDim.x) {
     float acc = bo[c];
+#pragma unroll 8
     for (int m = 0; m < mip; ++m) acc = fmaf(__ldg(wo + (long long)c * mip + m), tm[m], acc);
     dst[c] = 1.f / (1.f + __expf(-acc));
   }
