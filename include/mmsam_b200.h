@@ -42,6 +42,19 @@ int mmsam_msda_forward(const void* value, const int64_t* spatial_shapes_dev,
                        const void* attn_weight, void* out, int N, int S, int M, int D, int Lq, int L,
                        int P, int value_dtype, int aux_dtype, void* stream);
 
+/* Multi-scale deformable attention, backward (training; the inference path never calls it).
+ * Replaces MSDA.ms_deform_attn_backward = ms_deform_attn_cuda_backward (ops/src/vision.cpp:13-16,
+ * ops/src/cuda/ms_deform_attn_cuda.cu:83-153) and the ms_deformable_col2im_* kernels
+ * (ops/src/cuda/ms_deform_im2col_cuda.cuh:301-921), as called by MSDeformAttnFunction.backward
+ * (ops/functions/ms_deform_attn_func.py:39-50). Inputs as in mmsam_msda_forward plus grad_output [N,Lq,M*D]; every
+ * floating tensor has the same dtype (MMSAM_F32 or MMSAM_F64, the two the reference's gradient checks use).
+ * Outputs: grad_value [N,S,M,D] (zeroed by this call, accumulated with atomics like the reference's),
+ * grad_sampling_loc [N,Lq,M,L,P,2], grad_attn_weight [N,Lq,M,L,P] (plain stores: deterministic). */
+int mmsam_msda_backward(const void* value, const int64_t* spatial_shapes_dev, const int64_t* level_start_index_dev,
+                        const void* sampling_loc, const void* attn_weight, const void* grad_output, void* grad_value,
+                        void* grad_sampling_loc, void* grad_attn_weight, int N, int S, int M, int D, int Lq, int L, int P,
+                        int dtype, void* stream);
+
 /* Row LayerNorm over the last dim of a [rows, C] matrix, fp32 affine, biased variance. x_dtype / y_dtype: MMSAM_BF16 or
  * MMSAM_F32 (bf16 -> bf16, fp32 -> bf16, fp32 -> fp32; the fp32 forms serve the fp32 residual streams).
  * Replaces nn.LayerNorm / LayerNorm2d calls on the path (base/image_encoder.py:398,421;

@@ -17,6 +17,7 @@ _vp, _i, _ll, _f = _c.c_void_p, _c.c_int, _c.c_longlong, _c.c_float
 SIGNATURES = {
     "mmsam_arch": [],
     "mmsam_msda_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mmsam_msda_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mmsam_layernorm": [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _ll, _i, _ll, _ll, _f, _i, _i, _vp],
     "mmsam_gemm_bf16": [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _i, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp,
                         _i, _i, _i, _i, _i, _vp],

@@ -66,6 +66,30 @@ def msda_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_we
     return out
 
 
+def msda_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output):
+    """Gradients of msda_forward (fp32 / fp64, all floating tensors in one dtype):
+    -> (grad_value [N,S,M,D], grad_sampling_loc [N,Lq,M,L,P,2], grad_attn_weight [N,Lq,M,L,P])."""
+    _need_cuda(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output)
+    for t in (value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output):
+        if not t.is_contiguous():
+            raise _lib.MMSamError("msda_backward: all tensors must be contiguous")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise _lib.MMSamError("msda_backward: spatial_shapes / level_start_index must be int64")
+    if value.dtype not in (torch.float32, torch.float64) or any(t.dtype != value.dtype for t in (sampling_loc, attn_weight, grad_output)):
+        raise _lib.MMSamError("msda_backward: value / sampling_loc / attn_weight / grad_output must all be fp32 or all fp64")
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_loc.shape
+    gv = torch.empty_like(value)
+    gl = torch.empty_like(sampling_loc)
+    ga = torch.empty_like(attn_weight)
+    rc = _lib.load().mmsam_msda_backward(
+        _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc), _ptr(attn_weight), _ptr(grad_output),
+        _ptr(gv), _ptr(gl), _ptr(ga), N, S, M, D, Lq, L, P, _DT[value.dtype], _stream())
+    _lib.check(rc, "mmsam_msda_backward")
+    _count()
+    return gv, gl, ga
+
+
 def layernorm(x, gamma, beta, eps, out=None, row_map=None, out_rows=None, patchify_hw=None, out2=None,
               out_dtype=torch.bfloat16):
     """x bf16 or fp32 [..., C] (rows contiguous) -> LN over C (bf16, or fp32 for an fp32 input when out_dtype says so).

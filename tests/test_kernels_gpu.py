@@ -181,6 +181,52 @@ def test_msda_staged_vs_oracle(N, M, levels, qgrids, anchor, tile, noise, margin
     assert (out - out2).abs().max() <= 0.008 * exp.abs().max() + 1e-6
 
 
+@pytest.mark.parametrize("N,M,D,Lq,levels,P,dtype,spread", [
+    (1, 2, 2, 2, [(6, 4), (3, 2)], 2, torch.float64, 1.0),      # the reference's own check shape (ops/test.py:16-75)
+    (2, 8, 32, 37, [(16, 12), (8, 6), (4, 3)], 4, torch.float64, 1.0),
+    (1, 3, 48, 20, [(9, 7)], 4, torch.float64, 1.6),            # D > 32 (strided lanes), samples outside the map
+    (2, 4, 16, 33, [(10, 14), (5, 7)], 4, torch.float32, 1.2),
+])
+def test_msda_backward_vs_autograd_of_the_oracle(N, M, D, Lq, levels, P, dtype, spread):
+    """mmsam_msda_backward (MSDA.ms_deform_attn_backward, ops/src/cuda/ms_deform_attn_cuda.cu:83-153) against autograd
+    through the oracle's forward (the arithmetic of ms_deform_attn_core_pytorch / the reference kernel)."""
+    from oracle.msda import ms_deform_attn_core
+    k = _k()
+    g = torch.Generator().manual_seed(N * 100 + M * 10 + D)
+    L = len(levels)
+    shapes_t = torch.as_tensor(levels, dtype=torch.long)
+    S = int(shapes_t.prod(1).sum())
+    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+    value = torch.randn(N, S, M, D, generator=g, dtype=dtype).requires_grad_()
+    loc = ((torch.rand(N, Lq, M, L, P, 2, generator=g, dtype=dtype) - 0.5) * spread + 0.5).requires_grad_()
+    aw = torch.rand(N, Lq, M, L, P, generator=g, dtype=dtype) + 1e-5
+    aw = (aw / aw.sum((-1, -2), keepdim=True)).requires_grad_()
+    go = torch.randn(N, Lq, M * D, generator=g, dtype=dtype)
+    ms_deform_attn_core(value, shapes_t, loc, aw).backward(go)
+    gv, gl, ga = k.msda_backward(value.detach().cuda(), shapes_t.cuda(), lsi.cuda(), loc.detach().cuda(), aw.detach().cuda(), go.cuda())
+    tol = 1e-9 if dtype == torch.float64 else 2e-4
+    for name, got, want in (("grad_value", gv, value.grad), ("grad_sampling_loc", gl, loc.grad), ("grad_attn_weight", ga, aw.grad)):
+        err = (got.cpu() - want).abs().max().item()
+        assert err <= tol * max(1.0, want.abs().max().item()), (name, err)
+
+
+def test_msda_function_numerical_gradcheck():
+    """The reference's check_gradient_numerical (ops/test.py:55-75): torch.autograd.gradcheck of MSDeformAttnFunction in
+    double, every differentiable input."""
+    import mmsam_b200  # noqa
+    from mmsam_b200.ops.functions import MSDeformAttnFunction
+    g = torch.Generator().manual_seed(3)
+    N, M, D, Lq, L, P = 1, 2, 4, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long).cuda()
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    value = (torch.rand(N, S, M, D, generator=g, dtype=torch.float64) * 0.01).cuda().requires_grad_()
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g, dtype=torch.float64).cuda().requires_grad_()
+    aw = torch.rand(N, Lq, M, L, P, generator=g, dtype=torch.float64) + 1e-5
+    aw = (aw / aw.sum((-1, -2), keepdim=True)).cuda().requires_grad_()
+    assert torch.autograd.gradcheck(MSDeformAttnFunction.apply, (value, shapes, lsi, loc, aw, 2), nondet_tol=1e-12)
+
+
 def test_msda_empty():
     k = _k()
     shapes = torch.as_tensor([(4, 4)], dtype=torch.long).cuda()

@@ -99,7 +99,9 @@ def test_drop_in_extension_module_runs_reference_check():
     with pytest.raises(RuntimeError):
         MSDA.ms_deform_attn_forward(f["value"], shapes, lsi, f["loc"].cuda(), f["aw"].cuda(), 2)   # CPU value
     with pytest.raises(RuntimeError):
-        MSDA.ms_deform_attn_backward(f["value"].cuda(), shapes, lsi, f["loc"].cuda(), f["aw"].cuda(), out, 2)
+        MSDA.ms_deform_attn_backward(f["value"], shapes, lsi, f["loc"].cuda(), f["aw"].cuda(), out, 2)      # CPU value
+    gv, gl, ga = MSDA.ms_deform_attn_backward(f["value"].cuda(), shapes, lsi, f["loc"].cuda(), f["aw"].cuda(), torch.ones_like(out), 2)
+    assert gv.shape == f["value"].shape and gl.shape == f["loc"].shape and ga.shape == f["aw"].shape
 
 
 @pytest.fixture(scope="module")
