@@ -401,7 +401,9 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(o[8 * i + j]) * inv;
-            sts128(stg + i * 16, pack8(f));
+            // SWIZZLE_128B staging (the store's tensor map says so): a thread owns a 128-byte row, and with the chunks
+            // in place the 8 rows of a quarter warp would all hit the same four banks (8-way conflict, ~930 cycles per tile)
+            sts128(stg + ((i ^ (row & 7)) << 4), pack8(f));
           }
         }
         WIN_TRACE(3 + g, it, 2);
@@ -526,9 +528,9 @@ static int attention_win_launch(const void* qkv, void* out, const int* out_row_m
     cuuint64_t odims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t ostr[3] = {C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     cuuint32_t boxa[4] = {D, KS, 9, 1}, boxb[4] = {D, KS, 5, 1};
-    if (enc(&tmOA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, odims, ostr, boxa, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+    if (enc(&tmOA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, odims, ostr, boxa, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
-        enc(&tmOB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, odims, ostr, boxb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+        enc(&tmOB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, odims, ostr, boxb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return MMSAM_ERR_DRIVER;
   }
