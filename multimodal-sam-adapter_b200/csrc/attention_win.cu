@@ -317,6 +317,10 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
     for (int it = 0; it < n_my; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
       const int head = item % p.nh, bp = item / p.nh;
+      // window coordinates of the un-partition store, off the critical path (the divisions cost the issuing warp ~300
+      // cycles when they sat in front of the TMA store)
+      const int o_wx = p.H > 0 ? (bp % p.nww) * KS : 0, o_wy = p.H > 0 ? ((bp / p.nww) % p.nwh) * KS + (g ? 9 : 0) : 0;
+      const int o_b = p.H > 0 ? bp / (p.nww * p.nwh) : 0;
       WIN_TRACE(g, it, 0);
       mbar_wait(&s_full[g], it & 1);
       tc_fence_after();
@@ -412,10 +416,9 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
         WIN_TRACE(3 + g, it, 3);
         if (wq == 0) {
           if (elect_one()) {
-            const int wx = bp % p.nww, wy = (bp / p.nww) % p.nwh, b = bp / (p.nww * p.nwh);
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                              reinterpret_cast<uint64_t>(g ? &tmOB : &tmOA)),
-                         "r"(grp_stg), "r"(head * D), "r"(wx * KS), "r"(wy * KS + (g ? 9 : 0)), "r"(b)
+                         "r"(grp_stg), "r"(head * D), "r"(o_wx), "r"(o_wy), "r"(o_b)
                          : "memory");
           }
           __syncwarp();
