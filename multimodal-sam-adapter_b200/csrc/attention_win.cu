@@ -439,7 +439,8 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_cons
         if (row_valid && p.out_map) orow = p.out_map[orow];
         if (!row_valid) orow = -1;
         WIN_TRACE(3 + g, it, 1);
-        uint8_t* stg = reinterpret_cast<uint8_t*>(sG + (g * 4 + wq) * G_WARP_FLOATS) + lane * 128;   // 32 x 128 B of the warp's 7 KB
+        // 32 rows of the warp's 7 KB at a 144-byte pitch: with 128 the 8 rows of a quarter warp share four banks (8-way conflict)
+        uint8_t* stg = reinterpret_cast<uint8_t*>(sG + (g * 4 + wq) * G_WARP_FLOATS) + lane * 144;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float f[8];
